@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (oracle/_ref, built by oracle/Makefile from /root/reference).
+
+Only runs where /root/reference exists (the build container). The outputs -
+small .agmv streams plus golden.json with sizes and sha256 digests - are
+committed so that the CPU test-suite and the GPU box (which has no
+/root/reference) can check the oracle and the CUDA path against the reference.
+
+    python tests/golden/make_golden.py [--skip-high] [--only NAME]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+from agmv_testlib import (GOLDEN_DIR, LZSS, OPT, QUALITY, REF_DIR, ref_decode_raw, ref_encode, sha256,  # noqa: E402
+                          synth_frames)
+
+# name, w, h, n_frames, create_n, fps, opt, quality, keep_file
+ENCODE_CASES = [
+    ("syn64_III_LOW", 64, 64, 12, 11, 24, "III", "LOW", True),
+    ("syn64_I_MID", 64, 64, 12, 11, 24, "I", "MID", True),
+    ("syn64_II_LOW", 64, 64, 12, 11, 24, "II", "LOW", True),
+    ("syn64_ANIM_LOW", 64, 64, 20, 19, 24, "ANIM", "LOW", True),
+    ("syn96x80_III_LOW", 96, 80, 24, 23, 30, "III", "LOW", True),
+    ("gba240_GBA_I_LOW", 240, 160, 40, 39, 16, "GBA_I", "LOW", True),
+    ("nds240_NDS_LOW", 240, 160, 24, 23, 16, "NDS", "LOW", True),
+    ("c1_320x240_I_LOW", 320, 240, 212, 212, 24, "I", "LOW", False),
+    ("c2_gba_full_GBA_I_LOW", 240, 160, 212, 211, 16, "GBA_I", "LOW", False),
+    ("syn64_III_HIGH", 64, 64, 12, 11, 24, "III", "HIGH", True),
+]
+
+
+def lzss_vectors():
+    """Known-answer tests for the exported AGMV_LZSS (src/agmv_encode.c:106-177)."""
+    rng = np.random.default_rng(7)
+    vecs = {}
+    vecs["random_4k"] = rng.integers(0, 256, 4096, dtype=np.uint8)
+    vecs["four_symbols_20k"] = rng.integers(0, 4, 20000, dtype=np.uint8)
+    vecs["all_equal_5k"] = np.full(5000, 0x5E, dtype=np.uint8)
+    vecs["period5_3k"] = np.tile(np.array([1, 2, 3, 4, 5], dtype=np.uint8), 600)
+    a = rng.integers(0, 256, 70000, dtype=np.uint8)
+    a[66000:66040] = a[465:505]      # distance 65535: reachable
+    a[67000:67040] = a[1464:1504]    # distance 65536: one past the window
+    a[68000:68040] = a[2466:2506]    # distance 65534
+    vecs["window_edges_70k"] = a
+    vecs["empty"] = np.zeros(0, dtype=np.uint8)
+    vecs["two_bytes"] = np.array([9, 9], dtype=np.uint8)
+    vecs["tail_run"] = np.concatenate([rng.integers(0, 256, 100, dtype=np.uint8), np.full(17, 7, dtype=np.uint8)])
+    return vecs
+
+
+def ref_lzss(buf):
+    """Call the reference's AGMV_LZSS + AGMV_FlushWriteBits through ctypes on a temp FILE*."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libagmv_ref.so"))
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+
+    class BS(C.Structure):  # AGMV_BITSTREAM, include/agmv_defines.h:140-144 (u32 = unsigned long)
+        _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_ulong), ("pos", C.c_ulong)]
+
+    lib.AGMV_LZSS.restype = C.c_ulong
+    lib.AGMV_LZSS.argtypes = [C.c_void_p, C.POINTER(BS)]
+    lib.AGMV_FlushWriteBits.argtypes = [C.c_void_p]
+    arr = np.concatenate([buf, np.zeros(32, dtype=np.uint8)])
+    bs = BS(arr.ctypes.data_as(C.POINTER(C.c_uint8)), len(arr), len(buf))
+    path = b"/tmp/_agmv_lzss_golden.bin"
+    f = libc.fopen(path, b"wb")
+    csize = lib.AGMV_LZSS(f, C.byref(bs))
+    lib.AGMV_FlushWriteBits(f)
+    libc.fclose(f)
+    with open(path, "rb") as fh:
+        out = fh.read()
+    os.unlink(path)
+    return int(csize), out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-high", action="store_true")
+    ap.add_argument("--only")
+    args = ap.parse_args()
+    jpath = os.path.join(GOLDEN_DIR, "golden.json")
+    gold = json.load(open(jpath)) if os.path.exists(jpath) else {}
+    gold.setdefault("encode", {})
+    gold.setdefault("lzss", {})
+    gold.setdefault("decode_fixture", {})
+
+    for name, w, h, n, create_n, fps, opt, q, keep in ENCODE_CASES:
+        if args.only and args.only != name:
+            continue
+        if args.skip_high and q == "HIGH":
+            continue
+        t0 = time.time()
+        frames = synth_frames(w, h, n, seed=1234)
+        timing = {}
+        data = ref_encode(frames, create_n, fps, OPT[opt], QUALITY[q], LZSS, timing=timing)
+        rc, dec = ref_decode_raw(data)
+        assert rc == 0
+        entry = dict(w=w, h=h, n=n, create_n=create_n, fps=fps, opt=opt, quality=q, seed=1234,
+                     size=len(data), sha256=sha256(data), ref_encode_seconds=timing.get("seconds"),
+                     decoded_shape=list(dec.shape), decoded_sha256=sha256(dec.tobytes()),
+                     decoded_frame_sha256=[sha256(dec[k].tobytes()) for k in range(dec.shape[0])])
+        if keep:
+            with open(os.path.join(GOLDEN_DIR, name + ".agmv"), "wb") as f:
+                f.write(data)
+            entry["file"] = name + ".agmv"
+        gold["encode"][name] = entry
+        print(f"{name}: {len(data)} B, {dec.shape[0]} frames, {time.time() - t0:.1f}s", flush=True)
+        json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
+
+    if not args.only:
+        for name, buf in lzss_vectors().items():
+            csize, out = ref_lzss(buf)
+            gold["lzss"][name] = dict(n=len(buf), csize=csize, nbytes=len(out), sha256=sha256(out),
+                                      input_sha256=sha256(buf.tobytes()))
+            print(f"lzss {name}: n={len(buf)} csize={csize} nbytes={len(out)}", flush=True)
+
+        # decode-only fixtures shipped with the reference (not copied: digests only)
+        for rel in ["agmv_splash.agmv", "examples/simple_decoding/FOXLOGO.agmv", "agmv_spash.agmv"]:
+            p = os.path.join("/root/reference", rel)
+            data = open(p, "rb").read()
+            rc, dec = ref_decode_raw(data)
+            e = dict(rc=rc, input_sha256=sha256(data), size=len(data))
+            if dec is not None and rc == 0:
+                e.update(decoded_shape=list(dec.shape), decoded_sha256=sha256(dec.tobytes()))
+            gold["decode_fixture"][rel] = e
+            print(f"fixture {rel}: rc={rc}", flush=True)
+    json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()
