@@ -1,0 +1,142 @@
+/* agmv_b200.h - C-ABI of libagmv_b200.so: the B200 (sm_100a) implementation of
+ * libagmv's per-frame encode / decode hot path.
+ *
+ * Plain C: opaque context, raw pointers and sizes, int status codes; no CUDA or
+ * torch types in any signature (a CUDA stream crosses as void*). Pixels are
+ * 32-bit 0x00RRGGBB words; the drop-in layer (agmv_dropin.h) narrows the
+ * reference's 8-byte `u32` pixels before they get here.
+ *
+ * The library has NO CPU fallback: every entry point that computes launches
+ * CUDA kernels and fails with AGMVB_ERR_CUDA when no device is usable.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout).
+ */
+#ifndef AGMV_B200_H
+#define AGMV_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes: 0..3 are the reference's `enum Error` (include/agmv_defines.h:37-42) */
+#define AGMVB_OK 0
+#define AGMVB_ERR_HEADER 1      /* INVALID_HEADER_FORMATTING_ERR */
+#define AGMVB_ERR_FILE 2        /* FILE_NOT_FOUND_ERR */
+#define AGMVB_ERR_MEMORY 3      /* MEMORY_CORRUPTION_ERR */
+#define AGMVB_ERR_ARG 4
+#define AGMVB_ERR_CUDA 5
+#define AGMVB_ERR_UNSUPPORTED 6
+
+/* AGMV_OPT / AGMV_QUALITY / AGMV_COMPRESSION values, include/agmv_defines.h:56-76 */
+enum { AGMVB_OPT_I = 1, AGMVB_OPT_II, AGMVB_OPT_III, AGMVB_OPT_ANIM, AGMVB_OPT_GBA_I, AGMVB_OPT_GBA_II, AGMVB_OPT_GBA_III, AGMVB_OPT_NDS };
+enum { AGMVB_HIGH_QUALITY = 1, AGMVB_MID_QUALITY, AGMVB_LOW_QUALITY };
+enum { AGMVB_LZSS = 1, AGMVB_LZ77 };
+
+typedef struct agmvb_ctx agmvb_ctx;
+
+/* ---- context ------------------------------------------------------------- */
+/* device: CUDA ordinal. stream: a cudaStream_t to launch on (NULL = the context
+ * creates its own). Replaces CreateAGMV's allocations (src/agmv_utils.c:332-369)
+ * for the device side. */
+int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream);
+void agmvb_destroy(agmvb_ctx* ctx);
+const char* agmvb_last_error(const agmvb_ctx* ctx);
+/* kernels launched by this context so far (bench.py's gpu_launches) */
+uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx);
+/* wait for everything queued on the context's stream */
+int agmvb_sync(agmvb_ctx* ctx);
+
+/* ---- encoder: the pieces of AGMV_EncodeAGMV (src/agmv_encode.c:2270-3657) --- */
+/* Start a sequence: source size, profile, quality, entropy coder. GBA / NDS
+ * profiles code at 120x80 / 128x96 (include/agmv_encode.h:21-24). Clears the
+ * histogram, the colour memo table and the frame counter. */
+int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, int opt, int quality, int compression);
+
+/* Pass 1 (:2371-2568): add n_frames source frames to the quantised-colour
+ * histogram. `frames` is host memory unless on_device != 0. */
+int agmvb_enc_histogram(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames, int on_device);
+/* Device pointer / bin count of the 64-bit histogram, for the caller's
+ * all-reduce when the sequence is sharded over several GPUs. */
+int agmvb_enc_histogram_ptr(agmvb_ctx* ctx, uint64_t** dev_bins, uint32_t* n_bins);
+
+/* AGMV_BubbleSort + greedy pick + split (src/agmv_utils.c:995-1010,
+ * src/agmv_encode.c:2570-2656) on the device. */
+int agmvb_enc_build_palette(agmvb_ctx* ctx);
+int agmvb_enc_get_palette(agmvb_ctx* ctx, uint32_t pal0[256], uint32_t pal1[256]);
+/* AGMV_SetICP0 / AGMV_SetICP1 (src/agmv_utils.c:259-271) for callers that
+ * bring their own palettes (the per-frame API). */
+int agmvb_enc_set_palette(agmvb_ctx* ctx, const uint32_t pal0[256], const uint32_t pal1[256]);
+
+/* I-frame entry state of the per-frame API (agmv->iframe_entries,
+ * src/agmv_encode.c:626-630): (pal_num << 8 | index) per coded pixel. */
+int agmvb_enc_set_iframe_entries(agmvb_ctx* ctx, const uint16_t* entries);
+int agmvb_enc_get_iframe_entries(agmvb_ctx* ctx, uint16_t* entries);
+
+/* Pass 2: encode n_enc frames = AGMV_EncodeFrame (+ the empty AGMV_EncodeAudioChunk)
+ * n_enc times (src/agmv_encode.c:529-634, :707-717). Encoded frame k is
+ * frames[src_a[k]] when src_b[k] < 0, else AGMV_InterpFrame(frames[src_a[k]],
+ * frames[src_b[k]]) (src/agmv_utils.c:949-969). first_frame_count is
+ * agmv->frame_count of the first one (I-frame iff frame_count % 4 == 0; the
+ * AGFC header carries frame_count + 1). The result - for every frame
+ * 'AGFC' hdr | csize payload bytes | 8 x 0xFF | 'AGAC' 0 - stays on the device;
+ * *image_bytes receives its length. */
+int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames_in_buffer, int on_device,
+                     const int32_t* src_a, const int32_t* src_b, uint32_t n_enc, uint32_t first_frame_count,
+                     uint64_t* image_bytes);
+/* Copy the last agmvb_enc_frames result to host: chunk image and per-frame
+ * usize / csize (either size array may be NULL). */
+int agmvb_enc_fetch(agmvb_ctx* ctx, uint8_t* image, uint64_t cap, uint32_t* usize, uint32_t* csize);
+int agmvb_enc_image_ptr(agmvb_ctx* ctx, uint8_t** dev_image, uint64_t* bytes);
+
+/* The whole of AGMV_EncodeAGMV on in-memory source frames start..end
+ * (n_src = end - start + 1): histogram, palette, header (src/agmv_encode.c:21-94),
+ * PDIFS schedule (:2727-2770, :3610-3612), frame chunks, header back-patch
+ * (:3615-3620). Writes the .agmv image to `out` (host). */
+int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                          uint32_t create_n, uint32_t fps, int opt, int quality, int compression,
+                          uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+/* Header only (AGMV_EncodeHeader, src/agmv_encode.c:21-94) with the current palette. */
+int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps, uint8_t* out, uint64_t cap, uint64_t* len);
+
+/* ---- decoder: AGMV_DecodeAGMV / AGMV_DecodeFrameChunk (src/agmv_decode.c:91-410, 527-647) --- */
+/* Parse header + palettes (AGMV_DecodeHeader), index the frame chunks the way
+ * AGMV_FindNextFrameChunk walks them (src/agmv_utils.c:140-166), upload the
+ * stream. Returns a stream handle (>= 0) in *stream. Several streams may be
+ * open at once (batched decode of independent streams). */
+int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len, int* stream,
+                   uint32_t* w, uint32_t* h, uint32_t* n_frames);
+/* Decode the next `count` frames of one stream into out (count*w*h pixels;
+ * host memory unless on_device). Frames must be taken in order: the decoder
+ * state (pixels, I-frame, expanded-bitstream leftovers, frame_count) carries
+ * over exactly like the reference's AGMV handle. */
+int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint32_t* out, int on_device);
+/* Batched decode: the next `count` frames of each of n_streams streams of
+ * equal size. outs[s] is a device pointer (count*w*h pixels) or NULL to keep
+ * only a ring of recent frames on the device; checksums (nullable, host,
+ * n_streams*count) receives a 64-bit position-weighted sum per frame. */
+int agmvb_dec_batch(agmvb_ctx* ctx, const int* streams, uint32_t n_streams, uint32_t count,
+                    uint32_t* const* outs, uint64_t* checksums);
+int agmvb_dec_close(agmvb_ctx* ctx, int stream);
+
+/* ---- unit-test hooks (thin wrappers over single kernels) ---------------------- */
+/* AGMV_LZSS (src/agmv_encode.c:106-177) over F byte buffers concatenated in
+ * `data` (frame_start has F+1 entries). out receives, per buffer, the bytes the
+ * reference writes (ceil(outbits/8), at out + out_off[f]); csize/outbits as the
+ * reference computes them. */
+int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F,
+                    uint8_t* out, uint64_t out_cap, uint64_t* out_off, uint32_t* csize, uint32_t* outbits);
+/* AGMV_FindNearestEntry / AGMV_FindNearestColor over n colours (src/agmv_utils.c:785-895) */
+int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint64_t n, const uint32_t pal0[256],
+                        const uint32_t pal1[256], int dual, uint16_t* entries);
+/* AGMV_Assemble{I,P}FrameBitstream on ready-made entries (src/agmv_encode.c:354-527) */
+int agmvb_test_assemble(agmvb_ctx* ctx, const uint16_t* entries, const uint16_t* iframe_entries /* NULL: I-frame */,
+                        uint32_t w, uint32_t h, int dual, const uint32_t pal0[256], const uint32_t pal1[256],
+                        uint8_t* out, uint64_t cap, uint32_t* usize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

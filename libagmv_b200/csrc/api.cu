@@ -1,0 +1,1022 @@
+// C-ABI of libagmv_b200.so (include/agmv_b200.h): context, workspaces and the
+// host-side orchestration of the sm_100a kernels. No CPU fallback: every
+// compute entry point launches kernels on the context's stream.
+#include "../../include/agmv_b200.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+#include "decode.cuh"
+#include "encode.cuh"
+#include "lzss.cuh"
+#include "radix.cuh"
+#include "scan.cuh"
+
+using namespace agmvb;
+
+namespace {
+
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct DecStream {
+    bool open = false;
+    uint32_t w = 0, h = 0, n_frames = 0, next = 0, version = 0;
+    int dual = 0, lz77 = 0;
+    uint8_t* d_file = nullptr;
+    uint64_t file_len = 0;
+    std::vector<uint64_t> data_off;
+    std::vector<uint32_t> usize, csize;
+    uint32_t* d_pal = nullptr;      // 512
+    uint32_t* d_img = nullptr;      // P: pixels after the last decoded frame
+    uint32_t* d_ifr = nullptr;      // P: I-frame snapshot
+    uint8_t* d_persist = nullptr;   // carried-over expanded bitstream
+    uint32_t persist_len = 0;
+    uint32_t* d_ring = nullptr;     // optional ring of frames for agmvb_dec_batch without outputs
+    uint32_t last_bpos = 0, last_consumed = 0;
+};
+
+}  // namespace
+
+struct agmvb_ctx {
+    int device = 0;
+    cudaStream_t st = nullptr;
+    bool own_stream = false;
+    char err[512] = {0};
+    uint64_t launches = 0;
+
+    // ---- encoder state ----
+    bool enc_ready = false;
+    uint32_t src_w = 0, src_h = 0, cw = 0, ch = 0, mc = 0;
+    int opt = 0, quality = 0, compression = 0, dual = 1, light = 0;
+    unsigned long long* d_hist = nullptr;
+    unsigned long long* d_keys[2] = {nullptr, nullptr};
+    uint32_t* d_pal = nullptr;  // 512
+    uint32_t h_pal[512];
+    bool pal_valid = false;
+    uint16_t* d_lut = nullptr;  // 2^24
+    uint32_t* d_map = nullptr;  // coded pixel -> source pixel (GBA / NDS profiles)
+    uint16_t* d_ient = nullptr; // persistent I-frame entries
+    DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small;
+    LzWork lz;
+    DBuf lzbuf[40];
+    uint64_t image_bytes = 0;
+    std::vector<uint32_t> last_usize, last_csize;
+    void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
+    size_t h_pinned_cap = 0;
+
+    // ---- decoder state ----
+    std::vector<DecStream> streams;
+    DBuf d_frames, d_ebuf, d_bpos, d_consumed, d_stale, d_recs, d_steps, d_out, d_cksum, d_count;
+};
+
+#define CK(expr) AGMVB_CUDA_OK(expr)
+#define FAIL(code, ...)                                 \
+    do {                                                \
+        snprintf(ctx->err, sizeof ctx->err, __VA_ARGS__); \
+        return code;                                    \
+    } while (0)
+#define TRY(expr)                 \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc != OK) return _rc; \
+    } while (0)
+
+static int ensure(agmvb_ctx* ctx, DBuf& b, size_t bytes) {
+    if (b.cap >= bytes && b.p) return OK;
+    if (b.p) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(b.p)); b.p = nullptr; b.cap = 0; }
+    size_t want = bytes + bytes / 4 + 256;
+    CK(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return OK;
+}
+
+static int ensure_pinned(agmvb_ctx* ctx, size_t bytes) {
+    if (ctx->h_pinned_cap >= bytes) return OK;
+    if (ctx->h_pinned) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFreeHost(ctx->h_pinned)); }
+    CK(cudaMallocHost(&ctx->h_pinned, bytes * 2 + 4096));
+    ctx->h_pinned_cap = bytes * 2 + 4096;
+    return OK;
+}
+
+static int check_launch(agmvb_ctx* ctx, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) FAIL(ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return OK;
+}
+
+// ===========================================================================
+// context
+// ===========================================================================
+extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
+    if (!out) return ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ERR_CUDA;
+    agmvb_ctx* ctx = new agmvb_ctx();
+    ctx->device = device;
+    if (cuda_stream) ctx->st = (cudaStream_t)cuda_stream;
+    else {
+        if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ERR_CUDA; }
+        ctx->own_stream = true;
+    }
+    if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) {
+        delete ctx;
+        return ERR_CUDA;
+    }
+    *out = ctx;
+    return OK;
+}
+
+static void free_stream(DecStream& s) {
+    cudaFree(s.d_file); cudaFree(s.d_pal); cudaFree(s.d_img); cudaFree(s.d_ifr); cudaFree(s.d_persist); cudaFree(s.d_ring);
+    s = DecStream();
+}
+
+extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->st);
+    cudaFree(ctx->d_hist); cudaFree(ctx->d_keys[0]); cudaFree(ctx->d_keys[1]); cudaFree(ctx->d_pal); cudaFree(ctx->d_lut);
+    cudaFree(ctx->d_map); cudaFree(ctx->d_ient);
+    DBuf* bufs[] = {&ctx->stage, &ctx->entries, &ctx->rec, &ctx->boff, &ctx->bs, &ctx->fs, &ctx->image, &ctx->srcpairs, &ctx->entpairs,
+                    &ctx->scanws, &ctx->small, &ctx->d_frames, &ctx->d_ebuf, &ctx->d_bpos, &ctx->d_consumed, &ctx->d_stale, &ctx->d_recs,
+                    &ctx->d_steps, &ctx->d_out, &ctx->d_cksum, &ctx->d_count};
+    for (DBuf* b : bufs) cudaFree(b->p);
+    for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
+    for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+
+extern "C" const char* agmvb_last_error(const agmvb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int agmvb_sync(agmvb_ctx* ctx) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// ===========================================================================
+// encoder
+// ===========================================================================
+extern "C" int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, int opt, int quality, int compression) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (opt < OPT_I || opt > OPT_NDS || quality < Q_HIGH || quality > Q_LOW) FAIL(ERR_ARG, "bad opt/quality");
+    if (compression != COMP_LZSS) FAIL(ERR_UNSUPPORTED, "LZ77 entropy coder (stream versions 3/4) is not built yet (SURVEY 8f N2)");
+    ctx->src_w = src_w; ctx->src_h = src_h; ctx->opt = opt; ctx->quality = quality; ctx->compression = compression;
+    ctx->dual = opt_is_dual(opt); ctx->light = opt_is_light(opt);
+    ctx->cw = src_w; ctx->ch = src_h;
+    if (opt == OPT_GBA_I || opt == OPT_GBA_II || opt == OPT_GBA_III) { ctx->cw = 120; ctx->ch = 80; }  // include/agmv_encode.h:21-24
+    if (opt == OPT_NDS) { ctx->cw = 128; ctx->ch = 96; }
+    if (ctx->cw == 0 || ctx->ch == 0 || (ctx->cw & 3) || (ctx->ch & 3) || (src_w & 3))
+        FAIL(ERR_UNSUPPORTED, "width and height must be multiples of 4 (got %ux%u, coded %ux%u)", src_w, src_h, ctx->cw, ctx->ch);
+    ctx->mc = max_clr(quality);
+    const size_t P = (size_t)ctx->cw * ctx->ch;
+    if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(unsigned long long) * (524287 + 1)));
+    if (!ctx->d_keys[0]) { CK(cudaMalloc(&ctx->d_keys[0], 8 * 524288)); CK(cudaMalloc(&ctx->d_keys[1], 8 * 524288)); }
+    if (!ctx->d_pal) CK(cudaMalloc(&ctx->d_pal, 512 * 4));
+    if (!ctx->d_lut) CK(cudaMalloc(&ctx->d_lut, sizeof(uint16_t) << 24));
+    CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned long long) * (524287 + 1), ctx->st));
+    CK(cudaMemsetAsync(ctx->d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));
+    if (ctx->d_ient) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_ient)); ctx->d_ient = nullptr; }
+    CK(cudaMalloc(&ctx->d_ient, P * 2));
+    CK(cudaMemsetAsync(ctx->d_ient, 0, P * 2, ctx->st));
+    if (ctx->d_map) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_map)); ctx->d_map = nullptr; }
+    if (ctx->cw != src_w || ctx->ch != src_h) {
+        // AGIDL_ScaleImgDataNearest (extern/agidl/src/agidl_imgp_scale.c:262-293), called with
+        // sx = (f32)W/w + 0.001f (src/agmv_encode.c:2707-2721). The float32 index math runs here,
+        // on the host, once per sequence; the kernel just gathers through the table.
+        unsigned long worg = src_w, horg = src_h;
+        float sx = ((float)ctx->cw / worg) + 0.001f, sy = ((float)ctx->ch / horg) + 0.001f;
+        unsigned long neww = (unsigned long)(worg * sx), newh = (unsigned long)(horg * sy);
+        if (neww != ctx->cw || newh != ctx->ch) FAIL(ERR_UNSUPPORTED, "source %ux%u does not scale to %ux%u", src_w, src_h, ctx->cw, ctx->ch);
+        float xscale = (float)(worg - 1) / neww, yscale = (float)(horg - 1) / newh;
+        std::vector<uint32_t> map(P);
+        for (unsigned long y = 0; y < newh; y++)
+            for (unsigned long x = 0; x < neww; x++) {
+                unsigned long x2 = (unsigned long)(x * xscale), y2 = (unsigned long)(y * yscale);
+                map[y * neww + x] = (uint32_t)(y2 * worg + x2);
+            }
+        CK(cudaMalloc(&ctx->d_map, P * 4));
+        CK(cudaMemcpyAsync(ctx->d_map, map.data(), P * 4, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    ctx->pal_valid = false;
+    ctx->image_bytes = 0;
+    ctx->enc_ready = true;
+    return OK;
+}
+
+static int hist_launch(agmvb_ctx* ctx, const uint32_t* d_px, uint64_t npx) {
+    if (npx == 0) return OK;
+    if (((uintptr_t)d_px & 15) == 0) {
+        uint64_t groups = npx / 4;
+        if (groups) {
+            int grid = (int)std::min<uint64_t>((groups + 255) / 256, 148 * 16);
+            hist_vec4_k<<<grid, 256, 0, ctx->st>>>(reinterpret_cast<const uint4*>(d_px), groups, ctx->quality, ctx->mc, ctx->d_hist);
+            ctx->launches++;
+        }
+        uint64_t tail = npx - groups * 4;
+        if (tail) {
+            hist_scalar_k<<<1, 256, 0, ctx->st>>>(d_px + groups * 4, tail, ctx->quality, ctx->mc, ctx->d_hist);
+            ctx->launches++;
+        }
+    } else {
+        int grid = (int)std::min<uint64_t>((npx + 255) / 256, 148 * 16);
+        hist_scalar_k<<<grid, 256, 0, ctx->st>>>(d_px, npx, ctx->quality, ctx->mc, ctx->d_hist);
+        ctx->launches++;
+    }
+    return check_launch(ctx, "histogram");
+}
+
+extern "C" int agmvb_enc_histogram(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames, int on_device) {
+    if (!ctx || !ctx->enc_ready) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t fpx = (uint64_t)ctx->src_w * ctx->src_h;
+    if (on_device) return hist_launch(ctx, frames, fpx * n_frames);
+    // host frames: stream them through a staging buffer
+    const uint64_t chunk_frames = std::max<uint64_t>(1, (256ull << 20) / (fpx * 4));
+    TRY(ensure(ctx, ctx->stage, std::min(chunk_frames, n_frames) * fpx * 4));
+    for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk_frames) {
+        uint64_t nf = std::min(chunk_frames, n_frames - f0);
+        CK(cudaMemcpyAsync(ctx->stage.p, frames + f0 * fpx, nf * fpx * 4, cudaMemcpyHostToDevice, ctx->st));
+        TRY(hist_launch(ctx, ctx->stage.as<uint32_t>(), nf * fpx));
+        CK(cudaStreamSynchronize(ctx->st));  // the staging buffer is reused
+    }
+    return OK;
+}
+
+extern "C" int agmvb_enc_histogram_ptr(agmvb_ctx* ctx, uint64_t** dev_bins, uint32_t* n_bins) {
+    if (!ctx || !ctx->enc_ready) return ERR_ARG;
+    if (dev_bins) *dev_bins = reinterpret_cast<uint64_t*>(ctx->d_hist);
+    if (n_bins) *n_bins = ctx->mc;
+    return OK;
+}
+
+extern "C" int agmvb_enc_build_palette(agmvb_ctx* ctx) {
+    if (!ctx || !ctx->enc_ready) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t mc = ctx->mc;
+    pal_keys_k<<<cdiv(mc, 256), 256, 0, ctx->st>>>(ctx->d_hist, mc, ctx->d_keys[0]);
+    ctx->launches++;
+    const uint32_t nt = cdiv(mc, RX_TILE);
+    TRY(ensure(ctx, ctx->small, (size_t)256 * nt * 4));
+    TRY(ensure(ctx, ctx->scanws, ((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2) * 4));
+    int cur = 0;
+    for (uint32_t shift = 0; shift < 64; shift += 8) {  // stable LSD passes == stable sort by (count, index)
+        radix_pass(KeyDigit{ctx->d_keys[cur], shift}, KeyMove{ctx->d_keys[cur], ctx->d_keys[cur ^ 1]}, mc, ctx->small.as<uint32_t>(),
+                   ctx->scanws.as<uint32_t>(), ctx->st, ctx->launches);
+        cur ^= 1;
+    }
+    pal_pick_k<<<1, 32, (mc + 1) / 8, ctx->st>>>(ctx->d_keys[cur], mc, ctx->quality, ctx->dual, ctx->d_pal);
+    ctx->launches++;
+    TRY(check_launch(ctx, "palette"));
+    CK(cudaMemcpyAsync(ctx->h_pal, ctx->d_pal, 512 * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->pal_valid = true;
+    return OK;
+}
+
+extern "C" int agmvb_enc_get_palette(agmvb_ctx* ctx, uint32_t pal0[256], uint32_t pal1[256]) {
+    if (!ctx || !ctx->pal_valid) return ERR_ARG;
+    if (pal0) memcpy(pal0, ctx->h_pal, 1024);
+    if (pal1) memcpy(pal1, ctx->h_pal + 256, 1024);
+    return OK;
+}
+
+extern "C" int agmvb_enc_set_palette(agmvb_ctx* ctx, const uint32_t pal0[256], const uint32_t pal1[256]) {
+    if (!ctx || !ctx->enc_ready || !pal0) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    bool same = ctx->pal_valid && !memcmp(ctx->h_pal, pal0, 1024) && (!pal1 || !memcmp(ctx->h_pal + 256, pal1, 1024));
+    if (same) return OK;
+    memcpy(ctx->h_pal, pal0, 1024);
+    if (pal1) memcpy(ctx->h_pal + 256, pal1, 1024); else memset(ctx->h_pal + 256, 0, 1024);
+    for (int i = 0; i < 512; i++) ctx->h_pal[i] &= 0xFFFFFFu;
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaMemcpyAsync(ctx->d_pal, ctx->h_pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));  // the memo table belongs to a palette
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->pal_valid = true;
+    return OK;
+}
+
+extern "C" int agmvb_enc_set_iframe_entries(agmvb_ctx* ctx, const uint16_t* entries) {
+    if (!ctx || !ctx->enc_ready || !entries) return ERR_ARG;
+    CK(cudaMemcpyAsync(ctx->d_ient, entries, (size_t)ctx->cw * ctx->ch * 2, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+extern "C" int agmvb_enc_get_iframe_entries(agmvb_ctx* ctx, uint16_t* entries) {
+    if (!ctx || !ctx->enc_ready || !entries) return ERR_ARG;
+    CK(cudaMemcpyAsync(entries, ctx->d_ient, (size_t)ctx->cw * ctx->ch * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// LZSS workspace for up to n positions and F frames
+static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
+    LzWork& w = ctx->lz;
+    if (n + 64 > w.cap_n || !w.maxlen) {
+        uint32_t cap = std::max<uint32_t>(n + n / 4 + 4096, 1u << 20);
+        int k = 0;
+        auto grab = [&](size_t bytes, void** dst) -> int {
+            TRY(ensure(ctx, ctx->lzbuf[k], bytes));
+            *dst = ctx->lzbuf[k].p;
+            k++;
+            return OK;
+        };
+        TRY(grab(cap, (void**)&w.maxlen));
+        TRY(grab(cap, (void**)&w.bestlen));
+        for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
+        TRY(grab((size_t)cap * 4, (void**)&w.gs[0]));
+        TRY(grab((size_t)cap * 4, (void**)&w.gs[1]));
+        TRY(grab((size_t)cap * 4, (void**)&w.lvlidx));
+        TRY(grab((size_t)cap * 4, (void**)&w.gsat));
+        TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
+        uint32_t nt = cdiv(cap, RX_TILE);
+        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist));
+        TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + cdiv(cap, SCAN_TILE) + 8) * 4, (void**)&w.scan_ws));
+        uint32_t ptile = cdiv(cap, PARSE_TILE) + 1;
+        TRY(grab((size_t)ptile * 16, (void**)&w.exit_tab));
+        TRY(grab((size_t)ptile * 32, (void**)&w.w_tab));
+        TRY(grab((size_t)ptile, (void**)&w.entry_tab));
+        TRY(grab((size_t)ptile * 4, (void**)&w.cumbase));
+        w.cap_n = cap;
+    }
+    size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 16;
+    if (words > w.out_words_cap || F + 2 > w.cap_frames || !w.out_words) {
+        uint32_t capF = std::max<uint32_t>(F + F / 4 + 16, 64);
+        size_t capW = std::max(words, (((size_t)w.cap_n * 9) >> 5) + 3 * (size_t)capF + 16);
+        TRY(ensure(ctx, ctx->lzbuf[32], capW * 4)); w.out_words = ctx->lzbuf[32].as<uint32_t>(); w.out_words_cap = capW;
+        TRY(ensure(ctx, ctx->lzbuf[33], (size_t)(capF + 2) * 4)); w.wbase = ctx->lzbuf[33].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[34], (size_t)(capF + 2) * 4)); w.outbits = ctx->lzbuf[34].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[35], (size_t)(capF + 2) * 4)); w.csize = ctx->lzbuf[35].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[36], (size_t)(capF + 2) * 4)); w.chunk_off = ctx->lzbuf[36].as<uint32_t>();
+        w.cap_frames = capF;
+    }
+    return OK;
+}
+
+// Compress F bitstreams that sit back to back in `d_bs` (n bytes, frame starts
+// h_fs[0..F], h_fs[0] == 0) and append their chunk images to ctx->image.
+static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, uint32_t F, uint32_t first_fc) {
+    const uint32_t n = h_fs[F];
+    TRY(ensure_lz(ctx, n, F));
+    TRY(ensure_pinned(ctx, (size_t)(F + 2) * 8));
+    uint32_t* hp = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+    memcpy(hp, h_fs, (size_t)(F + 1) * 4);
+    TRY(ensure(ctx, ctx->fs, (size_t)(F + 2) * 4));
+    CK(cudaMemcpyAsync(ctx->fs.p, hp, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
+    size_t need = ctx->image_bytes + (size_t)32 * F + (((size_t)n * 9) >> 3) + 64;
+    if (need > ctx->image.cap) {  // grow, keeping what is already there
+        DBuf nb;
+        TRY(ensure(ctx, nb, need + need / 2));
+        if (ctx->image_bytes) CK(cudaMemcpyAsync(nb.p, ctx->image.p, ctx->image_bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (ctx->image.p) CK(cudaFree(ctx->image.p));
+        ctx->image = nb;
+    }
+    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->st,
+                      ctx->launches);
+    TRY(check_launch(ctx, "lzss"));
+    uint32_t* hcs = hp + (F + 2);
+    CK(cudaMemcpyAsync(hcs, ctx->lz.csize, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (uint32_t f = 0; f < F; f++) {
+        ctx->last_usize.push_back(h_fs[f + 1] - h_fs[f]);
+        ctx->last_csize.push_back(hcs[f]);
+        ctx->image_bytes += 32ull + hcs[f];
+    }
+    return OK;
+}
+
+static const uint32_t LZ_GROUP_TARGET = 24u << 20;  // positions per LZSS batch (~2.3 GB of workspace)
+
+// classify + assemble n frames whose entries are on the device; runs LZSS group by group
+static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_t F, uint32_t first_fc) {
+    const uint32_t W = ctx->cw, H = ctx->ch, B = (W >> 2) * (H >> 2);
+    const size_t nb = (size_t)F * B;
+    TRY(ensure(ctx, ctx->entpairs, F * sizeof(EntPair)));
+    TRY(ensure(ctx, ctx->rec, nb));
+    TRY(ensure(ctx, ctx->boff, nb * 4));
+    TRY(ensure(ctx, ctx->scanws, ((size_t)cdiv(nb, SCAN_TILE) + 2) * 4));
+    TRY(ensure(ctx, ctx->bs, nb * 33 + 256));
+    TRY(ensure(ctx, ctx->fs, (size_t)(F + 2) * 4));
+    TRY(ensure_pinned(ctx, (size_t)(F + 2) * 8));
+    CK(cudaMemcpyAsync(ctx->entpairs.p, h_pairs, F * sizeof(EntPair), cudaMemcpyHostToDevice, ctx->st));
+    dim3 grid(cdiv(B, 256), F);
+    classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->d_pal, ctx->dual, ctx->rec.as<uint8_t>());
+    device_scan<SumOp, true>(RecLen{ctx->rec.as<uint8_t>()}, StoreU32{ctx->boff.as<uint32_t>()}, (uint32_t)nb, ctx->scanws.as<uint32_t>(),
+                             ctx->st, ctx->launches);
+    frame_starts_k<<<cdiv(F + 1, 256), 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, F, ctx->scanws.as<uint32_t>() + cdiv(nb, SCAN_TILE),
+                                                          ctx->fs.as<uint32_t>());
+    emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(),
+                                      ctx->bs.as<uint8_t>());
+    ctx->launches += 3;
+    TRY(check_launch(ctx, "assemble"));
+    std::vector<uint32_t> fs(F + 1);
+    CK(cudaMemcpyAsync(ctx->h_pinned, ctx->fs.p, (size_t)(F + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    memcpy(fs.data(), ctx->h_pinned, (size_t)(F + 1) * 4);
+    std::vector<uint32_t> rebased;
+    for (uint32_t g0 = 0; g0 < F;) {
+        uint32_t g1 = g0 + 1;
+        while (g1 < F && fs[g1 + 1] - fs[g0] <= LZ_GROUP_TARGET) g1++;
+        rebased.resize(g1 - g0 + 1);
+        for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
+        TRY(lz_group(ctx, ctx->bs.as<uint8_t>() + fs[g0], rebased.data(), g1 - g0, first_fc + g0));
+        g0 = g1;
+    }
+    return OK;
+}
+
+extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames_in_buffer, int on_device,
+                                const int32_t* src_a, const int32_t* src_b, uint32_t n_enc, uint32_t first_frame_count,
+                                uint64_t* image_bytes) {
+    if (!ctx || !ctx->enc_ready || !frames || !src_a || !src_b) return ERR_ARG;
+    if (!ctx->pal_valid) FAIL(ERR_ARG, "no palette: call agmvb_enc_build_palette or agmvb_enc_set_palette first");
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t W = ctx->cw, H = ctx->ch;
+    const size_t P = (size_t)W * H, SP = (size_t)ctx->src_w * ctx->src_h;
+    ctx->image_bytes = 0;
+    ctx->last_usize.clear();
+    ctx->last_csize.clear();
+    for (uint32_t k = 0; k < n_enc; k++)
+        if (src_a[k] < 0 || (uint64_t)src_a[k] >= n_frames_in_buffer || (src_b[k] >= 0 && (uint64_t)src_b[k] >= n_frames_in_buffer))
+            FAIL(ERR_ARG, "frame index out of range at encoded frame %u", k);
+    const uint32_t QB = (uint32_t)std::max<size_t>(4, std::min<size_t>(256, (768ull << 20) / (P * 2)));  // frames per quantise batch
+    std::vector<SrcPair> sp;
+    std::vector<EntPair> ep;
+    for (uint32_t q0 = 0; q0 < n_enc; q0 += QB) {
+        const uint32_t F = std::min(QB, n_enc - q0);
+        sp.resize(F);
+        ep.resize(F);
+        if (on_device) {
+            for (uint32_t k = 0; k < F; k++) {
+                sp[k].a = frames + (size_t)src_a[q0 + k] * SP;
+                sp[k].b = src_b[q0 + k] >= 0 ? frames + (size_t)src_b[q0 + k] * SP : nullptr;
+            }
+        } else {
+            // upload the source frames this batch touches (each at most once)
+            std::vector<int32_t> uniq;
+            for (uint32_t k = 0; k < F; k++) { uniq.push_back(src_a[q0 + k]); if (src_b[q0 + k] >= 0) uniq.push_back(src_b[q0 + k]); }
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            TRY(ensure(ctx, ctx->stage, uniq.size() * SP * 4));
+            for (size_t u = 0; u < uniq.size(); u++)
+                CK(cudaMemcpyAsync(ctx->stage.as<uint32_t>() + u * SP, frames + (size_t)uniq[u] * SP, SP * 4, cudaMemcpyHostToDevice, ctx->st));
+            auto slot = [&](int32_t idx) { return (size_t)(std::lower_bound(uniq.begin(), uniq.end(), idx) - uniq.begin()); };
+            for (uint32_t k = 0; k < F; k++) {
+                sp[k].a = ctx->stage.as<uint32_t>() + slot(src_a[q0 + k]) * SP;
+                sp[k].b = src_b[q0 + k] >= 0 ? ctx->stage.as<uint32_t>() + slot(src_b[q0 + k]) * SP : nullptr;
+            }
+        }
+        TRY(ensure(ctx, ctx->srcpairs, F * sizeof(SrcPair)));
+        TRY(ensure(ctx, ctx->entries, (size_t)F * P * 2));
+        CK(cudaMemcpyAsync(ctx->srcpairs.p, sp.data(), F * sizeof(SrcPair), cudaMemcpyHostToDevice, ctx->st));
+        dim3 qgrid(cdiv(P / 4, 256), F);
+        quantize_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), ctx->d_map, (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
+                                               ctx->entries.as<uint16_t>());
+        ctx->launches++;
+        TRY(check_launch(ctx, "quantize"));
+        int last_i = -1;
+        for (uint32_t k = 0; k < F; k++) {
+            uint32_t fc = first_frame_count + q0 + k;
+            ep[k].ent = ctx->entries.as<uint16_t>() + (size_t)k * P;
+            if (fc % 4 == 0) { ep[k].ient = nullptr; last_i = (int)k; }
+            else {
+                int ik = (int)k - (int)(fc % 4);
+                ep[k].ient = ik >= 0 ? ctx->entries.as<uint16_t>() + (size_t)ik * P : ctx->d_ient;
+            }
+        }
+        TRY(assemble_and_compress(ctx, ep.data(), F, first_frame_count + q0));
+        if (last_i >= 0)  // agmv->iframe_entries <- img_entry, src/agmv_encode.c:626-630
+            CK(cudaMemcpyAsync(ctx->d_ient, ctx->entries.as<uint16_t>() + (size_t)last_i * P, P * 2, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));  // host vectors and the staging buffer are reused by the next batch
+    }
+    if (image_bytes) *image_bytes = ctx->image_bytes;
+    return OK;
+}
+
+extern "C" int agmvb_enc_fetch(agmvb_ctx* ctx, uint8_t* image, uint64_t cap, uint32_t* usize, uint32_t* csize) {
+    if (!ctx) return ERR_ARG;
+    if (image) {
+        if (cap < ctx->image_bytes) FAIL(ERR_ARG, "image buffer too small: %llu < %llu", (unsigned long long)cap, (unsigned long long)ctx->image_bytes);
+        if (ctx->image_bytes) CK(cudaMemcpyAsync(image, ctx->image.p, ctx->image_bytes, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    if (usize) memcpy(usize, ctx->last_usize.data(), ctx->last_usize.size() * 4);
+    if (csize) memcpy(csize, ctx->last_csize.data(), ctx->last_csize.size() * 4);
+    return OK;
+}
+
+extern "C" int agmvb_enc_image_ptr(agmvb_ctx* ctx, uint8_t** dev_image, uint64_t* bytes) {
+    if (!ctx) return ERR_ARG;
+    if (dev_image) *dev_image = ctx->image.as<uint8_t>();
+    if (bytes) *bytes = ctx->image_bytes;
+    return OK;
+}
+
+static void put32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
+static uint32_t get32(const uint8_t* p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24; }
+
+// AGMV_EncodeHeader, src/agmv_encode.c:21-94 (no audio: CreateAGMV's defaults, src/agmv_utils.c:358-366)
+extern "C" int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps, uint8_t* out, uint64_t cap, uint64_t* len) {
+    if (!ctx || !ctx->enc_ready || !ctx->pal_valid || !out) return ERR_ARG;
+    const uint64_t need = 38 + 768 * (ctx->dual ? 2 : 1);
+    if (cap < need) FAIL(ERR_ARG, "header needs %llu bytes", (unsigned long long)need);
+    memset(out, 0, need);
+    memcpy(out, "AGMV", 4);
+    put32(out + 4, n_frames);
+    put32(out + 8, ctx->cw);
+    put32(out + 12, ctx->ch);
+    out[16] = 1;
+    out[17] = (uint8_t)((ctx->compression == COMP_LZSS ? 0 : 2) + (ctx->dual ? 1 : 2));  // src/agmv_utils.c:487-545
+    put32(out + 18, fps);
+    out[36] = 16;  // bits per sample
+    uint8_t* p = out + 38;
+    for (int i = 0; i < (ctx->dual ? 512 : 256); i++) {
+        uint32_t c = ctx->h_pal[i];
+        *p++ = (uint8_t)(c >> 16); *p++ = (uint8_t)(c >> 8); *p++ = (uint8_t)c;
+    }
+    if (len) *len = need;
+    return OK;
+}
+
+extern "C" int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                                     uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
+                                     uint64_t* out_len, uint32_t* n_encoded) {
+    if (!ctx || !frames || !out || n_src < 2) return ERR_ARG;
+    TRY(agmvb_enc_begin(ctx, w, h, opt, quality, compression));
+    TRY(agmvb_enc_histogram(ctx, frames, n_src, on_device));  // every source frame, unscaled (:2371-2568)
+    TRY(agmvb_enc_build_palette(ctx));
+    // PDIFS schedule (:2727-2770) and loop exit (:3610-3612); frame numbers are 1-based in the reference
+    const uint32_t start = 1, end = n_src;
+    std::vector<int32_t> sa, sb;
+    for (uint32_t i = start; i <= end;) {
+        if (ctx->light) {
+            if (i + 3 > end) FAIL(ERR_ARG, "sequence too short for the LIGHT schedule");
+            sa.push_back(i - 1); sb.push_back(-1);
+            sa.push_back(i); sb.push_back(i + 1);
+            sa.push_back(i + 2); sb.push_back(-1);
+            i += 4;
+        } else {
+            if (i + 1 > end) FAIL(ERR_ARG, "sequence too short for the HEAVY schedule");
+            sa.push_back(i - 1); sb.push_back(i);
+            i += 2;
+        }
+        if (i + 4 >= end) break;
+    }
+    uint64_t hdr_len = 0, img = 0;
+    TRY(agmvb_enc_header(ctx, create_n, fps, out, cap, &hdr_len));
+    TRY(agmvb_enc_frames(ctx, frames, n_src, on_device, sa.data(), sb.data(), (uint32_t)sa.size(), 0, &img));
+    if (hdr_len + img > cap) FAIL(ERR_ARG, "output buffer too small: need %llu", (unsigned long long)(hdr_len + img));
+    TRY(agmvb_enc_fetch(ctx, out + hdr_len, cap - hdr_len, nullptr, nullptr));
+    // back-patch (:3615-3620)
+    uint32_t adjusted = end - start;
+    switch (opt) {  // :2296-2353
+        case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
+        case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
+        default: adjusted = (uint32_t)(adjusted * 0.75); break;
+    }
+    put32(out + 4, (uint32_t)sa.size());
+    float rate = (float)adjusted / (create_n + 1);
+    put32(out + 18, (uint32_t)round(fps * rate));
+    if (out_len) *out_len = hdr_len + img;
+    if (n_encoded) *n_encoded = (uint32_t)sa.size();
+    return OK;
+}
+
+// ===========================================================================
+// decoder
+// ===========================================================================
+__global__ void count_fourcc_k(const uint8_t* __restrict__ d, uint64_t len, uint32_t fourcc, unsigned long long* __restrict__ count) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool hit = false;
+    if (i + 4 <= len) hit = (d[i] | d[i + 1] << 8 | d[i + 2] << 16 | (uint32_t)d[i + 3] << 24) == fourcc;
+    unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m && lane_id() == 0) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
+// Walk the file the way AGMV_DecodeAGMV does: AGMV_FindNextFrameChunk (src/agmv_utils.c:140-166) checks the
+// four bytes at the cursor, then every offset from cursor+4 on. `cursor` after a frame is wherever the bit
+// reader stopped; when no stray 'AGFC' hides in a payload (verified on the device by counting occurrences)
+// any cursor inside the payload finds the same next chunk, so the index can be built before decoding.
+static int64_t find_next_agfc(const uint8_t* f, uint64_t len, uint64_t p) {
+    if (p + 4 <= len && !memcmp(f + p, "AGFC", 4)) return (int64_t)p;
+    for (uint64_t q = p + 4; q + 4 <= len; q++) {
+        const uint8_t* a = (const uint8_t*)memchr(f + q, 'A', len - 3 - q);
+        if (!a) return -1;
+        q = (uint64_t)(a - f);
+        if (!memcmp(a, "AGFC", 4)) return (int64_t)q;
+    }
+    return -1;
+}
+
+// exact number of payload bytes the reference's bit reader touches for one LZSS chunk (host, tokens only)
+static uint64_t lzss_consumed_host(const uint8_t* f, uint64_t len, uint64_t data_off, uint32_t usize, uint32_t csize) {
+    uint64_t rp = data_off, bits = 0, nbits = (uint64_t)csize * 8, bpos = 0;
+    uint32_t acc = 0, navail = 0;
+    auto rd = [&](uint32_t nb) {
+        while (navail < nb) { uint32_t b = rp < len ? f[rp] : 0; rp++; acc |= b << navail; navail += 8; }
+        uint32_t v = acc & ((1u << nb) - 1); acc >>= nb; navail -= nb; return v;
+    };
+    while (bits < nbits && bpos < usize) {
+        uint32_t flag = rd(1); bits++;
+        if (flag) { rd(8); bits += 8; bpos++; }
+        else { uint64_t off = rd(16); uint32_t l = rd(4); bits += 20; if (off >= 1 && off <= bpos) bpos += l; }
+    }
+    return rp - data_off;
+}
+
+extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len, int* stream, uint32_t* w, uint32_t* h, uint32_t* n_frames) {
+    if (!ctx || !file || !stream) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    // AGMV_DecodeHeader, src/agmv_decode.c:91-143
+    if (len < 38 || memcmp(file, "AGMV", 4)) FAIL(ERR_HEADER, "not an AGMV stream");
+    const uint32_t nfr = get32(file + 4), W = get32(file + 8), H = get32(file + 12);
+    const int version = file[17];
+    const uint32_t fps = get32(file + 18);
+    const int bps = file[36] | file[37] << 8;
+    if (!(version >= 1 && version <= 4) || fps >= 200 || !(bps == 16 || bps == 8)) FAIL(ERR_HEADER, "invalid header fields");
+    if (W == 0 || H == 0 || (W & 3) || (H & 3)) FAIL(ERR_UNSUPPORTED, "width and height must be multiples of 4");
+    const int dual = version == 1 || version == 3;
+    const uint64_t pal_bytes = 768ull * (dual ? 2 : 1);
+    if (len < 38 + pal_bytes) FAIL(ERR_HEADER, "truncated palette");
+    uint32_t pal[512];
+    memset(pal, 0, sizeof pal);
+    for (int i = 0; i < (dual ? 512 : 256); i++) {
+        const uint8_t* p = file + 38 + 3 * i;
+        pal[i] = (uint32_t)p[0] << 16 | (uint32_t)p[1] << 8 | p[2];  // AGIDL_RGB(r,g,b,RGB_888)
+    }
+    DecStream s;
+    s.w = W; s.h = H; s.n_frames = nfr; s.version = (uint32_t)version; s.dual = dual; s.lz77 = version >= 3; s.file_len = len;
+    const uint32_t audio_duration = get32(file + 22);
+    const size_t P = (size_t)W * H;
+    // chunk index
+    uint64_t cursor = 38 + pal_bytes;
+    bool need_exact_cursor = false;
+    for (uint32_t i = 0; i < nfr; i++) {
+        int64_t at = find_next_agfc(file, len, cursor);
+        if (at < 0 || (uint64_t)at + 16 > len) FAIL(ERR_HEADER, "frame chunk %u not found", i);
+        uint32_t us = get32(file + at + 8), cs = get32(file + at + 12);
+        if (us > 2 * P + 64 || (s.lz77 && (uint64_t)(cs / 4 + 1) * 256 > 2 * P + 64))
+            FAIL(ERR_MEMORY, "frame %u: uncompressed size %u exceeds the reference's bitstream buffer", i, us);
+        s.data_off.push_back((uint64_t)at + 16);
+        s.usize.push_back(us);
+        s.csize.push_back(cs);
+        cursor = (uint64_t)at + 16 + cs;
+        if (audio_duration != 0) {
+            // AGMV_FindNextAudioChunk + AGMV_DecodeAudioChunk consume 'AGAC', size, payload (src/agmv_decode.c:412-453)
+            uint64_t q = cursor;
+            int64_t aa = -1;
+            if (q + 4 <= len && !memcmp(file + q, "AGAC", 4)) aa = (int64_t)q;
+            else for (uint64_t r = q + 4; r + 4 <= len; r++) if (!memcmp(file + r, "AGAC", 4)) { aa = (int64_t)r; break; }
+            if (aa >= 0 && (uint64_t)aa + 8 <= len) cursor = (uint64_t)aa + 8 + get32(file + aa + 4);
+        }
+    }
+    (void)need_exact_cursor;
+    CK(cudaMalloc(&s.d_file, len + 64));
+    CK(cudaMemcpyAsync(s.d_file, file, len, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(s.d_file + len, 0, 64, ctx->st));
+    CK(cudaMalloc(&s.d_pal, 512 * 4));
+    CK(cudaMemcpyAsync(s.d_pal, pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMalloc(&s.d_img, P * 4));
+    CK(cudaMalloc(&s.d_ifr, P * 4));
+    s.persist_len = (uint32_t)(2 * P + 64);
+    CK(cudaMalloc(&s.d_persist, s.persist_len));
+    CK(cudaMemsetAsync(s.d_img, 0, P * 4, ctx->st));      // defined start state: zero pages
+    CK(cudaMemsetAsync(s.d_ifr, 0, P * 4, ctx->st));
+    CK(cudaMemsetAsync(s.d_persist, 0, s.persist_len, ctx->st));
+    // stray 'AGFC' inside a payload would make the chunk walk depend on where the bit reader stopped
+    TRY(ensure(ctx, ctx->d_count, 8));
+    CK(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->st));
+    count_fourcc_k<<<cdiv(len, 256), 256, 0, ctx->st>>>(s.d_file, len, 0x43464741u, ctx->d_count.as<unsigned long long>());
+    ctx->launches++;
+    unsigned long long hits = 0;
+    CK(cudaMemcpyAsync(&hits, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (hits != nfr && !s.lz77) {
+        // rare slow path: replay the token stream on the host to learn the exact cursor after every frame
+        s.data_off.clear(); s.usize.clear(); s.csize.clear();
+        cursor = 38 + pal_bytes;
+        for (uint32_t i = 0; i < nfr; i++) {
+            int64_t at = find_next_agfc(file, len, cursor);
+            if (at < 0 || (uint64_t)at + 16 > len) { free_stream(s); FAIL(ERR_HEADER, "frame chunk %u not found", i); }
+            uint32_t us = get32(file + at + 8), cs = get32(file + at + 12);
+            if (us > 2 * P + 64) { free_stream(s); FAIL(ERR_MEMORY, "frame %u too large", i); }
+            s.data_off.push_back((uint64_t)at + 16); s.usize.push_back(us); s.csize.push_back(cs);
+            cursor = (uint64_t)at + 16 + lzss_consumed_host(file, len, (uint64_t)at + 16, us, cs);
+            if (audio_duration != 0) {
+                int64_t aa = -1;
+                if (cursor + 4 <= len && !memcmp(file + cursor, "AGAC", 4)) aa = (int64_t)cursor;
+                else for (uint64_t r = cursor + 4; r + 4 <= len; r++) if (!memcmp(file + r, "AGAC", 4)) { aa = (int64_t)r; break; }
+                if (aa >= 0 && (uint64_t)aa + 8 <= len) cursor = (uint64_t)aa + 8 + get32(file + aa + 4);
+            }
+        }
+    }
+    s.open = true;
+    int id = -1;
+    for (size_t k = 0; k < ctx->streams.size(); k++) if (!ctx->streams[k].open) { id = (int)k; break; }
+    if (id < 0) { ctx->streams.push_back(DecStream()); id = (int)ctx->streams.size() - 1; }
+    ctx->streams[id] = s;
+    *stream = id;
+    if (w) *w = W;
+    if (h) *h = H;
+    if (n_frames) *n_frames = nfr;
+    return OK;
+}
+
+extern "C" int agmvb_dec_close(agmvb_ctx* ctx, int stream) {
+    if (!ctx || stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) return ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->st));
+    free_stream(ctx->streams[stream]);
+    return OK;
+}
+
+__global__ void checksum_k(const uint32_t* __restrict__ px, uint32_t P, unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
+        acc += (unsigned long long)px[i] * (2654435761ull + 2ull * i);
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane_id() == 0) atomicAdd(out, acc);
+}
+
+constexpr uint32_t DEC_RING = 8;
+
+// Decode the next `count` frames of each listed stream (all of one size).
+// outs[s]: device destination (count*P pixels) or nullptr for the per-stream ring.
+static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t count, uint32_t* const* outs, uint64_t* cks) {
+    if (S == 0 || count == 0) return OK;
+    for (uint32_t s = 0; s < S; s++) {
+        if (ids[s] < 0 || (size_t)ids[s] >= ctx->streams.size() || !ctx->streams[ids[s]].open) FAIL(ERR_ARG, "bad stream handle");
+        DecStream& d = ctx->streams[ids[s]];
+        if (d.w != ctx->streams[ids[0]].w || d.h != ctx->streams[ids[0]].h) FAIL(ERR_ARG, "streams of one batch must share a frame size");
+        if (d.next + count > d.n_frames) FAIL(ERR_ARG, "stream %d has only %u frames left", ids[s], d.n_frames - d.next);
+    }
+    const uint32_t W = ctx->streams[ids[0]].w, H = ctx->streams[ids[0]].h, B = (W >> 2) * (H >> 2);
+    const size_t P = (size_t)W * H;
+    for (uint32_t s = 0; s < S; s++) {
+        DecStream& d = ctx->streams[ids[s]];
+        if (!outs[s] && !d.d_ring) { CK(cudaMalloc(&d.d_ring, (size_t)DEC_RING * P * 4)); }
+    }
+    if (cks) {
+        TRY(ensure(ctx, ctx->d_cksum, (size_t)S * count * 8));
+        CK(cudaMemsetAsync(ctx->d_cksum.p, 0, (size_t)S * count * 8, ctx->st));
+    }
+    // frames per stream per chunk: bound the expansion + record workspace (~3 GB)
+    uint64_t worst = 0;
+    for (uint32_t s = 0; s < S; s++) {
+        DecStream& d = ctx->streams[ids[s]];
+        for (uint32_t k = 0; k < count; k++) {
+            uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.next + k] / 4 + 1) * 256 : d.usize[d.next + k];
+            worst = std::max<uint64_t>(worst, e + DEC_SLACK);
+        }
+    }
+    const uint64_t per_frame = worst + (uint64_t)B * 4;
+    uint32_t C = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(count, (3ull << 30) / (per_frame * S)));
+    if (C > 4) C &= ~3u;
+
+    std::vector<DecFrame> fr;
+    std::vector<DecStep> steps;
+    for (uint32_t c0 = 0; c0 < count; c0 += C) {
+        const uint32_t cn = std::min(C, count - c0);
+        const uint32_t F = S * cn;
+        fr.resize(F);
+        uint64_t eoff = 0;
+        for (uint32_t s = 0; s < S; s++) {
+            DecStream& d = ctx->streams[ids[s]];
+            for (uint32_t k = 0; k < cn; k++) {
+                DecFrame& x = fr[s * cn + k];
+                uint32_t g = d.next + k;
+                x.file = d.d_file; x.file_len = d.file_len; x.data_off = d.data_off[g]; x.ebuf_off = eoff;
+                x.persist = d.d_persist; x.persist_len = d.persist_len; x.usize = d.usize[g]; x.csize = d.csize[g];
+                x.stream_first = s * cn; x.lz77 = d.lz77; x.dual = d.dual;
+                uint64_t e = d.lz77 ? (uint64_t)(d.csize[g] / 4 + 1) * 256 : d.usize[g];
+                eoff += (e + DEC_SLACK + 15) & ~15ull;
+            }
+        }
+        TRY(ensure(ctx, ctx->d_frames, F * sizeof(DecFrame)));
+        TRY(ensure(ctx, ctx->d_ebuf, eoff + 64));
+        TRY(ensure(ctx, ctx->d_bpos, (size_t)F * 4));
+        TRY(ensure(ctx, ctx->d_consumed, (size_t)F * 4));
+        TRY(ensure(ctx, ctx->d_stale, (size_t)F * 4));
+        TRY(ensure(ctx, ctx->d_recs, (size_t)F * B * 4));
+        TRY(ensure(ctx, ctx->d_steps, F * sizeof(DecStep)));
+        CK(cudaMemcpyAsync(ctx->d_frames.p, fr.data(), F * sizeof(DecFrame), cudaMemcpyHostToDevice, ctx->st));
+        const DecFrame* dfr = ctx->d_frames.as<DecFrame>();
+        expand_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>());
+        stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>());
+        index_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
+                                                 ctx->d_recs.as<uint32_t>());
+        ctx->launches += 3;
+        TRY(check_launch(ctx, "expand/index"));
+        // reconstruction, frame by frame; step layout [k][s]
+        steps.resize(F);
+        for (uint32_t k = 0; k < cn; k++)
+            for (uint32_t s = 0; s < S; s++) {
+                DecStream& d = ctx->streams[ids[s]];
+                const uint32_t g = d.next + k;       // global frame index == frame_count before this frame
+                const uint32_t gi = g % 4 == 0 ? (g >= 4 ? g - 4 : EMPTY32) : g - g % 4;  // frame holding the I snapshot
+                const uint32_t call_first = d.next - c0;  // first frame of this API call
+                DecStep& x = steps[k * S + s];
+                x.dst = outs[s] ? outs[s] + (size_t)(c0 + k) * P : d.d_ring + (size_t)(g % DEC_RING) * P;
+                if (g == call_first) x.prev = d.d_img;
+                else x.prev = outs[s] ? outs[s] + (size_t)(c0 + k - 1) * P : d.d_ring + (size_t)((g - 1) % DEC_RING) * P;
+                if (gi == EMPTY32 || gi < call_first) x.ifr = d.d_ifr;
+                else x.ifr = outs[s] ? outs[s] + (size_t)(gi - call_first) * P : d.d_ring + (size_t)(gi % DEC_RING) * P;
+                x.recs = ctx->d_recs.as<uint32_t>() + (size_t)(s * cn + k) * B;
+                x.ebuf = ctx->d_ebuf.as<uint8_t>() + fr[s * cn + k].ebuf_off;
+                x.bpos = ctx->d_bpos.as<uint32_t>() + (s * cn + k);
+                x.stale = ctx->d_stale.as<uint8_t>() + (size_t)(s * cn + k) * 4;
+                x.pal = d.d_pal;
+                x.dual = d.dual;
+            }
+        CK(cudaMemcpyAsync(ctx->d_steps.p, steps.data(), F * sizeof(DecStep), cudaMemcpyHostToDevice, ctx->st));
+        for (uint32_t k = 0; k < cn; k++) {
+            dim3 grid(cdiv(B, 128), S);
+            reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>() + (size_t)k * S, W, H);
+            ctx->launches++;
+            if (cks) {
+                for (uint32_t s = 0; s < S; s++) {
+                    checksum_k<<<std::min<uint32_t>(cdiv(P, 256), 592), 256, 0, ctx->st>>>(steps[k * S + s].dst, (uint32_t)P,
+                                                                                           ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k);
+                    ctx->launches++;
+                }
+            }
+        }
+        TRY(check_launch(ctx, "reconstruct"));
+        // carry the state over: expanded-bitstream leftovers, last pixels, last I-frame snapshot
+        for (uint32_t s = 0; s < S; s++) {
+            DecStream& d = ctx->streams[ids[s]];
+            persist_update_k<<<cdiv(d.persist_len, 256), 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), s * cn, cn, ctx->d_ebuf.as<uint8_t>(),
+                                                                             d.d_persist, d.persist_len);
+            ctx->launches++;
+        }
+        if (c0 + cn == count) {
+            for (uint32_t s = 0; s < S; s++) {
+                DecStream& d = ctx->streams[ids[s]];
+                const uint32_t call_first = d.next - c0, last = d.next + cn - 1;
+                CK(cudaMemcpyAsync(d.d_img, steps[(cn - 1) * S + s].dst, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+                const uint32_t gi = last - last % 4;  // most recent frame with frame_count % 4 == 0
+                if (gi >= call_first) {
+                    const uint32_t* src = outs[s] ? outs[s] + (size_t)(gi - call_first) * P : d.d_ring + (size_t)(gi % DEC_RING) * P;
+                    CK(cudaMemcpyAsync(d.d_ifr, src, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+                }
+                CK(cudaMemcpyAsync(&d.last_bpos, ctx->d_bpos.as<uint32_t>() + (s * cn + cn - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
+                CK(cudaMemcpyAsync(&d.last_consumed, ctx->d_consumed.as<uint32_t>() + (s * cn + cn - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
+            }
+        }
+        CK(cudaStreamSynchronize(ctx->st));  // host vectors are rebuilt for the next chunk
+        for (uint32_t s = 0; s < S; s++) ctx->streams[ids[s]].next += cn;
+    }
+    if (cks) {
+        CK(cudaMemcpyAsync(cks, ctx->d_cksum.p, (size_t)S * count * 8, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    return OK;
+}
+
+extern "C" int agmvb_dec_batch(agmvb_ctx* ctx, const int* streams, uint32_t n_streams, uint32_t count, uint32_t* const* outs, uint64_t* checksums) {
+    if (!ctx || !streams) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    std::vector<uint32_t*> none(n_streams, nullptr);
+    return dec_batch_impl(ctx, streams, n_streams, count, outs ? outs : none.data(), checksums);
+}
+
+extern "C" int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint32_t* out, int on_device) {
+    if (!ctx || !out) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) FAIL(ERR_ARG, "bad stream handle");
+    if (on_device) { uint32_t* o = out; return dec_batch_impl(ctx, &stream, 1, count, &o, nullptr); }
+    const size_t P = (size_t)ctx->streams[stream].w * ctx->streams[stream].h;
+    // host destination: decode into device staging, at most ~1 GB at a time
+    const uint32_t chunk = (uint32_t)std::max<size_t>(4, ((1ull << 30) / (P * 4)) & ~3ull);
+    for (uint32_t c0 = 0; c0 < count; c0 += chunk) {
+        uint32_t cn = std::min(chunk, count - c0);
+        TRY(ensure(ctx, ctx->d_out, (size_t)cn * P * 4));
+        uint32_t* o = ctx->d_out.as<uint32_t>();
+        TRY(dec_batch_impl(ctx, &stream, 1, cn, &o, nullptr));
+        CK(cudaMemcpyAsync(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    return OK;
+}
+
+// ===========================================================================
+// unit-test hooks
+// ===========================================================================
+extern "C" int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F, uint8_t* out, uint64_t out_cap,
+                               uint64_t* out_off, uint32_t* csize, uint32_t* outbits) {
+    if (!ctx || !frame_start || F == 0) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = frame_start[F];
+    TRY(ensure(ctx, ctx->bs, (size_t)n + 256));
+    CK(cudaMemsetAsync(ctx->bs.p, 0, (size_t)n + 256, ctx->st));
+    if (n) CK(cudaMemcpyAsync(ctx->bs.p, data, n, cudaMemcpyHostToDevice, ctx->st));
+    ctx->image_bytes = 0;
+    ctx->last_usize.clear();
+    ctx->last_csize.clear();
+    TRY(lz_group(ctx, ctx->bs.as<uint8_t>(), frame_start, F, 0));
+    std::vector<uint32_t> ob(F), wb(F + 1);
+    CK(cudaMemcpyAsync(ob.data(), ctx->lz.outbits, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(wb.data(), ctx->lz.wbase, (size_t)(F + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    uint64_t o = 0;
+    for (uint32_t f = 0; f < F; f++) {
+        uint64_t nbytes = ((uint64_t)ob[f] + 7) / 8;
+        if (o + nbytes > out_cap) FAIL(ERR_ARG, "output buffer too small");
+        if (nbytes) CK(cudaMemcpyAsync(out + o, ctx->lz.out_words + wb[f], nbytes, cudaMemcpyDeviceToHost, ctx->st));
+        if (out_off) out_off[f] = o;
+        if (csize) csize[f] = ctx->last_csize[f];
+        if (outbits) outbits[f] = ob[f];
+        o += nbytes;
+    }
+    if (out_off) out_off[F] = o;
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+extern "C" int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint64_t n, const uint32_t pal0[256], const uint32_t pal1[256],
+                                   int dual, uint16_t* entries) {
+    if (!ctx || !colors || !pal0 || !entries || (n & 3) || n > 0xFFFFFFFCull) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    uint32_t pal[512];
+    memset(pal, 0, sizeof pal);
+    memcpy(pal, pal0, 1024);
+    if (dual && pal1) memcpy(pal + 256, pal1, 1024);
+    uint32_t* d_pal; uint16_t* d_lut;
+    CK(cudaMalloc(&d_pal, 2048));
+    CK(cudaMalloc(&d_lut, sizeof(uint16_t) << 24));
+    CK(cudaMemsetAsync(d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));
+    CK(cudaMemcpyAsync(d_pal, pal, 2048, cudaMemcpyHostToDevice, ctx->st));
+    TRY(ensure(ctx, ctx->stage, n * 4));
+    TRY(ensure(ctx, ctx->entries, n * 2));
+    TRY(ensure(ctx, ctx->srcpairs, sizeof(SrcPair)));
+    CK(cudaMemcpyAsync(ctx->stage.p, colors, n * 4, cudaMemcpyHostToDevice, ctx->st));
+    SrcPair sp{ctx->stage.as<uint32_t>(), nullptr};
+    CK(cudaMemcpyAsync(ctx->srcpairs.p, &sp, sizeof sp, cudaMemcpyHostToDevice, ctx->st));
+    dim3 grid(cdiv(n / 4, 256), 1);
+    quantize_k<<<grid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), nullptr, (uint32_t)n, d_pal, dual ? 512 : 256, d_lut, ctx->entries.as<uint16_t>());
+    ctx->launches++;
+    TRY(check_launch(ctx, "quantize"));
+    CK(cudaMemcpyAsync(entries, ctx->entries.p, n * 2, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    cudaFree(d_pal);
+    cudaFree(d_lut);
+    return OK;
+}
+
+extern "C" int agmvb_test_assemble(agmvb_ctx* ctx, const uint16_t* entries, const uint16_t* iframe_entries, uint32_t w, uint32_t h, int dual,
+                                   const uint32_t pal0[256], const uint32_t pal1[256], uint8_t* out, uint64_t cap, uint32_t* usize) {
+    if (!ctx || !entries || !pal0 || !out || (w & 3) || (h & 3)) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t P = (size_t)w * h;
+    const uint32_t B = (w >> 2) * (h >> 2);
+    uint32_t pal[512];
+    memset(pal, 0, sizeof pal);
+    memcpy(pal, pal0, 1024);
+    if (pal1) memcpy(pal + 256, pal1, 1024);
+    uint32_t* d_pal;
+    CK(cudaMalloc(&d_pal, 2048));
+    CK(cudaMemcpyAsync(d_pal, pal, 2048, cudaMemcpyHostToDevice, ctx->st));
+    TRY(ensure(ctx, ctx->entries, P * 4));
+    uint16_t* d_e = ctx->entries.as<uint16_t>();
+    CK(cudaMemcpyAsync(d_e, entries, P * 2, cudaMemcpyHostToDevice, ctx->st));
+    if (iframe_entries) CK(cudaMemcpyAsync(d_e + P, iframe_entries, P * 2, cudaMemcpyHostToDevice, ctx->st));
+    EntPair ep{d_e, iframe_entries ? d_e + P : nullptr};
+    TRY(ensure(ctx, ctx->entpairs, sizeof ep));
+    TRY(ensure(ctx, ctx->rec, B));
+    TRY(ensure(ctx, ctx->boff, (size_t)B * 4));
+    TRY(ensure(ctx, ctx->scanws, ((size_t)cdiv(B, SCAN_TILE) + 2) * 4));
+    TRY(ensure(ctx, ctx->bs, (size_t)B * 33 + 256));
+    TRY(ensure(ctx, ctx->fs, 16));
+    CK(cudaMemcpyAsync(ctx->entpairs.p, &ep, sizeof ep, cudaMemcpyHostToDevice, ctx->st));
+    dim3 grid(cdiv(B, 256), 1);
+    classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, d_pal, dual, ctx->rec.as<uint8_t>());
+    device_scan<SumOp, true>(RecLen{ctx->rec.as<uint8_t>()}, StoreU32{ctx->boff.as<uint32_t>()}, B, ctx->scanws.as<uint32_t>(), ctx->st, ctx->launches);
+    frame_starts_k<<<1, 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, 1, ctx->scanws.as<uint32_t>() + cdiv(B, SCAN_TILE), ctx->fs.as<uint32_t>());
+    emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(), ctx->bs.as<uint8_t>());
+    ctx->launches += 3;
+    TRY(check_launch(ctx, "assemble"));
+    uint32_t fs[2];
+    CK(cudaMemcpyAsync(fs, ctx->fs.p, 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (fs[1] > cap) { cudaFree(d_pal); FAIL(ERR_ARG, "output buffer too small"); }
+    CK(cudaMemcpyAsync(out, ctx->bs.p, fs[1], cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (usize) *usize = fs[1];
+    cudaFree(d_pal);
+    return OK;
+}

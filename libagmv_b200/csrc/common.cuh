@@ -17,6 +17,9 @@ constexpr int LZ_WINDOW = 65535;
 constexpr int LZ_MAXLEN = 15;
 constexpr int LZ_MINLEN = 3;
 
+// block record types shared by the encoder (K3) and the decoder (D3)
+constexpr uint32_t BT_FILL = 1, BT_COPY = 2, BT_NORMAL = 3;
+
 constexpr uint32_t EMPTY32 = 0xFFFFFFFFu;
 constexpr uint16_t LUT_EMPTY = 0xFFFFu;
 

@@ -244,7 +244,6 @@ __global__ void __launch_bounds__(256) quantize_k(const SrcPair* __restrict__ sr
 // AGMV_CompareIFrameBlock / AGMV_ComparePFrameBlock (src/agmv_encode.c:240-352)
 // and AGMV_Assemble{I,P}FrameBitstream (:354-527). Record byte: type << 6 | len.
 // ---------------------------------------------------------------------------
-constexpr uint32_t BT_FILL = 1, BT_COPY = 2, BT_NORMAL = 3;
 
 __device__ __forceinline__ bool within2(uint32_t a, uint32_t b) {
     int dr = (int)((a >> 16) & 255) - (int)((b >> 16) & 255);

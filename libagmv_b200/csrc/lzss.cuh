@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
 // wk.outbits, wk.chunk_off on the device and the chunk image written to
 // `image` (capacity >= 32*F + 9n/8 + 8).
 inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n,
-                              uint32_t first_frame_count, uint8_t* image, cudaStream_t st) {
+                              uint32_t first_frame_count, uint8_t* image, cudaStream_t st, uint64_t& launches) {
     const uint32_t nthreads = 256;
     uint32_t cover = (n + 1 > F + 1 ? n + 1 : F + 1);
     lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(n, fs, F, wk.A[0], wk.gs[0], wk.maxlen, wk.bestlen, wk.bitcum, wk.wbase);
@@ -309,9 +309,9 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
             // gs[0]: group starts in A[L] order. The scatter carries them into gs[1] (A[L+1] order);
             // the running max over head flags reads gs[1] and writes the new starts back to gs[0].
-            radix_pass(LzDigit{bs, wk.A[L], L}, LzMove{wk.A[L], wk.gs[0], wk.A[L + 1], wk.gs[1]}, n, wk.tile_hist, wk.scan_ws, st);
+            radix_pass(LzDigit{bs, wk.A[L], L}, LzMove{wk.A[L], wk.gs[0], wk.A[L + 1], wk.gs[1]}, n, wk.tile_hist, wk.scan_ws, st, launches);
             device_scan<MaxOp, false>(LzHead{bs, wk.A[L + 1], wk.gs[1], L},
-                                      LzGroupOut{wk.A[L + 1], wk.gs[0], wk.maxlen, wk.bestlen, wk.lvlidx, wk.gsat, L + 1}, n, wk.scan_ws, st);
+                                      LzGroupOut{wk.A[L + 1], wk.gs[0], wk.maxlen, wk.bestlen, wk.lvlidx, wk.gsat, L + 1}, n, wk.scan_ws, st, launches);
         }
         uint32_t ntile = cdiv(n, PARSE_TILE);
         lz_parse_spec_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.exit_tab, wk.w_tab);
@@ -322,10 +322,12 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         APtrs ap;
         for (int l = 0; l <= LZ_LEVELS; l++) ap.a[l] = wk.A[l];
         lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.bestlen, wk.lvlidx, wk.gsat, wk.bitcum, ap, wk.wbase, wk.out_words);
+        launches += 4;
     }
     lz_finalize_k<<<1, 1024, 0, st>>>(fs, F, wk.bitcum, wk.outbits, wk.csize, wk.chunk_off);
     dim3 grid(32, F);
     lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, image);
+    launches += 3;
 }
 
 }  // namespace agmvb

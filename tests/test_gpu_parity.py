@@ -1,0 +1,229 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C-ABI, against the
+oracle and the reference's golden vectors. Bit-exact: integer / byte / index work, no tolerance."""
+import os
+
+import numpy as np
+import pytest
+
+from agmv_testlib import (GOLDEN_DIR, LZSS, OPT, QUALITY, oracle, oracle_decode, oracle_encode, oracle_lzss, ptr, sha256,
+                          synth_frames)
+from golden.make_golden import lzss_vectors
+import ctypes as C
+
+pytestmark = pytest.mark.gpu
+
+ENC_CASES = ["syn64_III_LOW", "syn64_I_MID", "syn64_II_LOW", "syn64_ANIM_LOW", "syn96x80_III_LOW", "gba240_GBA_I_LOW",
+             "nds240_NDS_LOW", "syn64_III_HIGH", "c1_320x240_I_LOW", "c2_gba_full_GBA_I_LOW"]
+
+
+def _palettes(frames, quality, opt):
+    lib = oracle()
+    mc = lib.orc_max_clr(quality)
+    hist = np.zeros(mc + 1, np.uint64)
+    fr = np.ascontiguousarray(frames, np.uint32)
+    lib.orc_histogram_add(ptr(hist, C.POINTER(C.c_uint64)), ptr(fr, C.POINTER(C.c_uint32)), fr.size, quality)
+    p0, p1 = np.zeros(256, np.uint32), np.zeros(256, np.uint32)
+    lib.orc_build_palette(ptr(hist, C.POINTER(C.c_uint64)), quality, opt, ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)))
+    return p0, p1
+
+
+# ---- K4: LZSS -------------------------------------------------------------------
+def test_lzss_known_answers(ctx, golden):
+    vecs = lzss_vectors()
+    names = list(vecs)
+    res = ctx.test_lzss([vecs[n] for n in names])  # all buffers in ONE batch: also checks frame isolation
+    for n, (csize, out, bits) in zip(names, res):
+        g = golden["lzss"][n]
+        assert (csize, len(out), sha256(out)) == (g["csize"], g["nbytes"], g["sha256"]), n
+
+
+def test_lzss_random_against_oracle(ctx):
+    rng = np.random.default_rng(5)
+    bufs = []
+    for k in range(24):
+        n = int(rng.integers(1, 9000))
+        alphabet = int(rng.choice([2, 3, 16, 256]))
+        b = rng.integers(0, alphabet, n, dtype=np.uint8)
+        if k % 3 == 0:  # plant repeats and runs
+            b[n // 2:n // 2 + n // 8] = b[: n // 8]
+            b[-min(n, 40):] = 0x5E
+        bufs.append(b)
+    bufs.append(np.zeros(0, np.uint8))
+    res = ctx.test_lzss(bufs)
+    for b, (csize, out, bits) in zip(bufs, res):
+        ocs, oout, obits = oracle_lzss(b)
+        assert (csize, bits) == (ocs, obits)
+        assert out == oout
+
+
+def test_lzss_window_boundary_large(ctx):
+    """180 KB buffer with few symbols: long-range ties, matches at distance 65534/65535/65536."""
+    rng = np.random.default_rng(11)
+    a = rng.integers(0, 256, 180000, dtype=np.uint8)
+    a[70000:70030] = a[70000 - 65535:70030 - 65535]
+    a[90000:90030] = a[90000 - 65536:90030 - 65536]
+    a[110000:110030] = a[110000 - 65534:110030 - 65534]
+    a[150000:170000] = rng.integers(0, 3, 20000, dtype=np.uint8)
+    (csize, out, bits), = ctx.test_lzss([a])
+    ocs, oout, obits = oracle_lzss(a)
+    assert (csize, bits, sha256(out)) == (ocs, obits, sha256(oout))
+
+
+# ---- K2: quantise ---------------------------------------------------------------
+@pytest.mark.parametrize("dual", [1, 0])
+def test_quantize_against_oracle(ctx, dual):
+    frames = synth_frames(96, 80, 6, seed=3)
+    p0, p1 = _palettes(frames, QUALITY["LOW"], OPT["III"] if dual else OPT["II"])
+    rng = np.random.default_rng(2)
+    # all palette colours, their +-1 neighbours (ties), random colours, grey ramp
+    cols = np.concatenate([p0, p1, (p0 + 0x010101) & 0xFFFFFF, rng.integers(0, 1 << 24, 200000, dtype=np.uint32),
+                           np.arange(256, dtype=np.uint32) * 0x010101]).astype(np.uint32)
+    cols = np.concatenate([cols, np.zeros((-len(cols)) % 4, np.uint32)])
+    ent = ctx.test_quantize(cols, p0, p1, dual)
+    lib = oracle()
+    exp = np.zeros(cols.size, np.uint16)
+    lib.orc_quantize_frame(ptr(cols, C.POINTER(C.c_uint32)), cols.size, ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)),
+                           dual, ptr(exp, C.POINTER(C.c_uint16)))
+    assert np.array_equal(ent, exp)
+
+
+def test_quantize_degenerate_palette_ties(ctx):
+    """Duplicate palette entries and an all-zero palette 1: lowest index / palette 0 must win."""
+    p0 = np.zeros(256, np.uint32)
+    p0[10:20] = 0x808080
+    p0[200] = 0xFFFFFF
+    p1 = p0.copy()
+    cols = np.array([0, 0x808080, 0x7f7f7f, 0xFFFFFF, 0x404040, 0xC0C0C0, 0x123456, 0xFEFEFE], np.uint32)
+    ent = ctx.test_quantize(cols, p0, p1, 1)
+    lib = oracle()
+    exp = np.array([lib.orc_nearest_entry(ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)), 1, int(c)) for c in cols], np.uint16)
+    assert np.array_equal(ent, exp)
+    assert (ent >> 8).max() == 0
+
+
+# ---- K3: classify + assemble ----------------------------------------------------
+@pytest.mark.parametrize("dual", [1, 0])
+def test_assemble_against_oracle(ctx, dual):
+    lib = oracle()
+    w, h = 96, 80
+    frames = synth_frames(w, h, 3, seed=8)
+    opt = OPT["III"] if dual else OPT["II"]
+    p0, p1 = _palettes(frames, QUALITY["LOW"], opt)
+    ents = []
+    for k in range(3):
+        e = np.zeros(w * h, np.uint16)
+        fr = np.ascontiguousarray(frames[k])
+        lib.orc_quantize_frame(ptr(fr, C.POINTER(C.c_uint32)), fr.size, ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)), dual,
+                               ptr(e, C.POINTER(C.c_uint16)))
+        ents.append(e)
+    for cur, ifr in [(ents[0], None), (ents[1], ents[0]), (ents[2], ents[0])]:
+        got = ctx.test_assemble(cur, ifr, w, h, dual, p0, p1)
+        out = np.zeros(w * h * 3, np.uint8)
+        n = lib.orc_assemble(ptr(cur, C.POINTER(C.c_uint16)), ptr(ifr if ifr is not None else cur, C.POINTER(C.c_uint16)), w, h,
+                             1 if ifr is None else 0, dual, ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)),
+                             ptr(out, C.POINTER(C.c_uint8)))
+        assert got == out[:n].tobytes()
+
+
+# ---- whole path: .agmv byte identity and decoded frames ---------------------------
+@pytest.mark.parametrize("name", ENC_CASES)
+def test_encode_matches_reference_golden(ctx, golden, name):
+    g = golden["encode"][name]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    data, n_enc = ctx.encode_sequence(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert n_enc == g["decoded_shape"][0]
+    assert (len(data), sha256(data.tobytes())) == (g["size"], g["sha256"])
+
+
+@pytest.mark.parametrize("name", [c for c in ENC_CASES if not c.startswith("c")])
+def test_decode_matches_reference_golden(ctx, golden, name):
+    g = golden["encode"][name]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        data = f.read()
+    dec = ctx.decode_all(data)
+    assert list(dec.shape) == g["decoded_shape"]
+    assert [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+
+
+@pytest.mark.parametrize("name", ["c1_320x240_I_LOW", "c2_gba_full_GBA_I_LOW"])
+def test_roundtrip_full_configs(ctx, golden, name):
+    """BASELINE configs 1 and 2 end to end: GPU encode == reference bytes, GPU decode == reference frames."""
+    g = golden["encode"][name]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    data, _ = ctx.encode_sequence(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert sha256(data.tobytes()) == g["sha256"]
+    dec = ctx.decode_all(data.tobytes())
+    assert sha256(dec.tobytes()) == g["decoded_sha256"]
+
+
+def test_decode_in_pieces_keeps_state(ctx, golden):
+    """Frames taken 1, 3, 2, rest: the carried-over state (pixels, I-frame, stale bitstream bytes) must match."""
+    g = golden["encode"]["gba240_GBA_I_LOW"]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        data = f.read()
+    sid, w, h, n = ctx.dec_open(data)
+    parts, left = [], n
+    for c in [1, 3, 2, n - 6]:
+        parts.append(ctx.dec_frames(sid, c, w, h))
+    ctx.dec_close(sid)
+    dec = np.concatenate(parts)
+    assert [sha256(dec[k].tobytes()) for k in range(n)] == g["decoded_frame_sha256"]
+
+
+def test_batched_streams_match_single(ctx, golden):
+    """Stream-parallel decode (BASELINE config 5 in miniature): 3 different streams in one batch."""
+    streams = []
+    for seed in (1000, 1001, 1002):
+        fr = synth_frames(96, 80, 24, seed=seed)
+        streams.append(oracle_encode(fr, 23, 30, OPT["III"], QUALITY["LOW"], LZSS))
+    exp = [oracle_decode(s)[1] for s in streams]
+    import torch
+    sids, outs = [], []
+    for s in streams:
+        sid, w, h, n = ctx.dec_open(s)
+        sids.append(sid)
+        outs.append(torch.zeros((n, h, w), dtype=torch.int32, device="cuda"))
+    ck = ctx.dec_batch(sids, n, [o.data_ptr() for o in outs], checksums=True)
+    for k, sid in enumerate(sids):
+        got = outs[k].cpu().numpy().view(np.uint32)
+        assert np.array_equal(got, exp[k])
+        ctx.dec_close(sid)
+    # ring mode (no output arrays) must produce the same per-frame checksums
+    sids = [ctx.dec_open(s)[0] for s in streams]
+    ck2 = ctx.dec_batch(sids, n, None, checksums=True)
+    assert np.array_equal(ck, ck2)
+    for sid in sids:
+        ctx.dec_close(sid)
+
+
+def test_1080p_prefix_against_oracle(ctx):
+    """BASELINE config 3's profile (1920x1080, OPT_III) on a prefix the CPU oracle can finish."""
+    frames = synth_frames(1920, 1080, 12, seed=1234)
+    data, n_enc = ctx.encode_sequence(frames, 11, 24, OPT["III"], QUALITY["LOW"], LZSS)
+    assert n_enc == 6
+    # known answer recorded from the unmodified reference
+    assert (len(data), sha256(data.tobytes())) == (1056907, "5e721b92b2396240b87a8f821fb3c240e2c4fea6cac1cc76337814cedc24e2c4")
+    dec = ctx.decode_all(data.tobytes())
+    rc, odec = oracle_decode(data.tobytes())
+    assert rc == 0 and np.array_equal(dec, odec)
+
+
+def test_device_resident_frames_and_determinism(ctx):
+    import torch
+    frames = synth_frames(320, 240, 40, seed=77)
+    host, _ = ctx.encode_sequence(frames, 39, 24, OPT["III"], QUALITY["MID"], LZSS)
+    t = torch.from_numpy(frames.view(np.int32)).cuda()
+    dev, _ = ctx.encode_sequence(None, 39, 24, OPT["III"], QUALITY["MID"], LZSS, device_ptr=t.data_ptr(), shape=frames.shape)
+    assert host.tobytes() == dev.tobytes()
+    assert host.tobytes() == oracle_encode(frames, 39, 24, OPT["III"], QUALITY["MID"], LZSS)
+
+
+def test_corrupt_header_rejected(ctx):
+    hdr = bytearray(38 + 1536)
+    hdr[0:4] = b"AGMV"
+    hdr[17] = 1
+    hdr[36:38] = (36904).to_bytes(2, "little")
+    import libagmv_b200
+    with pytest.raises(libagmv_b200.AgmvError) as e:
+        ctx.dec_open(bytes(hdr))
+    assert e.value.code == 1

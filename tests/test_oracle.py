@@ -1,0 +1,85 @@
+"""CPU tests: the C restatement (oracle/agmv_oracle.c) against the golden vectors
+produced by the unmodified reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+
+from agmv_testlib import (GOLDEN_DIR, LZSS, OPT, QUALITY, have_ref, oracle_decode, oracle_encode, oracle_lzss, ref_decode_raw,
+                          ref_encode, sha256, synth_frames)
+from golden.make_golden import lzss_vectors
+
+FAST_CASES = ["syn64_III_LOW", "syn64_I_MID", "syn64_II_LOW", "syn64_ANIM_LOW", "syn96x80_III_LOW", "gba240_GBA_I_LOW",
+              "nds240_NDS_LOW", "syn64_III_HIGH"]
+
+
+@pytest.mark.parametrize("name", FAST_CASES)
+def test_oracle_encode_matches_reference_golden(golden, name):
+    g = golden["encode"][name]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    data = oracle_encode(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert len(data) == g["size"]
+    assert sha256(data) == g["sha256"]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        assert f.read() == data
+
+
+@pytest.mark.parametrize("name", FAST_CASES)
+def test_oracle_decode_matches_reference_golden(golden, name):
+    g = golden["encode"][name]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        data = f.read()
+    rc, frames = oracle_decode(data)
+    assert rc == 0
+    assert list(frames.shape) == g["decoded_shape"]
+    assert [sha256(frames[k].tobytes()) for k in range(frames.shape[0])] == g["decoded_frame_sha256"]
+
+
+def test_oracle_c1_full_length(golden):
+    """BASELINE config 1 (212 frames 320x240, OPT_I / LOW / LZSS): 104 encoded frames, byte-identical, then decode."""
+    g = golden["encode"]["c1_320x240_I_LOW"]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    data = oracle_encode(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"])
+    rc, dec = oracle_decode(data)
+    assert rc == 0 and sha256(dec.tobytes()) == g["decoded_sha256"]
+
+
+def test_oracle_lzss_known_answers(golden):
+    for name, buf in lzss_vectors().items():
+        g = golden["lzss"][name]
+        assert sha256(buf.tobytes()) == g["input_sha256"], name
+        csize, out, bits = oracle_lzss(buf)
+        assert (csize, len(out), sha256(out)) == (g["csize"], g["nbytes"], g["sha256"]), name
+
+
+def test_oracle_rejects_corrupt_header():
+    # the shipped agmv_spash.agmv has bits_per_sample = 36904 and must be rejected with error 1
+    hdr = bytearray(38 + 1536)
+    hdr[0:4] = b"AGMV"
+    hdr[17] = 1
+    hdr[36:38] = (36904).to_bytes(2, "little")
+    rc, _ = oracle_decode(bytes(hdr))
+    assert rc == 1
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference fixtures live only in the build container")
+def test_oracle_decodes_shipped_streams(golden):
+    for rel, g in golden["decode_fixture"].items():
+        data = open(os.path.join("/root/reference", rel), "rb").read()
+        assert sha256(data) == g["input_sha256"]
+        rc, frames = oracle_decode(data)
+        assert rc == g["rc"], rel
+        if rc == 0:
+            assert sha256(frames.tobytes()) == g["decoded_sha256"], rel
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_matches_live_reference_random_profile():
+    """A case that is NOT in the golden set, checked against the reference run live (fresh processes)."""
+    frames = synth_frames(48, 32, 16, seed=99)
+    ref = ref_encode(frames, 15, 20, OPT["III"], QUALITY["LOW"], LZSS)
+    assert oracle_encode(frames, 15, 20, OPT["III"], QUALITY["LOW"], LZSS) == ref
+    rc, rf = ref_decode_raw(ref)
+    rc2, of = oracle_decode(ref)
+    assert rc == rc2 == 0 and np.array_equal(rf, of)
