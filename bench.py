@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the libagmv frame hot path on B200.
+
+One "step" = one pass of the hot path over one batch of synthetic input: encode the
+BASELINE.json config-3 sequence (1920x1080, AGMV_OPT_III, AGMV_HIGH_QUALITY, LZSS; 2000
+source frames per GPU) and decode the stream it produced. The metric is the one
+BASELINE.json names - encode & decode frames/sec at 1080p - reported as round-trip
+source frames per second (the encode-only and decode-only rates are in `detail`).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA, C-ABI)
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path on the host cores
+
+N > 1 (one process per GPU under torchrun): weak scaling. The job is one sequence of
+2000*N source frames sharded by GOP-aligned frame range; the colour histogram is
+all-reduced over NCCL (the palette is global), every rank encodes its range, chunk sizes
+are all-gathered and the payload is gathered on rank 0 for container assembly. Decode is
+stream-parallel: each rank decodes its own independent stream. value = frames all ranks
+processed / max-over-ranks device time.
+
+Timing: W >= 3 untimed warm-up steps, then exactly K steps between barrier +
+torch.cuda.synchronize() on both sides, timed with CUDA events on the launching stream
+(the library launches everything on torch's current stream). Inputs (16.6 GB of frames) are
+far larger than the 126 MB L2, so nothing needs flushing between iterations.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H = 1920, 1080
+OPT_III, HIGH, LZSS_C = 3, 1, 1
+METRIC = "encode & decode frames/sec at 1080p"
+UNIT = "source frames/s (encode+decode round trip)"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi DURING the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception as e:  # nvidia-smi missing: report that instead of a number
+            self.proc = None
+            self.err = str(e)
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """Samples taken before this call are dropped (nvidia-smi is started early so that its start-up cost stays
+        outside the timed region)."""
+        self.t0 = time.time()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        rows = [r for t, r in self.rows if t >= getattr(self, "t0", 0.0)]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# schedule helpers (host logic; tested on CPU in tests/test_sharding.py)
+# --------------------------------------------------------------------------------------
+def pdifs_schedule(n_src, light):
+    """(src_a, src_b) per encoded frame for source frames 1..n_src; 0-based indices (src/agmv_encode.c:2727-2770, 3610-3612)."""
+    sa, sb, i, end = [], [], 1, n_src
+    while i <= end:
+        if light:
+            sa += [i - 1, i, i + 2]
+            sb += [-1, i + 1, -1]
+            i += 4
+        else:
+            sa.append(i - 1)
+            sb.append(i)
+            i += 2
+        if i + 4 >= end:
+            break
+    return np.array(sa, np.int32), np.array(sb, np.int32)
+
+
+def shard_ranges(n_enc, world, gop_group):
+    """Contiguous encoded-frame ranges whose boundaries are multiples of `gop_group` encoded frames
+    (12 for LIGHT profiles = 3 GOPs = 4 PDIFS groups, 4 for HEAVY)."""
+    units = (n_enc + gop_group - 1) // gop_group
+    per = (units + world - 1) // world
+    out = []
+    for r in range(world):
+        a = min(r * per * gop_group, n_enc)
+        b = min((r + 1) * per * gop_group, n_enc)
+        out.append((a, b))
+    return out
+
+
+def assemble_container(header, images, n_enc, fps_field):
+    """Container assembly on rank 0: header | chunk images in rank order; back-patch frame count and fps."""
+    out = bytearray(header)
+    for img in images:
+        out += img
+    out[4:8] = int(n_enc).to_bytes(4, "little")
+    out[18:22] = int(fps_field).to_bytes(4, "little")
+    return bytes(out)
+
+
+def fps_field(n_src, create_n, fps, light):
+    adjusted = n_src - 1
+    adjusted = int(adjusted * 0.75) if light else adjusted // 2
+    rate = np.float32(adjusted) / np.float32(create_n + 1)
+    v = float(np.float32(fps) * rate)
+    return int(np.floor(v + 0.5))
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import libagmv_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    # a real (non-default) stream: the library launches on it and torch's events time it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx = libagmv_b200.Context(local, stream.cuda_stream)
+
+    n_local = args.frames                      # source frames per GPU
+    n_total = n_local * world
+    P = W * H
+    # inputs resident in HBM before the timed region
+    frames = torch.empty((n_local, H, W), dtype=torch.int32, device=dev)
+    ctx.synth_frames(frames.data_ptr(), W, H, 1 + rank * n_local, n_local, 1234)
+    torch.cuda.synchronize()
+
+    light = True
+    sa_all, sb_all = pdifs_schedule(n_total, light)
+    n_enc_total = len(sa_all)
+    ranges = shard_ranges(n_enc_total, world, 12)
+    e0, e1 = ranges[rank]
+    sa = sa_all[e0:e1] - rank * n_local
+    sb = np.where(sb_all[e0:e1] >= 0, sb_all[e0:e1] - rank * n_local, -1).astype(np.int32)
+    assert sa.min() >= 0 and max(sa.max(), sb.max()) < n_local, "shard needs frames outside its range"
+    n_enc = e1 - e0
+    create_n, fps = n_total - 1, 24
+
+    dec_out = torch.empty((n_enc, H, W), dtype=torch.int32, device=dev)
+    host_stream = {}
+
+    def encode_step(fetch=False):
+        ctx.enc_begin(W, H, OPT_III, HIGH, LZSS_C)
+        ctx.enc_histogram(frames.data_ptr(), n_local, True)
+        if world > 1:
+            p, nb = ctx.enc_histogram_ptr()
+            # wrap the library's device histogram (u64 bins) as a tensor without copying
+            ht = torch.as_tensor(_DevArray(p, nb, "<i8"), device=dev)
+            dist.all_reduce(ht)
+        ctx.enc_build_palette()
+        nbytes = ctx.enc_frames(frames.data_ptr(), n_local, True, sa, sb, e0)
+        if world > 1:
+            sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+            sizes[rank] = nbytes
+            dist.all_reduce(sizes)  # chunk-image sizes of every rank -> file offsets
+            host_stream["sizes"] = sizes
+        return nbytes
+
+    def decode_step(stream_bytes):
+        sid, w, h, n = ctx.dec_open(stream_bytes)
+        ctx.dec_frames(sid, n, w, h, device_ptr=dec_out.data_ptr())
+        ctx.dec_close(sid)
+        return n
+
+    def local_stream(nbytes):
+        img, _, _ = ctx.enc_fetch(nbytes, n_enc)
+        hdr = ctx.enc_header(create_n, fps)
+        return assemble_container(hdr.tobytes(), [img.tobytes()], n_enc, fps_field(n_total, create_n, fps, light))
+
+    # one untimed pass builds the stream the decode half works on (and warms every workspace)
+    nbytes = encode_step()
+    stream_bytes = local_stream(nbytes)
+    stream_np = np.frombuffer(stream_bytes, dtype=np.uint8)
+    n_dec = decode_step(stream_np)
+    assert n_dec == n_enc
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(steps):
+            fn()
+        b.record(stream)
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def full_step():
+        encode_step()
+        decode_step(stream_np)
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        full_step()
+    sampler.mark()
+    l0 = ctx.launches
+    ctx.profile(True)
+    total_ms = timed(full_step, args.steps)
+    prof = ctx.profile_read()
+    ctx.profile(False)
+    launches = ctx.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # encode-only / decode-only rates (same rules, separate regions)
+    enc_ms = timed(encode_step, args.steps)
+    dec_ms = timed(lambda: decode_step(stream_np), args.steps)
+
+    # ---- e2e: the same step through the public API with HOST buffers -------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_frames = min(n_local, args.e2e_frames)
+        sa_e, sb_e = pdifs_schedule(e2e_frames, light)
+        host_frames = torch.empty((e2e_frames, H, W), dtype=torch.int32, pin_memory=True)
+        host_frames.copy_(frames[:e2e_frames])
+        out_host = torch.empty(4096 + e2e_frames * (P // 2), dtype=torch.uint8, pin_memory=True)
+        dec_host = torch.empty((len(sa_e), H, W), dtype=torch.int32, pin_memory=True)
+        out_np = out_host.numpy()
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            data, ne = ctx.encode_sequence(host_frames.numpy().view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, LZSS_C, out=out_np)
+            sid, w, h, n = ctx.dec_open(data)
+            ctx.dec_frames(sid, n, w, h, host_ptr=dec_host.data_ptr())
+            ctx.dec_close(sid)
+            h2d = e2e_frames * P * 4 + len(data)
+            d2h = len(data) + n * P * 4
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(1, args.steps // 2)):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": e2e_frames * world * max(1, args.steps // 2) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "frames_per_step": e2e_frames,
+               "note": "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers, host wall clock"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+
+    # dominant kernel class by device time inside the timed region
+    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
+    roof = None
+    if dom:
+        name, (cnt, ms) = dom
+        alg = ALG_BYTES.get(name)
+        per_launch_ms = ms / cnt
+        roof = {"kernel": name, "bound": "hbm", "launches_in_region": cnt, "avg_launch_ms": per_launch_ms, "peak": peak, "unit": "GB/s",
+                "peak_source": peak_src, "traffic": None}
+        if alg is not None:
+            bytes_per_launch = alg(stream_stats(ctx, n_enc, nbytes)) * args.steps / cnt
+            roof["achieved"] = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
+            roof["frac"] = roof["achieved"] / peak
+            roof["algorithmic_bytes_per_launch"] = bytes_per_launch
+
+    value = n_total * args.steps / (total_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 3: {n_local} source frames/GPU 1920x1080 24fps, AGMV_OPT_III, AGMV_HIGH_QUALITY, LZSS; "
+                               f"encode then decode of the {n_enc}-frame stream", "source_frames_per_gpu": n_local,
+                   "encoded_frames_per_gpu": n_enc, "stream_bytes_per_gpu": len(stream_bytes),
+                   "l2_policy": "inputs (16.6 GB/GPU) exceed the 126 MB L2; no flush needed",
+                   "parallelism": f"frame-range shard x{world}" if world > 1 else "single GPU"},
+        "detail": {"encode_source_fps": n_total * args.steps / (enc_ms * 1e-3), "encode_encoded_fps": n_enc * world * args.steps / (enc_ms * 1e-3),
+                   "decode_fps": n_enc * world * args.steps / (dec_ms * 1e-3),
+                   "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}},
+        "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, bounded_seconds=25)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of library-owned device memory (no copy)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def stream_stats(ctx, n_enc, nbytes):
+    return {"n_enc": n_enc, "image_bytes": nbytes}
+
+
+# algorithmic bytes per step for each kernel class, as a function of the step's statistics
+ALG_BYTES = {}
+
+
+# --------------------------------------------------------------------------------------
+# CPU legs: the reference's own implementation on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_clip_roundtrip(n_src, procs, use_ref):
+    """Each of `procs` processes encodes its own n_src-frame 1080p clip (OPT_III/HIGH/LZSS) and decodes it.
+    Returns (seconds wall, frames total)."""
+    from agmv_testlib import REF_DIR  # noqa: F401
+    worker = os.path.join(ROOT, "tests", "cpu_worker.py")
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([sys.executable, worker, str(n_src), str(1000 + k), "ref" if use_ref else "port"],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for k in range(procs)]
+    outs = [p.communicate()[0] for p in ps]
+    dt = time.perf_counter() - t0
+    ok = all(p.returncode == 0 for p in ps)
+    return dt, n_src * procs, ok, outs
+
+
+def cpu_baseline(args, bounded_seconds=25):
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.cpu_procs or cores))
+    n_src = 8
+    dt, frames, ok, outs = cpu_clip_roundtrip(n_src, procs, use_ref=False)
+    return {"value": frames / dt if ok else None, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), oracle port encode + decode, "
+                      f"{dt:.1f} s wall",
+            "note": "oracle/agmv_oracle.c (qsort instead of the reference's O(n^2) bubble sort, memoised quantiser): faster than the "
+                    "unmodified reference, so this flatters the CPU"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, args.cpu_procs or cores))
+    n_src = 8
+    vals, dts = [], []
+    for _ in range(args.warmup + args.steps):
+        dt, frames, ok, _ = cpu_clip_roundtrip(n_src, procs, use_ref=False)
+        vals.append(frames / dt)
+        dts.append(dt)
+    vals, dts = vals[args.warmup:], dts[args.warmup:]
+    v = float(np.mean(vals))
+    sample = (f"each step: {procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), encode + decode with the "
+              f"oracle port of the reference algorithm")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": float(np.mean(dts)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE config 3 profile (1920x1080, AGMV_OPT_III, AGMV_HIGH_QUALITY, LZSS), bounded sample"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=2000, help="source frames per GPU (BASELINE config 3: 2000)")
+    ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-procs", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,25 @@ int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint32_t* out, 
 int agmvb_dec_batch(agmvb_ctx* ctx, const int* streams, uint32_t n_streams, uint32_t count,
                     uint32_t* const* outs, uint64_t* checksums);
 int agmvb_dec_close(agmvb_ctx* ctx, int stream);
+/* Streaming entry: one AGMV_DecodeFrameChunk (src/agmv_decode.c:145-410) at a time, for callers that own the
+ * FILE* (AGMV_PlayAGMV, src/agmv_playback.c:102-115). agmvb_dec_open_raw takes what AGMV_DecodeHeader left in
+ * the handle (size, version, palettes); agmvb_dec_chunk takes the bytes after the 16-byte 'AGFC' header
+ * (csize payload bytes plus at least the 8-byte trailer), agmv->frame_count, and returns the frame (host,
+ * w*h pixels), bitstream->pos and the number of payload bytes the bit reader consumed (the new file cursor). */
+int agmvb_dec_open_raw(agmvb_ctx* ctx, uint32_t w, uint32_t h, int version, const uint32_t pal0[256], const uint32_t pal1[256], int* stream);
+int agmvb_dec_chunk(agmvb_ctx* ctx, int stream, const uint8_t* payload, uint64_t payload_len, uint32_t usize, uint32_t csize,
+                    uint32_t frame_count, uint32_t* out_px, uint32_t* bpos, uint32_t* consumed);
+
+/* ---- measurement utilities ------------------------------------------------------ */
+/* Fill dev_out with n synthetic w x h frames t = first_t .. first_t+n-1 (the deterministic integer generator
+ * of SURVEY.md 8d; same formula as oracle/agmv_oracle.c). Benchmark input only. */
+int agmvb_synth_frames(agmvb_ctx* ctx, uint32_t* dev_out, uint32_t w, uint32_t h, uint32_t first_t, uint32_t n, uint32_t seed);
+/* Bracket every kernel launch with CUDA events on the launching stream and read back, per kernel class,
+ * the launch count and the summed device milliseconds (arrays of agmvb_profile_classes() entries). */
+int agmvb_profile(agmvb_ctx* ctx, int enable);
+int agmvb_profile_classes(void);
+const char* agmvb_profile_name(int cls);
+int agmvb_profile_read(agmvb_ctx* ctx, uint64_t* counts, double* total_ms);
 
 /* ---- unit-test hooks (thin wrappers over single kernels) ---------------------- */
 /* AGMV_LZSS (src/agmv_encode.c:106-177) over F byte buffers concatenated in

@@ -50,6 +50,13 @@ SYMBOLS = {
     "agmvb_dec_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int]),
     "agmvb_dec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
     "agmvb_dec_close": (C.c_int, [C.c_void_p, C.c_int]),
+    "agmvb_dec_open_raw": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, C.POINTER(C.c_int)]),
+    "agmvb_dec_chunk": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p]),
+    "agmvb_synth_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "agmvb_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "agmvb_profile_classes": (C.c_int, []),
+    "agmvb_profile_name": (C.c_char_p, [C.c_int]),
+    "agmvb_profile_read": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_double)]),
     "agmvb_test_lzss": (C.c_int, [C.c_void_p, _u8p, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p, _u32p, _u32p]),
     "agmvb_test_quantize": (C.c_int, [C.c_void_p, _u32p, C.c_uint64, _u32p, _u32p, C.c_int, _u16p]),
     "agmvb_test_assemble": (C.c_int, [C.c_void_p, _u16p, _u16p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, _u8p,
@@ -220,6 +227,20 @@ class Context:
             return self.dec_frames(sid, n, w, h)
         finally:
             self.dec_close(sid)
+
+    # ---- measurement utilities ----------------------------------------------------
+    def synth_frames(self, device_ptr, w, h, first_t, n, seed=1234):
+        self._ck(self.lib.agmvb_synth_frames(self.h, C.c_void_p(device_ptr), w, h, first_t, n, seed))
+
+    def profile(self, enable):
+        self._ck(self.lib.agmvb_profile(self.h, 1 if enable else 0))
+
+    def profile_read(self):
+        n = self.lib.agmvb_profile_classes()
+        cnt = np.zeros(n, np.uint64)
+        ms = np.zeros(n, np.float64)
+        self._ck(self.lib.agmvb_profile_read(self.h, _p(cnt, _u64p), _p(ms, C.POINTER(C.c_double))))
+        return {self.lib.agmvb_profile_name(k).decode(): (int(cnt[k]), float(ms[k])) for k in range(n) if cnt[k]}
 
     # ---- unit-test hooks -------------------------------------------------------
     def test_lzss(self, buffers):

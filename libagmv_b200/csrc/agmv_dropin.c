@@ -1,0 +1,508 @@
+/* libagmv_dropin.so - the reference's C API for the frame hot path (include/agmv_dropin.h)
+ * implemented on top of the C-ABI of libagmv_b200.so (include/agmv_b200.h).
+ *
+ * Host side only: file I/O, handle bookkeeping, 8-byte <-> 4-byte pixel conversion and the
+ * container framing the reference does around its per-frame calls. Every pixel-, block- and
+ * bitstream-level computation happens in CUDA kernels behind agmvb_*; there is no CPU path
+ * (if the GPU layer fails, the encode functions report to stderr and the decode functions
+ * return MEMORY_CORRUPTION_ERR, the only channel the reference API offers - SURVEY.md 8b).
+ *
+ * Out of scope here: audio tracks (#16), image formats other than BMP
+ * (#18, AGIDL), the similarity-gated / full encoders (#14, #15).
+ */
+#include "agmv_dropin.h"
+
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "agmv_b200.h"
+
+#define WEAK __attribute__((weak))
+
+static agmvb_ctx* g_ctx = NULL;
+static int g_device = 0;
+static char g_err[600] = "";
+
+const char* AGMV_B200_LastError(void) { return g_err; }
+void AGMV_B200_SetDevice(int device) { g_device = device; }
+
+static agmvb_ctx* ctx_get(void) {
+    if (!g_ctx) {
+        int rc = agmvb_create(&g_ctx, g_device, NULL);
+        if (rc != AGMVB_OK) {
+            snprintf(g_err, sizeof g_err, "agmvb_create failed with %d: no usable CUDA device (this build has no CPU path)", rc);
+            fprintf(stderr, "libagmv_dropin: %s\n", g_err);
+            g_ctx = NULL;
+        }
+    }
+    return g_ctx;
+}
+
+static int fail(int rc, const char* where) {
+    snprintf(g_err, sizeof g_err, "%s: error %d: %s", where, rc, g_ctx ? agmvb_last_error(g_ctx) : "no context");
+    fprintf(stderr, "libagmv_dropin: %s\n", g_err);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* handle lifecycle (src/agmv_utils.c:332-421), weak: the reference's agmv_utils.o wins     */
+/* ------------------------------------------------------------------------------------ */
+WEAK AGMV* CreateAGMV(u32 num_of_frames, u32 width, u32 height, u32 frames_per_second) {
+    AGMV* a = (AGMV*)malloc(sizeof(AGMV));
+    a->frame_chunk = (AGMV_FRAME_CHUNK*)malloc(sizeof(AGMV_FRAME_CHUNK));
+    a->audio_chunk = (AGMV_AUDIO_CHUNK*)malloc(sizeof(AGMV_AUDIO_CHUNK));
+    a->bitstream = (AGMV_BITSTREAM*)malloc(sizeof(AGMV_BITSTREAM));
+    a->bitstream->len = width * height * 2;
+    a->bitstream->pos = 0;
+    a->bitstream->data = (u8*)malloc(a->bitstream->len);
+    a->frame = (AGMV_FRAME*)malloc(sizeof(AGMV_FRAME));
+    a->frame->img_data = (u32*)malloc(sizeof(u32) * width * height);
+    a->iframe = (AGMV_FRAME*)malloc(sizeof(AGMV_FRAME));
+    a->iframe->img_data = (u32*)malloc(sizeof(u32) * width * height);
+    a->audio_track = (AGMV_AUDIO_TRACK*)malloc(sizeof(AGMV_AUDIO_TRACK));
+    a->iframe_entries = (AGMV_ENTRY*)malloc(sizeof(AGMV_ENTRY) * width * height);
+    a->audio_track->pcm = NULL;
+    a->audio_track->pcm8 = NULL;
+    a->audio_track->start_point = 0;
+    a->audio_chunk->atsample = NULL;
+    a->frame_count = 0;
+    a->header.width = a->frame->width = a->iframe->width = width;
+    a->header.height = a->frame->height = a->iframe->height = height;
+    a->header.num_of_frames = num_of_frames;
+    a->header.frames_per_second = frames_per_second;
+    a->header.total_audio_duration = 0;
+    a->header.sample_rate = 0;
+    a->header.audio_size = 0;
+    a->header.num_of_channels = 0;
+    a->header.bits_per_sample = 16;
+    a->leniency = 0.1282f;
+    a->opt = AGMV_OPT_I;
+    a->compression = AGMV_LZSS_COMPRESSION;
+    a->volume = 1.0f;
+    return a;
+}
+
+WEAK void DestroyAGMV(AGMV* a) {
+    if (!a) return;
+    free(a->iframe_entries);
+    free(a->frame->img_data);
+    free(a->iframe->img_data);
+    free(a->frame);
+    free(a->iframe);
+    free(a->bitstream->data);
+    free(a->bitstream);
+    free(a->frame_chunk);
+    if (a->header.total_audio_duration != 0) {
+        if (a->header.bits_per_sample == 16) free(a->audio_track->pcm); else free(a->audio_track->pcm8);
+        free(a->audio_chunk->atsample);
+    }
+    free(a->audio_chunk);
+    free(a->audio_track);
+    free(a);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* small host helpers                                                                      */
+/* ------------------------------------------------------------------------------------ */
+static void w32(FILE* f, u32 v) { uint32_t x = (uint32_t)v; fwrite(&x, 4, 1, f); }
+static void w16(FILE* f, u32 v) { uint16_t x = (uint16_t)v; fwrite(&x, 2, 1, f); }
+static u32 r32(FILE* f) { uint32_t x = 0; if (fread(&x, 1, 4, f) != 4) { /* short read leaves what arrived */ } return x; }
+static u32 r16(FILE* f) { uint16_t x = 0; if (fread(&x, 1, 2, f) != 2) { } return x; }
+static u32 r8(FILE* f) { uint8_t x = 0; if (fread(&x, 1, 1, f) != 1) { } return x; }
+
+static int opt_is_dual(AGMV_OPT o) { return !(o == AGMV_OPT_II || o == AGMV_OPT_ANIM || o == AGMV_OPT_GBA_II); }
+static int opt_is_light(AGMV_OPT o) { return !(o == AGMV_OPT_I || o == AGMV_OPT_ANIM || o == AGMV_OPT_GBA_I || o == AGMV_OPT_GBA_II); }
+/* src/agmv_utils.c:487-545 */
+static u8 version_of(AGMV_OPT o, AGMV_COMPRESSION c) { return (u8)((c == AGMV_LZSS_COMPRESSION ? 0 : 2) + (opt_is_dual(o) ? 1 : 2)); }
+
+/* 24/32-bit uncompressed BMP -> 0x00RRGGBB words in file row order (what AGIDL_LoadBMP +
+ * AGIDL_ColorConvertBMP(RGB_888) hand the encoder, extern/agidl/src/agidl_img_bmp.c:973-1002). */
+static int load_bmp(const char* path, u32 w, u32 h, uint32_t* out) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { fprintf(stderr, "libagmv_dropin: cannot open %s\n", path); return -1; }
+    uint8_t hd[54];
+    if (fread(hd, 1, 54, f) != 54 || hd[0] != 'B' || hd[1] != 'M') { fclose(f); return -2; }
+    uint32_t off, bw, bh, bits, comp;
+    memcpy(&off, hd + 10, 4); memcpy(&bw, hd + 18, 4); memcpy(&bh, hd + 22, 4);
+    bits = hd[28] | hd[29] << 8; memcpy(&comp, hd + 30, 4);
+    if (bw != w || bh != h || !(bits == 24 || bits == 32) || comp != 0) {
+        fprintf(stderr, "libagmv_dropin: %s: only uncompressed 24/32-bit BMPs of %lux%lu are served\n", path, w, h);
+        fclose(f);
+        return -3;
+    }
+    size_t bpp = bits / 8, stride = (w * bpp + 3) & ~(size_t)3;
+    uint8_t* row = (uint8_t*)malloc(stride);
+    fseek(f, (long)off, SEEK_SET);
+    for (u32 y = 0; y < h; y++) {
+        if (fread(row, 1, stride, f) != stride) { free(row); fclose(f); return -4; }
+        for (u32 x = 0; x < w; x++) out[y * w + x] = (uint32_t)row[x * bpp + 2] << 16 | (uint32_t)row[x * bpp + 1] << 8 | row[x * bpp];
+    }
+    free(row);
+    fclose(f);
+    return 0;
+}
+
+static unsigned long g_expcount = 0; /* AGIDL's process-global export counter, extern/agidl/src/agidl_img_export.c:18 */
+
+/* AGIDL_QuickExport for BMP / RGB_888 (extern/agidl/src/agidl_img_export.c:20-41, agidl_img_bmp.c:1041-1110):
+ * 54-byte header with zero resolution fields, rows in buffer order, BGR. */
+static void quick_export_bmp(const uint32_t* px, u32 w, u32 h) {
+    char name[64];
+    g_expcount++;
+    snprintf(name, sizeof name, "quick_export_%lu.bmp", g_expcount);
+    FILE* f = fopen(name, "wb");
+    if (!f) return;
+    uint8_t hd[54];
+    memset(hd, 0, sizeof hd);
+    uint32_t v;
+    hd[0] = 'B'; hd[1] = 'M';
+    v = (uint32_t)(54 + w * h * 3); memcpy(hd + 2, &v, 4);
+    v = 54; memcpy(hd + 10, &v, 4);
+    v = 40; memcpy(hd + 14, &v, 4);
+    v = (uint32_t)w; memcpy(hd + 18, &v, 4);
+    v = (uint32_t)h; memcpy(hd + 22, &v, 4);
+    hd[26] = 1; hd[28] = 24;
+    v = (uint32_t)(w * h * 3); memcpy(hd + 34, &v, 4);
+    fwrite(hd, 1, 54, f);
+    uint8_t* row = (uint8_t*)malloc(w * 3);
+    for (u32 y = 0; y < h; y++) {
+        for (u32 x = 0; x < w; x++) {
+            uint32_t c = px[y * w + x];
+            row[3 * x] = (uint8_t)c; row[3 * x + 1] = (uint8_t)(c >> 8); row[3 * x + 2] = (uint8_t)(c >> 16);
+        }
+        fwrite(row, 1, w * 3, f);
+    }
+    free(row);
+    fclose(f);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* encode                                                                                  */
+/* ------------------------------------------------------------------------------------ */
+/* src/agmv_encode.c:21-94 */
+void AGMV_EncodeHeader(FILE* file, AGMV* agmv) {
+    fwrite("AGMV", 1, 4, file);
+    w32(file, agmv->header.num_of_frames);
+    w32(file, agmv->header.width);
+    w32(file, agmv->header.height);
+    fputc(1, file);
+    fputc(version_of(agmv->opt, agmv->compression), file);
+    w32(file, agmv->header.frames_per_second);
+    w32(file, agmv->header.total_audio_duration);
+    w32(file, agmv->header.sample_rate);
+    w32(file, agmv->header.audio_size);
+    w16(file, agmv->header.num_of_channels);
+    w16(file, agmv->header.bits_per_sample);
+    for (int p = 0; p < (opt_is_dual(agmv->opt) ? 2 : 1); p++) {
+        const u32* pal = p ? agmv->header.palette1 : agmv->header.palette0;
+        for (int i = 0; i < 256; i++) { fputc((int)((pal[i] >> 16) & 255), file); fputc((int)((pal[i] >> 8) & 255), file); fputc((int)(pal[i] & 255), file); }
+    }
+}
+
+/* encoder configuration currently loaded in the GPU context (per-frame API) */
+static struct { u32 w, h; int opt, comp, valid; } g_enc = {0, 0, 0, 0, 0};
+
+static int enc_prepare(agmvb_ctx* c, AGMV* agmv) {
+    u32 w = agmv->header.width, h = agmv->header.height;
+    if (!g_enc.valid || g_enc.w != w || g_enc.h != h || g_enc.opt != (int)agmv->opt || g_enc.comp != (int)agmv->compression) {
+        /* coded size == handle size here: scaling (GBA / NDS) is AGMV_EncodeAGMV's job, the per-frame call gets scaled frames */
+        int o = agmv->opt;
+        if (o == AGMV_OPT_GBA_I || o == AGMV_OPT_GBA_III || o == AGMV_OPT_NDS) o = AGMV_OPT_III; /* same codec path, no rescale */
+        if (o == AGMV_OPT_GBA_II) o = AGMV_OPT_II;
+        int rc = agmvb_enc_begin(c, (uint32_t)w, (uint32_t)h, o, AGMVB_HIGH_QUALITY, (int)agmv->compression);
+        if (rc) return rc;
+        g_enc.w = w; g_enc.h = h; g_enc.opt = (int)agmv->opt; g_enc.comp = (int)agmv->compression; g_enc.valid = 1;
+    }
+    uint32_t p0[256], p1[256];
+    for (int i = 0; i < 256; i++) { p0[i] = (uint32_t)agmv->header.palette0[i]; p1[i] = (uint32_t)agmv->header.palette1[i]; }
+    return agmvb_enc_set_palette(c, p0, p1);
+}
+
+/* src/agmv_encode.c:529-634 */
+void AGMV_EncodeFrame(FILE* file, AGMV* agmv, u32* img_data) {
+    agmvb_ctx* c = ctx_get();
+    if (!c) return;
+    const size_t P = (size_t)agmv->header.width * agmv->header.height;
+    int rc = enc_prepare(c, agmv);
+    if (rc) { fail(rc, "AGMV_EncodeFrame"); return; }
+    uint32_t* px = (uint32_t*)malloc(P * 4);
+    uint16_t* ent = (uint16_t*)malloc(P * 2);
+    for (size_t i = 0; i < P; i++) { px[i] = (uint32_t)img_data[i]; agmv->frame->img_data[i] = img_data[i]; } /* AGMV_SyncFrameAndImage */
+    const int is_i = agmv->frame_count % 4 == 0;
+    if (!is_i) { /* the I-frame entries live in the caller's handle */
+        for (size_t i = 0; i < P; i++) ent[i] = (uint16_t)((agmv->iframe_entries[i].pal_num & 1) << 8 | agmv->iframe_entries[i].index);
+        rc = agmvb_enc_set_iframe_entries(c, ent);
+    }
+    int32_t sa = 0, sb = -1;
+    uint64_t nbytes = 0;
+    if (!rc) rc = agmvb_enc_frames(c, px, 1, 0, &sa, &sb, 1, (uint32_t)agmv->frame_count, &nbytes);
+    uint8_t* img = (uint8_t*)malloc(nbytes + 16);
+    uint32_t us = 0, cs = 0;
+    if (!rc) rc = agmvb_enc_fetch(c, img, nbytes, &us, &cs);
+    if (!rc) {
+        fwrite(img, 1, (size_t)nbytes - 8, file); /* chunk + trailer; the 'AGAC' stub is AGMV_EncodeAudioChunk's, not ours */
+        agmv->bitstream->pos = us;
+        if (is_i) {
+            rc = agmvb_enc_get_iframe_entries(c, ent);
+            if (!rc) for (size_t i = 0; i < P; i++) { agmv->iframe_entries[i].pal_num = (u8)(ent[i] >> 8); agmv->iframe_entries[i].index = (u8)ent[i]; }
+        }
+        agmv->frame_count++;
+    }
+    if (rc) fail(rc, "AGMV_EncodeFrame");
+    free(px); free(ent); free(img);
+}
+
+/* src/agmv_encode.c:2270-3657, BMP input */
+void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame,
+                     u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
+                     AGMV_COMPRESSION compression) {
+    (void)frames_per_second; /* the reference writes the handle's rate, not this argument (:41, :3620) */
+    agmvb_ctx* c = ctx_get();
+    if (!c) { DestroyAGMV(agmv); return; }
+    if (img_type != AGMV_IMG_BMP) {
+        fprintf(stderr, "libagmv_dropin: AGMV_EncodeAGMV serves BMP input only (image decoding is AGIDL's, out of scope)\n");
+        DestroyAGMV(agmv);
+        return;
+    }
+    if (agmv->header.audio_size != 0) fprintf(stderr, "libagmv_dropin: audio track ignored (audio codec is out of scope); empty AGAC chunks are written\n");
+    agmv->opt = opt;
+    agmv->compression = compression;
+    agmv->leniency = 0;
+    u32 adjusted = end_frame - start_frame;
+    u32 cw = width, ch = height;
+    switch (opt) { /* :2296-2353 */
+        case AGMV_OPT_I: case AGMV_OPT_ANIM: adjusted /= 2; break;
+        case AGMV_OPT_II: case AGMV_OPT_III: adjusted *= 0.75; break;
+        case AGMV_OPT_GBA_I: case AGMV_OPT_GBA_II: cw = 120; ch = 80; adjusted /= 2; break;
+        case AGMV_OPT_GBA_III: cw = 120; ch = 80; adjusted *= 0.75f; break;
+        case AGMV_OPT_NDS: cw = 128; ch = 96; adjusted *= 0.75; break;
+    }
+    if (cw != width || ch != height) {
+        agmv->header.width = agmv->frame->width = agmv->iframe->width = cw;
+        agmv->header.height = agmv->frame->height = agmv->iframe->height = ch;
+        free(agmv->frame->img_data);
+        agmv->frame->img_data = (u32*)malloc(sizeof(u32) * cw * ch);
+    }
+    const int light = opt_is_light(opt);
+    const size_t SP = (size_t)width * height;
+    const u32 n_src = end_frame - start_frame + 1;
+    const int cur_dir = dir[0] == 'c' && dir[1] == 'u' && dir[2] == 'r'; /* :2373 */
+    char path[512];
+    int rc = agmvb_enc_begin(c, (uint32_t)width, (uint32_t)height, (int)opt, (int)quality, (int)compression);
+    g_enc.valid = 0;
+    /* frames are streamed from disk twice, like the reference: once for the histogram, once for the encode */
+    const u32 CH = 64; /* source frames per upload; a multiple of 16 keeps LIGHT groups and GOPs whole */
+    uint32_t* buf = (uint32_t*)malloc((size_t)(CH + 4) * SP * 4);
+    for (u32 f0 = 0; !rc && f0 < n_src; f0 += CH) {
+        u32 nf = n_src - f0 < CH ? n_src - f0 : CH;
+        for (u32 k = 0; k < nf; k++) {
+            if (cur_dir) snprintf(path, sizeof path, "%s%lu.bmp", basename, start_frame + f0 + k);
+            else snprintf(path, sizeof path, "%s/%s%lu.bmp", dir, basename, start_frame + f0 + k);
+            if (load_bmp(path, width, height, buf + (size_t)k * SP)) { rc = AGMVB_ERR_FILE; break; }
+        }
+        if (!rc) rc = agmvb_enc_histogram(c, buf, nf, 0);
+    }
+    if (!rc) rc = agmvb_enc_build_palette(c);
+    uint32_t p0[256], p1[256];
+    if (!rc) rc = agmvb_enc_get_palette(c, p0, p1);
+    if (rc) { fail(rc, "AGMV_EncodeAGMV (palette pass)"); free(buf); DestroyAGMV(agmv); return; }
+    for (int i = 0; i < 256; i++) { agmv->header.palette0[i] = p0[i]; agmv->header.palette1[i] = p1[i]; }
+    FILE* file = fopen(filename, "wb");
+    if (!file) { fprintf(stderr, "libagmv_dropin: cannot create %s\n", filename); free(buf); DestroyAGMV(agmv); return; }
+    AGMV_EncodeHeader(file, agmv);
+
+    /* pass 2: PDIFS schedule (:2727-2770), loop exit (:3610-3612); encode in batches of whole groups */
+    u32 encoded = 0;
+    const u32 step = light ? 4 : 2, per = light ? 3 : 1, groups_per_batch = CH / step;
+    int32_t* sa = (int32_t*)malloc(sizeof(int32_t) * groups_per_batch * 3);
+    int32_t* sb = (int32_t*)malloc(sizeof(int32_t) * groups_per_batch * 3);
+    uint8_t* img = NULL;
+    size_t img_cap = 0;
+    u32 i = start_frame;
+    int done = 0;
+    while (!done && !rc) {
+        u32 base = i, g = 0, ne = 0;
+        while (g < groups_per_batch) {
+            u32 o = i - base;
+            if (light) { sa[ne] = o; sb[ne] = -1; sa[ne + 1] = o + 1; sb[ne + 1] = o + 2; sa[ne + 2] = o + 3; sb[ne + 2] = -1; }
+            else { sa[ne] = o; sb[ne] = o + 1; }
+            ne += per; g++; i += step;
+            if (i + 4 >= end_frame || i > end_frame) { done = 1; break; }
+        }
+        u32 nf = g * step; /* source frames base .. base+nf-1 (HEAVY loads but ignores the 3rd and 4th frame of a group) */
+        for (u32 k = 0; k < nf && !rc; k++) {
+            if (!light && base + k > end_frame) break;
+            if (cur_dir) snprintf(path, sizeof path, "%s%lu.bmp", basename, base + k);
+            else snprintf(path, sizeof path, "%s/%s%lu.bmp", dir, basename, base + k);
+            if (load_bmp(path, width, height, buf + (size_t)k * SP)) rc = AGMVB_ERR_FILE;
+        }
+        uint64_t nbytes = 0;
+        if (!rc) rc = agmvb_enc_frames(c, buf, nf, 0, sa, sb, ne, (uint32_t)encoded, &nbytes);
+        if (!rc && nbytes > img_cap) { free(img); img_cap = nbytes * 2; img = (uint8_t*)malloc(img_cap); }
+        if (!rc) rc = agmvb_enc_fetch(c, img, img_cap, NULL, NULL);
+        if (!rc) fwrite(img, 1, nbytes, file);
+        encoded += ne;
+        agmv->frame_count += ne;
+    }
+    if (rc) fail(rc, "AGMV_EncodeAGMV (encode pass)");
+    /* back-patch (:3615-3620) */
+    fseek(file, 4, SEEK_SET);
+    w32(file, encoded);
+    fseek(file, 18, SEEK_SET);
+    f32 rate = (f32)adjusted / (agmv->header.num_of_frames + 1);
+    w32(file, (u32)round(agmv->header.frames_per_second * rate));
+    fclose(file);
+    free(buf); free(sa); free(sb); free(img);
+    DestroyAGMV(agmv); /* the reference consumes the caller's handle (:3625) */
+
+    if (opt == AGMV_OPT_GBA_I || opt == AGMV_OPT_GBA_II || opt == AGMV_OPT_GBA_III) { /* :3627-3656 */
+        FILE* in = fopen(filename, "rb");
+        if (!in) return;
+        fseek(in, 0, SEEK_END);
+        long size = ftell(in);
+        fseek(in, 0, SEEK_SET);
+        uint8_t* data = (uint8_t*)malloc((size_t)size);
+        if (fread(data, 1, (size_t)size, in) != (size_t)size) { }
+        fclose(in);
+        FILE* out = fopen("GBA_GEN_AGMV.h", "w");
+        if (out) {
+            fprintf(out, "#ifndef GBA_GEN_AGMV_H\n#define GBA_GEN_AGMV_H\n\nconst unsigned char GBA_AGMV_FILE[%ld] = {\n", size);
+            for (long k = 0; k < size; k++) {
+                if (k != 0 && k % 4000 == 0) fprintf(out, "\n");
+                fprintf(out, "%d,", data[k]);
+            }
+            fprintf(out, "};\n\n#endif");
+            fclose(out);
+        }
+        free(data);
+    }
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* decode                                                                                  */
+/* ------------------------------------------------------------------------------------ */
+/* src/agmv_decode.c:91-143 */
+int AGMV_DecodeHeader(FILE* file, AGMV* agmv) {
+    if (fread(agmv->header.fourcc, 1, 4, file) != 4) { }
+    agmv->header.num_of_frames = r32(file);
+    agmv->header.width = r32(file);
+    agmv->header.height = r32(file);
+    agmv->header.fmt = (u8)r8(file);
+    agmv->header.version = (u8)r8(file);
+    agmv->header.frames_per_second = r32(file);
+    agmv->header.total_audio_duration = r32(file);
+    agmv->header.sample_rate = r32(file);
+    agmv->header.audio_size = r32(file);
+    agmv->header.num_of_channels = (u16)r16(file);
+    agmv->header.bits_per_sample = (u16)r16(file);
+    u8 v = agmv->header.version;
+    if (memcmp(agmv->header.fourcc, "AGMV", 4) || !(v >= 1 && v <= 4) || agmv->header.frames_per_second >= 200 ||
+        !(agmv->header.bits_per_sample == 16 || agmv->header.bits_per_sample == 8))
+        return INVALID_HEADER_FORMATTING_ERR;
+    for (int p = 0; p < ((v == 1 || v == 3) ? 2 : 1); p++) {
+        u32* pal = p ? agmv->header.palette1 : agmv->header.palette0;
+        for (int i = 0; i < 256; i++) { u32 r = r8(file), g = r8(file), b = r8(file); pal[i] = r << 16 | g << 8 | b; }
+    }
+    return NO_ERR;
+}
+
+/* decoder state on the GPU for handles driven through AGMV_DecodeFrameChunk */
+#define MAX_BOUND 16
+static struct { AGMV* key; int stream; u32 w, h; int version; uint32_t palsum; } g_bound[MAX_BOUND];
+
+static uint32_t pal_sum(const AGMV* a) {
+    uint32_t s = 2166136261u;
+    for (int i = 0; i < 256; i++) { s = (s ^ (uint32_t)a->header.palette0[i]) * 16777619u; s = (s ^ (uint32_t)a->header.palette1[i]) * 16777619u; }
+    return s;
+}
+
+static int bound_stream(agmvb_ctx* c, AGMV* agmv, int* stream) {
+    int slot = -1;
+    uint32_t ps = pal_sum(agmv);
+    for (int k = 0; k < MAX_BOUND; k++) if (g_bound[k].key == agmv) slot = k;
+    if (slot >= 0) {
+        if (g_bound[slot].w == agmv->header.width && g_bound[slot].h == agmv->header.height &&
+            g_bound[slot].version == agmv->header.version && g_bound[slot].palsum == ps && agmv->frame_count != 0) {
+            *stream = g_bound[slot].stream;
+            return 0;
+        }
+        agmvb_dec_close(c, g_bound[slot].stream); /* new stream on an old handle (or a rewind to frame 0) */
+        g_bound[slot].key = NULL;
+    }
+    for (int k = 0; k < MAX_BOUND && slot < 0; k++) if (!g_bound[k].key) slot = k;
+    if (slot < 0) { agmvb_dec_close(c, g_bound[0].stream); slot = 0; }
+    uint32_t p0[256], p1[256];
+    for (int i = 0; i < 256; i++) { p0[i] = (uint32_t)agmv->header.palette0[i]; p1[i] = (uint32_t)agmv->header.palette1[i]; }
+    int rc = agmvb_dec_open_raw(c, (uint32_t)agmv->header.width, (uint32_t)agmv->header.height, agmv->header.version, p0, p1, stream);
+    if (rc) return rc;
+    g_bound[slot].key = agmv; g_bound[slot].stream = *stream; g_bound[slot].w = agmv->header.width; g_bound[slot].h = agmv->header.height;
+    g_bound[slot].version = agmv->header.version; g_bound[slot].palsum = ps;
+    return 0;
+}
+
+/* src/agmv_decode.c:145-410 */
+int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
+    agmv->bitstream->pos = 0;
+    if (fread(agmv->frame_chunk->fourcc, 1, 4, file) != 4) { }
+    agmv->frame_chunk->frame_num = r32(file);
+    agmv->frame_chunk->uncompressed_size = r32(file);
+    agmv->frame_chunk->compressed_size = r32(file);
+    if (memcmp(agmv->frame_chunk->fourcc, "AGFC", 4)) return INVALID_HEADER_FORMATTING_ERR;
+    agmvb_ctx* c = ctx_get();
+    if (!c) return MEMORY_CORRUPTION_ERR;
+    const u32 usize = agmv->frame_chunk->uncompressed_size, csize = agmv->frame_chunk->compressed_size;
+    const size_t P = (size_t)agmv->header.width * agmv->header.height;
+    const long data_start = ftell(file);
+    size_t want = (size_t)csize + 64;
+    uint8_t* pay = (uint8_t*)malloc(want);
+    size_t got = fread(pay, 1, want, file);
+    int stream = -1;
+    int rc = bound_stream(c, agmv, &stream);
+    uint32_t* px = (uint32_t*)malloc(P * 4);
+    uint32_t bpos = 0, consumed = 0;
+    if (!rc) rc = agmvb_dec_chunk(c, stream, pay, got, (uint32_t)usize, (uint32_t)csize, (uint32_t)agmv->frame_count, px, &bpos, &consumed);
+    if (!rc) {
+        for (size_t i = 0; i < P; i++) agmv->frame->img_data[i] = px[i];
+        if (agmv->frame_count % 4 == 0) for (size_t i = 0; i < P; i++) agmv->iframe->img_data[i] = px[i];
+        agmv->bitstream->pos = bpos;
+        agmv->frame_count++;
+        fseek(file, data_start + (long)consumed, SEEK_SET); /* where the reference's bit reader leaves the cursor */
+    }
+    free(pay); free(px);
+    if (rc) { fail(rc, "AGMV_DecodeFrameChunk"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    return NO_ERR;
+}
+
+/* src/agmv_decode.c:527-647 (video frames; the audio track is skipped) */
+int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type) {
+    (void)audio_type;
+    FILE* f = fopen(filename, "rb");
+    if (!f) return FILE_NOT_FOUND_ERR;
+    fseek(f, 0, SEEK_END);
+    long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    uint8_t* data = (uint8_t*)malloc((size_t)size + 1);
+    if (fread(data, 1, (size_t)size, f) != (size_t)size) { }
+    fclose(f);
+    agmvb_ctx* c = ctx_get();
+    if (!c) { free(data); return MEMORY_CORRUPTION_ERR; }
+    int stream = -1;
+    uint32_t w = 0, h = 0, n = 0;
+    int rc = agmvb_dec_open(c, data, (uint64_t)size, &stream, &w, &h, &n);
+    free(data);
+    if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    const size_t P = (size_t)w * h;
+    const uint32_t CH = 32;
+    uint32_t* px = (uint32_t*)malloc((size_t)CH * P * 4);
+    for (uint32_t f0 = 0; f0 < n && !rc; f0 += CH) {
+        uint32_t nf = n - f0 < CH ? n - f0 : CH;
+        rc = agmvb_dec_frames(c, stream, nf, px, 0);
+        if (!rc && img_type == AGMV_IMG_BMP) for (uint32_t k = 0; k < nf; k++) quick_export_bmp(px + (size_t)k * P, w, h);
+    }
+    free(px);
+    agmvb_dec_close(c, stream);
+    if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    return NO_ERR;
+}

@@ -41,6 +41,9 @@ struct DecStream {
     uint32_t persist_len = 0;
     uint32_t* d_ring = nullptr;     // optional ring of frames for agmvb_dec_batch without outputs
     uint32_t last_bpos = 0, last_consumed = 0;
+    bool raw = false;               // fed chunk by chunk (agmvb_dec_chunk): the vectors hold one entry
+    uint64_t file_cap = 0;
+    size_t at(uint32_t g) const { return raw ? 0 : g; }
 };
 
 }  // namespace
@@ -50,7 +53,7 @@ struct agmvb_ctx {
     cudaStream_t st = nullptr;
     bool own_stream = false;
     char err[512] = {0};
-    uint64_t launches = 0;
+    LaunchCtx lc;
 
     // ---- encoder state ----
     bool enc_ready = false;
@@ -128,6 +131,7 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
         if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return ERR_CUDA; }
         ctx->own_stream = true;
     }
+    ctx->lc.st = ctx->st;
     if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) {
         delete ctx;
         return ERR_CUDA;
@@ -159,7 +163,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
 }
 
 extern "C" const char* agmvb_last_error(const agmvb_ctx* ctx) { return ctx ? ctx->err : "null context"; }
-extern "C" uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx) { return ctx ? ctx->lc.launches : 0; }
 extern "C" int agmvb_sync(agmvb_ctx* ctx) {
     if (!ctx) return ERR_ARG;
     CK(cudaStreamSynchronize(ctx->st));
@@ -224,18 +228,15 @@ static int hist_launch(agmvb_ctx* ctx, const uint32_t* d_px, uint64_t npx) {
         uint64_t groups = npx / 4;
         if (groups) {
             int grid = (int)std::min<uint64_t>((groups + 255) / 256, 148 * 16);
-            hist_vec4_k<<<grid, 256, 0, ctx->st>>>(reinterpret_cast<const uint4*>(d_px), groups, ctx->quality, ctx->mc, ctx->d_hist);
-            ctx->launches++;
+            KL(ctx->lc, KC_HIST, (hist_vec4_k<<<grid, 256, 0, ctx->st>>>(reinterpret_cast<const uint4*>(d_px), groups, ctx->quality, ctx->mc, ctx->d_hist)));
         }
         uint64_t tail = npx - groups * 4;
         if (tail) {
-            hist_scalar_k<<<1, 256, 0, ctx->st>>>(d_px + groups * 4, tail, ctx->quality, ctx->mc, ctx->d_hist);
-            ctx->launches++;
+            KL(ctx->lc, KC_HIST, (hist_scalar_k<<<1, 256, 0, ctx->st>>>(d_px + groups * 4, tail, ctx->quality, ctx->mc, ctx->d_hist)));
         }
     } else {
         int grid = (int)std::min<uint64_t>((npx + 255) / 256, 148 * 16);
-        hist_scalar_k<<<grid, 256, 0, ctx->st>>>(d_px, npx, ctx->quality, ctx->mc, ctx->d_hist);
-        ctx->launches++;
+        KL(ctx->lc, KC_HIST, (hist_scalar_k<<<grid, 256, 0, ctx->st>>>(d_px, npx, ctx->quality, ctx->mc, ctx->d_hist)));
     }
     return check_launch(ctx, "histogram");
 }
@@ -268,19 +269,17 @@ extern "C" int agmvb_enc_build_palette(agmvb_ctx* ctx) {
     if (!ctx || !ctx->enc_ready) return ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     const uint32_t mc = ctx->mc;
-    pal_keys_k<<<cdiv(mc, 256), 256, 0, ctx->st>>>(ctx->d_hist, mc, ctx->d_keys[0]);
-    ctx->launches++;
+    KL(ctx->lc, KC_PALETTE, (pal_keys_k<<<cdiv(mc, 256), 256, 0, ctx->st>>>(ctx->d_hist, mc, ctx->d_keys[0])));
     const uint32_t nt = cdiv(mc, RX_TILE);
     TRY(ensure(ctx, ctx->small, (size_t)256 * nt * 4));
     TRY(ensure(ctx, ctx->scanws, ((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2) * 4));
     int cur = 0;
     for (uint32_t shift = 0; shift < 64; shift += 8) {  // stable LSD passes == stable sort by (count, index)
         radix_pass(KeyDigit{ctx->d_keys[cur], shift}, KeyMove{ctx->d_keys[cur], ctx->d_keys[cur ^ 1]}, mc, ctx->small.as<uint32_t>(),
-                   ctx->scanws.as<uint32_t>(), ctx->st, ctx->launches);
+                   ctx->scanws.as<uint32_t>(), ctx->lc);
         cur ^= 1;
     }
-    pal_pick_k<<<1, 32, (mc + 1) / 8, ctx->st>>>(ctx->d_keys[cur], mc, ctx->quality, ctx->dual, ctx->d_pal);
-    ctx->launches++;
+    KL(ctx->lc, KC_PALETTE, (pal_pick_k<<<1, 32, (mc + 1) / 8, ctx->st>>>(ctx->d_keys[cur], mc, ctx->quality, ctx->dual, ctx->d_pal)));
     TRY(check_launch(ctx, "palette"));
     CK(cudaMemcpyAsync(ctx->h_pal, ctx->d_pal, 512 * 4, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -387,8 +386,7 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
         if (ctx->image.p) CK(cudaFree(ctx->image.p));
         ctx->image = nb;
     }
-    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->st,
-                      ctx->launches);
+    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
     TRY(check_launch(ctx, "lzss"));
     uint32_t* hcs = hp + (F + 2);
     CK(cudaMemcpyAsync(hcs, ctx->lz.csize, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
@@ -416,14 +414,13 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
     TRY(ensure_pinned(ctx, (size_t)(F + 2) * 8));
     CK(cudaMemcpyAsync(ctx->entpairs.p, h_pairs, F * sizeof(EntPair), cudaMemcpyHostToDevice, ctx->st));
     dim3 grid(cdiv(B, 256), F);
-    classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->d_pal, ctx->dual, ctx->rec.as<uint8_t>());
+    KL(ctx->lc, KC_CLASSIFY, (classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->d_pal, ctx->dual, ctx->rec.as<uint8_t>())));
     device_scan<SumOp, true>(RecLen{ctx->rec.as<uint8_t>()}, StoreU32{ctx->boff.as<uint32_t>()}, (uint32_t)nb, ctx->scanws.as<uint32_t>(),
-                             ctx->st, ctx->launches);
-    frame_starts_k<<<cdiv(F + 1, 256), 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, F, ctx->scanws.as<uint32_t>() + cdiv(nb, SCAN_TILE),
-                                                          ctx->fs.as<uint32_t>());
-    emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(),
-                                      ctx->bs.as<uint8_t>());
-    ctx->launches += 3;
+                             ctx->lc, KC_BLOCKSCAN);
+    KL(ctx->lc, KC_BLOCKSCAN, (frame_starts_k<<<cdiv(F + 1, 256), 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, F, ctx->scanws.as<uint32_t>() + cdiv(nb, SCAN_TILE),
+                                                          ctx->fs.as<uint32_t>())));
+    KL(ctx->lc, KC_EMIT, (emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), W, H, ctx->dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(),
+                                      ctx->bs.as<uint8_t>())));
     TRY(check_launch(ctx, "assemble"));
     std::vector<uint32_t> fs(F + 1);
     CK(cudaMemcpyAsync(ctx->h_pinned, ctx->fs.p, (size_t)(F + 1) * 4, cudaMemcpyDeviceToHost, ctx->st));
@@ -486,9 +483,8 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
         TRY(ensure(ctx, ctx->entries, (size_t)F * P * 2));
         CK(cudaMemcpyAsync(ctx->srcpairs.p, sp.data(), F * sizeof(SrcPair), cudaMemcpyHostToDevice, ctx->st));
         dim3 qgrid(cdiv(P / 4, 256), F);
-        quantize_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), ctx->d_map, (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
-                                               ctx->entries.as<uint16_t>());
-        ctx->launches++;
+        KL(ctx->lc, KC_QUANT, (quantize_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), ctx->d_map, (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
+                                               ctx->entries.as<uint16_t>())));
         TRY(check_launch(ctx, "quantize"));
         int last_i = -1;
         for (uint32_t k = 0; k < F; k++) {
@@ -702,8 +698,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     // stray 'AGFC' inside a payload would make the chunk walk depend on where the bit reader stopped
     TRY(ensure(ctx, ctx->d_count, 8));
     CK(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->st));
-    count_fourcc_k<<<cdiv(len, 256), 256, 0, ctx->st>>>(s.d_file, len, 0x43464741u, ctx->d_count.as<unsigned long long>());
-    ctx->launches++;
+    KL(ctx->lc, KC_MISC, (count_fourcc_k<<<cdiv(len, 256), 256, 0, ctx->st>>>(s.d_file, len, 0x43464741u, ctx->d_count.as<unsigned long long>())));
     unsigned long long hits = 0;
     CK(cudaMemcpyAsync(&hits, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -763,7 +758,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         if (ids[s] < 0 || (size_t)ids[s] >= ctx->streams.size() || !ctx->streams[ids[s]].open) FAIL(ERR_ARG, "bad stream handle");
         DecStream& d = ctx->streams[ids[s]];
         if (d.w != ctx->streams[ids[0]].w || d.h != ctx->streams[ids[0]].h) FAIL(ERR_ARG, "streams of one batch must share a frame size");
-        if (d.next + count > d.n_frames) FAIL(ERR_ARG, "stream %d has only %u frames left", ids[s], d.n_frames - d.next);
+        if (!d.raw && d.next + count > d.n_frames) FAIL(ERR_ARG, "stream %d has only %u frames left", ids[s], d.n_frames - d.next);
     }
     const uint32_t W = ctx->streams[ids[0]].w, H = ctx->streams[ids[0]].h, B = (W >> 2) * (H >> 2);
     const size_t P = (size_t)W * H;
@@ -780,7 +775,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
     for (uint32_t s = 0; s < S; s++) {
         DecStream& d = ctx->streams[ids[s]];
         for (uint32_t k = 0; k < count; k++) {
-            uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.next + k] / 4 + 1) * 256 : d.usize[d.next + k];
+            uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.at(d.next + k)] / 4 + 1) * 256 : d.usize[d.at(d.next + k)];
             worst = std::max<uint64_t>(worst, e + DEC_SLACK);
         }
     }
@@ -800,10 +795,10 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
             for (uint32_t k = 0; k < cn; k++) {
                 DecFrame& x = fr[s * cn + k];
                 uint32_t g = d.next + k;
-                x.file = d.d_file; x.file_len = d.file_len; x.data_off = d.data_off[g]; x.ebuf_off = eoff;
-                x.persist = d.d_persist; x.persist_len = d.persist_len; x.usize = d.usize[g]; x.csize = d.csize[g];
+                x.file = d.d_file; x.file_len = d.file_len; x.data_off = d.data_off[d.at(g)]; x.ebuf_off = eoff;
+                x.persist = d.d_persist; x.persist_len = d.persist_len; x.usize = d.usize[d.at(g)]; x.csize = d.csize[d.at(g)];
                 x.stream_first = s * cn; x.lz77 = d.lz77; x.dual = d.dual;
-                uint64_t e = d.lz77 ? (uint64_t)(d.csize[g] / 4 + 1) * 256 : d.usize[g];
+                uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.at(g)] / 4 + 1) * 256 : d.usize[d.at(g)];
                 eoff += (e + DEC_SLACK + 15) & ~15ull;
             }
         }
@@ -816,11 +811,10 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         TRY(ensure(ctx, ctx->d_steps, F * sizeof(DecStep)));
         CK(cudaMemcpyAsync(ctx->d_frames.p, fr.data(), F * sizeof(DecFrame), cudaMemcpyHostToDevice, ctx->st));
         const DecFrame* dfr = ctx->d_frames.as<DecFrame>();
-        expand_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>());
-        stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>());
-        index_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
-                                                 ctx->d_recs.as<uint32_t>());
-        ctx->launches += 3;
+        KL(ctx->lc, KC_EXPAND, (expand_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>())));
+        KL(ctx->lc, KC_STALE, (stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>())));
+        KL(ctx->lc, KC_INDEX, (index_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
+                                                 ctx->d_recs.as<uint32_t>())));
         TRY(check_launch(ctx, "expand/index"));
         // reconstruction, frame by frame; step layout [k][s]
         steps.resize(F);
@@ -846,13 +840,11 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         CK(cudaMemcpyAsync(ctx->d_steps.p, steps.data(), F * sizeof(DecStep), cudaMemcpyHostToDevice, ctx->st));
         for (uint32_t k = 0; k < cn; k++) {
             dim3 grid(cdiv(B, 128), S);
-            reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>() + (size_t)k * S, W, H);
-            ctx->launches++;
+            KL(ctx->lc, KC_RECON, (reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>() + (size_t)k * S, W, H)));
             if (cks) {
                 for (uint32_t s = 0; s < S; s++) {
-                    checksum_k<<<std::min<uint32_t>(cdiv(P, 256), 592), 256, 0, ctx->st>>>(steps[k * S + s].dst, (uint32_t)P,
-                                                                                           ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k);
-                    ctx->launches++;
+                    KL(ctx->lc, KC_CHECKSUM, (checksum_k<<<std::min<uint32_t>(cdiv(P, 256), 592), 256, 0, ctx->st>>>(steps[k * S + s].dst, (uint32_t)P,
+                                                                                           ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k)));
                 }
             }
         }
@@ -860,9 +852,8 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         // carry the state over: expanded-bitstream leftovers, last pixels, last I-frame snapshot
         for (uint32_t s = 0; s < S; s++) {
             DecStream& d = ctx->streams[ids[s]];
-            persist_update_k<<<cdiv(d.persist_len, 256), 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), s * cn, cn, ctx->d_ebuf.as<uint8_t>(),
-                                                                             d.d_persist, d.persist_len);
-            ctx->launches++;
+            KL(ctx->lc, KC_STALE, (persist_update_k<<<cdiv(d.persist_len, 256), 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), s * cn, cn, ctx->d_ebuf.as<uint8_t>(),
+                                                                             d.d_persist, d.persist_len)));
         }
         if (c0 + cn == count) {
             for (uint32_t s = 0; s < S; s++) {
@@ -911,6 +902,148 @@ extern "C" int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint
         CK(cudaMemcpyAsync(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
     }
+    return OK;
+}
+
+// ---- per-chunk entry for the reference's streaming callers ------------------------
+// AGMV_DecodeFrameChunk (src/agmv_decode.c:145-410) is called with a FILE* at 'AGFC' by AGMV_PlayAGMV
+// (src/agmv_playback.c:102-115) and players; the drop-in reads the chunk and hands the payload here.
+extern "C" int agmvb_dec_open_raw(agmvb_ctx* ctx, uint32_t w, uint32_t h, int version, const uint32_t pal0[256], const uint32_t pal1[256],
+                                  int* stream) {
+    if (!ctx || !stream || !pal0) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (version < 1 || version > 4) FAIL(ERR_HEADER, "bad stream version %d", version);
+    if (w == 0 || h == 0 || (w & 3) || (h & 3)) FAIL(ERR_UNSUPPORTED, "width and height must be multiples of 4");
+    DecStream s;
+    s.w = w; s.h = h; s.n_frames = 0xFFFFFFFFu; s.version = (uint32_t)version; s.dual = version == 1 || version == 3; s.lz77 = version >= 3;
+    s.raw = true;
+    s.data_off.assign(1, 0); s.usize.assign(1, 0); s.csize.assign(1, 0);
+    const size_t P = (size_t)w * h;
+    uint32_t pal[512];
+    memset(pal, 0, sizeof pal);
+    for (int i = 0; i < 256; i++) pal[i] = pal0[i] & 0xFFFFFFu;
+    if (s.dual && pal1) for (int i = 0; i < 256; i++) pal[256 + i] = pal1[i] & 0xFFFFFFu;
+    CK(cudaMalloc(&s.d_pal, 512 * 4));
+    CK(cudaMemcpyAsync(s.d_pal, pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMalloc(&s.d_img, P * 4));
+    CK(cudaMalloc(&s.d_ifr, P * 4));
+    s.persist_len = (uint32_t)(2 * P + 64);
+    CK(cudaMalloc(&s.d_persist, s.persist_len));
+    CK(cudaMemsetAsync(s.d_img, 0, P * 4, ctx->st));
+    CK(cudaMemsetAsync(s.d_ifr, 0, P * 4, ctx->st));
+    CK(cudaMemsetAsync(s.d_persist, 0, s.persist_len, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    s.open = true;
+    int id = -1;
+    for (size_t k = 0; k < ctx->streams.size(); k++) if (!ctx->streams[k].open) { id = (int)k; break; }
+    if (id < 0) { ctx->streams.push_back(DecStream()); id = (int)ctx->streams.size() - 1; }
+    ctx->streams[id] = s;
+    *stream = id;
+    return OK;
+}
+
+// payload: the bytes that follow the 16-byte chunk header in the file (csize bytes plus whatever comes after,
+// at least 8 more if available: the bit reader may run into the trailer). frame_count: agmv->frame_count before
+// this frame. Outputs: pixels (host, w*h), bitstream->pos, and how many payload bytes the reader consumed.
+extern "C" int agmvb_dec_chunk(agmvb_ctx* ctx, int stream, const uint8_t* payload, uint64_t payload_len, uint32_t usize, uint32_t csize,
+                               uint32_t frame_count, uint32_t* out_px, uint32_t* bpos, uint32_t* consumed) {
+    if (!ctx || !payload || !out_px) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open || !ctx->streams[stream].raw)
+        FAIL(ERR_ARG, "bad raw stream handle");
+    DecStream& d = ctx->streams[stream];
+    const size_t P = (size_t)d.w * d.h;
+    if (usize > 2 * P + 64) FAIL(ERR_MEMORY, "uncompressed size %u exceeds the reference's bitstream buffer", usize);
+    if (payload_len + 64 > d.file_cap) {
+        CK(cudaStreamSynchronize(ctx->st));
+        if (d.d_file) CK(cudaFree(d.d_file));
+        d.file_cap = payload_len * 2 + 4096;
+        CK(cudaMalloc(&d.d_file, d.file_cap));
+    }
+    CK(cudaMemcpyAsync(d.d_file, payload, payload_len, cudaMemcpyHostToDevice, ctx->st));
+    d.file_len = payload_len;
+    d.data_off[0] = 0; d.usize[0] = usize; d.csize[0] = csize;
+    d.next = frame_count;
+    TRY(ensure(ctx, ctx->d_out, P * 4));
+    uint32_t* o = ctx->d_out.as<uint32_t>();
+    TRY(dec_batch_impl(ctx, &stream, 1, 1, &o, nullptr));
+    CK(cudaMemcpyAsync(out_px, o, P * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    if (bpos) *bpos = d.last_bpos;
+    if (consumed) *consumed = d.last_consumed;
+    return OK;
+}
+
+// ===========================================================================
+// bench / test utilities
+// ===========================================================================
+// Deterministic synthetic frames (SURVEY.md 8d / BASELINE.md 4), generated on the device so that large
+// benchmark inputs need not be produced on the host. Same integer formula as oracle/agmv_oracle.c:orc_synth_frame.
+__device__ __forceinline__ uint32_t mix32(uint32_t h) {
+    h ^= h >> 13;
+    h *= 0x5bd1e995u;
+    h ^= h >> 15;
+    return h;
+}
+__global__ void synth_k(uint32_t* __restrict__ out, int w, int h, int first_t, uint32_t seed) {
+    const int t = first_t + blockIdx.y;
+    const size_t P = (size_t)w * h;
+    const int s = w / 8 > 8 ? w / 8 : 8;
+    const int mx = w - s > 1 ? w - s : 1, my = h - s > 1 ? h - s : 1;
+    const int sx = (5 * t) % mx, sy = (3 * t) % my;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(p % w), y = (int)(p / w);
+        uint32_t r, g, b;
+        if (x >= sx && x < sx + s && y >= sy && y < sy + s) {
+            uint32_t nh = mix32(((uint32_t)x * 73856093u) ^ ((uint32_t)y * 19349663u) ^ ((uint32_t)t * 83492791u) ^ seed);
+            r = nh & 255; g = (nh >> 8) & 255; b = (nh >> 16) & 255;
+        } else if (y >= h / 3 && y < 2 * h / 3) {
+            r = (uint32_t)(x * 255 / (w - 1) + 2 * t) & 255;
+            g = (uint32_t)(y * 255 / (h - 1)) & 255;
+            b = (uint32_t)(x + y + 4 * t) & 255;
+        } else {
+            uint32_t th = mix32(((uint32_t)(x / 32) * 73856093u) ^ ((uint32_t)(y / 32) * 19349663u) ^ seed);
+            r = th & 255; g = (th >> 8) & 255; b = (th >> 16) & 255;
+        }
+        out[(size_t)blockIdx.y * P + p] = r << 16 | g << 8 | b;
+    }
+}
+
+extern "C" int agmvb_synth_frames(agmvb_ctx* ctx, uint32_t* dev_out, uint32_t w, uint32_t h, uint32_t first_t, uint32_t n, uint32_t seed) {
+    if (!ctx || !dev_out || !w || !h) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (uint32_t f0 = 0; f0 < n; f0 += 32768) {
+        uint32_t nf = std::min<uint32_t>(32768, n - f0);
+        dim3 grid(std::min<uint32_t>(cdiv((size_t)w * h, 256), 1184), nf);
+        KL(ctx->lc, KC_MISC, (synth_k<<<grid, 256, 0, ctx->st>>>(dev_out + (size_t)f0 * w * h, (int)w, (int)h, (int)(first_t + f0), seed)));
+    }
+    return check_launch(ctx, "synth");
+}
+
+// Per-kernel-class device time from CUDA events recorded around every launch on the launching stream.
+extern "C" int agmvb_profile(agmvb_ctx* ctx, int enable) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->st));
+    ctx->lc.prof = enable != 0;
+    ctx->lc.nrec = 0;
+    ctx->lc.npool = 0;
+    return OK;
+}
+extern "C" int agmvb_profile_classes(void) { return KC_COUNT; }
+extern "C" const char* agmvb_profile_name(int cls) { return kclass_name(cls); }
+// Sums and clears what was recorded since the last read: per class, launch count and total milliseconds.
+extern "C" int agmvb_profile_read(agmvb_ctx* ctx, uint64_t* counts, double* total_ms) {
+    if (!ctx || !counts || !total_ms) return ERR_ARG;
+    CK(cudaStreamSynchronize(ctx->st));
+    for (int c = 0; c < KC_COUNT; c++) { counts[c] = 0; total_ms[c] = 0.0; }
+    for (size_t k = 0; k < ctx->lc.nrec; k++) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, ctx->lc.recs[k].a, ctx->lc.recs[k].b));
+        counts[ctx->lc.recs[k].cls]++;
+        total_ms[ctx->lc.recs[k].cls] += ms;
+    }
+    ctx->lc.nrec = 0;
+    ctx->lc.npool = 0;
     return OK;
 }
 
@@ -968,8 +1101,7 @@ extern "C" int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint6
     SrcPair sp{ctx->stage.as<uint32_t>(), nullptr};
     CK(cudaMemcpyAsync(ctx->srcpairs.p, &sp, sizeof sp, cudaMemcpyHostToDevice, ctx->st));
     dim3 grid(cdiv(n / 4, 256), 1);
-    quantize_k<<<grid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), nullptr, (uint32_t)n, d_pal, dual ? 512 : 256, d_lut, ctx->entries.as<uint16_t>());
-    ctx->launches++;
+    KL(ctx->lc, KC_QUANT, (quantize_k<<<grid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), nullptr, (uint32_t)n, d_pal, dual ? 512 : 256, d_lut, ctx->entries.as<uint16_t>())));
     TRY(check_launch(ctx, "quantize"));
     CK(cudaMemcpyAsync(entries, ctx->entries.p, n * 2, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));
@@ -1004,11 +1136,10 @@ extern "C" int agmvb_test_assemble(agmvb_ctx* ctx, const uint16_t* entries, cons
     TRY(ensure(ctx, ctx->fs, 16));
     CK(cudaMemcpyAsync(ctx->entpairs.p, &ep, sizeof ep, cudaMemcpyHostToDevice, ctx->st));
     dim3 grid(cdiv(B, 256), 1);
-    classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, d_pal, dual, ctx->rec.as<uint8_t>());
-    device_scan<SumOp, true>(RecLen{ctx->rec.as<uint8_t>()}, StoreU32{ctx->boff.as<uint32_t>()}, B, ctx->scanws.as<uint32_t>(), ctx->st, ctx->launches);
-    frame_starts_k<<<1, 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, 1, ctx->scanws.as<uint32_t>() + cdiv(B, SCAN_TILE), ctx->fs.as<uint32_t>());
-    emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(), ctx->bs.as<uint8_t>());
-    ctx->launches += 3;
+    KL(ctx->lc, KC_CLASSIFY, (classify_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, d_pal, dual, ctx->rec.as<uint8_t>())));
+    device_scan<SumOp, true>(RecLen{ctx->rec.as<uint8_t>()}, StoreU32{ctx->boff.as<uint32_t>()}, B, ctx->scanws.as<uint32_t>(), ctx->lc, KC_BLOCKSCAN);
+    KL(ctx->lc, KC_BLOCKSCAN, (frame_starts_k<<<1, 256, 0, ctx->st>>>(ctx->boff.as<uint32_t>(), B, 1, ctx->scanws.as<uint32_t>() + cdiv(B, SCAN_TILE), ctx->fs.as<uint32_t>())));
+    KL(ctx->lc, KC_EMIT, (emit_k<<<grid, 256, 0, ctx->st>>>(ctx->entpairs.as<EntPair>(), w, h, dual, ctx->rec.as<uint8_t>(), ctx->boff.as<uint32_t>(), ctx->bs.as<uint8_t>())));
     TRY(check_launch(ctx, "assemble"));
     uint32_t fs[2];
     CK(cudaMemcpyAsync(fs, ctx->fs.p, 8, cudaMemcpyDeviceToHost, ctx->st));

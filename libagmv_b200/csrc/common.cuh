@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace agmvb {
 
@@ -54,6 +55,55 @@ inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
             return ERR_CUDA;                                                                 \
         }                                                                                    \
     } while (0)
+
+// ---- launch bookkeeping -------------------------------------------------------
+// Every kernel launch goes through LaunchCtx: it counts launches (bench.py's
+// gpu_launches) and, when profiling is on, brackets the launch with CUDA events
+// on the launching stream so per-kernel-class device time can be read back live.
+enum KClass {
+    KC_HIST = 0, KC_PALETTE, KC_QUANT, KC_CLASSIFY, KC_BLOCKSCAN, KC_EMIT, KC_LZ_INIT, KC_RX_HIST, KC_RX_SCAN, KC_RX_SCATTER,
+    KC_LZ_GROUP, KC_LZ_PARSE, KC_LZ_PACK, KC_LZ_CHUNK, KC_EXPAND, KC_STALE, KC_INDEX, KC_RECON, KC_CHECKSUM, KC_MISC, KC_COUNT
+};
+inline const char* kclass_name(int c) {
+    static const char* n[] = {"hist", "palette", "quantize", "classify", "block_scan", "emit", "lz_init", "rx_hist", "rx_scan",
+                              "rx_scatter", "lz_group", "lz_parse", "lz_pack", "lz_chunk", "expand", "stale", "index", "reconstruct",
+                              "checksum", "misc"};
+    return c >= 0 && c < KC_COUNT ? n[c] : "?";
+}
+struct LaunchCtx {
+    cudaStream_t st = nullptr;
+    uint64_t launches = 0;
+    bool prof = false;
+    struct Rec { int cls; cudaEvent_t a, b; };
+    Rec* recs = nullptr;
+    size_t nrec = 0, cap = 0;
+    cudaEvent_t* pool = nullptr;
+    size_t npool = 0, pool_cap = 0;
+    cudaEvent_t get_event() {
+        if (npool == pool_cap) {
+            size_t nc = pool_cap ? pool_cap * 2 : 4096;
+            pool = (cudaEvent_t*)realloc(pool, nc * sizeof(cudaEvent_t));
+            for (size_t k = pool_cap; k < nc; k++) cudaEventCreate(&pool[k]);
+            pool_cap = nc;
+        }
+        return pool[npool++];
+    }
+    void begin(int cls) {
+        if (!prof) return;
+        if (nrec == cap) { cap = cap ? cap * 2 : 4096; recs = (Rec*)realloc(recs, cap * sizeof(Rec)); }
+        recs[nrec].cls = cls;
+        recs[nrec].a = get_event();
+        recs[nrec].b = get_event();
+        cudaEventRecord(recs[nrec].a, st);
+    }
+    void end(int) {
+        launches++;
+        if (!prof) return;
+        cudaEventRecord(recs[nrec].b, st);
+        nrec++;
+    }
+};
+#define KL(lc, cls, ...) do { (lc).begin(cls); __VA_ARGS__; (lc).end(cls); } while (0)
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31; }
 __device__ __forceinline__ unsigned lanemask_lt() {

@@ -301,33 +301,33 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
 // wk.outbits, wk.chunk_off on the device and the chunk image written to
 // `image` (capacity >= 32*F + 9n/8 + 8).
 inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n,
-                              uint32_t first_frame_count, uint8_t* image, cudaStream_t st, uint64_t& launches) {
+                              uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
+    cudaStream_t st = lc.st;
     const uint32_t nthreads = 256;
     uint32_t cover = (n + 1 > F + 1 ? n + 1 : F + 1);
-    lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(n, fs, F, wk.A[0], wk.gs[0], wk.maxlen, wk.bestlen, wk.bitcum, wk.wbase);
+    KL(lc, KC_LZ_INIT, (lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(n, fs, F, wk.A[0], wk.gs[0], wk.maxlen, wk.bestlen, wk.bitcum, wk.wbase)));
     if (n > 0) {
         for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
             // gs[0]: group starts in A[L] order. The scatter carries them into gs[1] (A[L+1] order);
             // the running max over head flags reads gs[1] and writes the new starts back to gs[0].
-            radix_pass(LzDigit{bs, wk.A[L], L}, LzMove{wk.A[L], wk.gs[0], wk.A[L + 1], wk.gs[1]}, n, wk.tile_hist, wk.scan_ws, st, launches);
+            radix_pass(LzDigit{bs, wk.A[L], L}, LzMove{wk.A[L], wk.gs[0], wk.A[L + 1], wk.gs[1]}, n, wk.tile_hist, wk.scan_ws, lc);
             device_scan<MaxOp, false>(LzHead{bs, wk.A[L + 1], wk.gs[1], L},
-                                      LzGroupOut{wk.A[L + 1], wk.gs[0], wk.maxlen, wk.bestlen, wk.lvlidx, wk.gsat, L + 1}, n, wk.scan_ws, st, launches);
+                                      LzGroupOut{wk.A[L + 1], wk.gs[0], wk.maxlen, wk.bestlen, wk.lvlidx, wk.gsat, L + 1}, n, wk.scan_ws, lc,
+                                      KC_LZ_GROUP);
         }
         uint32_t ntile = cdiv(n, PARSE_TILE);
-        lz_parse_spec_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.exit_tab, wk.w_tab);
-        lz_parse_chain_k<<<1, 1024, 0, st>>>(ntile, wk.exit_tab, wk.w_tab, wk.entry_tab, wk.cumbase);
-        lz_parse_mark_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.entry_tab, wk.cumbase, wk.bitcum);
+        KL(lc, KC_LZ_PARSE, (lz_parse_spec_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.exit_tab, wk.w_tab)));
+        KL(lc, KC_LZ_PARSE, (lz_parse_chain_k<<<1, 1024, 0, st>>>(ntile, wk.exit_tab, wk.w_tab, wk.entry_tab, wk.cumbase)));
+        KL(lc, KC_LZ_PARSE, (lz_parse_mark_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.entry_tab, wk.cumbase, wk.bitcum)));
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         APtrs ap;
         for (int l = 0; l <= LZ_LEVELS; l++) ap.a[l] = wk.A[l];
-        lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.bestlen, wk.lvlidx, wk.gsat, wk.bitcum, ap, wk.wbase, wk.out_words);
-        launches += 4;
+        KL(lc, KC_LZ_PACK, (lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.bestlen, wk.lvlidx, wk.gsat, wk.bitcum, ap, wk.wbase, wk.out_words)));
     }
-    lz_finalize_k<<<1, 1024, 0, st>>>(fs, F, wk.bitcum, wk.outbits, wk.csize, wk.chunk_off);
+    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(fs, F, wk.bitcum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
-    lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, image);
-    launches += 3;
+    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, image)));
 }
 
 }  // namespace agmvb

@@ -100,13 +100,13 @@ struct StoreU32 {
 
 // tile_hist: 256 * ntiles words; scan_ws: cdiv(256*ntiles, SCAN_TILE) + 1 words
 template <class DigitF, class MoveF>
-inline void radix_pass(DigitF dg, MoveF mv, uint32_t n, uint32_t* tile_hist, uint32_t* scan_ws, cudaStream_t st, uint64_t& launches) {
+inline void radix_pass(DigitF dg, MoveF mv, uint32_t n, uint32_t* tile_hist, uint32_t* scan_ws, LaunchCtx& lc) {
+    cudaStream_t st = lc.st;
     if (n == 0) return;
     uint32_t nt = (n + RX_TILE - 1) / RX_TILE;
-    radix_hist_k<DigitF><<<nt, RX_THREADS, 0, st>>>(dg, n, nt, tile_hist);
-    device_scan<SumOp, true>(LoadU32{tile_hist}, StoreU32{tile_hist}, 256u * nt, scan_ws, st, launches);
-    radix_scatter_k<DigitF, MoveF><<<nt, RX_THREADS, 0, st>>>(dg, mv, n, nt, tile_hist);
-    launches += 2;
+    KL(lc, KC_RX_HIST, (radix_hist_k<DigitF><<<nt, RX_THREADS, 0, st>>>(dg, n, nt, tile_hist)));
+    device_scan<SumOp, true>(LoadU32{tile_hist}, StoreU32{tile_hist}, 256u * nt, scan_ws, lc, KC_RX_SCAN);
+    KL(lc, KC_RX_SCATTER, (radix_scatter_k<DigitF, MoveF><<<nt, RX_THREADS, 0, st>>>(dg, mv, n, nt, tile_hist)));
 }
 
 }  // namespace agmvb

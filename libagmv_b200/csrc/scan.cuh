@@ -120,16 +120,16 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_k(InF in, OutF out, u
 // ws must hold cdiv(n, SCAN_TILE) + 1 words. After the call ws[ntiles] holds
 // the grand total (sum) / maximum.
 template <class Op, bool EXCLUSIVE, class InF, class OutF>
-inline void device_scan(InF in, OutF out, uint32_t n, uint32_t* ws, cudaStream_t st, uint64_t& launches) {
+inline void device_scan(InF in, OutF out, uint32_t n, uint32_t* ws, LaunchCtx& lc, int cls) {
+    cudaStream_t st = lc.st;
     if (n == 0) {
         cudaMemsetAsync(ws, 0, sizeof(uint32_t), st);
         return;
     }
     uint32_t nt = (n + SCAN_TILE - 1) / SCAN_TILE;
-    scan_reduce_k<Op, InF><<<nt, SCAN_THREADS, 0, st>>>(in, n, ws);
-    scan_partials_k<Op><<<1, 1024, 0, st>>>(ws, nt);
-    scan_apply_k<Op, EXCLUSIVE, InF, OutF><<<nt, SCAN_THREADS, 0, st>>>(in, out, n, ws);
-    launches += 3;
+    KL(lc, cls, (scan_reduce_k<Op, InF><<<nt, SCAN_THREADS, 0, st>>>(in, n, ws)));
+    KL(lc, cls, (scan_partials_k<Op><<<1, 1024, 0, st>>>(ws, nt)));
+    KL(lc, cls, (scan_apply_k<Op, EXCLUSIVE, InF, OutF><<<nt, SCAN_THREADS, 0, st>>>(in, out, n, ws)));
 }
 
 }  // namespace agmvb

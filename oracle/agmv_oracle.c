@@ -503,6 +503,39 @@ done:
     return rc;
 }
 
+/* AGMV_EncodeFrame + the empty AGMV_EncodeAudioChunk for n_enc frames with a given palette, starting at
+ * agmv->frame_count == first_fc (src/agmv_encode.c:529-634, :707-717). Used by the sharding tests: a rank
+ * encodes only its GOP-aligned range of the sequence. No rescaling (coded size == frame size). */
+long orc_encode_frames(const uint32_t* frames, int w, int h, const int32_t* src_a, const int32_t* src_b, int n_enc, uint32_t first_fc,
+                       const uint32_t* pal0, const uint32_t* pal1, int dual, uint8_t* out, size_t cap) {
+    size_t px = (size_t)w * h, o = 0;
+    uint16_t* ent = (uint16_t*)malloc(px * 2);
+    uint16_t* ient = (uint16_t*)calloc(px, 2);
+    uint32_t* tmp = (uint32_t*)malloc(px * 4);
+    uint8_t* bs = (uint8_t*)calloc(px * 33 / 16 + 64, 1);
+    uint8_t* lz = (uint8_t*)malloc((px * 33 / 16 + 64) * 4 + 16);
+    long rc = 0;
+    for (int k = 0; k < n_enc; k++) {
+        const uint32_t* img = frames + (size_t)src_a[k] * px;
+        if (src_b[k] >= 0) { orc_interp(tmp, img, frames + (size_t)src_b[k] * px, px); img = tmp; }
+        uint32_t fc = first_fc + (uint32_t)k;
+        int is_i = fc % 4 == 0;
+        orc_quantize_frame(img, px, pal0, pal1, dual, ent);
+        size_t usize = orc_assemble(ent, ient, w, h, is_i, dual, pal0, pal1, bs), nbytes;
+        uint32_t csize = orc_lzss(bs, usize, lz, &nbytes, NULL);
+        if (o + 32 + nbytes + 8 > cap) { rc = -2; break; }
+        memcpy(out + o, "AGFC", 4);
+        put32(out + o + 4, fc + 1); put32(out + o + 8, (uint32_t)usize); put32(out + o + 12, csize);
+        memcpy(out + o + 16, lz, nbytes);
+        o += 16 + csize;
+        memset(out + o, 0xff, 8); o += 8;
+        memcpy(out + o, "AGAC", 4); put32(out + o + 4, 0); o += 8;
+        if (is_i) memcpy(ient, ent, px * 2);
+    }
+    free(ent); free(ient); free(tmp); free(bs); free(lz);
+    return rc ? rc : (long)o;
+}
+
 /* ------------------------------------------------------------------ */
 /* decode: src/agmv_decode.c:91-410, 527-647                            */
 /* ------------------------------------------------------------------ */

@@ -1,0 +1,223 @@
+"""The reference-facing C API (include/agmv_dropin.h, libagmv_dropin.so).
+
+CPU part: handle layout is binary compatible with the reference's headers.
+GPU part (-m gpu): CreateAGMV / AGMV_EncodeAGMV / AGMV_DecodeAGMV / AGMV_EncodeFrame / AGMV_DecodeFrameChunk
+called the way the reference's examples call them, results compared with the reference's golden output.
+"""
+import ctypes as C
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import libagmv_b200
+from agmv_testlib import GOLDEN_DIR, LZSS, OPT, QUALITY, REF_DIR, have_ref, sha256, synth_frames, write_bmps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+UL = C.c_ulong
+
+
+class Hdr(C.Structure):
+    _fields_ = [("fourcc", C.c_char * 4), ("num_of_frames", UL), ("width", UL), ("height", UL), ("fmt", C.c_uint8), ("version", C.c_uint8),
+                ("frames_per_second", UL), ("total_audio_duration", UL), ("sample_rate", UL), ("audio_size", UL),
+                ("num_of_channels", C.c_uint16), ("bits_per_sample", C.c_uint16), ("palette0", UL * 256), ("palette1", UL * 256)]
+
+
+class Frame(C.Structure):
+    _fields_ = [("width", UL), ("height", UL), ("img_data", C.POINTER(UL))]
+
+
+class Bitstream(C.Structure):
+    _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", UL), ("pos", UL)]
+
+
+class Entry(C.Structure):
+    _fields_ = [("pal_num", C.c_uint8), ("index", C.c_uint8), ("occurence", UL)]
+
+
+class AGMV(C.Structure):
+    _fields_ = [("header", Hdr), ("frame_chunk", C.c_void_p), ("audio_chunk", C.c_void_p), ("bitstream", C.POINTER(Bitstream)),
+                ("frame", C.POINTER(Frame)), ("iframe", C.POINTER(Frame)), ("audio_track", C.c_void_p), ("iframe_entries", C.POINTER(Entry)),
+                ("opt", C.c_int), ("compression", C.c_int), ("frame_count", UL), ("leniency", C.c_float), ("offset_table", UL * 40000),
+                ("enable_audio", C.c_int), ("volume", C.c_float)]
+
+
+def test_handle_layout_matches_reference_abi():
+    """sizeof / offsetof through a C compiler: our header vs the numbers measured on the reference."""
+    src = r'''
+    #include <stddef.h>
+    #include <stdio.h>
+    #include "INCLUDE_ME"
+    int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(AGMV), sizeof(AGMV_ENTRY), sizeof(u32), offsetof(AGMV, frame_count),
+                           offsetof(AGMV, iframe_entries), offsetof(AGMV_MAIN_HEADER, palette0)); return 0; }
+    '''
+    def run(header, inc):
+        with tempfile.TemporaryDirectory() as td:
+            open(os.path.join(td, "t.c"), "w").write(src.replace("INCLUDE_ME", header))
+            subprocess.run(["gcc", "-o", os.path.join(td, "t"), os.path.join(td, "t.c")] + [f"-I{i}" for i in inc], check=True)
+            return subprocess.run([os.path.join(td, "t")], capture_output=True, text=True, check=True).stdout.split()
+    ours = run("agmv_dropin.h", [os.path.join(ROOT, "include")])
+    assert ours[:3] == ["324264", "16", "8"]
+    assert C.sizeof(AGMV) == 324264 and C.sizeof(Entry) == 16
+    if os.path.isdir("/root/reference/include"):
+        theirs = run("agmv_defines.h", ["/root/reference/include"])
+        assert ours == theirs
+
+
+def _dropin():
+    lib = C.CDLL(libagmv_b200.DROPIN_PATH)
+    lib.CreateAGMV.restype = C.POINTER(AGMV)
+    lib.CreateAGMV.argtypes = [UL, UL, UL, UL]
+    lib.DestroyAGMV.argtypes = [C.POINTER(AGMV)]
+    lib.AGMV_EncodeAGMV.restype = None
+    lib.AGMV_EncodeAGMV.argtypes = [C.POINTER(AGMV), C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint8, UL, UL, UL, UL, UL, C.c_int, C.c_int, C.c_int]
+    lib.AGMV_DecodeAGMV.restype = C.c_int
+    lib.AGMV_DecodeAGMV.argtypes = [C.c_char_p, C.c_uint8, C.c_int]
+    lib.AGMV_DecodeHeader.restype = C.c_int
+    lib.AGMV_DecodeHeader.argtypes = [C.c_void_p, C.POINTER(AGMV)]
+    lib.AGMV_DecodeFrameChunk.restype = C.c_int
+    lib.AGMV_DecodeFrameChunk.argtypes = [C.c_void_p, C.POINTER(AGMV)]
+    lib.AGMV_EncodeFrame.restype = None
+    lib.AGMV_EncodeFrame.argtypes = [C.c_void_p, C.POINTER(AGMV), C.POINTER(UL)]
+    lib.AGMV_B200_LastError.restype = C.c_char_p
+    return lib
+
+
+def _libc():
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+    libc.ftell.restype = C.c_long
+    libc.ftell.argtypes = [C.c_void_p]
+    libc.fseek.argtypes = [C.c_void_p, C.c_long, C.c_int]
+    return libc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["syn96x80_III_LOW", "gba240_GBA_I_LOW", "syn64_II_LOW"])
+def test_encode_agmv_dropin_bytes(golden, name):
+    """examples/simple_video/simple_video.c, line for line: CreateAGMV + AGMV_EncodeAGMV on a BMP directory."""
+    g = golden["encode"][name]
+    lib = _dropin()
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        write_bmps(frames, td, "f", 1)
+        os.chdir(td)
+        try:
+            h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
+            lib.AGMV_EncodeAGMV(h, b"o.agmv", b".", b"f", 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            data = open("o.agmv", "rb").read()
+            if g["opt"].startswith("GBA"):
+                assert os.path.exists("GBA_GEN_AGMV.h")
+                txt = open("GBA_GEN_AGMV.h").read()
+                assert f"GBA_AGMV_FILE[{len(data)}]" in txt
+        finally:
+            os.chdir(cwd)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()
+
+
+@pytest.mark.gpu
+def test_decode_agmv_dropin_exports(golden):
+    """AGMV_DecodeAGMV writes ./quick_export_<k>.bmp; pixel content must equal the reference's frames and,
+    where the reference binary is present, the files must be byte-identical to its own export."""
+    g = golden["encode"]["syn64_III_LOW"]
+    path = os.path.join(GOLDEN_DIR, g["file"])
+    lib = _dropin()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td, tempfile.TemporaryDirectory() as td2:
+        os.chdir(td)
+        try:
+            assert lib.AGMV_DecodeAGMV(path.encode(), 1, 1) == 0
+            assert lib.AGMV_DecodeAGMV(b"does_not_exist.agmv", 1, 1) == 2
+            bad = bytearray(open(path, "rb").read())
+            bad[36:38] = (36904).to_bytes(2, "little")
+            open("bad.agmv", "wb").write(bad)
+            assert lib.AGMV_DecodeAGMV(b"bad.agmv", 1, 1) == 1
+            files = sorted(os.listdir(td))
+            bmps = [f for f in files if f.startswith("quick_export_")]
+            assert len(bmps) == g["decoded_shape"][0]
+            mine = {f: open(f, "rb").read() for f in bmps}
+        finally:
+            os.chdir(cwd)
+        for k in range(len(bmps)):
+            d = mine[f"quick_export_{k + 1}.bmp"]
+            px = np.frombuffer(d[54:], dtype=np.uint8).reshape(g["h"], g["w"], 3).astype(np.uint32)
+            frame = px[..., 2] << 16 | px[..., 1] << 8 | px[..., 0]
+            assert sha256(frame.astype(np.uint32).tobytes()) == g["decoded_frame_sha256"][k]
+        if have_ref():
+            subprocess.run([os.path.join(REF_DIR, "ref_decode"), "export", path], cwd=td2, check=True, capture_output=True)
+            for f, d in mine.items():
+                assert open(os.path.join(td2, f), "rb").read() == d, f
+
+
+@pytest.mark.gpu
+def test_decode_frame_chunk_dropin_streaming(golden):
+    """AGMV_PlayAGMV's loop (src/agmv_playback.c:102-115): find the next 'AGFC', AGMV_DecodeFrameChunk, repeat."""
+    g = golden["encode"]["gba240_GBA_I_LOW"]
+    path = os.path.join(GOLDEN_DIR, g["file"])
+    raw = open(path, "rb").read()
+    lib, libc = _dropin(), _libc()
+    f = libc.fopen(path.encode(), b"rb")
+    h = lib.CreateAGMV(0, 120, 80, 16)  # sizes are overwritten by the header
+    assert lib.AGMV_DecodeHeader(f, h) == 0
+    a = h.contents
+    assert (a.header.width, a.header.height, a.header.num_of_frames) == (120, 80, g["decoded_shape"][0])
+    a.frame.contents.width = a.iframe.contents.width = a.header.width
+    a.frame.contents.height = a.iframe.contents.height = a.header.height
+    a.frame_count = 0
+    P = 120 * 80
+    for k in range(a.header.num_of_frames):
+        pos = libc.ftell(f)
+        nxt = raw.find(b"AGFC", pos)  # AGMV_FindNextFrameChunk
+        libc.fseek(f, nxt, 0)
+        assert lib.AGMV_DecodeFrameChunk(f, h) == 0, lib.AGMV_B200_LastError()
+        px = np.ctypeslib.as_array(a.frame.contents.img_data, shape=(P,)).astype(np.uint32)
+        assert sha256(px.tobytes()) == g["decoded_frame_sha256"][k], k
+        assert a.frame_count == k + 1
+    libc.fclose(f)
+    lib.DestroyAGMV(h)
+
+
+@pytest.mark.gpu
+def test_encode_frame_dropin_per_frame(golden):
+    """AGMV_EncodeFrame frame by frame (palettes taken from the reference's stream) reproduces the reference's chunks."""
+    g = golden["encode"]["syn64_III_LOW"]
+    ref = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
+    lib, libc = _dropin(), _libc()
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"]).reshape(g["n"], -1)
+    h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
+    a = h.contents
+    a.opt, a.compression = OPT["III"], LZSS
+    pal = np.frombuffer(ref[38:38 + 1536], dtype=np.uint8).reshape(512, 3).astype(np.uint64)
+    for i in range(256):
+        a.header.palette0[i] = int(pal[i, 0] << 16 | pal[i, 1] << 8 | pal[i, 2])
+        a.header.palette1[i] = int(pal[256 + i, 0] << 16 | pal[256 + i, 1] << 8 | pal[256 + i, 2])
+    # LIGHT schedule of the first two groups: f1, interp(f2,f3), f4, f5, interp(f6,f7), f8
+    def interp(x, y):
+        out = np.zeros_like(x)
+        for sh in (16, 8, 0):
+            c1, c2 = ((x >> sh) & 255).astype(np.int64), ((y >> sh) & 255).astype(np.int64)
+            out |= ((c1 + ((c2 - c1) >> 1)).astype(np.uint32) & 255) << sh
+        return out
+    seq = [frames[0], interp(frames[1], frames[2]), frames[3], frames[4], interp(frames[5], frames[6]), frames[7]]
+    with tempfile.TemporaryDirectory() as td:
+        p = os.path.join(td, "o.bin").encode()
+        f = libc.fopen(p, b"wb")
+        for img in seq:
+            wide = img.astype(np.uint64)
+            lib.AGMV_EncodeFrame(f, h, wide.ctypes.data_as(C.POINTER(UL)))
+        libc.fclose(f)
+        got = open(p, "rb").read()
+    lib.DestroyAGMV(h)
+    # the reference interleaves an 8-byte empty AGAC chunk after every frame chunk; strip those from its stream
+    body = ref[38 + 1536:]
+    exp, o = b"", 0
+    for _ in range(6):
+        cs = int.from_bytes(body[o + 12:o + 16], "little")
+        exp += body[o:o + 16 + cs + 8]
+        o += 16 + cs + 8 + 8
+    assert got == exp
