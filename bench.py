@@ -318,20 +318,32 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
+    # per-step statistics the algorithmic byte counts are made of
+    us, cs = ctx.enc_sizes(n_enc)
+    usize_total, csize_total = float(us.sum()), float(cs.sum())
+    n_interp = int((sb >= 0).sum())
+    stats = {"P": P, "n_src": n_local, "n_enc": n_enc, "n_interp": n_interp, "usize": usize_total, "csize": csize_total,
+             "lz_levels": 15, "lz_groups": max(1, prof.get("lz_init", (1, 0))[0] // max(1, args.steps))}
     # dominant kernel class by device time inside the timed region
-    dom = max(prof.items(), key=lambda kv: kv[1][1]) if prof else None
     roof = None
-    if dom:
-        name, (cnt, ms) = dom
-        alg = ALG_BYTES.get(name)
+    if prof:
+        name, (cnt, ms) = max(prof.items(), key=lambda kv: kv[1][1])
+        alg_step = ALG_BYTES[name](stats) if name in ALG_BYTES else None
         per_launch_ms = ms / cnt
         roof = {"kernel": name, "bound": "hbm", "launches_in_region": cnt, "avg_launch_ms": per_launch_ms, "peak": peak, "unit": "GB/s",
-                "peak_source": peak_src, "traffic": None}
-        if alg is not None:
-            bytes_per_launch = alg(stream_stats(ctx, n_enc, nbytes)) * args.steps / cnt
+                "peak_source": peak_src, "traffic": TRAFFIC_NCU.get(name)}
+        if alg_step is not None:
+            bytes_per_launch = alg_step * args.steps / cnt
             roof["achieved"] = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
             roof["frac"] = roof["achieved"] / peak
             roof["algorithmic_bytes_per_launch"] = bytes_per_launch
+            roof["algorithmic_bytes_rule"] = ALG_RULE.get(name)
+        # the whole path against its compulsory traffic: encode 8*W*H per source frame + chunks out,
+        # decode chunks in + 4*W*H out per frame
+        enc_bytes = 8.0 * P * n_local + 24.0 * n_enc + csize_total
+        dec_bytes = 24.0 * n_enc + csize_total + 4.0 * P * n_enc
+        roof["path"] = {"encode_GBps": enc_bytes * args.steps / (enc_ms * 1e-3) / 1e9, "encode_frac": enc_bytes * args.steps / (enc_ms * 1e-3) / 1e9 / peak,
+                        "decode_GBps": dec_bytes * args.steps / (dec_ms * 1e-3) / 1e9, "decode_frac": dec_bytes * args.steps / (dec_ms * 1e-3) / 1e9 / peak}
 
     value = n_total * args.steps / (total_ms * 1e-3)
     line = {
@@ -362,12 +374,35 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
-def stream_stats(ctx, n_enc, nbytes):
-    return {"n_enc": n_enc, "image_bytes": nbytes}
-
-
-# algorithmic bytes per step for each kernel class, as a function of the step's statistics
-ALG_BYTES = {}
+# Algorithmic (compulsory) bytes PER STEP for each kernel class as a function of the step's statistics
+# (SURVEY.md 8d per-kernel figures). K4 (LZSS) is usize in + csize out for the whole stage;
+# its 15 refinement passes each have to touch every bitstream byte once, so each pass launch is charged usize.
+ALG_BYTES = {
+    "hist": lambda s: 4.0 * s["P"] * s["n_src"],
+    "quantize": lambda s: 4.0 * s["P"] * (s["n_enc"] + s["n_interp"]) + 2.0 * s["P"] * s["n_enc"],
+    "classify": lambda s: 2.0 * s["P"] * s["n_enc"] * 1.75 + s["n_enc"] * s["P"] / 16,
+    "emit": lambda s: 2.0 * s["P"] * s["n_enc"] + s["usize"],
+    "rx_scatter": lambda s: s["usize"] * s["lz_levels"],
+    "lz_group": lambda s: s["usize"] * s["lz_levels"] * 3 + s["usize"],
+    "lz_pack": lambda s: s["usize"] + s["csize"],
+    "expand": lambda s: s["csize"] + s["usize"],
+    "index": lambda s: s["usize"],
+    "reconstruct": lambda s: s["usize"] + 4.0 * s["P"] * s["n_enc"],
+}
+ALG_RULE = {
+    "rx_scatter": "K4 reads usize and writes csize once; each of the 15 refinement scatters is charged one pass over the bitstream (usize bytes) per launch",
+    "lz_group": "per launch (reduce / partials / apply, 15 levels): one pass over the bitstream bytes (usize / launch on average)",
+    "expand": "D2: csize in + usize out",
+    "reconstruct": "D3: usize in + 4*W*H out per frame",
+    "quantize": "K1+K2: 4 B per source pixel read (8 when interpolating) + 2 B entry written",
+    "hist": "K0a: 4 B per source pixel",
+}
+# dram__bytes_read + dram__bytes_write per launch from the committed ncu --set full captures (profiles/), bench config
+TRAFFIC_NCU = {}
+try:
+    TRAFFIC_NCU = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+except Exception:
+    pass
 
 
 # --------------------------------------------------------------------------------------

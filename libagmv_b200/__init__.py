@@ -180,6 +180,12 @@ class Context:
         self._ck(self.lib.agmvb_enc_fetch(self.h, C.c_void_p(host_ptr), nbytes, _p(us, _u32p), _p(cs, _u32p)))
         return img, us, cs
 
+    def enc_sizes(self, n_enc):
+        """usize / csize per frame of the last enc_frames call."""
+        us, cs = np.zeros(n_enc, np.uint32), np.zeros(n_enc, np.uint32)
+        self._ck(self.lib.agmvb_enc_fetch(self.h, None, 0, _p(us, _u32p), _p(cs, _u32p)))
+        return us, cs
+
     def enc_image_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()
         self._ck(self.lib.agmvb_enc_image_ptr(self.h, C.byref(p), C.byref(n)))

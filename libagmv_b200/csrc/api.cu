@@ -67,9 +67,9 @@ struct agmvb_ctx {
     uint16_t* d_lut = nullptr;  // 2^24
     uint32_t* d_map = nullptr;  // coded pixel -> source pixel (GBA / NDS profiles)
     uint16_t* d_ient = nullptr; // persistent I-frame entries
-    DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small;
+    DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small, seqbuf;
     LzWork lz;
-    DBuf lzbuf[40];
+    DBuf lzbuf[64];
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
     void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
@@ -78,6 +78,7 @@ struct agmvb_ctx {
     // ---- decoder state ----
     std::vector<DecStream> streams;
     DBuf d_frames, d_ebuf, d_bpos, d_consumed, d_stale, d_recs, d_steps, d_out, d_cksum, d_count;
+    DBuf d_code, d_segs, d_seglen, d_oexit, d_ow, d_oentry, d_ocum, d_ofinal;
 };
 
 #define CK(expr) AGMVB_CUDA_OK(expr)
@@ -152,8 +153,9 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
     cudaFree(ctx->d_hist); cudaFree(ctx->d_keys[0]); cudaFree(ctx->d_keys[1]); cudaFree(ctx->d_pal); cudaFree(ctx->d_lut);
     cudaFree(ctx->d_map); cudaFree(ctx->d_ient);
     DBuf* bufs[] = {&ctx->stage, &ctx->entries, &ctx->rec, &ctx->boff, &ctx->bs, &ctx->fs, &ctx->image, &ctx->srcpairs, &ctx->entpairs,
-                    &ctx->scanws, &ctx->small, &ctx->d_frames, &ctx->d_ebuf, &ctx->d_bpos, &ctx->d_consumed, &ctx->d_stale, &ctx->d_recs,
-                    &ctx->d_steps, &ctx->d_out, &ctx->d_cksum, &ctx->d_count};
+                    &ctx->scanws, &ctx->small, &ctx->seqbuf, &ctx->d_frames, &ctx->d_ebuf, &ctx->d_bpos, &ctx->d_consumed, &ctx->d_stale, &ctx->d_recs,
+                    &ctx->d_steps, &ctx->d_out, &ctx->d_cksum, &ctx->d_count, &ctx->d_code, &ctx->d_segs, &ctx->d_seglen, &ctx->d_oexit, &ctx->d_ow,
+                    &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
@@ -326,7 +328,8 @@ extern "C" int agmvb_enc_get_iframe_entries(agmvb_ctx* ctx, uint16_t* entries) {
 // LZSS workspace for up to n positions and F frames
 static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
     LzWork& w = ctx->lz;
-    if (n + 64 > w.cap_n || !w.maxlen) {
+    const uint32_t cap_before = w.cap_n;
+    if (n + 64 > w.cap_n || !w.bestlen) {
         uint32_t cap = std::max<uint32_t>(n + n / 4 + 4096, 1u << 20);
         int k = 0;
         auto grab = [&](size_t bytes, void** dst) -> int {
@@ -335,33 +338,40 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
             k++;
             return OK;
         };
-        TRY(grab(cap, (void**)&w.maxlen));
         TRY(grab(cap, (void**)&w.bestlen));
         for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
-        TRY(grab((size_t)cap * 4, (void**)&w.gs[0]));
-        TRY(grab((size_t)cap * 4, (void**)&w.gs[1]));
-        TRY(grab((size_t)cap * 4, (void**)&w.lvlidx));
-        TRY(grab((size_t)cap * 4, (void**)&w.gsat));
+        for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));
+        TRY(grab((size_t)cap * 4, (void**)&w.gs_tmp));
+        TRY(grab((size_t)cap * 4, (void**)&w.dig4[0]));
+        TRY(grab((size_t)cap * 4, (void**)&w.dig4[1]));
+        TRY(grab((size_t)cap * 4, (void**)&w.match_rec));
         TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
         uint32_t nt = cdiv(cap, RX_TILE);
-        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist));
+        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[0]));
+        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[1]));
         TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + cdiv(cap, SCAN_TILE) + 8) * 4, (void**)&w.scan_ws));
-        uint32_t ptile = cdiv(cap, PARSE_TILE) + 1;
-        TRY(grab((size_t)ptile * 16, (void**)&w.exit_tab));
-        TRY(grab((size_t)ptile * 32, (void**)&w.w_tab));
-        TRY(grab((size_t)ptile, (void**)&w.entry_tab));
-        TRY(grab((size_t)ptile * 4, (void**)&w.cumbase));
         w.cap_n = cap;
     }
     size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 16;
-    if (words > w.out_words_cap || F + 2 > w.cap_frames || !w.out_words) {
+    const bool grew = w.cap_n != cap_before;
+    if (words > w.out_words_cap || F + 2 > w.cap_frames || !w.out_words || grew) {
         uint32_t capF = std::max<uint32_t>(F + F / 4 + 16, 64);
         size_t capW = std::max(words, (((size_t)w.cap_n * 9) >> 5) + 3 * (size_t)capF + 16);
-        TRY(ensure(ctx, ctx->lzbuf[32], capW * 4)); w.out_words = ctx->lzbuf[32].as<uint32_t>(); w.out_words_cap = capW;
-        TRY(ensure(ctx, ctx->lzbuf[33], (size_t)(capF + 2) * 4)); w.wbase = ctx->lzbuf[33].as<uint32_t>();
-        TRY(ensure(ctx, ctx->lzbuf[34], (size_t)(capF + 2) * 4)); w.outbits = ctx->lzbuf[34].as<uint32_t>();
-        TRY(ensure(ctx, ctx->lzbuf[35], (size_t)(capF + 2) * 4)); w.csize = ctx->lzbuf[35].as<uint32_t>();
-        TRY(ensure(ctx, ctx->lzbuf[36], (size_t)(capF + 2) * 4)); w.chunk_off = ctx->lzbuf[36].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[52], capW * 4)); w.out_words = ctx->lzbuf[52].as<uint32_t>(); w.out_words_cap = capW;
+        TRY(ensure(ctx, ctx->lzbuf[53], (size_t)(capF + 2) * 4)); w.wbase = ctx->lzbuf[53].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[54], (size_t)(capF + 2) * 4)); w.outbits = ctx->lzbuf[54].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[55], (size_t)(capF + 2) * 4)); w.csize = ctx->lzbuf[55].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[56], (size_t)(capF + 2) * 4)); w.chunk_off = ctx->lzbuf[56].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[57], (size_t)(capF + 2) * sizeof(OrbitSeg))); w.segs = ctx->lzbuf[57].as<OrbitSeg>();
+        TRY(ensure(ctx, ctx->lzbuf[58], (size_t)(capF + 2) * 4)); w.seg_len = ctx->lzbuf[58].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[59], (size_t)(capF + 2) * 8)); w.orb.final_pos = ctx->lzbuf[59].as<uint32_t>();
+        w.orb.final_cum = w.orb.final_pos + (capF + 2);
+        // parse tables: every frame adds at most one partial tile
+        const size_t ptile = (size_t)w.cap_n / ORB_TILE + capF + 8;
+        TRY(ensure(ctx, ctx->lzbuf[49], ptile * ORB_SP)); w.orb.exit_tab = ctx->lzbuf[49].as<uint8_t>();
+        TRY(ensure(ctx, ctx->lzbuf[50], ptile * ORB_SP * 2)); w.orb.w_tab = ctx->lzbuf[50].as<uint16_t>();
+        TRY(ensure(ctx, ctx->lzbuf[51], ptile)); w.orb.entry_tab = ctx->lzbuf[51].as<uint8_t>();
+        TRY(ensure(ctx, ctx->lzbuf[47], ptile * 4)); w.orb.cumbase = ctx->lzbuf[47].as<uint32_t>();
         w.cap_frames = capF;
     }
     return OK;
@@ -386,7 +396,19 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
         if (ctx->image.p) CK(cudaFree(ctx->image.p));
         ctx->image = nb;
     }
-    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
+    // parse segments: one per frame
+    std::vector<OrbitSeg> segs(F);
+    std::vector<uint32_t> slen(F);
+    uint32_t ntile = 0;
+    for (uint32_t f = 0; f < F; f++) {
+        slen[f] = h_fs[f + 1] - h_fs[f];
+        segs[f].off = h_fs[f]; segs[f].cap_len = slen[f]; segs[f].tile_base = ntile;
+        ntile += orbit_tiles(slen[f]);
+    }
+    CK(cudaMemcpyAsync(ctx->lz.segs, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(ctx->lz.seg_len, slen.data(), F * 4, cudaMemcpyHostToDevice, ctx->st));
+    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, ntile, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
+    CK(cudaStreamSynchronize(ctx->st));  // segs / slen are stack vectors
     TRY(check_launch(ctx, "lzss"));
     uint32_t* hcs = hp + (F + 2);
     CK(cudaMemcpyAsync(hcs, ctx->lz.csize, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
@@ -555,6 +577,18 @@ extern "C" int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int
                                      uint64_t* out_len, uint32_t* n_encoded) {
     if (!ctx || !frames || !out || n_src < 2) return ERR_ARG;
     TRY(agmvb_enc_begin(ctx, w, h, opt, quality, compression));
+    if (!on_device) {
+        // both passes read every frame: upload once when the sequence fits comfortably, else stream it twice
+        size_t free_b = 0, total_b = 0;
+        const size_t bytes = (size_t)n_src * w * h * 4;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if (bytes + (8ull << 30) < free_b + ctx->seqbuf.cap) {
+            TRY(ensure(ctx, ctx->seqbuf, bytes));
+            CK(cudaMemcpyAsync(ctx->seqbuf.p, frames, bytes, cudaMemcpyHostToDevice, ctx->st));
+            frames = ctx->seqbuf.as<uint32_t>();
+            on_device = 1;
+        }
+    }
     TRY(agmvb_enc_histogram(ctx, frames, n_src, on_device));  // every source frame, unscaled (:2371-2568)
     TRY(agmvb_enc_build_palette(ctx));
     // PDIFS schedule (:2727-2770) and loop exit (:3610-3612); frame numbers are 1-based in the reference
@@ -811,10 +845,41 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         TRY(ensure(ctx, ctx->d_steps, F * sizeof(DecStep)));
         CK(cudaMemcpyAsync(ctx->d_frames.p, fr.data(), F * sizeof(DecFrame), cudaMemcpyHostToDevice, ctx->st));
         const DecFrame* dfr = ctx->d_frames.as<DecFrame>();
-        KL(ctx->lc, KC_EXPAND, (expand_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>())));
+        // block-index segments: one per frame over the safe prefix of its expansion
+        std::vector<OrbitSeg> segs(F);
+        uint32_t ntile = 0, max_tiles = 1;
+        for (uint32_t k = 0; k < F; k++) {
+            const uint64_t next_off = k + 1 < F ? fr[k + 1].ebuf_off : eoff;
+            segs[k].off = fr[k].ebuf_off;
+            segs[k].cap_len = (uint32_t)(next_off - fr[k].ebuf_off);
+            segs[k].tile_base = ntile;
+            ntile += orbit_tiles(segs[k].cap_len);
+            max_tiles = std::max(max_tiles, orbit_tiles(segs[k].cap_len));
+        }
+        TRY(ensure(ctx, ctx->d_code, eoff + 64));
+        TRY(ensure(ctx, ctx->d_segs, F * sizeof(OrbitSeg)));
+        TRY(ensure(ctx, ctx->d_seglen, (size_t)F * 4));
+        TRY(ensure(ctx, ctx->d_oexit, (size_t)ntile * ORB_SP + 64));
+        TRY(ensure(ctx, ctx->d_ow, (size_t)ntile * ORB_SP * 2 + 64));
+        TRY(ensure(ctx, ctx->d_oentry, (size_t)ntile + 64));
+        TRY(ensure(ctx, ctx->d_ocum, (size_t)ntile * 4 + 64));
+        TRY(ensure(ctx, ctx->d_ofinal, (size_t)F * 8 + 64));
+        CK(cudaMemcpyAsync(ctx->d_segs.p, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
+        OrbitTables tb;
+        tb.exit_tab = ctx->d_oexit.as<uint8_t>(); tb.w_tab = ctx->d_ow.as<uint16_t>(); tb.entry_tab = ctx->d_oentry.as<uint8_t>();
+        tb.cumbase = ctx->d_ocum.as<uint32_t>(); tb.final_pos = ctx->d_ofinal.as<uint32_t>(); tb.final_cum = tb.final_pos + F;
+        KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
+                                                                                        ctx->d_consumed.as<uint32_t>())));
         KL(ctx->lc, KC_STALE, (stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>())));
-        KL(ctx->lc, KC_INDEX, (index_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
-                                                 ctx->d_recs.as<uint32_t>())));
+        {
+            dim3 sgrid(std::min<uint32_t>(max_tiles * 4, 1024), F);
+            KL(ctx->lc, KC_INDEX, (index_steps_k<<<sgrid, 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), ctx->d_ebuf.as<uint8_t>(), ctx->d_code.as<uint8_t>(),
+                                                                            ctx->d_seglen.as<uint32_t>())));
+        }
+        orbit_run<33, IndexStep>(ctx->d_code.as<uint8_t>(), ctx->d_segs.as<OrbitSeg>(), F, ctx->d_seglen.as<uint32_t>(), ntile, tb,
+                                 IndexVisit{ctx->d_recs.as<uint32_t>(), B}, ctx->lc, KC_INDEX);
+        KL(ctx->lc, KC_INDEX, (index_tail_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
+                                                                            tb.final_pos, tb.final_cum, ctx->d_recs.as<uint32_t>())));
         TRY(check_launch(ctx, "expand/index"));
         // reconstruction, frame by frame; step layout [k][s]
         steps.resize(F);

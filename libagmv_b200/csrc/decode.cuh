@@ -15,6 +15,7 @@
 //     records or copies the previous frame's block.
 #pragma once
 #include "common.cuh"
+#include "orbit.cuh"
 
 namespace agmvb {
 
@@ -96,6 +97,128 @@ __global__ void __launch_bounds__(64) expand_k(const DecFrame* __restrict__ fr, 
     consumed_out[f] = (uint32_t)(rp - d.data_off);
 }
 
+// ---- D2, warp per frame ------------------------------------------------------
+// Token parsing is a serial bit walk (lane 0, payload staged through shared memory 1 KB at a time); the
+// copies of up to 32 tokens are then resolved together ("multi-round resolution"): a match may run as soon
+// as every byte it reads lies below the output offset of the first unfinished token, so independent matches
+// overlap their memory latency instead of paying it one token at a time.
+constexpr int EX_WARPS = 4;
+constexpr int EX_WIN = 256;  // payload words staged per refill
+
+__global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __restrict__ fr, uint32_t F, uint8_t* __restrict__ ebuf,
+                                                             uint32_t* __restrict__ bpos_out, uint32_t* __restrict__ consumed_out) {
+    __shared__ uint32_t win[EX_WARPS][EX_WIN + 2];
+    __shared__ uint32_t tk_o[EX_WARPS][32], tk_dl[EX_WARPS][32];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t f = blockIdx.x * EX_WARPS + warp;
+    if (f >= F) return;
+    const DecFrame d = fr[f];
+    uint8_t* e = ebuf + d.ebuf_off;
+    const uint8_t* __restrict__ file = d.file;
+    if (d.lz77) {  // 4-byte tokens (src/agmv_decode.c:200-218): rare profile, plain serial walk
+        if (lane == 0) {
+            uint64_t rp = d.data_off, bpos = 0;
+            for (uint32_t i = 0; i < d.csize; i += 4) {
+                uint32_t b0 = rp < d.file_len ? file[rp] : 0u; rp++;
+                uint32_t b1 = rp < d.file_len ? file[rp] : 0u; rp++;
+                uint32_t len = rp < d.file_len ? file[rp] : 0u; rp++;
+                uint8_t lit = rp < d.file_len ? file[rp] : 0u; rp++;
+                const uint64_t off = b0 | b1 << 8, p = bpos;
+                for (uint32_t k = 0; k < len; k++) {
+                    uint64_t s = p - off + k;
+                    if (s < bpos) { e[bpos] = e[s]; bpos++; }
+                }
+                e[bpos++] = lit;
+            }
+            bpos_out[f] = (uint32_t)bpos;
+            consumed_out[f] = (uint32_t)(rp - d.data_off);
+        }
+        return;
+    }
+    const uint64_t nbits = (uint64_t)d.csize * 8;
+    uint64_t bitp = 0;       // bits consumed so far (== the reference's `bits`), lane 0 is authoritative
+    uint32_t bpos = 0;
+    uint64_t win_word0 = 0;  // payload word index held in win[..][0]
+    bool more = nbits > 0 && d.usize > 0;
+    bool refill = true;
+    while (more) {
+        if (refill) {
+            win_word0 = bitp >> 5;
+            for (int k = lane; k < EX_WIN + 2; k += 32) {
+                uint64_t b = d.data_off + (win_word0 + k) * 4;
+                uint32_t w = 0;
+#pragma unroll
+                for (int j = 0; j < 4; j++) w |= (b + j < d.file_len ? (uint32_t)file[b + j] : 0u) << (8 * j);  // fread past EOF leaves 0
+                win[warp][k] = w;
+            }
+            __syncwarp();
+            refill = false;
+        }
+        uint32_t ntok = 0;
+        if (lane == 0) {
+            while (ntok < 32 && bitp < nbits && bpos < d.usize) {
+                uint64_t li = (bitp >> 5) - win_word0;
+                if (li >= (uint64_t)EX_WIN) { refill = true; break; }
+                uint32_t sh = (uint32_t)bitp & 31;
+                uint32_t w = __funnelshift_r(win[warp][li], win[warp][li + 1], sh);
+                if (w & 1u) {
+                    tk_o[warp][ntok] = bpos;
+                    tk_dl[warp][ntok] = (1u << 20) | (1u << 16) | (((w >> 1) & 255u) << 24);
+                    bitp += 9;
+                    bpos += 1;
+                } else {
+                    uint32_t off = (w >> 1) & 0xFFFFu, len = (w >> 17) & 15u;
+                    uint32_t l = (off >= 1 && off <= bpos) ? len : 0u;  // src index must be < bpos (unsigned compare in the reference)
+                    tk_o[warp][ntok] = bpos;
+                    tk_dl[warp][ntok] = off | (l << 16);
+                    bitp += 21;
+                    bpos += l;
+                }
+                ntok++;
+            }
+            more = bitp < nbits && bpos < d.usize;
+        }
+        ntok = __shfl_sync(0xffffffffu, ntok, 0);
+        more = __shfl_sync(0xffffffffu, (int)more, 0);
+        refill = __shfl_sync(0xffffffffu, (int)refill, 0);
+        bitp = __shfl_sync(0xffffffffu, bitp, 0);
+        __syncwarp();
+        // ---- resolve the copies of this chunk ----
+        const bool active = (uint32_t)lane < ntok;
+        const uint32_t o = active ? tk_o[warp][lane] : 0u, dl = active ? tk_dl[warp][lane] : 0u;
+        const uint32_t l = (dl >> 16) & 15u, dd = dl & 0xFFFFu;
+        const bool lit = (dl >> 20) & 1u;
+        bool done = !active || l == 0;
+        if (active && lit) { e[o] = (uint8_t)(dl >> 24); done = true; }
+        __syncwarp();
+        while (true) {
+            unsigned m = __ballot_sync(0xffffffffu, !done);
+            if (!m) break;
+            const uint32_t hwm = __shfl_sync(0xffffffffu, o, __ffs(m) - 1);
+            const bool can = !done && (o - dd + (l < dd ? l : dd) <= hwm);
+            if (can) {
+                const uint8_t* src = e + o - dd;
+                if (dd >= l) {
+                    uint8_t v[15];
+#pragma unroll
+                    for (int k = 0; k < 15; k++) if ((uint32_t)k < l) v[k] = src[k];
+#pragma unroll
+                    for (int k = 0; k < 15; k++) if ((uint32_t)k < l) e[o + k] = v[k];
+                } else {
+                    for (uint32_t k = 0; k < l; k++) e[o + k] = src[k];  // overlapping copy: byte order matters
+                }
+                done = true;
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        bpos_out[f] = bpos;
+        consumed_out[f] = (uint32_t)((bitp + 7) >> 3);
+    }
+}
+
 // ---- stale bytes -----------------------------------------------------------
 // stale[f*4+d] = content of the persistent bitstream buffer at index bpos_f + d
 // when frame f is walked: written by the latest earlier frame j of the same
@@ -140,21 +263,57 @@ struct VBuf {
 
 __device__ __forceinline__ bool is_flag(uint32_t b) { return b == FILL_FLAG || b == NORMAL_FLAG || b == COPY_FLAG; }
 
-// ---- D3a ----------------------------------------------------------------------
-// One thread per frame replays the reference's block walk (flags, re-sync
-// loop, every `bitpos > bpos` check) and records for each block either
-// EMPTY32 (nothing written) or (offset of the first byte after the flag) << 2 | type.
-__global__ void __launch_bounds__(64) index_k(const DecFrame* __restrict__ fr, const uint32_t* __restrict__ bpos_arr, uint32_t F,
-                                              const uint8_t* __restrict__ ebuf, const uint8_t* __restrict__ stale, uint32_t B,
-                                              uint32_t* __restrict__ recs) {
-    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const int dual = fr[f].dual;
+// ---- D3a, tile-parallel --------------------------------------------------------
+// Inside the "safe" prefix of the expanded data (everything more than 72 bytes before bpos) no bounds check of
+// the reference's walk can fire, so the walk is a plain pointer chase: flag byte -> record length, non-flag
+// byte -> skip one byte (the re-sync loop). index_steps_k turns every byte of the safe prefix into
+// (step, counts-as-a-block), the orbit (orbit.cuh) finds the record starts, and index_tail_k finishes the
+// last <= 72 bytes with the exact serial logic (index_walk) including stale bytes and escapes.
+constexpr uint32_t INDEX_GUARD = 72;
+
+struct IndexStep {
+    __device__ static uint32_t step(uint32_t c) { return c & 63u; }
+    __device__ static uint32_t weight(uint32_t c) { return c >> 7; }
+};
+
+// grid (tiles, F)
+__global__ void __launch_bounds__(256) index_steps_k(const DecFrame* __restrict__ fr, const uint32_t* __restrict__ bpos_arr,
+                                                     const uint8_t* __restrict__ ebuf, uint8_t* __restrict__ code, uint32_t* __restrict__ seg_len) {
+    const uint32_t f = blockIdx.y;
     const uint32_t bpos = bpos_arr[f];
-    const VBuf v{ebuf + fr[f].ebuf_off, bpos, stale + f * 4};
-    uint32_t* rec = recs + (size_t)f * B;
-    uint32_t bp = 0;
-    uint32_t b = 0;
+    const uint32_t limit = bpos > INDEX_GUARD ? bpos - INDEX_GUARD : 0u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) seg_len[f] = limit;
+    const int dual = fr[f].dual;
+    const uint8_t* e = ebuf + fr[f].ebuf_off;
+    uint8_t* c = code + fr[f].ebuf_off;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < limit; p += gridDim.x * blockDim.x) {
+        const uint32_t b = e[p];
+        uint32_t st = 1, w = 0;
+        if (b == COPY_FLAG) w = 1;
+        else if (b == FILL_FLAG) { w = 1; st = 2 + ((dual && (e[p + 1] & 0x7fu) == 127u) ? 1u : 0u); }
+        else if (b == NORMAL_FLAG) {
+            w = 1;
+            uint32_t q = p + 1;
+            for (int k = 0; k < 16; k++) q += (dual && (e[q] & 0x7fu) == 127u) ? 2u : 1u;
+            st = q - p;
+        }
+        c[p] = (uint8_t)(st | w << 7);
+    }
+}
+
+struct IndexVisit {
+    uint32_t* recs;
+    uint32_t B;
+    __device__ void operator()(uint32_t sg, uint32_t pos, uint32_t cum, uint32_t cc) const {
+        if (!(cc >> 7) || cum >= B) return;
+        const uint32_t st = cc & 63u;
+        const uint32_t type = st == 1 ? BT_COPY : (st <= 3 ? BT_FILL : BT_NORMAL);
+        recs[(size_t)sg * B + cum] = (pos + 1) << 2 | type;
+    }
+};
+
+// The reference's walk from byte offset bp / block b to the end of the frame (src/agmv_decode.c:224-399).
+__device__ inline void index_walk(const VBuf& v, uint32_t bpos, int dual, uint32_t B, uint32_t bp, uint32_t b, uint32_t* __restrict__ rec) {
     bool invalid = false;
     for (; b < B; b++) {
         if (bp > bpos) break;
@@ -187,6 +346,18 @@ __global__ void __launch_bounds__(64) index_k(const DecFrame* __restrict__ fr, c
         if (esc) { b++; break; }
     }
     for (; b < B; b++) rec[b] = EMPTY32;
+}
+
+__global__ void __launch_bounds__(64) index_tail_k(const DecFrame* __restrict__ fr, const uint32_t* __restrict__ bpos_arr, uint32_t F,
+                                                   const uint8_t* __restrict__ ebuf, const uint8_t* __restrict__ stale, uint32_t B,
+                                                   const uint32_t* __restrict__ final_pos, const uint32_t* __restrict__ final_cum,
+                                                   uint32_t* __restrict__ recs) {
+    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const uint32_t bpos = bpos_arr[f];
+    const VBuf v{ebuf + fr[f].ebuf_off, bpos, stale + f * 4};
+    uint32_t b0 = final_cum[f];
+    index_walk(v, bpos, fr[f].dual, B, final_pos[f], b0 < B ? b0 : B, recs + (size_t)f * B);
 }
 
 // ---- D3b ----------------------------------------------------------------------

@@ -26,39 +26,39 @@
 // data+csize so it clobbers the last partial byte exactly like the reference.
 #pragma once
 #include "common.cuh"
+#include "orbit.cuh"
 #include "radix.cuh"
 #include "scan.cuh"
 
 namespace agmvb {
 
 constexpr int LZ_LEVELS = 15;
-constexpr int PARSE_TILE = 1024;
-constexpr int PARSE_CHAIN_CHUNK = 512;
+constexpr uint32_t LZ_POS_MASK = 0x0FFFFFFFu;  // A[] words: position in the low 28 bits, min(15, bytes left in the frame) in the top 4
+constexpr uint32_t LZ_MAX_BATCH = 1u << 28;
 
 struct LzWork {
     uint32_t cap_n = 0, cap_frames = 0;
-    uint8_t* maxlen = nullptr;
-    uint8_t* bestlen = nullptr;
-    uint32_t* A[LZ_LEVELS + 1] = {};
-    uint32_t* gs[2] = {};
-    uint32_t* lvlidx = nullptr;
-    uint32_t* gsat = nullptr;
-    uint32_t* bitcum = nullptr;   // cap_n + 1
-    uint32_t* tile_hist = nullptr;
+    uint8_t* bestlen = nullptr;          // per position, filled after the last level (input of the parse)
+    uint32_t* A[LZ_LEVELS + 1] = {};     // level arrays: positions grouped by their first L bytes
+    uint32_t* GS[LZ_LEVELS + 1] = {};    // group start (index into A[L]) of every element of A[L]
+    uint32_t* gs_tmp = nullptr;          // level-L group starts carried into level-(L+1) order
+    uint32_t* dig4[2] = {};              // next four key bytes of every element, carried through the scatters
+    uint32_t* match_rec = nullptr;       // per position: best level << 28 | index in A[best level]; 0 = no match
+    uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
+    uint32_t* tile_hist[2] = {};         // key-byte counts / offsets per (digit, tile), double buffered across levels
     uint32_t* scan_ws = nullptr;
-    uint8_t* exit_tab = nullptr;  // ntile * 16
-    uint16_t* w_tab = nullptr;    // ntile * 16
-    uint8_t* entry_tab = nullptr; // ntile
-    uint32_t* cumbase = nullptr;  // ntile
+    OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
+    OrbitSeg* segs = nullptr;            // cap_frames
+    uint32_t* seg_len = nullptr;         // cap_frames
     uint32_t* out_words = nullptr;
     size_t out_words_cap = 0;
-    uint32_t* wbase = nullptr;    // cap_frames + 1
-    uint32_t* outbits = nullptr;  // cap_frames
-    uint32_t* csize = nullptr;    // cap_frames
-    uint32_t* chunk_off = nullptr;// cap_frames + 1
+    uint32_t* wbase = nullptr;           // cap_frames + 1
+    uint32_t* outbits = nullptr;         // cap_frames
+    uint32_t* csize = nullptr;           // cap_frames
+    uint32_t* chunk_off = nullptr;       // cap_frames + 1
 };
 
-struct APtrs { const uint32_t* a[LZ_LEVELS + 1]; };
+struct APtrs { const uint32_t* a[LZ_LEVELS + 1]; const uint32_t* gs[LZ_LEVELS + 1]; };
 
 __device__ __forceinline__ uint32_t frame_of(const uint32_t* __restrict__ fs, uint32_t F, uint32_t i) {
     // largest f with fs[f] <= i and fs[f+1] > i (empty frames are skipped)
@@ -70,164 +70,278 @@ __device__ __forceinline__ uint32_t frame_of(const uint32_t* __restrict__ fs, ui
     return lo;
 }
 
-__global__ void lz_init_k(uint32_t n, const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ A0,
-                          uint32_t* __restrict__ gs0, uint8_t* __restrict__ maxlen, uint8_t* __restrict__ bestlen,
+__device__ __forceinline__ uint32_t load4(const uint8_t* __restrict__ p) {
+    return (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16 | (uint32_t)p[3] << 24;
+}
+
+__global__ void lz_init_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ A0,
+                          uint32_t* __restrict__ gs0, uint32_t* __restrict__ dig4, uint32_t* __restrict__ match_rec,
                           uint32_t* __restrict__ bitcum, uint32_t* __restrict__ wbase) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= F) wbase[i] = (uint32_t)(((uint64_t)fs[i] * 9u) >> 5) + 3u * i;
-    if (i == n) bitcum[n] = EMPTY32;
     if (i >= n) return;
     uint32_t f = frame_of(fs, F, i);
     uint32_t rem = fs[f + 1] - i;
-    A0[i] = i;
+    A0[i] = i | (rem < (uint32_t)LZ_MAXLEN ? rem : (uint32_t)LZ_MAXLEN) << 28;
     gs0[i] = fs[f];
-    maxlen[i] = (uint8_t)(rem < (uint32_t)LZ_MAXLEN ? rem : (uint32_t)LZ_MAXLEN);
-    bestlen[i] = 0;
+    dig4[i] = load4(bs + i);
+    match_rec[i] = 0;
     bitcum[i] = EMPTY32;
 }
 
+// key byte of level L: carried, no gather (used for the level-0 histogram only)
 struct LzDigit {
-    const uint8_t* bs;
-    const uint32_t* pos;
-    uint32_t L;
-    __device__ uint32_t operator()(uint32_t i) const { return bs[pos[i] + L]; }
+    const uint32_t* dig4;
+    uint32_t sh;  // 8 * (L & 3)
+    __device__ uint32_t operator()(uint32_t i) const { return (dig4[i] >> sh) & 255u; }
 };
-struct LzMove {
-    const uint32_t* pos_in;
-    const uint32_t* gs_in;
-    uint32_t* pos_out;
-    uint32_t* gs_out;
-    __device__ void operator()(uint32_t s, uint32_t d) const {
-        pos_out[d] = pos_in[s];
-        gs_out[d] = gs_in[s];
+
+// ---- one refinement level: stable scatter by the level's key byte --------------------------
+// Same ranking scheme as radix_scatter_k (radix.cuh), specialised for the level arrays: the 16 key words of a
+// thread are loaded up front (and reused as payload), positions / group starts are loaded eight at a time before
+// any store so that the loads overlap, and every fourth level the next four key bytes are gathered from the
+// bitstream (positions of a group are close to sorted, the 4-byte read stays inside one or two sectors).
+__global__ void __launch_bounds__(RX_THREADS) lz_scatter_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ pos_in,
+                                                           const uint32_t* __restrict__ gs_in, const uint32_t* __restrict__ dig_in,
+                                                           uint32_t* __restrict__ pos_out, uint32_t* __restrict__ gs_out,
+                                                           uint32_t* __restrict__ dig_out, uint32_t L, uint32_t n, uint32_t ntiles,
+                                                           const uint32_t* __restrict__ tile_off) {
+    __shared__ uint32_t wc[RX_WARPS][256];
+    __shared__ uint32_t goff[256];
+#pragma unroll
+    for (int w = 0; w < RX_WARPS; w++) wc[w][threadIdx.x] = 0;
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * RX_TILE + warp * RX_WARP_SPAN + lane_id();
+    const uint32_t sh = 8u * (L & 3u);
+    uint32_t word[RX_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < RX_ROUNDS; r++) {
+        uint32_t i = base + r * 32;
+        word[r] = i < n ? dig_in[i] : 0u;
     }
-};
-// head flag of the refined array: value idx at group heads, 0 elsewhere
-struct LzHead {
-    const uint8_t* bs;
-    const uint32_t* pos;     // level L+1 order
-    const uint32_t* gs_old;  // level L group starts carried through the scatter
-    uint32_t L;
-    __device__ uint32_t operator()(uint32_t idx) const {
-        if (idx == 0) return 0;
-        bool head = gs_old[idx] != gs_old[idx - 1] || bs[pos[idx] + L] != bs[pos[idx - 1] + L];
-        return head ? idx : 0u;
+    __syncthreads();
+    uint32_t packed[RX_ROUNDS];  // digit << 16 | rank inside the warp's span
+#pragma unroll
+    for (int r = 0; r < RX_ROUNDS; r++) {
+        uint32_t i = base + r * 32;
+        bool valid = i < n;
+        uint32_t key = valid ? (word[r] >> sh) & 255u : 256u + lane_id();
+        unsigned peers = __match_any_sync(0xffffffffu, key);
+        int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && (int)lane_id() == leader) {
+            old = wc[warp][key];
+            wc[warp][key] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        packed[r] = (key << 16) | (old + __popc(peers & lanemask_lt()));
+        __syncwarp();
     }
-};
-struct LzGroupOut {
-    const uint32_t* pos;
-    uint32_t* gs_new;
-    const uint8_t* maxlen;
-    uint8_t* bestlen;
-    uint32_t* lvlidx;
-    uint32_t* gsat;
-    uint32_t Lnew;
-    __device__ void operator()(uint32_t idx, uint32_t g) const {
-        gs_new[idx] = g;
-        if (Lnew >= (uint32_t)LZ_MINLEN && g != idx) {
-            uint32_t p = pos[idx], prev = pos[idx - 1];
-            if (p - prev <= (uint32_t)LZ_WINDOW && Lnew <= maxlen[p]) {
-                bestlen[p] = (uint8_t)Lnew;
-                lvlidx[p] = idx;
-                gsat[p] = g;
+    __syncthreads();
+    {
+        uint32_t run = 0;
+        const int d = threadIdx.x;
+#pragma unroll
+        for (int w = 0; w < RX_WARPS; w++) {
+            uint32_t t = wc[w][d];
+            wc[w][d] = run;
+            run += t;
+        }
+        goff[d] = tile_off[d * ntiles + blockIdx.x];
+    }
+    __syncthreads();
+    const bool gather = (L & 3u) == 3u;
+#pragma unroll
+    for (int h = 0; h < RX_ROUNDS; h += 8) {
+        uint32_t p[8], g[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t i = base + (h + r) * 32;
+            p[r] = i < n ? pos_in[i] : 0u;
+            g[r] = i < n ? gs_in[i] : 0u;
+        }
+        uint32_t nd[8];
+        if (gather) {
+#pragma unroll
+            for (int r = 0; r < 8; r++) nd[r] = load4(bs + (p[r] & LZ_POS_MASK) + L + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            uint32_t i = base + (h + r) * 32;
+            if (i < n) {
+                uint32_t d = packed[h + r] >> 16, rk = packed[h + r] & 0xffffu;
+                uint32_t dst = goff[d] + wc[warp][d] + rk;
+                pos_out[dst] = p[r];
+                gs_out[dst] = g[r];
+                dig_out[dst] = gather ? nd[r] : word[h + r];
             }
         }
     }
-};
+}
 
-// ---- greedy parse, tile-parallel ------------------------------------------
-__global__ void __launch_bounds__(256) lz_parse_spec_k(const uint8_t* __restrict__ bestlen, uint32_t n, uint32_t ntile,
-                                                       uint8_t* __restrict__ exit_tab, uint16_t* __restrict__ w_tab) {
-    __shared__ __align__(16) uint8_t s[8][PARSE_TILE];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t tile = blockIdx.x * 8 + warp;
-    if (tile >= ntile) return;
-    const uint32_t t0 = tile * PARSE_TILE;
-    const uint32_t end = min(t0 + PARSE_TILE, n);
-    for (uint32_t k = lane; k < PARSE_TILE; k += 32) s[warp][k] = (t0 + k < n) ? bestlen[t0 + k] : 0;
-    __syncwarp();
-    if (lane < LZ_MAXLEN) {
-        uint32_t i = t0 + lane, w = 0;
-        while (i < end) {
-            uint32_t l = s[warp][i - t0];
-            if (l >= (uint32_t)LZ_MINLEN) { w += 21; i += l; } else { w += 9; i += 1; }
-        }
-        exit_tab[tile * 16 + lane] = (uint8_t)(i - end);
-        w_tab[tile * 16 + lane] = (uint16_t)w;
+// ---- group starts of the refined array ------------------------------------------
+// After the scatter the array is ordered by (key byte, old group, position). An element heads a new group iff its
+// old group differs from its predecessor's or it is the first element of a key-byte bucket (bucket starts come
+// from the radix offsets: tile_off[d * ntiles]). New group start = running max over (head ? idx : 0): a device-wide
+// inclusive max-scan (tile reduce, scan of the partials, tile apply), with the bucket-start bitmap in shared memory.
+__device__ __forceinline__ void lz_bucket_bitmap(uint32_t* bm, const uint32_t* __restrict__ tile_off, uint32_t ntiles, uint32_t t0) {
+    if (threadIdx.x < SCAN_TILE / 32) bm[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t s = tile_off[threadIdx.x * ntiles];  // 256 threads: one bucket each
+    if (s >= t0 && s < t0 + SCAN_TILE) atomicOr(&bm[(s - t0) >> 5], 1u << ((s - t0) & 31));
+    __syncthreads();
+}
+
+// value of element (warp span, round r, this lane) and of its predecessor, from 16 up-front coalesced loads
+__device__ __forceinline__ void lz_load_with_prev(const uint32_t* __restrict__ a, uint32_t base, uint32_t n, uint32_t cur[SCAN_ROUNDS],
+                                                  uint32_t prv[SCAN_ROUNDS]) {
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        uint32_t i = base + r * 32;
+        cur[r] = i < n ? a[i] : 0u;
+    }
+    const uint32_t first = base - lane_id();  // index of lane 0's element in round 0
+    uint32_t before = (lane_id() == 0 && first > 0 && first - 1 < n) ? a[first - 1] : 0u;
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        uint32_t up = __shfl_up_sync(0xffffffffu, cur[r], 1);
+        uint32_t wrap = r > 0 ? __shfl_sync(0xffffffffu, cur[r > 0 ? r - 1 : 0], 31) : before;
+        prv[r] = lane_id() == 0 ? wrap : up;
     }
 }
 
-__global__ void __launch_bounds__(1024) lz_parse_chain_k(uint32_t ntile, const uint8_t* __restrict__ exit_tab,
-                                                         const uint16_t* __restrict__ w_tab, uint8_t* __restrict__ entry_tab,
-                                                         uint32_t* __restrict__ cumbase) {
-    __shared__ uint8_t se[PARSE_CHAIN_CHUNK * 16];
-    __shared__ uint16_t sw[PARSE_CHAIN_CHUNK * 16];
-    __shared__ uint32_t s_e, s_cum;
-    if (threadIdx.x == 0) { s_e = 0; s_cum = 0; }
-    for (uint32_t c0 = 0; c0 < ntile; c0 += PARSE_CHAIN_CHUNK) {
-        uint32_t cnt = min((uint32_t)PARSE_CHAIN_CHUNK, ntile - c0);
-        __syncthreads();
-        for (uint32_t k = threadIdx.x; k < cnt * 16; k += 1024) {
-            se[k] = exit_tab[(size_t)c0 * 16 + k];
-            sw[k] = w_tab[(size_t)c0 * 16 + k];
+__global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
+                                                                  uint32_t ntiles, uint32_t n, uint32_t* __restrict__ partial) {
+    __shared__ uint32_t bm[SCAN_TILE / 32];
+    __shared__ uint32_t wmax[SCAN_THREADS / 32];
+    const uint32_t t0 = blockIdx.x * SCAN_TILE;
+    lz_bucket_bitmap(bm, tile_off, ntiles, t0);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
+    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS];
+    lz_load_with_prev(gs_old, base, n, cur, prv);
+    uint32_t acc = 0;
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        uint32_t idx = base + r * 32;
+        if (idx < n && idx > 0) {
+            bool head = cur[r] != prv[r] || ((bm[(idx - t0) >> 5] >> ((idx - t0) & 31)) & 1u);
+            if (head) acc = idx;  // idx grows with r, so the last head seen is the maximum
         }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            uint32_t e = s_e, cum = s_cum;
-            for (uint32_t k = 0; k < cnt; k++) {
-                entry_tab[c0 + k] = (uint8_t)e;
-                cumbase[c0 + k] = cum;
-                cum += sw[k * 16 + e];
-                e = se[k * 16 + e];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, d));
+    if (lane_id() == 0) wmax[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; w++) t = max(t, wmax[w]);
+        partial[blockIdx.x] = t;
+    }
+}
+
+// Writes GS[L+1]; for levels >= 3 records a match of length Lnew for every position whose predecessor in its
+// group lies inside the window (exists_L is monotone in L, so the last write is the longest match); and counts
+// the next level's key bytes of this tile (the tile is exactly the next scatter's tile), saving a histogram pass.
+template <bool MATCH, bool NEXT_HIST>
+__global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
+                                                                 uint32_t ntiles, uint32_t n, const uint32_t* __restrict__ partial,
+                                                                 const uint32_t* __restrict__ pos, uint32_t* __restrict__ gs_new,
+                                                                 uint32_t* __restrict__ match_rec, uint32_t Lnew,
+                                                                 const uint32_t* __restrict__ dig_next, uint32_t* __restrict__ hist_next) {
+    __shared__ uint32_t bm[SCAN_TILE / 32];
+    __shared__ uint32_t wtot[SCAN_THREADS / 32];
+    __shared__ uint32_t h[256];
+    const uint32_t t0 = blockIdx.x * SCAN_TILE;
+    h[threadIdx.x] = 0;
+    lz_bucket_bitmap(bm, tile_off, ntiles, t0);
+    const int warp = threadIdx.x >> 5;
+    const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
+    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS];
+    lz_load_with_prev(gs_old, base, n, cur, prv);
+    uint32_t v[SCAN_ROUNDS];
+    uint32_t carry = 0;
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        uint32_t idx = base + r * 32;
+        uint32_t x = 0;
+        if (idx < n && idx > 0) {
+            bool head = cur[r] != prv[r] || ((bm[(idx - t0) >> 5] >> ((idx - t0) & 31)) & 1u);
+            x = head ? idx : 0u;
+        }
+        x = warp_inclusive<MaxOp>(x);
+        x = max(carry, x);
+        v[r] = x;
+        carry = __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane_id() == 0) wtot[warp] = carry;
+    if (MATCH) lz_load_with_prev(pos, base, n, cur, prv);  // reuse the registers: positions and predecessor positions
+    __syncthreads();
+    uint32_t pre = partial[blockIdx.x];
+    for (int w = 0; w < warp; w++) pre = max(pre, wtot[w]);
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) {
+        uint32_t idx = base + r * 32;
+        if (idx < n) {
+            const uint32_t g = max(pre, v[r]);
+            gs_new[idx] = g;
+            if (MATCH && g != idx) {
+                const uint32_t p = cur[r] & LZ_POS_MASK, prev = prv[r] & LZ_POS_MASK;
+                if (p - prev <= (uint32_t)LZ_WINDOW && Lnew <= (cur[r] >> 28)) match_rec[p] = Lnew << 28 | idx;
             }
-            s_e = e; s_cum = cum;
         }
+    }
+    if (NEXT_HIST) {
+        const uint32_t sh = 8u * (Lnew & 3u);
+#pragma unroll 4
+        for (int r = 0; r < SCAN_ROUNDS; r++) {
+            uint32_t idx = base + r * 32;
+            bool valid = idx < n;
+            uint32_t key = valid ? (dig_next[idx] >> sh) & 255u : 256u + lane_id();
+            unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[key], __popc(peers));
+        }
+        __syncthreads();
+        hist_next[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
     }
 }
 
-__global__ void __launch_bounds__(256) lz_parse_mark_k(const uint8_t* __restrict__ bestlen, uint32_t n, uint32_t ntile,
-                                                       const uint8_t* __restrict__ entry_tab, const uint32_t* __restrict__ cumbase,
-                                                       uint32_t* __restrict__ bitcum) {
-    __shared__ __align__(16) uint8_t s[8][PARSE_TILE];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t tile = blockIdx.x * 8 + warp;
-    if (tile >= ntile) return;
-    const uint32_t t0 = tile * PARSE_TILE;
-    const uint32_t end = min(t0 + PARSE_TILE, n);
-    for (uint32_t k = lane; k < PARSE_TILE; k += 32) s[warp][k] = (t0 + k < n) ? bestlen[t0 + k] : 0;
-    __syncwarp();
-    if (lane == 0) {
-        uint32_t i = t0 + entry_tab[tile], cum = cumbase[tile];
-        while (i < end) {
-            bitcum[i] = cum;
-            uint32_t l = s[warp][i - t0];
-            if (l >= (uint32_t)LZ_MINLEN) { cum += 21; i += l; } else { cum += 9; i += 1; }
-        }
-        if (end == n) bitcum[n] = cum;  // the orbit ends exactly at n
-    }
+__global__ void lz_bestlen_k(const uint32_t* __restrict__ match_rec, uint32_t n, uint8_t* __restrict__ bestlen) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bestlen[i] = (uint8_t)(match_rec[i] >> 28);
 }
+
+// ---- greedy parse: orbit over bestlen[] (orbit.cuh) -------------------------
+struct LzStep {
+    __device__ static uint32_t step(uint32_t c) { return c >= (uint32_t)LZ_MINLEN ? c : 1u; }
+    __device__ static uint32_t weight(uint32_t c) { return c >= (uint32_t)LZ_MINLEN ? 21u : 9u; }  // bits per token
+};
+struct LzVisit {
+    const OrbitSeg* segs;
+    uint32_t* bitcum;
+    __device__ void operator()(uint32_t sg, uint32_t pos, uint32_t cum, uint32_t) const { bitcum[segs[sg].off + pos] = cum; }
+};
 
 // ---- token emission ----------------------------------------------------------
 __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs, uint32_t F,
-                                                 const uint8_t* __restrict__ bestlen, const uint32_t* __restrict__ lvlidx,
-                                                 const uint32_t* __restrict__ gsat, const uint32_t* __restrict__ bitcum, APtrs A,
+                                                 const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum, APtrs A,
                                                  const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    uint32_t c = bitcum[i];
-    if (c == EMPTY32) return;
+    const uint32_t rel = bitcum[i];
+    if (rel == EMPTY32) return;
     uint32_t f = frame_of(fs, F, i);
-    uint32_t rel = c - bitcum[fs[f]];
-    uint32_t l = bestlen[i], v, nb;
+    const uint32_t rec = match_rec[i];
+    uint32_t l = rec >> 28, v, nb;
     if (l >= (uint32_t)LZ_MINLEN) {
         const uint32_t* a = A.a[l];
-        uint32_t lo = gsat[i], hi = lvlidx[i];
+        uint32_t hi = rec & LZ_POS_MASK, lo = A.gs[l][hi];
         uint32_t target = i > (uint32_t)LZ_WINDOW ? i - (uint32_t)LZ_WINDOW : 0u;
         while (lo < hi) {  // first j in [lo,hi) with a[j] >= target; a[hi-1] qualifies by construction
             uint32_t mid = (lo + hi) >> 1;
-            if (a[mid] >= target) hi = mid; else lo = mid + 1;
+            if ((a[mid] & LZ_POS_MASK) >= target) hi = mid; else lo = mid + 1;
         }
-        uint32_t off = i - a[lo];
+        uint32_t off = i - (a[lo] & LZ_POS_MASK);
         v = (off << 1) | (l << 17);
         nb = 21;
     } else {
@@ -239,7 +353,7 @@ __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs,
     if (sh + nb > 32) atomicOr(&out_words[w + 1], v >> (32 - sh));
 }
 
-__global__ void __launch_bounds__(1024) lz_finalize_k(const uint32_t* __restrict__ fs, uint32_t F, const uint32_t* __restrict__ bitcum,
+__global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, const uint32_t* __restrict__ total_bits,
                                                       uint32_t* __restrict__ outbits, uint32_t* __restrict__ csize,
                                                       uint32_t* __restrict__ chunk_off) {
     __shared__ uint32_t wsum[32];
@@ -250,8 +364,7 @@ __global__ void __launch_bounds__(1024) lz_finalize_k(const uint32_t* __restrict
         uint32_t f = base + threadIdx.x;
         uint32_t len = 0;
         if (f < F) {
-            uint32_t a = fs[f], b = fs[f + 1];
-            uint32_t ob = (a == b) ? 0u : bitcum[b] - bitcum[a];
+            uint32_t ob = total_bits[f];
             uint32_t cs = (uint32_t)((float)(int)ob / 8.0f);  // src/agmv_encode.c:176
             outbits[f] = ob;
             csize[f] = cs;
@@ -297,35 +410,50 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
 }
 
 // Host driver. bs: batch bitstream (n bytes + >=16 bytes of readable padding);
-// fs: device array of F+1 frame starts (fs[0]=0, fs[F]=n). Results: wk.csize,
-// wk.outbits, wk.chunk_off on the device and the chunk image written to
-// `image` (capacity >= 32*F + 9n/8 + 8).
-inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n,
+// fs: device array of F+1 frame starts (fs[0]=0, fs[F]=n); wk.segs / wk.seg_len
+// describe the same frames for the parse (filled by the caller, ntile tiles in
+// total). Results: wk.csize, wk.outbits, wk.chunk_off on the device and the chunk
+// image written to `image` (capacity >= 32*F + 9n/8 + 8).
+inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n, uint32_t ntile,
                               uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
     cudaStream_t st = lc.st;
     const uint32_t nthreads = 256;
     uint32_t cover = (n + 1 > F + 1 ? n + 1 : F + 1);
-    KL(lc, KC_LZ_INIT, (lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(n, fs, F, wk.A[0], wk.gs[0], wk.maxlen, wk.bestlen, wk.bitcum, wk.wbase)));
+    KL(lc, KC_LZ_INIT, (lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.A[0], wk.GS[0], wk.dig4[0], wk.match_rec, wk.bitcum, wk.wbase)));
     if (n > 0) {
+        const uint32_t nt = cdiv(n, RX_TILE);
+        KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{wk.dig4[0], 0u}, n, nt, wk.tile_hist[0])));
         for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
-            // gs[0]: group starts in A[L] order. The scatter carries them into gs[1] (A[L+1] order);
-            // the running max over head flags reads gs[1] and writes the new starts back to gs[0].
-            radix_pass(LzDigit{bs, wk.A[L], L}, LzMove{wk.A[L], wk.gs[0], wk.A[L + 1], wk.gs[1]}, n, wk.tile_hist, wk.scan_ws, lc);
-            device_scan<MaxOp, false>(LzHead{bs, wk.A[L + 1], wk.gs[1], L},
-                                      LzGroupOut{wk.A[L + 1], wk.gs[0], wk.maxlen, wk.bestlen, wk.lvlidx, wk.gsat, L + 1}, n, wk.scan_ws, lc,
-                                      KC_LZ_GROUP);
+            uint32_t* din = wk.dig4[L & 1];
+            uint32_t* dout = wk.dig4[(L & 1) ^ 1];
+            uint32_t* th = wk.tile_hist[L & 1];          // counts of this level's key byte (from the previous level's apply)
+            uint32_t* th_next = wk.tile_hist[(L & 1) ^ 1];
+            device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
+            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, RX_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[L + 1], wk.gs_tmp, dout, L, n, nt, th)));
+            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws)));
+            KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
+            const uint32_t Lnew = L + 1;
+            if (Lnew < (uint32_t)LZ_MINLEN)
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                                wk.match_rec, Lnew, dout, th_next)));
+            else if (Lnew < (uint32_t)LZ_LEVELS)
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                               wk.match_rec, Lnew, dout, th_next)));
+            else
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                                wk.match_rec, Lnew, dout, th_next)));
         }
-        uint32_t ntile = cdiv(n, PARSE_TILE);
-        KL(lc, KC_LZ_PARSE, (lz_parse_spec_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.exit_tab, wk.w_tab)));
-        KL(lc, KC_LZ_PARSE, (lz_parse_chain_k<<<1, 1024, 0, st>>>(ntile, wk.exit_tab, wk.w_tab, wk.entry_tab, wk.cumbase)));
-        KL(lc, KC_LZ_PARSE, (lz_parse_mark_k<<<cdiv(ntile, 8), 256, 0, st>>>(wk.bestlen, n, ntile, wk.entry_tab, wk.cumbase, wk.bitcum)));
+        KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));
+    }
+    orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
+    if (n > 0) {
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         APtrs ap;
-        for (int l = 0; l <= LZ_LEVELS; l++) ap.a[l] = wk.A[l];
-        KL(lc, KC_LZ_PACK, (lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.bestlen, wk.lvlidx, wk.gsat, wk.bitcum, ap, wk.wbase, wk.out_words)));
+        for (int l = 0; l <= LZ_LEVELS; l++) { ap.a[l] = wk.A[l]; ap.gs[l] = wk.GS[l]; }
+        KL(lc, KC_LZ_PACK, (lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, wk.wbase, wk.out_words)));
     }
-    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(fs, F, wk.bitcum, wk.outbits, wk.csize, wk.chunk_off)));
+    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
     KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, image)));
 }
