@@ -227,3 +227,18 @@ def test_corrupt_header_rejected(ctx):
     with pytest.raises(libagmv_b200.AgmvError) as e:
         ctx.dec_open(bytes(hdr))
     assert e.value.code == 1
+
+
+def test_multi_gpu_sharded_encode_identical():
+    """N-GPU frame-range sharded encode (NCCL histogram all-reduce, size exchange, payload gather) == 1-GPU == oracle.
+    Needs >= 2 visible GPUs; skipped on a single-GPU box."""
+    import subprocess
+    import sys
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("single GPU box")
+    script = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multigpu_check.py")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29617", script], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
