@@ -258,12 +258,14 @@ def run_b200(args):
         full_step()
     sampler.mark()
     l0 = ctx.launches
-    ctx.profile(True)
-    total_ms = timed(full_step, args.steps)
-    prof = ctx.profile_read()
-    ctx.profile(False)
+    total_ms = timed(full_step, args.steps)          # the headline: K steps, no profiling events in the stream
     launches = ctx.launches - l0
     clocks = sampler.stop() if rank == 0 else None
+    # same K steps again with a CUDA event pair around every launch: per-kernel-class device time, live
+    ctx.profile(True)
+    prof_ms = timed(full_step, args.steps)
+    prof = ctx.profile_read()
+    ctx.profile(False)
 
     # encode-only / decode-only rates (same rules, separate regions)
     enc_ms = timed(encode_step, args.steps)
@@ -357,7 +359,8 @@ def run_b200(args):
                    "parallelism": f"frame-range shard x{world}" if world > 1 else "single GPU"},
         "detail": {"encode_source_fps": n_total * args.steps / (enc_ms * 1e-3), "encode_encoded_fps": n_enc * world * args.steps / (enc_ms * 1e-3),
                    "decode_fps": n_enc * world * args.steps / (dec_ms * 1e-3),
-                   "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}},
+                   "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+                   "profiled_ms_per_step": prof_ms / args.steps},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
     }
     if not args.no_cpu_baseline:

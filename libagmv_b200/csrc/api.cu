@@ -421,7 +421,7 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     return OK;
 }
 
-static const uint32_t LZ_GROUP_TARGET = 24u << 20;  // positions per LZSS batch (~2.3 GB of workspace)
+static const uint32_t LZ_GROUP_TARGET = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
 
 // classify + assemble n frames whose entries are on the device; runs LZSS group by group
 static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_t F, uint32_t first_fc) {

@@ -35,6 +35,8 @@ namespace agmvb {
 constexpr int LZ_LEVELS = 15;
 constexpr uint32_t LZ_POS_MASK = 0x0FFFFFFFu;  // A[] words: position in the low 28 bits, min(15, bytes left in the frame) in the top 4
 constexpr uint32_t LZ_MAX_BATCH = 1u << 28;
+constexpr uint32_t LZ_ALIVE = 0x80000000u;     // GS / gs_tmp words: bit 31 = "a match of this level's length exists for the element"
+constexpr uint32_t LZ_GS_MASK = 0x7FFFFFFFu;
 
 struct LzWork {
     uint32_t cap_n = 0, cap_frames = 0;
@@ -43,7 +45,7 @@ struct LzWork {
     uint32_t* GS[LZ_LEVELS + 1] = {};    // group start (index into A[L]) of every element of A[L]
     uint32_t* gs_tmp = nullptr;          // level-L group starts carried into level-(L+1) order
     uint32_t* dig4[2] = {};              // next four key bytes of every element, carried through the scatters
-    uint32_t* match_rec = nullptr;       // per position: best level << 28 | index in A[best level]; 0 = no match
+    uint32_t* match_rec = nullptr;       // per position: best level << 28 | group start in A[best level]; 0 = no match
     uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
     uint32_t* tile_hist[2] = {};         // key-byte counts / offsets per (digit, tile), double buffered across levels
     uint32_t* scan_ws = nullptr;
@@ -210,24 +212,34 @@ __device__ __forceinline__ void lz_load_with_prev(const uint32_t* __restrict__ a
     }
 }
 
+// head test shared by the reduce and apply kernels. BY_KEY (level 3 only, levels 1 and 2 run no group phase):
+// old group = frame, refined by the 3-byte key carried in the key-byte word.
+template <bool BY_KEY>
+__device__ __forceinline__ bool lz_is_head(uint32_t gcur, uint32_t gprv, uint32_t kcur, uint32_t kprv, const uint32_t* bm, uint32_t t0, uint32_t idx) {
+    if (((gcur ^ gprv) & LZ_GS_MASK) != 0) return true;
+    if (BY_KEY) return ((kcur ^ kprv) & 0xFFFFFFu) != 0;
+    return (bm[(idx - t0) >> 5] >> ((idx - t0) & 31)) & 1u;
+}
+
+template <bool BY_KEY>
 __global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
-                                                                  uint32_t ntiles, uint32_t n, uint32_t* __restrict__ partial) {
+                                                                  uint32_t ntiles, uint32_t n, const uint32_t* __restrict__ dig,
+                                                                  uint32_t* __restrict__ partial) {
     __shared__ uint32_t bm[SCAN_TILE / 32];
     __shared__ uint32_t wmax[SCAN_THREADS / 32];
     const uint32_t t0 = blockIdx.x * SCAN_TILE;
-    lz_bucket_bitmap(bm, tile_off, ntiles, t0);
+    if (!BY_KEY) lz_bucket_bitmap(bm, tile_off, ntiles, t0);
     const int warp = threadIdx.x >> 5;
     const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
-    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS];
+    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS], kc[SCAN_ROUNDS], kp[SCAN_ROUNDS];
     lz_load_with_prev(gs_old, base, n, cur, prv);
+    if (BY_KEY) lz_load_with_prev(dig, base, n, kc, kp);
     uint32_t acc = 0;
 #pragma unroll
     for (int r = 0; r < SCAN_ROUNDS; r++) {
         uint32_t idx = base + r * 32;
-        if (idx < n && idx > 0) {
-            bool head = cur[r] != prv[r] || ((bm[(idx - t0) >> 5] >> ((idx - t0) & 31)) & 1u);
-            if (head) acc = idx;  // idx grows with r, so the last head seen is the maximum
-        }
+        if (idx < n && idx > 0 && lz_is_head<BY_KEY>(cur[r], prv[r], BY_KEY ? kc[r] : 0u, BY_KEY ? kp[r] : 0u, bm, t0, idx))
+            acc = idx;  // idx grows with r, so the last head seen is the maximum
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) acc = max(acc, __shfl_xor_sync(0xffffffffu, acc, d));
@@ -240,10 +252,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t
     }
 }
 
-// Writes GS[L+1]; for levels >= 3 records a match of length Lnew for every position whose predecessor in its
-// group lies inside the window (exists_L is monotone in L, so the last write is the longest match); and counts
-// the next level's key bytes of this tile (the tile is exactly the next scatter's tile), saving a histogram pass.
-template <bool MATCH, bool NEXT_HIST>
+// Writes GS[Lnew] (group start | "a match of length Lnew exists" in bit 31). exists_L is monotone in L, so the
+// longest match of a position is the last level at which it exists: it is recorded exactly once, at the level
+// where it stops existing (with the previous level's group start, which the scatter carried along) or at level 15.
+// Also counts the next level's key bytes of this tile (the tile is exactly the next scatter's tile).
+template <bool BY_KEY, bool NEXT_HIST>
 __global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
                                                                  uint32_t ntiles, uint32_t n, const uint32_t* __restrict__ partial,
                                                                  const uint32_t* __restrict__ pos, uint32_t* __restrict__ gs_new,
@@ -254,28 +267,44 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t*
     __shared__ uint32_t h[256];
     const uint32_t t0 = blockIdx.x * SCAN_TILE;
     h[threadIdx.x] = 0;
-    lz_bucket_bitmap(bm, tile_off, ntiles, t0);
+    if (!BY_KEY) lz_bucket_bitmap(bm, tile_off, ntiles, t0); else __syncthreads();
     const int warp = threadIdx.x >> 5;
     const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
-    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS];
+    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS], kc[SCAN_ROUNDS], kp[SCAN_ROUNDS];
     lz_load_with_prev(gs_old, base, n, cur, prv);
+    if (BY_KEY || NEXT_HIST) {
+#pragma unroll
+        for (int r = 0; r < SCAN_ROUNDS; r++) { uint32_t i = base + r * 32; kc[r] = i < n ? dig_next[i] : 0u; }
+    }
+    if (BY_KEY) {
+        const uint32_t first = base - lane_id();
+        uint32_t before = (lane_id() == 0 && first > 0 && first - 1 < n) ? dig_next[first - 1] : 0u;
+#pragma unroll
+        for (int r = 0; r < SCAN_ROUNDS; r++) {
+            uint32_t up = __shfl_up_sync(0xffffffffu, kc[r], 1);
+            uint32_t wrap = r > 0 ? __shfl_sync(0xffffffffu, kc[r > 0 ? r - 1 : 0], 31) : before;
+            kp[r] = lane_id() == 0 ? wrap : up;
+        }
+    }
     uint32_t v[SCAN_ROUNDS];
+    uint32_t alive_old = 0;  // bit r: the element existed at level Lnew-1
     uint32_t carry = 0;
 #pragma unroll
     for (int r = 0; r < SCAN_ROUNDS; r++) {
         uint32_t idx = base + r * 32;
         uint32_t x = 0;
-        if (idx < n && idx > 0) {
-            bool head = cur[r] != prv[r] || ((bm[(idx - t0) >> 5] >> ((idx - t0) & 31)) & 1u);
-            x = head ? idx : 0u;
-        }
+        if (idx < n && idx > 0 && lz_is_head<BY_KEY>(cur[r], prv[r], BY_KEY ? kc[r] : 0u, BY_KEY ? kp[r] : 0u, bm, t0, idx)) x = idx;
+        alive_old |= (cur[r] >> 31) << r;
         x = warp_inclusive<MaxOp>(x);
         x = max(carry, x);
         v[r] = x;
         carry = __shfl_sync(0xffffffffu, x, 31);
     }
     if (lane_id() == 0) wtot[warp] = carry;
-    if (MATCH) lz_load_with_prev(pos, base, n, cur, prv);  // reuse the registers: positions and predecessor positions
+    uint32_t lo_old[SCAN_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SCAN_ROUNDS; r++) lo_old[r] = cur[r] & LZ_GS_MASK;
+    lz_load_with_prev(pos, base, n, cur, prv);  // reuse the registers: positions and predecessor positions
     __syncthreads();
     uint32_t pre = partial[blockIdx.x];
     for (int w = 0; w < warp; w++) pre = max(pre, wtot[w]);
@@ -284,20 +313,20 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t*
         uint32_t idx = base + r * 32;
         if (idx < n) {
             const uint32_t g = max(pre, v[r]);
-            gs_new[idx] = g;
-            if (MATCH && g != idx) {
-                const uint32_t p = cur[r] & LZ_POS_MASK, prev = prv[r] & LZ_POS_MASK;
-                if (p - prev <= (uint32_t)LZ_WINDOW && Lnew <= (cur[r] >> 28)) match_rec[p] = Lnew << 28 | idx;
-            }
+            const uint32_t p = cur[r] & LZ_POS_MASK, prev = prv[r] & LZ_POS_MASK;
+            const bool exists = g != idx && p - prev <= (uint32_t)LZ_WINDOW && Lnew <= (cur[r] >> 28);
+            gs_new[idx] = g | (exists ? LZ_ALIVE : 0u);
+            if (!exists && ((alive_old >> r) & 1u)) match_rec[p] = (Lnew - 1) << 28 | lo_old[r];
+            if (exists && Lnew == (uint32_t)LZ_LEVELS) match_rec[p] = Lnew << 28 | g;
         }
     }
     if (NEXT_HIST) {
         const uint32_t sh = 8u * (Lnew & 3u);
-#pragma unroll 4
+#pragma unroll
         for (int r = 0; r < SCAN_ROUNDS; r++) {
             uint32_t idx = base + r * 32;
             bool valid = idx < n;
-            uint32_t key = valid ? (dig_next[idx] >> sh) & 255u : 256u + lane_id();
+            uint32_t key = valid ? (kc[r] >> sh) & 255u : 256u + lane_id();
             unsigned peers = __match_any_sync(0xffffffffu, key);
             if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[key], __popc(peers));
         }
@@ -335,11 +364,17 @@ __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs,
     uint32_t l = rec >> 28, v, nb;
     if (l >= (uint32_t)LZ_MINLEN) {
         const uint32_t* a = A.a[l];
-        uint32_t hi = rec & LZ_POS_MASK, lo = A.gs[l][hi];
-        uint32_t target = i > (uint32_t)LZ_WINDOW ? i - (uint32_t)LZ_WINDOW : 0u;
-        while (lo < hi) {  // first j in [lo,hi) with a[j] >= target; a[hi-1] qualifies by construction
+        const uint32_t* g = A.gs[l];
+        const uint32_t glo = rec & LZ_POS_MASK;  // start of i's level-l group in A[l]; positions ascend inside the group
+        const uint32_t target = i > (uint32_t)LZ_WINDOW ? i - (uint32_t)LZ_WINDOW : 0u;
+        // first j >= glo with f(j) = (j outside the group) || (a[j] >= target). f is monotone, and the answer lies inside
+        // the group because i itself is a member with a[.] = i >= target. Gallop for an upper bound, then bisect.
+        auto f = [&](uint32_t j) { return j >= n || (g[j] & LZ_GS_MASK) != glo || (a[j] & LZ_POS_MASK) >= target; };
+        uint32_t lo = glo, hi = glo, step = 1;
+        while (!f(hi)) { lo = hi + 1; hi += step; step <<= 1; }
+        while (lo < hi) {
             uint32_t mid = (lo + hi) >> 1;
-            if ((a[mid] & LZ_POS_MASK) >= target) hi = mid; else lo = mid + 1;
+            if (f(mid)) hi = mid; else lo = mid + 1;
         }
         uint32_t off = i - (a[lo] & LZ_POS_MASK);
         v = (off << 1) | (l << 17);
@@ -426,22 +461,33 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
             uint32_t* din = wk.dig4[L & 1];
             uint32_t* dout = wk.dig4[(L & 1) ^ 1];
-            uint32_t* th = wk.tile_hist[L & 1];          // counts of this level's key byte (from the previous level's apply)
+            uint32_t* th = wk.tile_hist[L & 1];          // counts of this level's key byte
             uint32_t* th_next = wk.tile_hist[(L & 1) ^ 1];
-            device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
-            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, RX_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[L + 1], wk.gs_tmp, dout, L, n, nt, th)));
-            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws)));
-            KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
             const uint32_t Lnew = L + 1;
-            if (Lnew < (uint32_t)LZ_MINLEN)
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
-                                                                                                wk.match_rec, Lnew, dout, th_next)));
-            else if (Lnew < (uint32_t)LZ_LEVELS)
+            // levels 1 and 2 never carry a match: no group phase, the frame start rides along as the group; level 3 then
+            // derives its groups from (frame, 3-byte key)
+            uint32_t* gs_dst = Lnew < (uint32_t)LZ_MINLEN ? wk.GS[Lnew] : wk.gs_tmp;
+            device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
+            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, RX_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
+            if (Lnew < (uint32_t)LZ_MINLEN) {
+                KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{dout, 8u * (Lnew & 3u)}, n, nt, th_next)));
+                continue;
+            }
+            if (Lnew == (uint32_t)LZ_MINLEN) {
+                KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
+                KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
                 KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                wk.match_rec, Lnew, dout, th_next)));
-            else
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                continue;
+            }
+            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
+            KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
+            if (Lnew < (uint32_t)LZ_LEVELS)
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                 wk.match_rec, Lnew, dout, th_next)));
+            else
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                                 wk.match_rec, Lnew, dout, th_next)));
         }
         KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));
     }
