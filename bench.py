@@ -223,7 +223,9 @@ def run_b200(args):
     # one untimed pass builds the stream the decode half works on (and warms every workspace)
     nbytes = encode_step()
     stream_bytes = local_stream(nbytes)
-    stream_np = np.frombuffer(stream_bytes, dtype=np.uint8)
+    stream_pin = torch.empty(len(stream_bytes), dtype=torch.uint8, pin_memory=True)   # the compressed stream lives in pinned host memory
+    stream_pin.copy_(torch.frombuffer(bytearray(stream_bytes), dtype=torch.uint8))
+    stream_np = stream_pin.numpy()
     n_dec = decode_step(stream_np)
     assert n_dec == n_enc
 

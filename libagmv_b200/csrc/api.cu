@@ -67,6 +67,7 @@ struct agmvb_ctx {
     uint16_t* d_lut = nullptr;  // 2^24
     uint32_t* d_map = nullptr;  // coded pixel -> source pixel (GBA / NDS profiles)
     uint16_t* d_ient = nullptr; // persistent I-frame entries
+    size_t ient_px = 0;
     DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small, seqbuf;
     LzWork lz;
     DBuf lzbuf[64];
@@ -77,6 +78,7 @@ struct agmvb_ctx {
 
     // ---- decoder state ----
     std::vector<DecStream> streams;
+    std::vector<DecStream> parked;   // buffers of closed streams, reused by later opens
     DBuf d_frames, d_ebuf, d_bpos, d_consumed, d_stale, d_recs, d_steps, d_out, d_cksum, d_count;
     DBuf d_code, d_segs, d_seglen, d_oexit, d_ow, d_oentry, d_ocum, d_ofinal;
 };
@@ -146,6 +148,11 @@ static void free_stream(DecStream& s) {
     s = DecStream();
 }
 
+// Closing a stream parks its device buffers so that the next open of a stream of the same shape does not pay
+// cudaMalloc / cudaFree (both synchronise the device).
+static void park_stream(agmvb_ctx* ctx, DecStream& s);
+static bool unpark_stream(agmvb_ctx* ctx, DecStream& s, uint64_t file_bytes, size_t P);
+
 extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -159,6 +166,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
+    for (DecStream& s : ctx->parked) free_stream(s);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->st);
     delete ctx;
@@ -195,8 +203,8 @@ extern "C" int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, i
     if (!ctx->d_lut) CK(cudaMalloc(&ctx->d_lut, sizeof(uint16_t) << 24));
     CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned long long) * (524287 + 1), ctx->st));
     CK(cudaMemsetAsync(ctx->d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));
-    if (ctx->d_ient) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_ient)); ctx->d_ient = nullptr; }
-    CK(cudaMalloc(&ctx->d_ient, P * 2));
+    if (ctx->d_ient && ctx->ient_px != P) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_ient)); ctx->d_ient = nullptr; }
+    if (!ctx->d_ient) { CK(cudaMalloc(&ctx->d_ient, P * 2)); ctx->ient_px = P; }
     CK(cudaMemsetAsync(ctx->d_ient, 0, P * 2, ctx->st));
     if (ctx->d_map) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_map)); ctx->d_map = nullptr; }
     if (ctx->cw != src_w || ctx->ch != src_h) {
@@ -670,6 +678,26 @@ static uint64_t lzss_consumed_host(const uint8_t* f, uint64_t len, uint64_t data
     return rp - data_off;
 }
 
+static void park_stream(agmvb_ctx* ctx, DecStream& s) {
+    DecStream k;
+    k.d_file = s.d_file; k.file_cap = s.file_cap; k.d_pal = s.d_pal; k.d_img = s.d_img; k.d_ifr = s.d_ifr; k.d_persist = s.d_persist;
+    k.persist_len = s.persist_len; k.d_ring = s.d_ring; k.w = s.w; k.h = s.h;
+    if (ctx->parked.size() < 1024) ctx->parked.push_back(k); else free_stream(k);
+    s = DecStream();
+}
+static bool unpark_stream(agmvb_ctx* ctx, DecStream& s, uint64_t file_bytes, size_t P) {
+    for (size_t k = 0; k < ctx->parked.size(); k++) {
+        DecStream& c = ctx->parked[k];
+        if ((size_t)c.w * c.h == P && c.file_cap >= file_bytes + 64) {
+            s.d_file = c.d_file; s.file_cap = c.file_cap; s.d_pal = c.d_pal; s.d_img = c.d_img; s.d_ifr = c.d_ifr; s.d_persist = c.d_persist;
+            s.persist_len = c.persist_len; s.d_ring = c.d_ring;
+            ctx->parked.erase(ctx->parked.begin() + k);
+            return true;
+        }
+    }
+    return false;
+}
+
 extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len, int* stream, uint32_t* w, uint32_t* h, uint32_t* n_frames) {
     if (!ctx || !file || !stream) return ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -717,15 +745,18 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
         }
     }
     (void)need_exact_cursor;
-    CK(cudaMalloc(&s.d_file, len + 64));
+    if (!unpark_stream(ctx, s, len, P)) {
+        s.file_cap = len + len / 8 + 4096;
+        CK(cudaMalloc(&s.d_file, s.file_cap));
+        CK(cudaMalloc(&s.d_pal, 512 * 4));
+        CK(cudaMalloc(&s.d_img, P * 4));
+        CK(cudaMalloc(&s.d_ifr, P * 4));
+        s.persist_len = (uint32_t)(2 * P + 64);
+        CK(cudaMalloc(&s.d_persist, s.persist_len));
+    }
     CK(cudaMemcpyAsync(s.d_file, file, len, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(s.d_file + len, 0, 64, ctx->st));
-    CK(cudaMalloc(&s.d_pal, 512 * 4));
     CK(cudaMemcpyAsync(s.d_pal, pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMalloc(&s.d_img, P * 4));
-    CK(cudaMalloc(&s.d_ifr, P * 4));
-    s.persist_len = (uint32_t)(2 * P + 64);
-    CK(cudaMalloc(&s.d_persist, s.persist_len));
     CK(cudaMemsetAsync(s.d_img, 0, P * 4, ctx->st));      // defined start state: zero pages
     CK(cudaMemsetAsync(s.d_ifr, 0, P * 4, ctx->st));
     CK(cudaMemsetAsync(s.d_persist, 0, s.persist_len, ctx->st));
@@ -770,7 +801,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
 extern "C" int agmvb_dec_close(agmvb_ctx* ctx, int stream) {
     if (!ctx || stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) return ERR_ARG;
     CK(cudaStreamSynchronize(ctx->st));
-    free_stream(ctx->streams[stream]);
+    if (ctx->streams[stream].raw) free_stream(ctx->streams[stream]); else park_stream(ctx, ctx->streams[stream]);
     return OK;
 }
 

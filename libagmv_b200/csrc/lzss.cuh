@@ -35,6 +35,8 @@ namespace agmvb {
 constexpr int LZ_LEVELS = 15;
 constexpr uint32_t LZ_POS_MASK = 0x0FFFFFFFu;  // A[] words: position in the low 28 bits, min(15, bytes left in the frame) in the top 4
 constexpr uint32_t LZ_MAX_BATCH = 1u << 28;
+// work layout of the level kernels: 4096-element tiles (same tiling as radix.cuh / scan.cuh), 512 threads x 8 rounds
+constexpr int LZ_THREADS = 512, LZ_WARPS = 16, LZ_ROUNDS = 8, LZ_WARP_SPAN = 256, LZ_TILE = 4096;
 constexpr uint32_t LZ_ALIVE = 0x80000000u;     // GS / gs_tmp words: bit 31 = "a match of this level's length exists for the element"
 constexpr uint32_t LZ_GS_MASK = 0x7FFFFFFFu;
 
@@ -103,28 +105,27 @@ struct LzDigit {
 // thread are loaded up front (and reused as payload), positions / group starts are loaded eight at a time before
 // any store so that the loads overlap, and every fourth level the next four key bytes are gathered from the
 // bitstream (positions of a group are close to sorted, the 4-byte read stays inside one or two sectors).
-__global__ void __launch_bounds__(RX_THREADS) lz_scatter_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ pos_in,
+__global__ void __launch_bounds__(LZ_THREADS) lz_scatter_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ pos_in,
                                                            const uint32_t* __restrict__ gs_in, const uint32_t* __restrict__ dig_in,
                                                            uint32_t* __restrict__ pos_out, uint32_t* __restrict__ gs_out,
                                                            uint32_t* __restrict__ dig_out, uint32_t L, uint32_t n, uint32_t ntiles,
                                                            const uint32_t* __restrict__ tile_off) {
-    __shared__ uint32_t wc[RX_WARPS][256];
+    __shared__ uint32_t wc[LZ_WARPS][256];
     __shared__ uint32_t goff[256];
-#pragma unroll
-    for (int w = 0; w < RX_WARPS; w++) wc[w][threadIdx.x] = 0;
+    for (int k = threadIdx.x; k < LZ_WARPS * 256; k += LZ_THREADS) (&wc[0][0])[k] = 0;
     const int warp = threadIdx.x >> 5;
-    const uint32_t base = blockIdx.x * RX_TILE + warp * RX_WARP_SPAN + lane_id();
+    const uint32_t base = blockIdx.x * LZ_TILE + warp * LZ_WARP_SPAN + lane_id();
     const uint32_t sh = 8u * (L & 3u);
-    uint32_t word[RX_ROUNDS];
+    uint32_t word[LZ_ROUNDS];
 #pragma unroll
-    for (int r = 0; r < RX_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t i = base + r * 32;
         word[r] = i < n ? dig_in[i] : 0u;
     }
     __syncthreads();
-    uint32_t packed[RX_ROUNDS];  // digit << 16 | rank inside the warp's span
+    uint32_t packed[LZ_ROUNDS];  // digit << 16 | rank inside the warp's span
 #pragma unroll
-    for (int r = 0; r < RX_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t i = base + r * 32;
         bool valid = i < n;
         uint32_t key = valid ? (word[r] >> sh) & 255u : 256u + lane_id();
@@ -140,11 +141,11 @@ __global__ void __launch_bounds__(RX_THREADS) lz_scatter_k(const uint8_t* __rest
         __syncwarp();
     }
     __syncthreads();
-    {
+    if (threadIdx.x < 256) {
         uint32_t run = 0;
         const int d = threadIdx.x;
 #pragma unroll
-        for (int w = 0; w < RX_WARPS; w++) {
+        for (int w = 0; w < LZ_WARPS; w++) {
             uint32_t t = wc[w][d];
             wc[w][d] = run;
             run += t;
@@ -154,8 +155,9 @@ __global__ void __launch_bounds__(RX_THREADS) lz_scatter_k(const uint8_t* __rest
     __syncthreads();
     const bool gather = (L & 3u) == 3u;
 #pragma unroll
-    for (int h = 0; h < RX_ROUNDS; h += 8) {
+    for (int h = 0; h < LZ_ROUNDS; h += 8) {
         uint32_t p[8], g[8];
+        static_assert(LZ_ROUNDS % 8 == 0, "rounds are moved eight at a time");
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             uint32_t i = base + (h + r) * 32;
@@ -187,25 +189,27 @@ __global__ void __launch_bounds__(RX_THREADS) lz_scatter_k(const uint8_t* __rest
 // from the radix offsets: tile_off[d * ntiles]). New group start = running max over (head ? idx : 0): a device-wide
 // inclusive max-scan (tile reduce, scan of the partials, tile apply), with the bucket-start bitmap in shared memory.
 __device__ __forceinline__ void lz_bucket_bitmap(uint32_t* bm, const uint32_t* __restrict__ tile_off, uint32_t ntiles, uint32_t t0) {
-    if (threadIdx.x < SCAN_TILE / 32) bm[threadIdx.x] = 0;
+    if (threadIdx.x < LZ_TILE / 32) bm[threadIdx.x] = 0;
     __syncthreads();
-    const uint32_t s = tile_off[threadIdx.x * ntiles];  // 256 threads: one bucket each
-    if (s >= t0 && s < t0 + SCAN_TILE) atomicOr(&bm[(s - t0) >> 5], 1u << ((s - t0) & 31));
+    if (threadIdx.x < 256) {
+        const uint32_t s = tile_off[threadIdx.x * ntiles];  // one bucket per thread
+        if (s >= t0 && s < t0 + LZ_TILE) atomicOr(&bm[(s - t0) >> 5], 1u << ((s - t0) & 31));
+    }
     __syncthreads();
 }
 
 // value of element (warp span, round r, this lane) and of its predecessor, from 16 up-front coalesced loads
-__device__ __forceinline__ void lz_load_with_prev(const uint32_t* __restrict__ a, uint32_t base, uint32_t n, uint32_t cur[SCAN_ROUNDS],
-                                                  uint32_t prv[SCAN_ROUNDS]) {
+__device__ __forceinline__ void lz_load_with_prev(const uint32_t* __restrict__ a, uint32_t base, uint32_t n, uint32_t cur[LZ_ROUNDS],
+                                                  uint32_t prv[LZ_ROUNDS]) {
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t i = base + r * 32;
         cur[r] = i < n ? a[i] : 0u;
     }
     const uint32_t first = base - lane_id();  // index of lane 0's element in round 0
     uint32_t before = (lane_id() == 0 && first > 0 && first - 1 < n) ? a[first - 1] : 0u;
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t up = __shfl_up_sync(0xffffffffu, cur[r], 1);
         uint32_t wrap = r > 0 ? __shfl_sync(0xffffffffu, cur[r > 0 ? r - 1 : 0], 31) : before;
         prv[r] = lane_id() == 0 ? wrap : up;
@@ -222,21 +226,21 @@ __device__ __forceinline__ bool lz_is_head(uint32_t gcur, uint32_t gprv, uint32_
 }
 
 template <bool BY_KEY>
-__global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
+__global__ void __launch_bounds__(LZ_THREADS) lz_group_reduce_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
                                                                   uint32_t ntiles, uint32_t n, const uint32_t* __restrict__ dig,
                                                                   uint32_t* __restrict__ partial) {
-    __shared__ uint32_t bm[SCAN_TILE / 32];
-    __shared__ uint32_t wmax[SCAN_THREADS / 32];
-    const uint32_t t0 = blockIdx.x * SCAN_TILE;
+    __shared__ uint32_t bm[LZ_TILE / 32];
+    __shared__ uint32_t wmax[LZ_THREADS / 32];
+    const uint32_t t0 = blockIdx.x * LZ_TILE;
     if (!BY_KEY) lz_bucket_bitmap(bm, tile_off, ntiles, t0);
     const int warp = threadIdx.x >> 5;
-    const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
-    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS], kc[SCAN_ROUNDS], kp[SCAN_ROUNDS];
+    const uint32_t base = t0 + warp * LZ_WARP_SPAN + lane_id();
+    uint32_t cur[LZ_ROUNDS], prv[LZ_ROUNDS], kc[LZ_ROUNDS], kp[LZ_ROUNDS];
     lz_load_with_prev(gs_old, base, n, cur, prv);
     if (BY_KEY) lz_load_with_prev(dig, base, n, kc, kp);
     uint32_t acc = 0;
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t idx = base + r * 32;
         if (idx < n && idx > 0 && lz_is_head<BY_KEY>(cur[r], prv[r], BY_KEY ? kc[r] : 0u, BY_KEY ? kp[r] : 0u, bm, t0, idx))
             acc = idx;  // idx grows with r, so the last head seen is the maximum
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t t = 0;
-        for (int w = 0; w < SCAN_THREADS / 32; w++) t = max(t, wmax[w]);
+        for (int w = 0; w < LZ_THREADS / 32; w++) t = max(t, wmax[w]);
         partial[blockIdx.x] = t;
     }
 }
@@ -257,59 +261,60 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_reduce_k(const uint32_t
 // where it stops existing (with the previous level's group start, which the scatter carried along) or at level 15.
 // Also counts the next level's key bytes of this tile (the tile is exactly the next scatter's tile).
 template <bool BY_KEY, bool NEXT_HIST>
-__global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
+__global__ void __launch_bounds__(LZ_THREADS) lz_group_apply_k(const uint32_t* __restrict__ gs_old, const uint32_t* __restrict__ tile_off,
                                                                  uint32_t ntiles, uint32_t n, const uint32_t* __restrict__ partial,
                                                                  const uint32_t* __restrict__ pos, uint32_t* __restrict__ gs_new,
                                                                  uint32_t* __restrict__ match_rec, uint32_t Lnew,
                                                                  const uint32_t* __restrict__ dig_next, uint32_t* __restrict__ hist_next) {
-    __shared__ uint32_t bm[SCAN_TILE / 32];
-    __shared__ uint32_t wtot[SCAN_THREADS / 32];
+    __shared__ uint32_t bm[LZ_TILE / 32];
+    __shared__ uint32_t wtot[LZ_THREADS / 32];
     __shared__ uint32_t h[256];
-    const uint32_t t0 = blockIdx.x * SCAN_TILE;
-    h[threadIdx.x] = 0;
+    const uint32_t t0 = blockIdx.x * LZ_TILE;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0;
     if (!BY_KEY) lz_bucket_bitmap(bm, tile_off, ntiles, t0); else __syncthreads();
     const int warp = threadIdx.x >> 5;
-    const uint32_t base = t0 + warp * SCAN_WARP_SPAN + lane_id();
-    uint32_t cur[SCAN_ROUNDS], prv[SCAN_ROUNDS], kc[SCAN_ROUNDS], kp[SCAN_ROUNDS];
+    const uint32_t base = t0 + warp * LZ_WARP_SPAN + lane_id();
+    uint32_t cur[LZ_ROUNDS], prv[LZ_ROUNDS], kc[LZ_ROUNDS], kp[LZ_ROUNDS];
     lz_load_with_prev(gs_old, base, n, cur, prv);
     if (BY_KEY || NEXT_HIST) {
 #pragma unroll
-        for (int r = 0; r < SCAN_ROUNDS; r++) { uint32_t i = base + r * 32; kc[r] = i < n ? dig_next[i] : 0u; }
+        for (int r = 0; r < LZ_ROUNDS; r++) { uint32_t i = base + r * 32; kc[r] = i < n ? dig_next[i] : 0u; }
     }
     if (BY_KEY) {
         const uint32_t first = base - lane_id();
         uint32_t before = (lane_id() == 0 && first > 0 && first - 1 < n) ? dig_next[first - 1] : 0u;
 #pragma unroll
-        for (int r = 0; r < SCAN_ROUNDS; r++) {
+        for (int r = 0; r < LZ_ROUNDS; r++) {
             uint32_t up = __shfl_up_sync(0xffffffffu, kc[r], 1);
             uint32_t wrap = r > 0 ? __shfl_sync(0xffffffffu, kc[r > 0 ? r - 1 : 0], 31) : before;
             kp[r] = lane_id() == 0 ? wrap : up;
         }
     }
-    uint32_t v[SCAN_ROUNDS];
+    uint32_t v[LZ_ROUNDS];
     uint32_t alive_old = 0;  // bit r: the element existed at level Lnew-1
     uint32_t carry = 0;
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t idx = base + r * 32;
-        uint32_t x = 0;
-        if (idx < n && idx > 0 && lz_is_head<BY_KEY>(cur[r], prv[r], BY_KEY ? kc[r] : 0u, BY_KEY ? kp[r] : 0u, bm, t0, idx)) x = idx;
+        const bool hd = idx < n && idx > 0 && lz_is_head<BY_KEY>(cur[r], prv[r], BY_KEY ? kc[r] : 0u, BY_KEY ? kp[r] : 0u, bm, t0, idx);
         alive_old |= (cur[r] >> 31) << r;
-        x = warp_inclusive<MaxOp>(x);
-        x = max(carry, x);
-        v[r] = x;
-        carry = __shfl_sync(0xffffffffu, x, 31);
+        // running max of (head ? idx : 0) inside the warp span: the last head at or before this lane, else the carry
+        const unsigned hm = __ballot_sync(0xffffffffu, hd);
+        const unsigned upto = hm & (0xffffffffu >> (31 - lane_id()));
+        const uint32_t rbase = idx - lane_id();
+        v[r] = upto ? rbase + (31 - __clz(upto)) : carry;
+        carry = hm ? rbase + (31 - __clz(hm)) : carry;
     }
     if (lane_id() == 0) wtot[warp] = carry;
-    uint32_t lo_old[SCAN_ROUNDS];
+    uint32_t lo_old[LZ_ROUNDS];
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) lo_old[r] = cur[r] & LZ_GS_MASK;
+    for (int r = 0; r < LZ_ROUNDS; r++) lo_old[r] = cur[r] & LZ_GS_MASK;
     lz_load_with_prev(pos, base, n, cur, prv);  // reuse the registers: positions and predecessor positions
     __syncthreads();
     uint32_t pre = partial[blockIdx.x];
     for (int w = 0; w < warp; w++) pre = max(pre, wtot[w]);
 #pragma unroll
-    for (int r = 0; r < SCAN_ROUNDS; r++) {
+    for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t idx = base + r * 32;
         if (idx < n) {
             const uint32_t g = max(pre, v[r]);
@@ -323,7 +328,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t*
     if (NEXT_HIST) {
         const uint32_t sh = 8u * (Lnew & 3u);
 #pragma unroll
-        for (int r = 0; r < SCAN_ROUNDS; r++) {
+        for (int r = 0; r < LZ_ROUNDS; r++) {
             uint32_t idx = base + r * 32;
             bool valid = idx < n;
             uint32_t key = valid ? (kc[r] >> sh) & 255u : 256u + lane_id();
@@ -331,7 +336,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) lz_group_apply_k(const uint32_t*
             if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&h[key], __popc(peers));
         }
         __syncthreads();
-        hist_next[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+        if (threadIdx.x < 256) hist_next[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
     }
 }
 
@@ -468,25 +473,25 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
             // derives its groups from (frame, 3-byte key)
             uint32_t* gs_dst = Lnew < (uint32_t)LZ_MINLEN ? wk.GS[Lnew] : wk.gs_tmp;
             device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
-            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, RX_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
+            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, LZ_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
             if (Lnew < (uint32_t)LZ_MINLEN) {
                 KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{dout, 8u * (Lnew & 3u)}, n, nt, th_next)));
                 continue;
             }
             if (Lnew == (uint32_t)LZ_MINLEN) {
-                KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
+                KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
                 KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                wk.match_rec, Lnew, dout, th_next)));
                 continue;
             }
-            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
+            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
             KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
             if (Lnew < (uint32_t)LZ_LEVELS)
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                 wk.match_rec, Lnew, dout, th_next)));
             else
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<nt, SCAN_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                  wk.match_rec, Lnew, dout, th_next)));
         }
         KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));

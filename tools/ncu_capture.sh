@@ -9,9 +9,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-fi
 cap() { # name regex skip count
   ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c $4 -f -o gpurun_out/prof_${TAG}_$1 $CMD > gpurun_out/ncu_$1_$TAG.log 2>&1
 }
-cap scatter radix_scatter_k 12 2
+cap scatter lz_scatter_k 4 2
 cap group lz_group_apply_k 4 2
-cap rxhist radix_hist_k 12 1
+cap rxhist lz_group_reduce_k 4 1
 cap expand expand_mrr_k 0 1
 cap quantize quantize_k 0 2
 cap hist hist_vec4_k 0 1
