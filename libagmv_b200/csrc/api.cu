@@ -805,14 +805,6 @@ extern "C" int agmvb_dec_close(agmvb_ctx* ctx, int stream) {
     return OK;
 }
 
-__global__ void checksum_k(const uint32_t* __restrict__ px, uint32_t P, unsigned long long* __restrict__ out) {
-    unsigned long long acc = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P; i += gridDim.x * blockDim.x)
-        acc += (unsigned long long)px[i] * (2654435761ull + 2ull * i);
-    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-    if (lane_id() == 0) atomicAdd(out, acc);
-}
-
 constexpr uint32_t DEC_RING = 8;
 
 // Decode the next `count` frames of each listed stream (all of one size).
@@ -932,17 +924,13 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
                 x.stale = ctx->d_stale.as<uint8_t>() + (size_t)(s * cn + k) * 4;
                 x.pal = d.d_pal;
                 x.dual = d.dual;
+                x.is_snap = g % 4 == 0;
+                x.cksum = cks ? ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k : nullptr;
             }
         CK(cudaMemcpyAsync(ctx->d_steps.p, steps.data(), F * sizeof(DecStep), cudaMemcpyHostToDevice, ctx->st));
-        for (uint32_t k = 0; k < cn; k++) {
+        {
             dim3 grid(cdiv(B, 128), S);
-            KL(ctx->lc, KC_RECON, (reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>() + (size_t)k * S, W, H)));
-            if (cks) {
-                for (uint32_t s = 0; s < S; s++) {
-                    KL(ctx->lc, KC_CHECKSUM, (checksum_k<<<std::min<uint32_t>(cdiv(P, 256), 592), 256, 0, ctx->st>>>(steps[k * S + s].dst, (uint32_t)P,
-                                                                                           ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k)));
-                }
-            }
+            KL(ctx->lc, KC_RECON, (reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>(), cn, S, W, H)));
         }
         TRY(check_launch(ctx, "reconstruct"));
         // carry the state over: expanded-bitstream leftovers, last pixels, last I-frame snapshot

@@ -363,14 +363,16 @@ __global__ void __launch_bounds__(64) index_tail_k(const DecFrame* __restrict__ 
 // ---- D3b ----------------------------------------------------------------------
 struct DecStep {              // one frame to reconstruct (host-built)
     uint32_t* dst;
-    const uint32_t* prev;     // previous frame's pixels (may alias dst)
-    const uint32_t* ifr;      // I-frame pixels
+    const uint32_t* prev;     // pixels before this frame (read for the FIRST step of a launch only)
+    const uint32_t* ifr;      // I-frame snapshot before this frame (read for the first step only)
     const uint32_t* recs;
     const uint8_t* ebuf;
     const uint32_t* bpos;
     const uint8_t* stale;
     const uint32_t* pal;      // pal0[256] then pal1[256]
     int dual;
+    int is_snap;              // frame_count % 4 == 0: the frame becomes the I-frame snapshot after it is written
+    unsigned long long* cksum; // nullable: receives sum over pixels of value * (2654435761 + 2 * pixel index)
 };
 
 __device__ __forceinline__ uint32_t read_color(const VBuf& v, uint32_t& bp, const uint32_t* spal, int dual) {
@@ -381,63 +383,101 @@ __device__ __forceinline__ uint32_t read_color(const VBuf& v, uint32_t& bp, cons
     return spal[base + v[bp++]];
 }
 
-// pixel (i,j) of block `b` as the current frame leaves it
-__device__ uint32_t block_pixel(const DecStep& s, const VBuf& v, const uint32_t* spal, uint32_t W, uint32_t b, uint32_t bw, int i, int j) {
-    const uint32_t x = (b % bw) * 4 + i, y = (b / bw) * 4 + j;
-    const uint32_t r = s.recs[b];
-    if (r == EMPTY32) return s.prev[(size_t)y * W + x];
+// pixel number k (row-major 0..15) of a block given its record, the previous value and the snapshot value
+__device__ __forceinline__ uint32_t record_pixel(uint32_t r, const VBuf& v, const uint32_t* spal, int dual, int k, uint32_t prev, uint32_t ifr) {
+    if (r == EMPTY32) return prev;
     const uint32_t type = r & 3u;
     uint32_t bp = r >> 2;
-    if (type == BT_COPY) return s.ifr[(size_t)y * W + x];
-    if (type == BT_FILL) return read_color(v, bp, spal, s.dual);
+    if (type == BT_COPY) return ifr;
+    if (type == BT_FILL) return read_color(v, bp, spal, dual);
     uint32_t col = 0;
-    for (int k = 0; k <= j * 4 + i; k++) col = read_color(v, bp, spal, s.dual);
-    return bp <= v.bpos ? col : s.prev[(size_t)y * W + x];
+    for (int j = 0; j <= k; j++) col = read_color(v, bp, spal, dual);
+    return bp <= v.bpos ? col : prev;
 }
 
-// grid (cdiv(B,128), n_steps): one thread per 4x4 block, 16-byte row stores
-__global__ void __launch_bounds__(128) reconstruct_k(const DecStep* __restrict__ steps, uint32_t W, uint32_t H) {
+// grid (cdiv(B,128), n_streams): one thread per 4x4 block position walks the `count` frames of its stream in
+// order, keeping the block's previous pixels and its I-frame snapshot in registers. A frame therefore costs one
+// read of its records and codes and one 16-byte-per-row write of its pixels: COPY blocks and blocks a short frame
+// never reaches (they keep the previous frame) read nothing from HBM. The thread of the last block
+// also tracks pixel (3,1) of the block to its left for the reference's last-block FILL quirk (src/agmv_decode.c:264-266).
+__global__ void __launch_bounds__(128) reconstruct_k(const DecStep* __restrict__ steps, uint32_t count, uint32_t S, uint32_t W, uint32_t H) {
     __shared__ uint32_t spal[512];
-    const DecStep s = steps[blockIdx.y];
-    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = s.pal[k];
+    const uint32_t sidx = blockIdx.y;
+    const DecStep s0 = steps[sidx];
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = s0.pal[k];
     __syncthreads();
     const uint32_t bw = W >> 2, B = bw * (H >> 2);
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const uint32_t bb = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = bb < B;
+    const uint32_t b = valid ? bb : B - 1;  // surplus threads shadow the last block and write nothing
     const uint32_t x = (b % bw) * 4, y = (b / bw) * 4;
-    const uint32_t r = s.recs[b];
-    const VBuf v{s.ebuf, *s.bpos, s.stale};
-    uint4 row[4];
-    if (r == EMPTY32) {
-        if (s.dst == s.prev) return;
+    uint32_t prev[16], ifr[16];
 #pragma unroll
-        for (int j = 0; j < 4; j++) row[j] = *reinterpret_cast<const uint4*>(s.prev + (size_t)(y + j) * W + x);
-    } else if ((r & 3u) == BT_COPY) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) row[j] = *reinterpret_cast<const uint4*>(s.ifr + (size_t)(y + j) * W + x);
-    } else if ((r & 3u) == BT_FILL) {
-        uint32_t bp = r >> 2;
-        uint32_t col = read_color(v, bp, spal, s.dual);
-        if (b == B - 1) {
-            // src/agmv_decode.c:264-266: the last block takes the colour of img[(x-1)+(y+1)*W] as it stands
-            // at that moment, i.e. pixel (3,1) of the block to its left as THIS frame leaves it.
-            col = bw > 1 ? block_pixel(s, v, spal, W, b - 1, bw, 3, 1) : s.prev[(size_t)(y + 1) * W + x - 1];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) row[j] = make_uint4(col, col, col, col);
-    } else {
-        uint32_t bp = r >> 2;
-        uint32_t px[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++) {
-            uint32_t col = read_color(v, bp, spal, s.dual);
-            px[k] = bp <= v.bpos ? col : s.prev[(size_t)(y + (k >> 2)) * W + x + (k & 3)];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; j++) row[j] = make_uint4(px[j * 4], px[j * 4 + 1], px[j * 4 + 2], px[j * 4 + 3]);
+    for (int j = 0; j < 4; j++) {
+        uint4 p = *reinterpret_cast<const uint4*>(s0.prev + (size_t)(y + j) * W + x);
+        uint4 q = *reinterpret_cast<const uint4*>(s0.ifr + (size_t)(y + j) * W + x);
+        prev[j * 4] = p.x; prev[j * 4 + 1] = p.y; prev[j * 4 + 2] = p.z; prev[j * 4 + 3] = p.w;
+        ifr[j * 4] = q.x; ifr[j * 4 + 1] = q.y; ifr[j * 4 + 2] = q.z; ifr[j * 4 + 3] = q.w;
     }
+    const bool last = b == B - 1;
+    uint32_t nb_prev = 0, nb_ifr = 0;  // pixel (x-1, y+1): pixel (3,1) of the left neighbour (or, one block wide, the previous row's end)
+    if (last) {
+        nb_prev = s0.prev[(size_t)(y + 1) * W + x - 1];
+        nb_ifr = s0.ifr[(size_t)(y + 1) * W + x - 1];
+    }
+    for (uint32_t k = 0; k < count; k++) {
+        const DecStep s = steps[(size_t)k * S + sidx];
+        const uint32_t r = s.recs[b];
+        const VBuf v{s.ebuf, *s.bpos, s.stale};
+        uint32_t cur[16];
+        uint32_t nb_cur = 0;
+        if (last) nb_cur = bw > 1 ? record_pixel(s.recs[b - 1], v, spal, s.dual, 7, nb_prev, nb_ifr) : prev[3];
+        if (r == EMPTY32) {
 #pragma unroll
-    for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(s.dst + (size_t)(y + j) * W + x) = row[j];
+            for (int i = 0; i < 16; i++) cur[i] = prev[i];
+        } else if ((r & 3u) == BT_COPY) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) cur[i] = ifr[i];
+        } else if ((r & 3u) == BT_FILL) {
+            uint32_t bp = r >> 2;
+            uint32_t col = read_color(v, bp, spal, s.dual);
+            if (last) col = nb_cur;  // the last block takes img[(x-1)+(y+1)*W] as this frame has left it so far
+#pragma unroll
+            for (int i = 0; i < 16; i++) cur[i] = col;
+        } else {
+            uint32_t bp = r >> 2;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t col = read_color(v, bp, spal, s.dual);
+                cur[i] = bp <= v.bpos ? col : prev[i];
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                *reinterpret_cast<uint4*>(s.dst + (size_t)(y + j) * W + x) = make_uint4(cur[j * 4], cur[j * 4 + 1], cur[j * 4 + 2], cur[j * 4 + 3]);
+        }
+        if (s.cksum) {  // uniform per launch
+            unsigned long long acc = 0;
+            if (valid) {
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const unsigned long long idx = (unsigned long long)(y + (i >> 2)) * W + x + (i & 3);
+                    acc += (unsigned long long)cur[i] * (2654435761ull + 2ull * idx);
+                }
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+            if (lane_id() == 0) atomicAdd(s.cksum, acc);
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i++) prev[i] = cur[i];
+        if (s.is_snap) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) ifr[i] = cur[i];
+        }
+        if (last) { nb_prev = nb_cur; if (s.is_snap) nb_ifr = nb_cur; }
+    }
 }
 
 }  // namespace agmvb

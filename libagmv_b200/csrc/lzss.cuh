@@ -375,11 +375,26 @@ __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs,
         // first j >= glo with f(j) = (j outside the group) || (a[j] >= target). f is monotone, and the answer lies inside
         // the group because i itself is a member with a[.] = i >= target. Gallop for an upper bound, then bisect.
         auto f = [&](uint32_t j) { return j >= n || (g[j] & LZ_GS_MASK) != glo || (a[j] & LZ_POS_MASK) >= target; };
-        uint32_t lo = glo, hi = glo, step = 1;
-        while (!f(hi)) { lo = hi + 1; hi += step; step <<= 1; }
-        while (lo < hi) {
-            uint32_t mid = (lo + hi) >> 1;
-            if (f(mid)) hi = mid; else lo = mid + 1;
+        // Positions inside a group increase by at least 1 per index, so U = glo + (target - a[glo]) already satisfies f;
+        // in a dense run (the common large group) it is the exact answer: probe U-1 first. Otherwise gallop up from
+        // the group start (small or sparse groups end within a few probes), then bisect.
+        const uint32_t first = a[glo] & LZ_POS_MASK;
+        uint32_t lo = glo, hi = glo;
+        if (first < target) {
+            const uint32_t U = glo + (target - first);
+            lo = glo + 1;
+            hi = U;
+            if (hi > lo && !f(hi - 1)) lo = hi;
+            else if (hi > lo) {
+                hi = hi - 1;  // f(U-1) holds
+                uint32_t step = 1, probe = lo;
+                while (probe < hi && !f(probe)) { lo = probe + 1; probe += step; step <<= 1; }
+                if (probe < hi) hi = probe;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (f(mid)) hi = mid; else lo = mid + 1;
+                }
+            }
         }
         uint32_t off = i - (a[lo] & LZ_POS_MASK);
         v = (off << 1) | (l << 17);
