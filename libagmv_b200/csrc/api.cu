@@ -350,6 +350,17 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
         for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));
         TRY(grab((size_t)cap * 4, (void**)&w.gs_tmp));
+        TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[0]));
+        TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[1]));
+        TRY(grab((size_t)(LZ_LEVELS + 1) * 257 * 4, (void**)&w.bstart));
+        TRY(grab(256 * 4, (void**)&w.bytehist));
+        {
+            const size_t ct = cdiv(cap, LZ_TILE) + 1;
+            TRY(grab((ct * 257 + 4) * 4, (void**)&w.chain_mem));
+        }
+        // single-pass level kernel (decoupled look-back): exact, but measured slower than the three-kernel levels on B200
+        // (203 vs 186 ms per config-3 step); kept selectable for further work
+        w.fused = getenv("AGMVB_LZ_FUSED") ? atoi(getenv("AGMVB_LZ_FUSED")) != 0 : false;
         TRY(grab((size_t)cap * 4, (void**)&w.dig4[0]));
         TRY(grab((size_t)cap * 4, (void**)&w.dig4[1]));
         TRY(grab((size_t)cap * 4, (void**)&w.match_rec));

@@ -34,69 +34,6 @@ struct DecFrame {            // per frame of the batch (host-built, device-read)
     int dual;                // stream version 1/3
 };
 
-// ---- D2 ----------------------------------------------------------------------
-__global__ void __launch_bounds__(64) expand_k(const DecFrame* __restrict__ fr, uint32_t F, uint8_t* __restrict__ ebuf,
-                                               uint32_t* __restrict__ bpos_out, uint32_t* __restrict__ consumed_out) {
-    uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
-    if (f >= F) return;
-    const DecFrame d = fr[f];
-    const uint8_t* __restrict__ file = d.file;
-    const uint64_t file_len = d.file_len;
-    const int lz77 = d.lz77;
-    uint8_t* e = ebuf + d.ebuf_off;
-    uint64_t rp = d.data_off;   // next file byte
-    uint64_t bpos = 0;
-    if (!lz77) {
-        uint32_t acc = 0, navail = 0;
-        uint64_t bits = 0;
-        const uint64_t nbits = (uint64_t)d.csize * 8;
-        auto rd = [&](uint32_t nb) -> uint32_t {
-            while (navail < nb) {
-                uint32_t byte = rp < file_len ? file[rp] : 0u;  // fread past EOF leaves 0
-                rp++;
-                acc |= byte << navail;
-                navail += 8;
-            }
-            uint32_t v = acc & ((1u << nb) - 1u);
-            acc >>= nb;
-            navail -= nb;
-            return v;
-        };
-        while (bits < nbits && bpos < d.usize) {
-            uint32_t flag = rd(1);
-            bits++;
-            if (flag) {
-                e[bpos++] = (uint8_t)rd(8);
-                bits += 8;
-            } else {
-                uint64_t off = rd(16);
-                uint32_t len = rd(4);
-                bits += 20;
-                const uint64_t p = bpos;
-                for (uint32_t i = 0; i < len; i++) {
-                    uint64_t s = p - off + i;              // unsigned wrap on purpose: too-large offsets copy nothing
-                    if (s < bpos) { e[bpos] = e[s]; bpos++; }
-                }
-            }
-        }
-    } else {
-        for (uint32_t i = 0; i < d.csize; i += 4) {
-            uint32_t b0 = rp < file_len ? file[rp] : 0u; rp++;
-            uint32_t b1 = rp < file_len ? file[rp] : 0u; rp++;
-            uint32_t len = rp < file_len ? file[rp] : 0u; rp++;
-            uint8_t lit = rp < file_len ? file[rp] : 0u; rp++;
-            const uint64_t off = b0 | b1 << 8, p = bpos;
-            for (uint32_t k = 0; k < len; k++) {
-                uint64_t s = p - off + k;
-                if (s < bpos) { e[bpos] = e[s]; bpos++; }
-            }
-            e[bpos++] = lit;
-        }
-    }
-    bpos_out[f] = (uint32_t)bpos;
-    consumed_out[f] = (uint32_t)(rp - d.data_off);
-}
-
 // ---- D2, warp per frame ------------------------------------------------------
 // Token parsing is a serial bit walk (lane 0, payload staged through shared memory 1 KB at a time); the
 // copies of up to 32 tokens are then resolved together ("multi-round resolution"): a match may run as soon
@@ -107,8 +44,8 @@ constexpr int EX_WIN = 256;  // payload words staged per refill
 
 __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __restrict__ fr, uint32_t F, uint8_t* __restrict__ ebuf,
                                                              uint32_t* __restrict__ bpos_out, uint32_t* __restrict__ consumed_out) {
-    __shared__ uint32_t win[EX_WARPS][EX_WIN + 2];
-    __shared__ uint32_t tk_o[EX_WARPS][32], tk_dl[EX_WARPS][32];
+    __shared__ uint32_t win[EX_WARPS][EX_WIN + 3];
+    __shared__ uint32_t tk_o[EX_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t f = blockIdx.x * EX_WARPS + warp;
     if (f >= F) return;
@@ -136,82 +73,105 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
         return;
     }
     const uint64_t nbits = (uint64_t)d.csize * 8;
-    uint64_t bitp = 0;       // bits consumed so far (== the reference's `bits`), lane 0 is authoritative
-    uint32_t bpos = 0;
-    uint64_t win_word0 = 0;  // payload word index held in win[..][0]
+    uint64_t bitp = 0;       // bits consumed so far (== the reference's `bits`), warp-uniform
+    uint32_t bpos = 0;       // warp-uniform
     bool more = nbits > 0 && d.usize > 0;
-    bool refill = true;
     while (more) {
-        if (refill) {
-            win_word0 = bitp >> 5;
-            for (int k = lane; k < EX_WIN + 2; k += 32) {
-                uint64_t b = d.data_off + (win_word0 + k) * 4;
-                uint32_t w = 0;
+        // ---- stage the next EX_WIN payload words (plus slack for a token that straddles the end) ----
+        const uint64_t win_word0 = bitp >> 5;
+        for (int k = lane; k < EX_WIN + 3; k += 32) {
+            uint64_t b = d.data_off + (win_word0 + k) * 4;
+            uint32_t w = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) w |= (b + j < d.file_len ? (uint32_t)file[b + j] : 0u) << (8 * j);  // fread past EOF leaves 0
-                win[warp][k] = w;
-            }
-            __syncwarp();
-            refill = false;
+            for (int j = 0; j < 4; j++) w |= (b + j < d.file_len ? (uint32_t)file[b + j] : 0u) << (8 * j);  // fread past EOF leaves 0
+            win[warp][k] = w;
         }
-        uint32_t ntok = 0;
-        if (lane == 0) {
-            while (ntok < 32 && bitp < nbits && bpos < d.usize) {
-                uint64_t li = (bitp >> 5) - win_word0;
-                if (li >= (uint64_t)EX_WIN) { refill = true; break; }
-                uint32_t sh = (uint32_t)bitp & 31;
-                uint32_t w = __funnelshift_r(win[warp][li], win[warp][li + 1], sh);
-                if (w & 1u) {
-                    tk_o[warp][ntok] = bpos;
-                    tk_dl[warp][ntok] = (1u << 20) | (1u << 16) | (((w >> 1) & 255u) << 24);
-                    bitp += 9;
-                    bpos += 1;
-                } else {
-                    uint32_t off = (w >> 1) & 0xFFFFu, len = (w >> 17) & 15u;
-                    uint32_t l = (off >= 1 && off <= bpos) ? len : 0u;  // src index must be < bpos (unsigned compare in the reference)
-                    tk_o[warp][ntok] = bpos;
-                    tk_dl[warp][ntok] = off | (l << 16);
-                    bitp += 21;
-                    bpos += l;
+        __syncwarp();
+        const uint64_t wbit0 = win_word0 << 5;
+        const uint32_t limit = (uint32_t)((nbits - wbit0) < (uint64_t)(EX_WIN * 32) ? (nbits - wbit0) : (uint64_t)(EX_WIN * 32));  // tokens must start below it
+        bool window_left = true;
+        while (more && window_left) {
+            // ---- lane 0: the serial part, reduced to finding where the next <= 32 tokens start (9 or 21 bits each) ----
+            uint32_t ntok = 0;
+            const uint32_t rel0 = (uint32_t)(bitp - wbit0);
+            if (lane == 0) {
+                uint32_t rel = rel0;
+                uint32_t wi = rel >> 5;
+                uint64_t r = (((uint64_t)win[warp][wi + 1] << 32) | win[warp][wi]) >> (rel & 31);
+                int avail = 64 - (int)(rel & 31);
+                while (ntok < 32 && rel < limit) {
+                    tk_o[warp][ntok++] = rel;
+                    const uint32_t step = 21u - 12u * ((uint32_t)r & 1u);
+                    rel += step;
+                    r >>= step;
+                    avail -= (int)step;
+                    if (avail < 21) {
+                        wi = rel >> 5;
+                        r = (((uint64_t)win[warp][wi + 1] << 32) | win[warp][wi]) >> (rel & 31);
+                        avail = 64 - (int)(rel & 31);
+                    }
                 }
-                ntok++;
             }
+            ntok = __shfl_sync(0xffffffffu, ntok, 0);
+            __syncwarp();
+            if (ntok == 0) { window_left = false; break; }  // next token starts beyond the staged window (or at nbits)
+            // ---- all lanes: decode one token each ----
+            const bool have = (uint32_t)lane < ntok;
+            const uint32_t rel = have ? tk_o[warp][lane] : 0u;
+            const uint32_t w = __funnelshift_r(win[warp][rel >> 5], win[warp][(rel >> 5) + 1], rel & 31);
+            const bool lit = have && (w & 1u);
+            const uint32_t dd = (w >> 1) & 0xFFFFu;
+            uint32_t l = !have ? 0u : (lit ? 1u : ((w >> 17) & 15u));
+            const uint32_t tbits = lit ? 9u : 21u;
+            // output offsets = exclusive prefix of the lengths; a match whose source would start at or beyond the current
+            // output end copies nothing (unsigned compare in the reference) - only possible for damaged trailing tokens
+            uint32_t o;
+            while (true) {
+                uint32_t inc = l;
+#pragma unroll
+                for (int k = 1; k < 32; k <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= k) inc += y; }
+                o = bpos + inc - l;
+                const bool bad = have && !lit && l > 0 && !(dd >= 1 && dd <= o);
+                const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                if (!bm) break;
+                if (lane == __ffs(bm) - 1) l = 0;  // everything before the first offender is final, so it really is void
+            }
+            // the reference stops before a token when bpos has reached usize
+            const unsigned stop = __ballot_sync(0xffffffffu, have && o >= d.usize);
+            const uint32_t nuse = stop ? (uint32_t)(__ffs(stop) - 1) : ntok;
+            const bool active = (uint32_t)lane < nuse;
+            // new warp-uniform state, taken from the last token actually used
+            const uint32_t lastl = nuse - 1;  // nuse >= 1: the first token of a chunk always has o == bpos < usize
+            bitp = wbit0 + __shfl_sync(0xffffffffu, rel + tbits, lastl);
+            bpos = __shfl_sync(0xffffffffu, o + l, lastl);
             more = bitp < nbits && bpos < d.usize;
-        }
-        ntok = __shfl_sync(0xffffffffu, ntok, 0);
-        more = __shfl_sync(0xffffffffu, (int)more, 0);
-        refill = __shfl_sync(0xffffffffu, (int)refill, 0);
-        bitp = __shfl_sync(0xffffffffu, bitp, 0);
-        __syncwarp();
-        // ---- resolve the copies of this chunk ----
-        const bool active = (uint32_t)lane < ntok;
-        const uint32_t o = active ? tk_o[warp][lane] : 0u, dl = active ? tk_dl[warp][lane] : 0u;
-        const uint32_t l = (dl >> 16) & 15u, dd = dl & 0xFFFFu;
-        const bool lit = (dl >> 20) & 1u;
-        bool done = !active || l == 0;
-        if (active && lit) { e[o] = (uint8_t)(dl >> 24); done = true; }
-        __syncwarp();
-        while (true) {
-            unsigned m = __ballot_sync(0xffffffffu, !done);
-            if (!m) break;
-            const uint32_t hwm = __shfl_sync(0xffffffffu, o, __ffs(m) - 1);
-            const bool can = !done && (o - dd + (l < dd ? l : dd) <= hwm);
-            if (can) {
-                const uint8_t* src = e + o - dd;
-                if (dd >= l) {
-                    uint8_t v[15];
+            if ((uint32_t)(bitp - wbit0) >= limit && more) window_left = false;
+            // ---- resolve the copies of this chunk ----
+            bool done = !active || l == 0;
+            if (active && lit) { e[o] = (uint8_t)(w >> 1); done = true; }
+            __syncwarp();
+            while (true) {
+                unsigned m = __ballot_sync(0xffffffffu, !done);
+                if (!m) break;
+                const uint32_t hwm = __shfl_sync(0xffffffffu, o, __ffs(m) - 1);
+                const bool can = !done && (o - dd + (l < dd ? l : dd) <= hwm);
+                if (can) {
+                    const uint8_t* src = e + o - dd;
+                    if (dd >= l) {
+                        uint8_t v[15];
 #pragma unroll
-                    for (int k = 0; k < 15; k++) if ((uint32_t)k < l) v[k] = src[k];
+                        for (int k = 0; k < 15; k++) if ((uint32_t)k < l) v[k] = src[k];
 #pragma unroll
-                    for (int k = 0; k < 15; k++) if ((uint32_t)k < l) e[o + k] = v[k];
-                } else {
-                    for (uint32_t k = 0; k < l; k++) e[o + k] = src[k];  // overlapping copy: byte order matters
+                        for (int k = 0; k < 15; k++) if ((uint32_t)k < l) e[o + k] = v[k];
+                    } else {
+                        for (uint32_t k = 0; k < l; k++) e[o + k] = src[k];  // overlapping copy: byte order matters
+                    }
+                    done = true;
                 }
-                done = true;
+                __syncwarp();
             }
             __syncwarp();
         }
-        __syncwarp();
     }
     if (lane == 0) {
         bpos_out[f] = bpos;

@@ -40,12 +40,22 @@ constexpr int LZ_THREADS = 512, LZ_WARPS = 16, LZ_ROUNDS = 8, LZ_WARP_SPAN = 256
 constexpr uint32_t LZ_ALIVE = 0x80000000u;     // GS / gs_tmp words: bit 31 = "a match of this level's length exists for the element"
 constexpr uint32_t LZ_GS_MASK = 0x7FFFFFFFu;
 
+struct LzChain {
+    uint32_t* ticket;   // [1]
+    uint32_t* st_max;   // [ntiles]       flag << 30 | head index
+    uint32_t* st_cnt;   // [ntiles][256]  flag << 30 | count
+};
 struct LzWork {
     uint32_t cap_n = 0, cap_frames = 0;
     uint8_t* bestlen = nullptr;          // per position, filled after the last level (input of the parse)
     uint32_t* A[LZ_LEVELS + 1] = {};     // level arrays: positions grouped by their first L bytes
     uint32_t* GS[LZ_LEVELS + 1] = {};    // group start (index into A[L]) of every element of A[L]
     uint32_t* gs_tmp = nullptr;          // level-L group starts carried into level-(L+1) order
+    uint32_t* gs_carry[2] = {};          // fused path: carried group words, ping-pong
+    uint32_t* bstart = nullptr;          // fused path: [15][257] key-byte bucket starts per level
+    uint32_t* bytehist = nullptr;        // fused path: [256]
+    uint32_t* chain_mem = nullptr;       // fused path: look-back state (ticket, per-tile max, per-tile x 256 counts)
+    bool fused = false;
     uint32_t* dig4[2] = {};              // next four key bytes of every element, carried through the scatters
     uint32_t* match_rec = nullptr;       // per position: best level << 28 | group start in A[best level]; 0 = no match
     uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
@@ -345,6 +355,233 @@ __global__ void lz_bestlen_k(const uint32_t* __restrict__ match_rec, uint32_t n,
     if (i < n) bestlen[i] = (uint8_t)(match_rec[i] >> 28);
 }
 
+// =====================================================================================================
+// Fused level kernel: group phase of level `lvl` + stable scatter by key byte `lvl`, one pass over the data.
+//
+// The three-kernel formulation above (scatter / group reduce / group apply, plus offset scans) reads and writes
+// every element several times per level. Both cross-tile dependencies - the running max of head indices and the
+// per-key-byte offsets of the scatter - are prefix computations over tiles, so they can be resolved with a
+// decoupled look-back (tiles take tickets in order; each publishes its aggregate, then folds its predecessors'
+// until it meets an inclusive prefix). The global bucket bases need no pass at all: the number of elements whose
+// key byte `lvl` equals d is the byte histogram of bs[lvl .. n+lvl), known before the first level.
+// Per element and level: 12 B read, 4 B (GS) + 12 B (scattered) written.
+// =====================================================================================================
+constexpr uint32_t LB_AGG = 1u << 30, LB_INCL = 2u << 30, LB_VAL = (1u << 30) - 1u;
+
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_vol(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
+
+// byte histogram of bs[0 .. n+15) -> base[256]; then per level the counts of bs[lvl .. n+lvl) and their exclusive scan
+__global__ void __launch_bounds__(256) lz_bytehist_k(const uint8_t* __restrict__ bs, uint32_t total, uint32_t* __restrict__ base) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (total + 3) / 4; i += gridDim.x * blockDim.x) {
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (i * 4 + j < total) w |= (uint32_t)bs[i * 4 + j] << (8 * j);
+        const uint32_t cnt = min(4u, total - i * 4);
+        for (uint32_t j = 0; j < cnt; j++) atomicAdd(&h[(w >> (8 * j)) & 255u], 1u);
+    }
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&base[threadIdx.x], h[threadIdx.x]);
+}
+// bstart[lvl][d] (d = 0..256): first index of key byte d in the order sorted by byte offset lvl
+__global__ void __launch_bounds__(256) lz_bstart_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ base,
+                                                   uint32_t* __restrict__ bstart) {
+    __shared__ uint32_t c[256];
+    const uint32_t d = threadIdx.x, lvl = blockIdx.x;
+    uint32_t v = base[d];
+    for (uint32_t j = 0; j < lvl; j++) v -= bs[j] == d;                      // bytes before the range
+    for (uint32_t j = n + lvl; j < n + LZ_LEVELS; j++) v -= bs[j] == d;      // bytes after it
+    c[d] = v;
+    __syncthreads();
+    if (d == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < 256; k++) { uint32_t t = c[k]; c[k] = run; run += t; }
+        bstart[lvl * 257 + 256] = run;
+    }
+    __syncthreads();
+    bstart[lvl * 257 + d] = c[d];
+}
+
+template <bool GROUP, bool BY_KEY, bool SCATTER>
+__global__ void __launch_bounds__(LZ_THREADS) lz_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t lvl,
+                                                         const uint32_t* __restrict__ pos_in, const uint32_t* __restrict__ gs_in,
+                                                         const uint32_t* __restrict__ dig_in, uint32_t* __restrict__ gs_final,
+                                                         uint32_t* __restrict__ match_rec, uint32_t* __restrict__ pos_out,
+                                                         uint32_t* __restrict__ gs_out, uint32_t* __restrict__ dig_out,
+                                                         const uint32_t* __restrict__ bstart, LzChain ch) {
+    __shared__ uint32_t wc[LZ_WARPS][256];
+    __shared__ uint32_t goff[256];
+    __shared__ uint32_t bm[LZ_TILE / 32];
+    __shared__ uint32_t wtot[LZ_WARPS];
+    __shared__ uint32_t s_tile, s_pre;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ch.ticket, 1u);
+    if (SCATTER) for (int k = threadIdx.x; k < LZ_WARPS * 256; k += LZ_THREADS) (&wc[0][0])[k] = 0;
+    if (GROUP && !BY_KEY && threadIdx.x < LZ_TILE / 32) bm[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile, t0 = tile * LZ_TILE;
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t base = t0 + warp * LZ_WARP_SPAN + lane;
+    if (GROUP && !BY_KEY && threadIdx.x < 256) {   // heads at the key-byte bucket starts of the CURRENT order (sorted by byte lvl-1)
+        const uint32_t s = bstart[(lvl - 1) * 257 + threadIdx.x];
+        if (s >= t0 && s < t0 + LZ_TILE) atomicOr(&bm[(s - t0) >> 5], 1u << ((s - t0) & 31));
+    }
+    uint32_t pw[LZ_ROUNDS], gw[LZ_ROUNDS], dw[LZ_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < LZ_ROUNDS; r++) {
+        const uint32_t i = base + r * 32;
+        pw[r] = i < n ? pos_in[i] : 0u;
+        gw[r] = i < n ? gs_in[i] : 0u;
+        dw[r] = i < n ? dig_in[i] : 0u;
+    }
+    uint32_t v[LZ_ROUNDS];      // GROUP: running max of head indices inside the warp span
+    uint32_t pprev[LZ_ROUNDS];  // GROUP: predecessor position words
+    if (GROUP) {
+        const uint32_t first = base - lane;
+        uint32_t gb = 0, pb = 0, db = 0;
+        if (lane == 0 && first > 0 && first - 1 < n) { gb = gs_in[first - 1]; pb = pos_in[first - 1]; if (BY_KEY) db = dig_in[first - 1]; }
+        __syncthreads();  // bitmap complete
+        uint32_t carry = 0;
+#pragma unroll
+        for (int r = 0; r < LZ_ROUNDS; r++) {
+            const uint32_t idx = base + r * 32;
+            uint32_t gp = __shfl_up_sync(0xffffffffu, gw[r], 1), pp = __shfl_up_sync(0xffffffffu, pw[r], 1);
+            uint32_t dp = BY_KEY ? __shfl_up_sync(0xffffffffu, dw[r], 1) : 0u;
+            const uint32_t gwrap = r > 0 ? __shfl_sync(0xffffffffu, gw[r > 0 ? r - 1 : 0], 31) : gb;
+            const uint32_t pwrap = r > 0 ? __shfl_sync(0xffffffffu, pw[r > 0 ? r - 1 : 0], 31) : pb;
+            const uint32_t dwrap = BY_KEY ? (r > 0 ? __shfl_sync(0xffffffffu, dw[r > 0 ? r - 1 : 0], 31) : db) : 0u;
+            if (lane == 0) { gp = gwrap; pp = pwrap; dp = dwrap; }
+            pprev[r] = pp;
+            const bool hd = idx < n && idx > 0 && lz_is_head<BY_KEY>(gw[r], gp, dw[r], dp, bm, t0, idx);
+            const unsigned hm = __ballot_sync(0xffffffffu, hd);
+            const unsigned upto = hm & (0xffffffffu >> (31 - lane));
+            const uint32_t rbase = idx - lane;
+            v[r] = upto ? rbase + (31 - __clz(upto)) : carry;
+            carry = hm ? rbase + (31 - __clz(hm)) : carry;
+        }
+        if (lane == 0) wtot[warp] = carry;
+    }
+    uint32_t packed[LZ_ROUNDS];  // SCATTER: digit << 16 | rank inside the warp's span
+    const uint32_t sh = 8u * (lvl & 3u);
+    if (SCATTER) {
+#pragma unroll
+        for (int r = 0; r < LZ_ROUNDS; r++) {
+            const uint32_t i = base + r * 32;
+            const bool valid = i < n;
+            const uint32_t key = valid ? (dw[r] >> sh) & 255u : 256u + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = wc[warp][key];
+                wc[warp][key] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            packed[r] = (key << 16) | (old + __popc(peers & lanemask_lt()));
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // ---- cross-tile prefixes by decoupled look-back ----
+    if (SCATTER && threadIdx.x < 256) {
+        const int d = threadIdx.x;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < LZ_WARPS; w++) {
+            uint32_t t = wc[w][d];
+            wc[w][d] = run;
+            run += t;
+        }
+        st_vol(&ch.st_cnt[(size_t)tile * 256 + d], (tile == 0 ? LB_INCL : LB_AGG) | run);
+        // look back eight tiles per round trip: the states are read with independent loads, then folded in order. Folding
+        // aggregates instead of waiting for the predecessor's inclusive prefix keeps the tiles from forming a serial chain.
+        uint32_t excl = 0;
+        bool fin = false;
+        for (int64_t t = (int64_t)tile - 1; t >= 0 && !fin; t -= 16) {
+            uint32_t sv[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++) sv[k] = t - k >= 0 ? ld_vol(&ch.st_cnt[(size_t)(t - k) * 256 + d]) : LB_INCL;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                if (fin) break;
+                while ((sv[k] >> 30) == 0) sv[k] = ld_vol(&ch.st_cnt[(size_t)(t - k) * 256 + d]);
+                excl += sv[k] & LB_VAL;
+                if ((sv[k] >> 30) == 2u) fin = true;
+            }
+        }
+        if (tile != 0) st_vol(&ch.st_cnt[(size_t)tile * 256 + d], LB_INCL | (excl + run));
+        goff[d] = bstart[lvl * 257 + d] + excl;
+    }
+    if (GROUP && threadIdx.x == LZ_THREADS - 1) {
+        uint32_t agg = 0;
+        for (int w = 0; w < LZ_WARPS; w++) agg = max(agg, wtot[w]);
+        st_vol(&ch.st_max[tile], (tile == 0 ? LB_INCL : LB_AGG) | agg);
+        uint32_t pre = 0;
+        bool fin = false;
+        for (int64_t t = (int64_t)tile - 1; t >= 0 && !fin; t -= 8) {
+            uint32_t sv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) sv[k] = t - k >= 0 ? ld_vol(&ch.st_max[t - k]) : LB_INCL;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                if (fin) break;
+                while ((sv[k] >> 30) == 0) sv[k] = ld_vol(&ch.st_max[t - k]);
+                pre = max(pre, sv[k] & LB_VAL);
+                if ((sv[k] >> 30) == 2u) fin = true;
+            }
+        }
+        if (tile != 0) st_vol(&ch.st_max[tile], LB_INCL | max(pre, agg));
+        s_pre = pre;
+    }
+    __syncthreads();
+    // ---- group starts, match bookkeeping ----
+    uint32_t carried[LZ_ROUNDS];
+    if (GROUP) {
+        uint32_t pre = s_pre;
+        for (int w = 0; w < warp; w++) pre = max(pre, wtot[w]);
+#pragma unroll
+        for (int r = 0; r < LZ_ROUNDS; r++) {
+            const uint32_t idx = base + r * 32;
+            carried[r] = 0;
+            if (idx < n) {
+                const uint32_t g = max(pre, v[r]);
+                const uint32_t p = pw[r] & LZ_POS_MASK, prev = pprev[r] & LZ_POS_MASK;
+                const bool exists = g != idx && p - prev <= (uint32_t)LZ_WINDOW && lvl <= (pw[r] >> 28);
+                const uint32_t word = g | (exists ? LZ_ALIVE : 0u);
+                gs_final[idx] = word;
+                carried[r] = word;
+                if (!exists && (gw[r] & LZ_ALIVE)) match_rec[p] = (lvl - 1) << 28 | (gw[r] & LZ_GS_MASK);
+                if (exists && lvl == (uint32_t)LZ_LEVELS) match_rec[p] = lvl << 28 | g;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < LZ_ROUNDS; r++) carried[r] = gw[r];
+    }
+    // ---- scatter into the next level's order ----
+    if (SCATTER) {
+        const bool gather = (lvl & 3u) == 3u;
+        uint32_t nd[LZ_ROUNDS];
+        if (gather) {
+#pragma unroll
+            for (int r = 0; r < LZ_ROUNDS; r++) nd[r] = load4(bs + (pw[r] & LZ_POS_MASK) + lvl + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < LZ_ROUNDS; r++) {
+            const uint32_t i = base + r * 32;
+            if (i < n) {
+                const uint32_t d = packed[r] >> 16, rk = packed[r] & 0xffffu;
+                const uint32_t dst = goff[d] + wc[warp][d] + rk;
+                pos_out[dst] = pw[r];
+                gs_out[dst] = carried[r];
+                dig_out[dst] = gather ? nd[r] : dw[r];
+            }
+        }
+    }
+}
+
 // ---- greedy parse: orbit over bestlen[] (orbit.cuh) -------------------------
 struct LzStep {
     __device__ static uint32_t step(uint32_t c) { return c >= (uint32_t)LZ_MINLEN ? c : 1u; }
@@ -477,6 +714,35 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
     KL(lc, KC_LZ_INIT, (lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.A[0], wk.GS[0], wk.dig4[0], wk.match_rec, wk.bitcum, wk.wbase)));
     if (n > 0) {
         const uint32_t nt = cdiv(n, RX_TILE);
+        if (wk.fused) {
+            // key-byte bucket starts of all 15 levels from one byte histogram
+            cudaMemsetAsync(wk.bytehist, 0, 256 * 4, st);
+            KL(lc, KC_RX_HIST, (lz_bytehist_k<<<std::min<uint32_t>(cdiv((size_t)n + LZ_LEVELS, 1024), 1184), 256, 0, st>>>(bs, n + LZ_LEVELS, wk.bytehist)));
+            KL(lc, KC_RX_HIST, (lz_bstart_k<<<LZ_LEVELS, 256, 0, st>>>(bs, n, wk.bytehist, wk.bstart)));
+            // gs_carry[0] <- frame starts (the level-0 "groups")
+            cudaMemcpyAsync(wk.gs_carry[0], wk.GS[0], (size_t)n * 4, cudaMemcpyDeviceToDevice, st);
+            LzChain chain{wk.chain_mem, wk.chain_mem + 1, wk.chain_mem + 1 + nt};
+            for (uint32_t lvl = 0; lvl <= (uint32_t)LZ_LEVELS; lvl++) {
+                cudaMemsetAsync(wk.chain_mem, 0, ((size_t)nt * 257 + 1) * 4, st);  // ticket, st_max[nt], st_cnt[nt][256]
+                uint32_t* gin = wk.gs_carry[lvl & 1];
+                uint32_t* gout = wk.gs_carry[(lvl & 1) ^ 1];
+                uint32_t* din = wk.dig4[lvl & 1];
+                uint32_t* dout = wk.dig4[(lvl & 1) ^ 1];
+                uint32_t* pout = lvl < (uint32_t)LZ_LEVELS ? wk.A[lvl + 1] : nullptr;
+                if (lvl < (uint32_t)LZ_MINLEN)
+                    KL(lc, KC_RX_SCATTER, (lz_level_k<false, false, true><<<nt, LZ_THREADS, 0, st>>>(bs, n, lvl, wk.A[lvl], gin, din, wk.GS[lvl], wk.match_rec, pout,
+                                                                                                     gout, dout, wk.bstart, chain)));
+                else if (lvl == (uint32_t)LZ_MINLEN)
+                    KL(lc, KC_LZ_GROUP, (lz_level_k<true, true, true><<<nt, LZ_THREADS, 0, st>>>(bs, n, lvl, wk.A[lvl], gin, din, wk.GS[lvl], wk.match_rec, pout,
+                                                                                                 gout, dout, wk.bstart, chain)));
+                else if (lvl < (uint32_t)LZ_LEVELS)
+                    KL(lc, KC_LZ_GROUP, (lz_level_k<true, false, true><<<nt, LZ_THREADS, 0, st>>>(bs, n, lvl, wk.A[lvl], gin, din, wk.GS[lvl], wk.match_rec, pout,
+                                                                                                  gout, dout, wk.bstart, chain)));
+                else
+                    KL(lc, KC_LZ_GROUP, (lz_level_k<true, false, false><<<nt, LZ_THREADS, 0, st>>>(bs, n, lvl, wk.A[lvl], gin, din, wk.GS[lvl], wk.match_rec, pout,
+                                                                                                   gout, dout, wk.bstart, chain)));
+            }
+        } else {
         KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{wk.dig4[0], 0u}, n, nt, wk.tile_hist[0])));
         for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
             uint32_t* din = wk.dig4[L & 1];
@@ -508,6 +774,7 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
             else
                 KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                  wk.match_rec, Lnew, dout, th_next)));
+        }
         }
         KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));
     }
