@@ -141,6 +141,8 @@ const char* agmvb_profile_name(int cls);
 int agmvb_profile_read(agmvb_ctx* ctx, uint64_t* counts, double* total_ms);
 
 /* ---- unit-test hooks (thin wrappers over single kernels) ---------------------- */
+/* white-box access to the last decoded chunk's internal buffers (0 bpos, 1 block records, 2 consumed, 3 stale bytes, 4 expansions) */
+int agmvb_test_peek(agmvb_ctx* ctx, int which, void* dst, uint64_t bytes);
 /* AGMV_LZSS (src/agmv_encode.c:106-177) over F byte buffers concatenated in
  * `data` (frame_start has F+1 entries). out receives, per buffer, the bytes the
  * reference writes (ceil(outbits/8), at out + out_off[f]); csize/outbits as the

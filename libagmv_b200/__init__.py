@@ -57,6 +57,7 @@ SYMBOLS = {
     "agmvb_profile_classes": (C.c_int, []),
     "agmvb_profile_name": (C.c_char_p, [C.c_int]),
     "agmvb_profile_read": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_double)]),
+    "agmvb_test_peek": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
     "agmvb_test_lzss": (C.c_int, [C.c_void_p, _u8p, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p, _u32p, _u32p]),
     "agmvb_test_quantize": (C.c_int, [C.c_void_p, _u32p, C.c_uint64, _u32p, _u32p, C.c_int, _u16p]),
     "agmvb_test_assemble": (C.c_int, [C.c_void_p, _u16p, _u16p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, _u8p,
@@ -249,6 +250,11 @@ class Context:
         return {self.lib.agmvb_profile_name(k).decode(): (int(cnt[k]), float(ms[k])) for k in range(n) if cnt[k]}
 
     # ---- unit-test hooks -------------------------------------------------------
+    def test_peek(self, which, dtype, count):
+        out = np.zeros(count, dtype=dtype)
+        self._ck(self.lib.agmvb_test_peek(self.h, which, C.c_void_p(out.ctypes.data), out.nbytes))
+        return out
+
     def test_lzss(self, buffers):
         """buffers: list of bytes/uint8 arrays -> list of (csize, bytes, outbits) as AGMV_LZSS would produce."""
         arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b for b in buffers]

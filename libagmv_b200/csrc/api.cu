@@ -418,15 +418,16 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     // parse segments: one per frame
     std::vector<OrbitSeg> segs(F);
     std::vector<uint32_t> slen(F);
-    uint32_t ntile = 0;
+    uint32_t ntile = 0, max_usize = 1;
     for (uint32_t f = 0; f < F; f++) {
         slen[f] = h_fs[f + 1] - h_fs[f];
+        max_usize = std::max(max_usize, slen[f]);
         segs[f].off = h_fs[f]; segs[f].cap_len = slen[f]; segs[f].tile_base = ntile;
         ntile += orbit_tiles(slen[f]);
     }
     CK(cudaMemcpyAsync(ctx->lz.segs, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->lz.seg_len, slen.data(), F * 4, cudaMemcpyHostToDevice, ctx->st));
-    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, ntile, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
+    lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, ntile, max_usize, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
     CK(cudaStreamSynchronize(ctx->st));  // segs / slen are stack vectors
     TRY(check_launch(ctx, "lzss"));
     uint32_t* hcs = hp + (F + 2);
@@ -684,7 +685,11 @@ static uint64_t lzss_consumed_host(const uint8_t* f, uint64_t len, uint64_t data
     while (bits < nbits && bpos < usize) {
         uint32_t flag = rd(1); bits++;
         if (flag) { rd(8); bits += 8; bpos++; }
-        else { uint64_t off = rd(16); uint32_t l = rd(4); bits += 20; if (off >= 1 && off <= bpos) bpos += l; }
+        else {
+            uint64_t off = rd(16); uint32_t l = rd(4); bits += 20;
+            if (off >= 1 && off <= bpos) bpos += l;                                   // ordinary match
+            else if (off > bpos && off < bpos + l && bpos > 0) bpos += l - (off - bpos);  // unsigned wrap: the tail copies from index 0
+        }
     }
     return rp - data_off;
 }
@@ -849,7 +854,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
     }
     const uint64_t per_frame = worst + (uint64_t)B * 4;
     uint32_t C = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(count, (3ull << 30) / (per_frame * S)));
-    if (C > 4) C &= ~3u;
+    if (C < count && C > 4) C &= ~3u;
 
     std::vector<DecFrame> fr;
     std::vector<DecStep> steps;
@@ -1145,6 +1150,17 @@ extern "C" int agmvb_profile_read(agmvb_ctx* ctx, uint64_t* counts, double* tota
 // ===========================================================================
 // unit-test hooks
 // ===========================================================================
+// Copy an internal decode buffer of the last decoded chunk to the host (debugging / white-box tests):
+// 0 = bpos per frame, 1 = block records, 2 = consumed bytes per frame, 3 = stale bytes, 4 = expanded bitstreams.
+extern "C" int agmvb_test_peek(agmvb_ctx* ctx, int which, void* dst, uint64_t bytes) {
+    if (!ctx || !dst) return ERR_ARG;
+    DBuf* b = which == 0 ? &ctx->d_bpos : which == 1 ? &ctx->d_recs : which == 2 ? &ctx->d_consumed : which == 3 ? &ctx->d_stale : &ctx->d_ebuf;
+    if (!b->p || bytes > b->cap) FAIL(ERR_ARG, "peek: buffer %d has %zu bytes", which, b->cap);
+    CK(cudaMemcpyAsync(dst, b->p, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
 extern "C" int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F, uint8_t* out, uint64_t out_cap,
                                uint64_t* out_off, uint32_t* csize, uint32_t* outbits) {
     if (!ctx || !frame_start || F == 0) return ERR_ARG;

@@ -120,21 +120,33 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
             const uint32_t rel = have ? tk_o[warp][lane] : 0u;
             const uint32_t w = __funnelshift_r(win[warp][rel >> 5], win[warp][(rel >> 5) + 1], rel & 31);
             const bool lit = have && (w & 1u);
-            const uint32_t dd = (w >> 1) & 0xFFFFu;
-            uint32_t l = !have ? 0u : (lit ? 1u : ((w >> 17) & 15u));
+            const uint32_t off_raw = (w >> 1) & 0xFFFFu, len_raw = (w >> 17) & 15u;
+            uint32_t dd = off_raw;
+            uint32_t l = !have ? 0u : (lit ? 1u : len_raw);
             const uint32_t tbits = lit ? 9u : 21u;
-            // output offsets = exclusive prefix of the lengths; a match whose source would start at or beyond the current
-            // output end copies nothing (unsigned compare in the reference) - only possible for damaged trailing tokens
+            // Output offsets = exclusive prefix of the copy lengths. The reference copies byte i of a match iff
+            // (pos - offset + i) < bpos in UNSIGNED arithmetic (src/agmv_decode.c:192-196), so with o = bpos at the token:
+            //   1 <= offset <= o          all `len` bytes from o - offset (overlap allowed);
+            //   o < offset < o + len      the first (offset - o) indices wrap and are skipped, the rest copy from index 0
+            //                             on: len - (offset - o) bytes, i.e. a match of distance o (nothing if o == 0);
+            //   otherwise                 nothing.
+            // Only damaged streams leave the first case. Lengths are settled front to back: everything before the first
+            // lane whose length changes is final.
             uint32_t o;
             while (true) {
                 uint32_t inc = l;
 #pragma unroll
                 for (int k = 1; k < 32; k <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= k) inc += y; }
                 o = bpos + inc - l;
-                const bool bad = have && !lit && l > 0 && !(dd >= 1 && dd <= o);
-                const unsigned bm = __ballot_sync(0xffffffffu, bad);
+                uint32_t l2 = l, d2 = dd;
+                if (have && !lit) {
+                    if (off_raw >= 1 && off_raw <= o) { l2 = len_raw; d2 = off_raw; }
+                    else if (off_raw > o && off_raw < o + len_raw && o > 0) { l2 = len_raw - (off_raw - o); d2 = o; }
+                    else { l2 = 0; d2 = off_raw; }
+                }
+                const unsigned bm = __ballot_sync(0xffffffffu, l2 != l || (l2 > 0 && d2 != dd));
                 if (!bm) break;
-                if (lane == __ffs(bm) - 1) l = 0;  // everything before the first offender is final, so it really is void
+                if (lane == __ffs(bm) - 1) { l = l2; dd = d2; }
             }
             // the reference stops before a token when bpos has reached usize
             const unsigned stop = __ballot_sync(0xffffffffu, have && o >= d.usize);

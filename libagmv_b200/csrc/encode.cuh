@@ -22,6 +22,8 @@ __device__ __forceinline__ void hist_add(unsigned long long* hist, uint32_t q, b
     if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist[q], (unsigned long long)__popc(peers));
 }
 
+// Four pixels per thread. When every lane of the warp holds four equal quantised colours (flat content, the
+// common case in cartoon / UI video) one MATCH round with weight 4 replaces four.
 __global__ void __launch_bounds__(256) hist_vec4_k(const uint4* __restrict__ px4, uint64_t ngroups, int quality, uint32_t mc,
                                                    unsigned long long* __restrict__ hist) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -29,12 +31,20 @@ __global__ void __launch_bounds__(256) hist_vec4_k(const uint4* __restrict__ px4
         uint64_t g = base + threadIdx.x;
         bool valid = g < ngroups;
         uint4 v = valid ? __ldg(px4 + g) : make_uint4(0, 0, 0, 0);
-        uint32_t q0 = quantize_color(v.x, quality), q1 = quantize_color(v.y, quality);
-        uint32_t q2 = quantize_color(v.z, quality), q3 = quantize_color(v.w, quality);
-        hist_add(hist, q0, valid && q0 < mc);
-        hist_add(hist, q1, valid && q1 < mc);
-        hist_add(hist, q2, valid && q2 < mc);
-        hist_add(hist, q3, valid && q3 < mc);
+        const uint32_t q0 = quantize_color(v.x, quality), q1 = quantize_color(v.y, quality);
+        const uint32_t q2 = quantize_color(v.z, quality), q3 = quantize_color(v.w, quality);
+        const bool flat = !valid || (q0 == q1 && q1 == q2 && q2 == q3);
+        if (__all_sync(0xffffffffu, flat)) {
+            const bool ok = valid && q0 < mc;
+            const uint32_t key = ok ? q0 : 0x80000000u + lane_id();
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&hist[q0], 4ull * __popc(peers));
+        } else {
+            hist_add(hist, q0, valid && q0 < mc);
+            hist_add(hist, q1, valid && q1 < mc);
+            hist_add(hist, q2, valid && q2 < mc);
+            hist_add(hist, q3, valid && q3 < mc);
+        }
     }
 }
 

@@ -597,11 +597,11 @@ struct LzVisit {
 __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs, uint32_t F,
                                                  const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum, APtrs A,
                                                  const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
+    const uint32_t i = fs[f] + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fs[f + 1]) return;
     const uint32_t rel = bitcum[i];
     if (rel == EMPTY32) return;
-    uint32_t f = frame_of(fs, F, i);
     const uint32_t rec = match_rec[i];
     uint32_t l = rec >> 28, v, nb;
     if (l >= (uint32_t)LZ_MINLEN) {
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
 // describe the same frames for the parse (filled by the caller, ntile tiles in
 // total). Results: wk.csize, wk.outbits, wk.chunk_off on the device and the chunk
 // image written to `image` (capacity >= 32*F + 9n/8 + 8).
-inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n, uint32_t ntile,
+inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n, uint32_t ntile, uint32_t max_usize,
                               uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
     cudaStream_t st = lc.st;
     const uint32_t nthreads = 256;
@@ -784,7 +784,8 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         APtrs ap;
         for (int l = 0; l <= LZ_LEVELS; l++) { ap.a[l] = wk.A[l]; ap.gs[l] = wk.GS[l]; }
-        KL(lc, KC_LZ_PACK, (lz_pack_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, wk.wbase, wk.out_words)));
+        dim3 pgrid(cdiv(max_usize, nthreads), F);
+        KL(lc, KC_LZ_PACK, (lz_pack_k<<<pgrid, nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, wk.wbase, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
