@@ -335,13 +335,17 @@ def run_b200(args):
         alg_step = ALG_BYTES[name](stats) if name in ALG_BYTES else None
         per_launch_ms = ms / cnt
         roof = {"kernel": name, "bound": "hbm", "launches_in_region": cnt, "avg_launch_ms": per_launch_ms, "peak": peak, "unit": "GB/s",
-                "peak_source": peak_src, "traffic": TRAFFIC_NCU.get(name)}
+                "peak_source": peak_src, "traffic": None}
         if alg_step is not None:
             bytes_per_launch = alg_step * args.steps / cnt
             roof["achieved"] = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
             roof["frac"] = roof["achieved"] / peak
             roof["algorithmic_bytes_per_launch"] = bytes_per_launch
             roof["algorithmic_bytes_rule"] = ALG_RULE.get(name)
+            ratio = TRAFFIC_NCU.get("traffic_over_algorithmic", {}).get(name)
+            if ratio is not None:  # measured DRAM bytes per algorithmic byte (ncu --set full, profiles/), scaled to this run's launch size
+                roof["traffic"] = ratio * bytes_per_launch
+                roof["traffic_source"] = "profiles/traffic.json: dram__bytes_read+write per launch / algorithmic bytes per launch at capture, x this run's algorithmic bytes per launch"
         # the whole path against its compulsory traffic: encode 8*W*H per source frame + chunks out,
         # decode chunks in + 4*W*H out per frame
         enc_bytes = 8.0 * P * n_local + 24.0 * n_enc + csize_total
@@ -362,7 +366,8 @@ def run_b200(args):
         "detail": {"encode_source_fps": n_total * args.steps / (enc_ms * 1e-3), "encode_encoded_fps": n_enc * world * args.steps / (enc_ms * 1e-3),
                    "decode_fps": n_enc * world * args.steps / (dec_ms * 1e-3),
                    "kernel_ms_per_step": {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
-                   "profiled_ms_per_step": prof_ms / args.steps},
+                   "profiled_ms_per_step": prof_ms / args.steps,
+                   "alg_bytes_per_launch": {k: ALG_BYTES[k](stats) * args.steps / v[0] for k, v in prof.items() if k in ALG_BYTES}},
         "gpu_launches": int(launches), "clocks": clocks, "e2e": e2e, "roofline": roof,
     }
     if not args.no_cpu_baseline:

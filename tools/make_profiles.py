@@ -77,7 +77,16 @@ def main():
                 per.append(rd + wr)
             if m.group(1) in CLASS_OF and per:
                 traffic[CLASS_OF[m.group(1)]] = sum(per) / len(per)
-    json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, bench.py --frames 256 (ncu --set full)", **traffic},
+    ratio = {}
+    try:
+        plain = json.load(open(os.path.join(OUT, f"plain_{tag}.json")))
+        alg = plain["detail"]["alg_bytes_per_launch"]
+        ratio = {k: traffic[k] / alg[k] for k in traffic if k in alg and alg[k] > 0}
+    except Exception as e:
+        print("no algorithmic bytes in the plain run:", e)
+    json.dump({"note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu --set full) of bench.py --frames 256; "
+                       "traffic_over_algorithmic = that / the algorithmic bytes per launch of the same run",
+               "dram_bytes_per_launch": traffic, "traffic_over_algorithmic": ratio},
               open(os.path.join(PROF, "traffic.json"), "w"), indent=1)
     print(open(os.path.join(PROF, f"{tag}_launches.csv")).read()[:2500])
 
