@@ -98,6 +98,21 @@ int agmvb_enc_image_ptr(agmvb_ctx* ctx, uint8_t** dev_image, uint64_t* bytes);
 int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
                           uint32_t create_n, uint32_t fps, int opt, int quality, int compression,
                           uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+/* The reference's other two sequence encoders, same conventions as agmvb_encode_sequence:
+ * AGMV_EncodeVideo (src/agmv_encode.c:719-2268): a pair of frames is merged only if the fraction of grey-equal pixels
+ * (AGMV_CompareFrameSimilarity, src/agmv_utils.c:920-947) reaches the profile's leniency; no audio chunks;
+ * AGMV_EncodeFullAGMV (src/agmv_encode.c:3659-4407): every frame encoded, no audio chunks, header not back-patched. */
+int agmvb_encode_video(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h, uint32_t fps,
+                       int opt, int quality, int compression, uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+int agmvb_encode_full(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                      uint32_t create_n, uint32_t fps, int opt, int quality, int compression,
+                      uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+/* AGMV_CompareFrameSimilarity's numerator for n_pairs frame pairs (indices into `frames`, coded size). */
+int agmvb_frame_similarity(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames_in_buffer, int on_device,
+                           const int32_t* pair_a, const int32_t* pair_b, uint32_t n_pairs, uint64_t* counts);
+/* Whether agmvb_enc_frames appends the empty 'AGAC' chunk after every frame chunk (AGMV_EncodeAGMV does, the per-frame
+ * AGMV_EncodeFrame and the other two encoders do not). Default on. */
+int agmvb_enc_set_audio_stub(agmvb_ctx* ctx, int on);
 /* Header only (AGMV_EncodeHeader, src/agmv_encode.c:21-94) with the current palette. */
 int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps, uint8_t* out, uint64_t cap, uint64_t* len);
 

@@ -107,6 +107,13 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
                      u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
                      AGMV_COMPRESSION compression);
 
+/* the other two sequence encoders: include/agmv_encode.h:35,37 */
+void AGMV_EncodeVideo(const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame, u32 end_frame, u32 width,
+                      u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality, AGMV_COMPRESSION compression);
+void AGMV_EncodeFullAGMV(AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame,
+                         u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
+                         AGMV_COMPRESSION compression);
+
 /* decode: include/agmv_decode.h:21-22,26 */
 int AGMV_DecodeHeader(FILE* file, AGMV* agmv);
 int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv);

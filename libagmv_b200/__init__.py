@@ -46,6 +46,12 @@ SYMBOLS = {
     "agmvb_enc_header": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint64, _u64p]),
     "agmvb_encode_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "agmvb_encode_video": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "agmvb_encode_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
+                                    C.c_int, C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "agmvb_frame_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, _i32p, _i32p, C.c_uint32, _u64p]),
+    "agmvb_enc_set_audio_stub": (C.c_int, [C.c_void_p, C.c_int]),
     "agmvb_dec_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int), _u32p, _u32p, _u32p]),
     "agmvb_dec_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int]),
     "agmvb_dec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
@@ -138,6 +144,21 @@ class Context:
         ln, ne = C.c_uint64(), C.c_uint32()
         self._ck(self.lib.agmvb_encode_sequence(self.h, C.c_void_p(src), on_dev, n, w, h, create_n, fps, opt, quality,
                                                 compression, C.c_void_p(out.ctypes.data), out.size, C.byref(ln), C.byref(ne)))
+        return out[:ln.value], ne.value
+
+    def encode_mode(self, mode, frames, create_n, fps, opt, quality, compression=LZSS):
+        """mode 'video' = AGMV_EncodeVideo, 'full' = AGMV_EncodeFullAGMV, on host frames (n,h,w) uint32."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint32)
+        n, h, w = frames.shape
+        out = np.empty(4096 + n * (w * h * 3 + 64), dtype=np.uint8)
+        ln, ne = C.c_uint64(), C.c_uint32()
+        if mode == "video":
+            rc = self.lib.agmvb_encode_video(self.h, C.c_void_p(frames.ctypes.data), 0, n, w, h, fps, opt, quality, compression,
+                                             C.c_void_p(out.ctypes.data), out.size, C.byref(ln), C.byref(ne))
+        else:
+            rc = self.lib.agmvb_encode_full(self.h, C.c_void_p(frames.ctypes.data), 0, n, w, h, create_n, fps, opt, quality, compression,
+                                            C.c_void_p(out.ctypes.data), out.size, C.byref(ln), C.byref(ne))
+        self._ck(rc)
         return out[:ln.value], ne.value
 
     def enc_begin(self, w, h, opt, quality, compression=LZSS):

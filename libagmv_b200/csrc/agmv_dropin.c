@@ -7,8 +7,8 @@
  * (if the GPU layer fails, the encode functions report to stderr and the decode functions
  * return MEMORY_CORRUPTION_ERR, the only channel the reference API offers - SURVEY.md 8b).
  *
- * Out of scope here: audio tracks (#16), image formats other than BMP
- * (#18, AGIDL), the similarity-gated / full encoders (#14, #15).
+ * Out of scope here: audio tracks (#16) and image formats other than BMP
+ * (#18, AGIDL).
  */
 #include "agmv_dropin.h"
 
@@ -237,12 +237,13 @@ void AGMV_EncodeFrame(FILE* file, AGMV* agmv, u32* img_data) {
     }
     int32_t sa = 0, sb = -1;
     uint64_t nbytes = 0;
+    if (!rc) rc = agmvb_enc_set_audio_stub(c, 0); /* the 'AGAC' chunk is AGMV_EncodeAudioChunk's, not ours */
     if (!rc) rc = agmvb_enc_frames(c, px, 1, 0, &sa, &sb, 1, (uint32_t)agmv->frame_count, &nbytes);
     uint8_t* img = (uint8_t*)malloc(nbytes + 16);
     uint32_t us = 0, cs = 0;
     if (!rc) rc = agmvb_enc_fetch(c, img, nbytes, &us, &cs);
     if (!rc) {
-        fwrite(img, 1, (size_t)nbytes - 8, file); /* chunk + trailer; the 'AGAC' stub is AGMV_EncodeAudioChunk's, not ours */
+        fwrite(img, 1, (size_t)nbytes, file); /* 'AGFC' header, payload, 8 x 0xFF */
         agmv->bitstream->pos = us;
         if (is_i) {
             rc = agmvb_enc_get_iframe_entries(c, ent);
@@ -291,6 +292,7 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
     const int cur_dir = dir[0] == 'c' && dir[1] == 'u' && dir[2] == 'r'; /* :2373 */
     char path[512];
     int rc = agmvb_enc_begin(c, (uint32_t)width, (uint32_t)height, (int)opt, (int)quality, (int)compression);
+    if (!rc) rc = agmvb_enc_set_audio_stub(c, 1); /* AGMV_EncodeAudioChunk after every frame: 'AGAC' 0 when there is no audio */
     g_enc.valid = 0;
     /* frames are streamed from disk twice, like the reference: once for the histogram, once for the encode */
     const u32 CH = 64; /* source frames per upload; a multiple of 16 keeps LIGHT groups and GOPs whole */
@@ -378,6 +380,81 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
         }
         free(data);
     }
+}
+
+/* the GBA profiles also dump the stream as a C header (src/agmv_encode.c:3627-3656) */
+static void export_gba_header(const char* filename) {
+    FILE* in = fopen(filename, "rb");
+    if (!in) return;
+    fseek(in, 0, SEEK_END);
+    long size = ftell(in);
+    fseek(in, 0, SEEK_SET);
+    uint8_t* data = (uint8_t*)malloc((size_t)size);
+    if (fread(data, 1, (size_t)size, in) != (size_t)size) { }
+    fclose(in);
+    FILE* out = fopen("GBA_GEN_AGMV.h", "w");
+    if (out) {
+        fprintf(out, "#ifndef GBA_GEN_AGMV_H\n#define GBA_GEN_AGMV_H\n\nconst unsigned char GBA_AGMV_FILE[%ld] = {\n", size);
+        for (long k = 0; k < size; k++) {
+            if (k != 0 && k % 4000 == 0) fprintf(out, "\n");
+            fprintf(out, "%d,", data[k]);
+        }
+        fprintf(out, "};\n\n#endif");
+        fclose(out);
+    }
+    free(data);
+}
+
+/* AGMV_EncodeVideo (src/agmv_encode.c:719-2268) and AGMV_EncodeFullAGMV (:3659-4407), BMP input: the whole sequence is
+ * loaded and handed to the GPU layer in one call (the similarity-gated schedule needs every consecutive pair). */
+static void encode_whole(int video, AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame,
+                         u32 end_frame, u32 width, u32 height, u32 fps, AGMV_OPT opt, AGMV_QUALITY quality, AGMV_COMPRESSION compression) {
+    agmvb_ctx* c = ctx_get();
+    if (!c) { if (agmv) DestroyAGMV(agmv); return; }
+    if (img_type != AGMV_IMG_BMP) {
+        fprintf(stderr, "libagmv_dropin: only BMP input is served (image decoding is AGIDL's, out of scope)\n");
+        if (agmv) DestroyAGMV(agmv);
+        return;
+    }
+    const u32 n_src = end_frame - start_frame + 1;
+    const size_t SP = (size_t)width * height;
+    const int cur_dir = dir[0] == 'c' && dir[1] == 'u' && dir[2] == 'r';
+    uint32_t* buf = (uint32_t*)malloc((size_t)n_src * SP * 4);
+    char path[512];
+    int rc = 0;
+    for (u32 k = 0; k < n_src && !rc; k++) {
+        if (cur_dir) snprintf(path, sizeof path, "%s%lu.bmp", basename, start_frame + k);
+        else snprintf(path, sizeof path, "%s/%s%lu.bmp", dir, basename, start_frame + k);
+        if (load_bmp(path, width, height, buf + (size_t)k * SP)) rc = AGMVB_ERR_FILE;
+    }
+    uint64_t cap = 4096 + (uint64_t)n_src * (SP * 3 + 64), len = 0;
+    uint8_t* out = (uint8_t*)malloc(cap);
+    uint32_t nenc = 0;
+    if (!rc) {
+        if (video) rc = agmvb_encode_video(c, buf, 0, (uint32_t)n_src, (uint32_t)width, (uint32_t)height, (uint32_t)fps, (int)opt, (int)quality,
+                                           (int)compression, out, cap, &len, &nenc);
+        else rc = agmvb_encode_full(c, buf, 0, (uint32_t)n_src, (uint32_t)width, (uint32_t)height, (uint32_t)agmv->header.num_of_frames,
+                                    (uint32_t)agmv->header.frames_per_second, (int)opt, (int)quality, (int)compression, out, cap, &len, &nenc);
+    }
+    g_enc.valid = 0;
+    if (rc) fail(rc, video ? "AGMV_EncodeVideo" : "AGMV_EncodeFullAGMV");
+    else {
+        FILE* f = fopen(filename, "wb");
+        if (f) { fwrite(out, 1, (size_t)len, f); fclose(f); }
+    }
+    free(buf); free(out);
+    if (agmv) DestroyAGMV(agmv);
+    if (!rc && (opt == AGMV_OPT_GBA_I || opt == AGMV_OPT_GBA_II || opt == AGMV_OPT_GBA_III)) export_gba_header(filename);
+}
+
+void AGMV_EncodeVideo(const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame, u32 end_frame, u32 width,
+                      u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality, AGMV_COMPRESSION compression) {
+    encode_whole(1, NULL, filename, dir, basename, img_type, start_frame, end_frame, width, height, frames_per_second, opt, quality, compression);
+}
+
+void AGMV_EncodeFullAGMV(AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame, u32 end_frame,
+                         u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality, AGMV_COMPRESSION compression) {
+    encode_whole(0, agmv, filename, dir, basename, img_type, start_frame, end_frame, width, height, frames_per_second, opt, quality, compression);
 }
 
 /* ------------------------------------------------------------------------------------ */

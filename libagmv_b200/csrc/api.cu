@@ -436,7 +436,7 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     for (uint32_t f = 0; f < F; f++) {
         ctx->last_usize.push_back(h_fs[f + 1] - h_fs[f]);
         ctx->last_csize.push_back(hcs[f]);
-        ctx->image_bytes += 32ull + hcs[f];
+        ctx->image_bytes += 24ull + ctx->lz.stub_bytes + hcs[f];
     }
     return OK;
 }
@@ -547,6 +547,47 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
     return OK;
 }
 
+extern "C" int agmvb_enc_set_audio_stub(agmvb_ctx* ctx, int on) {
+    if (!ctx) return ERR_ARG;
+    ctx->lz.stub_bytes = on ? 8u : 0u;
+    return OK;
+}
+
+// counts[k] = number of grey-equal pixels of coded frames (pair_a[k], pair_b[k]) (AGMV_CompareFrameSimilarity)
+extern "C" int agmvb_frame_similarity(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_frames_in_buffer, int on_device,
+                                      const int32_t* pair_a, const int32_t* pair_b, uint32_t n_pairs, uint64_t* counts) {
+    if (!ctx || !ctx->enc_ready || !frames || !pair_a || !pair_b || !counts) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (n_pairs == 0) return OK;
+    const size_t SP = (size_t)ctx->src_w * ctx->src_h, P = (size_t)ctx->cw * ctx->ch;
+    const uint32_t* base = frames;
+    if (!on_device) {
+        TRY(ensure(ctx, ctx->stage, n_frames_in_buffer * SP * 4));
+        CK(cudaMemcpyAsync(ctx->stage.p, frames, n_frames_in_buffer * SP * 4, cudaMemcpyHostToDevice, ctx->st));
+        base = ctx->stage.as<uint32_t>();
+    }
+    std::vector<SrcPair> sp(n_pairs);
+    for (uint32_t k = 0; k < n_pairs; k++) {
+        if (pair_a[k] < 0 || pair_b[k] < 0 || (uint64_t)pair_a[k] >= n_frames_in_buffer || (uint64_t)pair_b[k] >= n_frames_in_buffer)
+            FAIL(ERR_ARG, "pair %u out of range", k);
+        sp[k].a = base + (size_t)pair_a[k] * SP;
+        sp[k].b = base + (size_t)pair_b[k] * SP;
+    }
+    TRY(ensure(ctx, ctx->srcpairs, n_pairs * sizeof(SrcPair)));
+    TRY(ensure(ctx, ctx->small, (size_t)n_pairs * 8));
+    CK(cudaMemcpyAsync(ctx->srcpairs.p, sp.data(), n_pairs * sizeof(SrcPair), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemsetAsync(ctx->small.p, 0, (size_t)n_pairs * 8, ctx->st));
+    for (uint32_t k0 = 0; k0 < n_pairs; k0 += 32768) {
+        dim3 grid(std::min<uint32_t>(cdiv(P, 1024), 64), std::min<uint32_t>(32768, n_pairs - k0));
+        KL(ctx->lc, KC_MISC, (similarity_k<<<grid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>() + k0, ctx->d_map, (uint32_t)P,
+                                                                    ctx->small.as<unsigned long long>() + k0)));
+    }
+    TRY(check_launch(ctx, "similarity"));
+    CK(cudaMemcpyAsync(counts, ctx->small.p, (size_t)n_pairs * 8, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
 extern "C" int agmvb_enc_fetch(agmvb_ctx* ctx, uint8_t* image, uint64_t cap, uint32_t* usize, uint32_t* csize) {
     if (!ctx) return ERR_ARG;
     if (image) {
@@ -592,11 +633,14 @@ extern "C" int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps,
     return OK;
 }
 
-extern "C" int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
-                                     uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
-                                     uint64_t* out_len, uint32_t* n_encoded) {
+enum { SEQ_AGMV = 0, SEQ_VIDEO = 1, SEQ_FULL = 2 };
+
+static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                                uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
+                                uint64_t* out_len, uint32_t* n_encoded) {
     if (!ctx || !frames || !out || n_src < 2) return ERR_ARG;
     TRY(agmvb_enc_begin(ctx, w, h, opt, quality, compression));
+    ctx->lz.stub_bytes = mode == SEQ_AGMV ? 8u : 0u;  // only AGMV_EncodeAGMV interleaves (empty) audio chunks
     if (!on_device) {
         // both passes read every frame: upload once when the sequence fits comfortably, else stream it twice
         size_t free_b = 0, total_b = 0;
@@ -611,41 +655,88 @@ extern "C" int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int
     }
     TRY(agmvb_enc_histogram(ctx, frames, n_src, on_device));  // every source frame, unscaled (:2371-2568)
     TRY(agmvb_enc_build_palette(ctx));
-    // PDIFS schedule (:2727-2770) and loop exit (:3610-3612); frame numbers are 1-based in the reference
+    // frame numbers are 1-based in the reference: source frame i is frames[i - 1]
     const uint32_t start = 1, end = n_src;
     std::vector<int32_t> sa, sb;
-    for (uint32_t i = start; i <= end;) {
-        if (ctx->light) {
-            if (i + 3 > end) FAIL(ERR_ARG, "sequence too short for the LIGHT schedule");
-            sa.push_back(i - 1); sb.push_back(-1);
-            sa.push_back(i); sb.push_back(i + 1);
-            sa.push_back(i + 2); sb.push_back(-1);
-            i += 4;
-        } else {
-            if (i + 1 > end) FAIL(ERR_ARG, "sequence too short for the HEAVY schedule");
-            sa.push_back(i - 1); sb.push_back(i);
-            i += 2;
+    if (mode == SEQ_FULL) {  // AGMV_EncodeFullAGMV (:4041-4370): every frame as it is
+        for (uint32_t i = start; i <= end; i++) { sa.push_back(i - 1); sb.push_back(-1); }
+    } else {
+        // AGMV_EncodeVideo (:1109-2222) merges a pair only if enough pixels have equal grey values; the ratios of all
+        // candidate pairs are measured up front (one launch), the data-dependent walk is then host logic
+        std::vector<uint64_t> eq;
+        float leniency = 0.f;
+        if (mode == SEQ_VIDEO) {
+            leniency = opt == OPT_II ? (float)0.1282 : ((opt == OPT_GBA_I || opt == OPT_GBA_II || opt == OPT_GBA_III) ? 0.0f : (float)0.2282);  // :741-790
+            std::vector<int32_t> pa(n_src - 1), pb(n_src - 1);
+            for (uint32_t k = 0; k + 1 < n_src; k++) { pa[k] = k; pb[k] = k + 1; }
+            eq.resize(n_src - 1);
+            TRY(agmvb_frame_similarity(ctx, frames, n_src, on_device, pa.data(), pb.data(), n_src - 1, eq.data()));
         }
-        if (i + 4 >= end) break;
+        const size_t P = (size_t)ctx->cw * ctx->ch;
+        // PDIFS schedule (:2727-2770) and loop exit (:3610-3612)
+        for (uint32_t i = start; i <= end;) {
+            bool merge = true;
+            if (mode == SEQ_VIDEO) {
+                const uint32_t a = ctx->light ? i + 1 : i;  // 1-based first frame of the pair that would be merged
+                if (a + 1 > end) FAIL(ERR_ARG, "sequence too short for AGMV_EncodeVideo's look-ahead");
+                merge = (eq[a - 1] / (float)P) >= leniency;
+            }
+            if (!merge) { sa.push_back(i - 1); sb.push_back(-1); i += 1; }
+            else if (ctx->light) {
+                if (i + 3 > end) FAIL(ERR_ARG, "sequence too short for the LIGHT schedule");
+                sa.push_back(i - 1); sb.push_back(-1);
+                sa.push_back(i); sb.push_back(i + 1);
+                sa.push_back(i + 2); sb.push_back(-1);
+                i += 4;
+            } else {
+                if (i + 1 > end) FAIL(ERR_ARG, "sequence too short for the HEAVY schedule");
+                sa.push_back(i - 1); sb.push_back(i);
+                i += 2;
+            }
+            if (i + 4 >= end) break;
+        }
     }
     uint64_t hdr_len = 0, img = 0;
     TRY(agmvb_enc_header(ctx, create_n, fps, out, cap, &hdr_len));
     TRY(agmvb_enc_frames(ctx, frames, n_src, on_device, sa.data(), sb.data(), (uint32_t)sa.size(), 0, &img));
     if (hdr_len + img > cap) FAIL(ERR_ARG, "output buffer too small: need %llu", (unsigned long long)(hdr_len + img));
     TRY(agmvb_enc_fetch(ctx, out + hdr_len, cap - hdr_len, nullptr, nullptr));
-    // back-patch (:3615-3620)
-    uint32_t adjusted = end - start;
-    switch (opt) {  // :2296-2353
-        case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
-        case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
-        default: adjusted = (uint32_t)(adjusted * 0.75); break;
+    if (mode == SEQ_AGMV) {  // back-patch (:3615-3620)
+        uint32_t adjusted = end - start;
+        switch (opt) {  // :2296-2353
+            case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
+            case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
+            default: adjusted = (uint32_t)(adjusted * 0.75); break;
+        }
+        put32(out + 4, (uint32_t)sa.size());
+        float rate = (float)adjusted / (create_n + 1);
+        put32(out + 18, (uint32_t)round(fps * rate));
+    } else if (mode == SEQ_VIDEO) {  // :2223-2230
+        put32(out + 4, (uint32_t)sa.size());
+        float rate = (float)sa.size() / create_n;
+        put32(out + 18, (uint32_t)round(fps * rate));
     }
-    put32(out + 4, (uint32_t)sa.size());
-    float rate = (float)adjusted / (create_n + 1);
-    put32(out + 18, (uint32_t)round(fps * rate));
+    ctx->lz.stub_bytes = 8;
     if (out_len) *out_len = hdr_len + img;
     if (n_encoded) *n_encoded = (uint32_t)sa.size();
     return OK;
+}
+
+extern "C" int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                                     uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
+                                     uint64_t* out_len, uint32_t* n_encoded) {
+    return encode_sequence_impl(ctx, SEQ_AGMV, frames, on_device, n_src, w, h, create_n, fps, opt, quality, compression, out, cap, out_len, n_encoded);
+}
+// AGMV_EncodeVideo (src/agmv_encode.c:719-2268): similarity-gated PDIFS; the reference creates its own handle with end-start frames
+extern "C" int agmvb_encode_video(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h, uint32_t fps,
+                                  int opt, int quality, int compression, uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded) {
+    return encode_sequence_impl(ctx, SEQ_VIDEO, frames, on_device, n_src, w, h, n_src - 1, fps, opt, quality, compression, out, cap, out_len, n_encoded);
+}
+// AGMV_EncodeFullAGMV (src/agmv_encode.c:3659-4407): no frame skipping, no audio chunks, header left as CreateAGMV set it
+extern "C" int agmvb_encode_full(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
+                                 uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
+                                 uint64_t* out_len, uint32_t* n_encoded) {
+    return encode_sequence_impl(ctx, SEQ_FULL, frames, on_device, n_src, w, h, create_n, fps, opt, quality, compression, out, cap, out_len, n_encoded);
 }
 
 // ===========================================================================

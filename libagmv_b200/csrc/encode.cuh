@@ -250,6 +250,28 @@ __global__ void __launch_bounds__(256) quantize_k(const SrcPair* __restrict__ sr
 }
 
 // ---------------------------------------------------------------------------
+// AGMV_CompareFrameSimilarity (src/agmv_utils.c:920-947), used by AGMV_EncodeVideo to gate frame merging: number of
+// pixels of two frames whose grey value (u8)((r+g+b)/3.0f) is equal. (r+g+b)/3.0f truncates to the integer quotient
+// for every sum in 0..765 (a multiple of 3 divides exactly, anything else stays strictly between two integers), so the
+// float expression is evaluated as an integer division here. grid (blocks, pairs).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) similarity_k(const SrcPair* __restrict__ pairs, const uint32_t* __restrict__ map, uint32_t P,
+                                                    unsigned long long* __restrict__ counts) {
+    const SrcPair sp = pairs[blockIdx.y];
+    uint32_t acc = 0;
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        const uint32_t s = map ? map[p] : p;
+        const uint32_t a = __ldg(sp.a + s), b = __ldg(sp.b + s);
+        const uint32_t ga = (((a >> 16) & 255u) + ((a >> 8) & 255u) + (a & 255u)) / 3u;
+        const uint32_t gb = (((b >> 16) & 255u) + ((b >> 8) & 255u) + (b & 255u)) / 3u;
+        acc += ga == gb;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane_id() == 0 && acc) atomicAdd(&counts[blockIdx.y], (unsigned long long)acc);
+}
+
+// ---------------------------------------------------------------------------
 // K3: 4x4 block classification and bitstream assembly.
 // AGMV_CompareIFrameBlock / AGMV_ComparePFrameBlock (src/agmv_encode.c:240-352)
 // and AGMV_Assemble{I,P}FrameBitstream (:354-527). Record byte: type << 6 | len.

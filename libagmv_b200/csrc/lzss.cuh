@@ -70,6 +70,7 @@ struct LzWork {
     uint32_t* outbits = nullptr;         // cap_frames
     uint32_t* csize = nullptr;           // cap_frames
     uint32_t* chunk_off = nullptr;       // cap_frames + 1
+    uint32_t stub_bytes = 8;             // empty 'AGAC' chunk after every frame chunk (AGMV_EncodeAGMV); 0 for the other encoders
 };
 
 struct APtrs { const uint32_t* a[LZ_LEVELS + 1]; const uint32_t* gs[LZ_LEVELS + 1]; };
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs,
     if (sh + nb > 32) atomicOr(&out_words[w + 1], v >> (32 - sh));
 }
 
-__global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, const uint32_t* __restrict__ total_bits,
+__global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, uint32_t stub, const uint32_t* __restrict__ total_bits,
                                                       uint32_t* __restrict__ outbits, uint32_t* __restrict__ csize,
                                                       uint32_t* __restrict__ chunk_off) {
     __shared__ uint32_t wsum[32];
@@ -660,7 +661,7 @@ __global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, const uint32_t
             uint32_t cs = (uint32_t)((float)(int)ob / 8.0f);  // src/agmv_encode.c:176
             outbits[f] = ob;
             csize[f] = cs;
-            len = 32u + cs;  // AGFC hdr 16 + payload + 8 x 0xFF + empty AGAC chunk 8
+            len = 24u + stub + cs;  // AGFC hdr 16 + payload + 8 x 0xFF (+ empty AGAC chunk 8)
         }
         uint32_t inc = warp_inclusive<SumOp>(len);
         if (lane_id() == 31) wsum[threadIdx.x >> 5] = inc;
@@ -680,9 +681,9 @@ __global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, const uint32_t
 __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restrict__ fs, const uint32_t* __restrict__ csize,
                                                          const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ wbase,
                                                          const uint32_t* __restrict__ out_words, uint32_t first_frame_count,
-                                                         uint8_t* __restrict__ image) {
+                                                         uint32_t stub, uint8_t* __restrict__ image) {
     const uint32_t f = blockIdx.y;
-    const uint32_t cs = csize[f], len = 32u + cs, usize = fs[f + 1] - fs[f];
+    const uint32_t cs = csize[f], len = 24u + stub + cs, usize = fs[f + 1] - fs[f];
     const uint8_t* pay = reinterpret_cast<const uint8_t*>(out_words + wbase[f]);
     uint8_t* dst = image + chunk_off[f];
     const uint32_t num = first_frame_count + f + 1;
@@ -787,9 +788,9 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         dim3 pgrid(cdiv(max_usize, nthreads), F);
         KL(lc, KC_LZ_PACK, (lz_pack_k<<<pgrid, nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, wk.wbase, wk.out_words)));
     }
-    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
+    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
-    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, image)));
+    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, wk.stub_bytes, image)));
 }
 
 }  // namespace agmvb

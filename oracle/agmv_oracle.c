@@ -397,8 +397,21 @@ uint32_t orc_lz77(const uint8_t* in, size_t n, uint8_t* out, size_t* nbytes) { r
 /* ------------------------------------------------------------------ */
 /* whole-sequence encode: src/agmv_encode.c:2270-3657 (BMP case)        */
 /* ------------------------------------------------------------------ */
-long orc_encode_agmv(const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
-                     int opt, int quality, int compression, uint8_t* out, size_t out_cap) {
+/* src/agmv_utils.c:920-947: fraction of pixels whose truncated float grey value is equal */
+static float frame_similarity(const uint32_t* a, const uint32_t* b, size_t n) {
+    unsigned long count = 0;
+    for (size_t i = 0; i < n; i++) {
+        uint8_t g1 = (uint8_t)((cr(a[i]) + cg(a[i]) + cb(a[i])) / 3.0f);
+        uint8_t g2 = (uint8_t)((cr(b[i]) + cg(b[i]) + cb(b[i])) / 3.0f);
+        if (g1 == g2) count++;
+    }
+    return count / (float)n;
+}
+
+enum { MODE_AGMV = 0, MODE_VIDEO = 1, MODE_FULL = 2 };
+
+static long encode_impl(int mode, const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
+                        int opt, int quality, int compression, uint8_t* out, size_t out_cap) {
     int dual = orc_opt_is_dual(opt), light = orc_opt_is_light(opt);
     uint32_t mc = orc_max_clr(quality);
     size_t src_px = (size_t)w * h;
@@ -448,12 +461,24 @@ long orc_encode_agmv(const uint32_t* frames, int n_src, int w, int h, uint32_t c
     long rc = 0;
     int scaled = (cw != w || ch != h);
     float fsx = (float)cw / (unsigned long)w + 0.001f, fsy = (float)ch / (unsigned long)h + 0.001f;
+    /* AGMV_EncodeVideo (src/agmv_encode.c:719-2268): leniency per profile (:741-790), groups gated by frame similarity */
+    float leniency = (opt == ORC_OPT_II) ? (float)0.1282 : ((opt == ORC_OPT_GBA_I || opt == ORC_OPT_GBA_II || opt == ORC_OPT_GBA_III) ? 0.0f : (float)0.2282);
+    uint32_t* sc = (uint32_t*)malloc(px * 4);
+    uint32_t* sd = (uint32_t*)malloc(px * 4);
 
     for (uint32_t i = start; i <= end;) {
         /* the frames this group encodes: LIGHT f(i), interp(f(i+1),f(i+2)), f(i+3); HEAVY interp(f(i),f(i+1)) */
-        int plan[3][2], np;
+        int plan[3][2], np, step = light ? 4 : 2;
         if (light) { np = 3; plan[0][0] = i; plan[0][1] = -1; plan[1][0] = i + 1; plan[1][1] = i + 2; plan[2][0] = i + 3; plan[2][1] = -1; }
         else { np = 1; plan[0][0] = i; plan[0][1] = i + 1; }
+        if (mode == MODE_FULL) { np = 1; plan[0][0] = i; plan[0][1] = -1; step = 1; } /* AGMV_EncodeFullAGMV: every frame as is (:4041-4370) */
+        if (mode == MODE_VIDEO) { /* :1153-1190: the pair that would be merged must be similar enough, else one plain frame */
+            int pa = light ? i + 1 : i, pb = light ? i + 2 : i + 1;
+            if (pb > (int)end) { rc = -3; goto done; }
+            const uint32_t* fa = frames + (size_t)(pa - start) * src_px; const uint32_t* fb = frames + (size_t)(pb - start) * src_px;
+            if (scaled) { int nw, nh; orc_scale_nearest(fa, w, h, fsx, fsy, sc, &nw, &nh); orc_scale_nearest(fb, w, h, fsx, fsy, sd, &nw, &nh); fa = sc; fb = sd; }
+            if (!(frame_similarity(fa, fb, px) >= leniency)) { np = 1; plan[0][0] = i; plan[0][1] = -1; step = 1; }
+        }
         for (int p = 0; p < np; p++) {
             const uint32_t* a; const uint32_t* b = NULL;
             if (plan[p][0] > (int)end || plan[p][1] > (int)end) { rc = -3; goto done; }
@@ -484,23 +509,40 @@ long orc_encode_agmv(const uint32_t* frames, int n_src, int w, int h, uint32_t c
             memcpy(out + o + 16, lz, nbytes);
             o += 16 + csize;                 /* fseek(pos-4), write csize, fseek(csize, CUR) */
             memset(out + o, 0xff, 8); o += 8; /* trailer clobbers the last partial byte */
-            memcpy(out + o, "AGAC", 4); put32(out + o + 4, 0); o += 8; /* empty audio chunk (:707-717) */
+            if (mode == MODE_AGMV) { memcpy(out + o, "AGAC", 4); put32(out + o + 4, 0); o += 8; } /* empty audio chunk (:707-717); the other two encoders write none */
             if (is_i) memcpy(ient, ent, px * 2);
             frame_count++; encoded++;
         }
-        i += light ? 4 : 2;
-        if (i + 4 >= end) break; /* :3610-3612 */
+        i += step;
+        if (mode != MODE_FULL && i + 4 >= end) break; /* :3610-3612, :2220-2222 */
     }
-    /* back-patch (:3615-3620) */
-    put32(out + 4, encoded);
-    {
+    if (mode == MODE_AGMV) { /* back-patch (:3615-3620) */
+        put32(out + 4, encoded);
         float rate = (float)adjusted / (create_n + 1);
+        put32(out + 18, (uint32_t)round(fps * rate));
+    } else if (mode == MODE_VIDEO) { /* :2223-2230 */
+        put32(out + 4, encoded);
+        float rate = (float)encoded / create_n;
         put32(out + 18, (uint32_t)round(fps * rate));
     }
     rc = (long)o;
 done:
-    free(ent); free(ient); free(tmp); free(sa); free(sb); free(bs); free(lz);
+    free(ent); free(ient); free(tmp); free(sa); free(sb); free(bs); free(lz); free(sc); free(sd);
     return rc;
+}
+
+long orc_encode_agmv(const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
+                     int opt, int quality, int compression, uint8_t* out, size_t out_cap) {
+    return encode_impl(MODE_AGMV, frames, n_src, w, h, create_n, fps, opt, quality, compression, out, out_cap);
+}
+/* AGMV_EncodeVideo creates its own handle: CreateAGMV(end-start, ...) (src/agmv_encode.c:722) */
+long orc_encode_video(const uint32_t* frames, int n_src, int w, int h, uint32_t fps, int opt, int quality, int compression,
+                      uint8_t* out, size_t out_cap) {
+    return encode_impl(MODE_VIDEO, frames, n_src, w, h, (uint32_t)(n_src - 1), fps, opt, quality, compression, out, out_cap);
+}
+long orc_encode_full(const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
+                     int opt, int quality, int compression, uint8_t* out, size_t out_cap) {
+    return encode_impl(MODE_FULL, frames, n_src, w, h, create_n, fps, opt, quality, compression, out, out_cap);
 }
 
 /* AGMV_EncodeFrame + the empty AGMV_EncodeAudioChunk for n_enc frames with a given palette, starting at

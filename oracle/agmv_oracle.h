@@ -60,6 +60,12 @@ uint32_t orc_lz77(const uint8_t* in, size_t n, uint8_t* out, size_t* nbytes);
 long orc_encode_agmv(const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
                      int opt, int quality, int compression, uint8_t* out, size_t out_cap);
 
+/* "next" row N1: AGMV_EncodeVideo (similarity-gated PDIFS, src/agmv_encode.c:719-2268) and AGMV_EncodeFullAGMV (:3659-4407) */
+long orc_encode_video(const uint32_t* frames, int n_src, int w, int h, uint32_t fps, int opt, int quality, int compression,
+                      uint8_t* out, size_t out_cap);
+long orc_encode_full(const uint32_t* frames, int n_src, int w, int h, uint32_t create_n, uint32_t fps,
+                     int opt, int quality, int compression, uint8_t* out, size_t out_cap);
+
 /* E11 for a range of encoded frames with a given palette (multi-GPU sharding tests) */
 long orc_encode_frames(const uint32_t* frames, int w, int h, const int32_t* src_a, const int32_t* src_b, int n_enc, uint32_t first_fc,
                        const uint32_t* pal0, const uint32_t* pal1, int dual, uint8_t* out, size_t cap);

@@ -5,13 +5,15 @@
  * a process with anything else). Links against oracle/_ref/libagmv_ref.so,
  * which is compiled from /root/reference where it lies.
  *
- *   ref_encode OUT DIR BASE START END W H FPS OPT QUALITY COMPRESSION CREATE_N
+ *   ref_encode OUT DIR BASE START END W H FPS OPT QUALITY COMPRESSION CREATE_N [MODE]
+ *   MODE: agmv (default) = AGMV_EncodeAGMV, video = AGMV_EncodeVideo, full = AGMV_EncodeFullAGMV
  *
  * mirrors the call sequence of the reference's own examples
  * (examples/simple_video/simple_video.c: CreateAGMV then AGMV_EncodeAGMV).
  */
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 #include <agmv.h>
 
@@ -30,9 +32,16 @@ int main(int argc, char** argv) {
 
     struct timespec t0, t1;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    AGMV* agmv = CreateAGMV(create_n, w, h, fps);
-    AGMV_EncodeAGMV(agmv, out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps,
-                    (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
+    const char* mode = argc > 13 ? argv[13] : "agmv";
+    if (!strcmp(mode, "video")) {
+        AGMV_EncodeVideo(out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps, (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
+    } else {
+        AGMV* agmv = CreateAGMV(create_n, w, h, fps);
+        if (!strcmp(mode, "full"))
+            AGMV_EncodeFullAGMV(agmv, out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps, (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
+        else
+            AGMV_EncodeAGMV(agmv, out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps, (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
+    }
     clock_gettime(CLOCK_MONOTONIC, &t1);
     fprintf(stderr, "ref_encode_seconds %.6f\n",
             (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));

@@ -102,6 +102,35 @@ def oracle_encode(frames, create_n, fps, opt, quality, compression=LZSS):
     return out[:ln].tobytes()
 
 
+def oracle_encode_mode(mode, frames, create_n, fps, opt, quality, compression=LZSS):
+    """mode 'video' = AGMV_EncodeVideo, 'full' = AGMV_EncodeFullAGMV."""
+    lib = oracle()
+    n, h, w = frames.shape
+    frames = np.ascontiguousarray(frames, dtype=np.uint32)
+    cap = 2048 + n * (w * h * 3 + 64)
+    out = np.zeros(cap, dtype=np.uint8)
+    if mode == "video":
+        lib.orc_encode_video.restype = C.c_long
+        lib.orc_encode_video.argtypes = [_u32p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_int, _u8p, C.c_size_t]
+        ln = lib.orc_encode_video(ptr(frames, _u32p), n, w, h, fps, opt, quality, compression, ptr(out, _u8p), cap)
+    else:
+        lib.orc_encode_full.restype = C.c_long
+        lib.orc_encode_full.argtypes = [_u32p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int, _u8p, C.c_size_t]
+        ln = lib.orc_encode_full(ptr(frames, _u32p), n, w, h, create_n, fps, opt, quality, compression, ptr(out, _u8p), cap)
+    assert ln > 0, f"oracle encode failed rc={ln}"
+    return out[:ln].tobytes()
+
+
+def scene_cut_frames(w, h, n, every=5, seed=1234):
+    """Synthetic frames with a scene cut (new tile colours) every `every` frames: consecutive frames inside a scene are
+    ~2/3 grey-equal, across a cut ~0, so AGMV_EncodeVideo's similarity gate takes both branches."""
+    out = np.empty((n, h, w), dtype=np.uint32)
+    lib = oracle()
+    for k in range(n):
+        lib.orc_synth_frame(w, h, k + 1, seed + 7 * (k // every), ptr(out[k], _u32p))
+    return out
+
+
 def oracle_decode(data):
     lib = oracle()
     buf = np.frombuffer(data, dtype=np.uint8).copy()
@@ -130,14 +159,14 @@ def have_ref():
     return os.path.exists(os.path.join(REF_DIR, "ref_encode")) and os.path.exists(os.path.join(REF_DIR, "ref_decode"))
 
 
-def ref_encode(frames, create_n, fps, opt, quality, compression=LZSS, workdir=None, timing=None):
+def ref_encode(frames, create_n, fps, opt, quality, compression=LZSS, workdir=None, timing=None, mode="agmv"):
     """Run the reference encoder on BMP files of `frames` (frames 1..n). Returns .agmv bytes."""
     n, h, w = frames.shape
     with tempfile.TemporaryDirectory(dir=workdir) as td:
         # the reference formats paths into char[60] (src/agmv_encode.c:2372): keep them short
         write_bmps(frames, td, "f", 1)
         res = subprocess.run([os.path.join(REF_DIR, "ref_encode"), "o.agmv", ".", "f", "1", str(n), str(w), str(h),
-                              str(fps), str(opt), str(quality), str(compression), str(create_n)],
+                              str(fps), str(opt), str(quality), str(compression), str(create_n), mode],
                              cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         if timing is not None:
             for line in res.stderr.decode().splitlines():

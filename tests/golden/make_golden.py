@@ -19,7 +19,7 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
-from agmv_testlib import (GOLDEN_DIR, LZSS, OPT, QUALITY, REF_DIR, ref_decode_raw, ref_encode, sha256,  # noqa: E402
+from agmv_testlib import (GOLDEN_DIR, LZSS, OPT, QUALITY, REF_DIR, ref_decode_raw, ref_encode, scene_cut_frames, sha256,  # noqa: E402
                           synth_frames)
 
 # name, w, h, n_frames, create_n, fps, opt, quality, keep_file
@@ -34,6 +34,17 @@ ENCODE_CASES = [
     ("c1_320x240_I_LOW", 320, 240, 212, 212, 24, "I", "LOW", False),
     ("c2_gba_full_GBA_I_LOW", 240, 160, 212, 211, 16, "GBA_I", "LOW", False),
     ("syn64_III_HIGH", 64, 64, 12, 11, 24, "III", "HIGH", True),
+]
+
+# "next" row N1: the other two sequence encoders, on frames with scene cuts so that AGMV_EncodeVideo's similarity gate
+# takes both branches. name, mode, w, h, n_frames, create_n, fps, opt, quality
+MODE_CASES = [
+    ("video64_III_LOW", "video", 64, 64, 24, 23, 24, "III", "LOW"),
+    ("video64_I_LOW", "video", 64, 64, 24, 23, 24, "I", "LOW"),
+    ("video64_II_MID", "video", 64, 64, 24, 23, 24, "II", "MID"),
+    ("video240_GBA_I_LOW", "video", 240, 160, 24, 23, 16, "GBA_I", "LOW"),
+    ("full64_III_LOW", "full", 64, 64, 24, 23, 24, "III", "LOW"),
+    ("full64_ANIM_LOW", "full", 64, 64, 10, 10, 24, "ANIM", "LOW"),
 ]
 
 
@@ -114,6 +125,26 @@ def main():
                 f.write(data)
             entry["file"] = name + ".agmv"
         gold["encode"][name] = entry
+        print(f"{name}: {len(data)} B, {dec.shape[0]} frames, {time.time() - t0:.1f}s", flush=True)
+        json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
+
+    gold.setdefault("encode_modes", {})
+    for name, mode, w, h, n, create_n, fps, opt, q in MODE_CASES:
+        if args.only and args.only != name:
+            continue
+        if name in gold["encode_modes"] and not args.only:
+            continue
+        t0 = time.time()
+        frames = scene_cut_frames(w, h, n)
+        data = ref_encode(frames, create_n, fps, OPT[opt], QUALITY[q], LZSS, mode=mode)
+        rc, dec = ref_decode_raw(data)
+        assert rc == 0
+        with open(os.path.join(GOLDEN_DIR, name + ".agmv"), "wb") as f:
+            f.write(data)
+        gold["encode_modes"][name] = dict(mode=mode, w=w, h=h, n=n, create_n=create_n, fps=fps, opt=opt, quality=q, size=len(data),
+                                          sha256=sha256(data), file=name + ".agmv", frames_field=int.from_bytes(data[4:8], "little"),
+                                          fps_field=int.from_bytes(data[18:22], "little"), decoded_shape=list(dec.shape),
+                                          decoded_frame_sha256=[sha256(dec[k].tobytes()) for k in range(dec.shape[0])])
         print(f"{name}: {len(data)} B, {dec.shape[0]} frames, {time.time() - t0:.1f}s", flush=True)
         json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
 

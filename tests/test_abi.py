@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 def test_dropin_exports_reference_api():
     dl = C.CDLL(libagmv_b200.DROPIN_PATH)
     for n in ["CreateAGMV", "DestroyAGMV", "AGMV_EncodeAGMV", "AGMV_DecodeAGMV", "AGMV_EncodeFrame", "AGMV_DecodeFrameChunk",
-              "AGMV_DecodeHeader", "AGMV_EncodeHeader"]:
+              "AGMV_DecodeHeader", "AGMV_EncodeHeader", "AGMV_EncodeVideo", "AGMV_EncodeFullAGMV"]:
         assert hasattr(dl, n), n
 
 

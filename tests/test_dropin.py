@@ -81,6 +81,10 @@ def _dropin():
     lib.AGMV_DecodeFrameChunk.argtypes = [C.c_void_p, C.POINTER(AGMV)]
     lib.AGMV_EncodeFrame.restype = None
     lib.AGMV_EncodeFrame.argtypes = [C.c_void_p, C.POINTER(AGMV), C.POINTER(UL)]
+    lib.AGMV_EncodeVideo.restype = None
+    lib.AGMV_EncodeVideo.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_uint8, UL, UL, UL, UL, UL, C.c_int, C.c_int, C.c_int]
+    lib.AGMV_EncodeFullAGMV.restype = None
+    lib.AGMV_EncodeFullAGMV.argtypes = lib.AGMV_EncodeAGMV.argtypes
     lib.AGMV_B200_LastError.restype = C.c_char_p
     return lib
 
@@ -221,3 +225,27 @@ def test_encode_frame_dropin_per_frame(golden):
         exp += body[o:o + 16 + cs + 8]
         o += 16 + cs + 8 + 8
     assert got == exp
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["video64_III_LOW", "video240_GBA_I_LOW", "full64_III_LOW"])
+def test_other_encoders_dropin_bytes(golden, name):
+    """AGMV_EncodeVideo / AGMV_EncodeFullAGMV called like tools/agmvcli/agmvcli.c:168 does, on a BMP directory."""
+    from agmv_testlib import scene_cut_frames
+    g = golden["encode_modes"][name]
+    lib = _dropin()
+    frames = scene_cut_frames(g["w"], g["h"], g["n"])
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        write_bmps(frames, td, "f", 1)
+        os.chdir(td)
+        try:
+            if g["mode"] == "video":
+                lib.AGMV_EncodeVideo(b"o.agmv", b".", b"f", 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            else:
+                h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
+                lib.AGMV_EncodeFullAGMV(h, b"o.agmv", b".", b"f", 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            data = open("o.agmv", "rb").read()
+        finally:
+            os.chdir(cwd)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()

@@ -327,3 +327,24 @@ def test_config3_scale_properties(ctx):
         exp = int((odec[k].reshape(-1).astype(np.uint64) * (np.uint64(2654435761) + np.uint64(2) * P)).sum(dtype=np.uint64))
         assert int(ck_all[k]) == exp, k
     assert np.array_equal(out[nf - 1].cpu().numpy().view(np.uint32), odec[nf - 1])
+
+
+MODE_CASES = ["video64_III_LOW", "video64_I_LOW", "video64_II_MID", "video240_GBA_I_LOW", "full64_III_LOW", "full64_ANIM_LOW"]
+
+
+@pytest.mark.parametrize("name", MODE_CASES)
+def test_other_sequence_encoders_match_reference_golden(ctx, golden, name):
+    """AGMV_EncodeVideo (similarity-gated PDIFS) and AGMV_EncodeFullAGMV through the C-ABI."""
+    from agmv_testlib import scene_cut_frames
+    g = golden["encode_modes"][name]
+    frames = scene_cut_frames(g["w"], g["h"], g["n"])
+    data, n_enc = ctx.encode_mode(g["mode"], frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert (len(data), sha256(data.tobytes())) == (g["size"], g["sha256"])
+    # AGMV_EncodeFullAGMV never back-patches the header: it encodes n frames but the header keeps CreateAGMV's count
+    assert n_enc == (g["n"] if g["mode"] == "full" else g["decoded_shape"][0])
+    dec = ctx.decode_all(data.tobytes())
+    assert [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+    # and the plain AGMV_EncodeAGMV path still interleaves its empty audio chunks afterwards
+    g0 = golden["encode"]["syn64_III_LOW"]
+    d0, _ = ctx.encode_sequence(synth_frames(64, 64, 12), 11, 24, OPT["III"], QUALITY["LOW"], LZSS)
+    assert sha256(d0.tobytes()) == g0["sha256"]

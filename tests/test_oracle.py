@@ -83,3 +83,18 @@ def test_oracle_matches_live_reference_random_profile():
     rc, rf = ref_decode_raw(ref)
     rc2, of = oracle_decode(ref)
     assert rc == rc2 == 0 and np.array_equal(rf, of)
+
+
+MODE_CASES = ["video64_III_LOW", "video64_I_LOW", "video64_II_MID", "video240_GBA_I_LOW", "full64_III_LOW", "full64_ANIM_LOW"]
+
+
+@pytest.mark.parametrize("name", MODE_CASES)
+def test_oracle_other_encoders_match_reference_golden(golden, name):
+    """AGMV_EncodeVideo (similarity-gated) and AGMV_EncodeFullAGMV restated: bytes and decoded frames vs the reference."""
+    from agmv_testlib import oracle_encode_mode, scene_cut_frames
+    g = golden["encode_modes"][name]
+    frames = scene_cut_frames(g["w"], g["h"], g["n"])
+    data = oracle_encode_mode(g["mode"], frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"])
+    rc, dec = oracle_decode(data)
+    assert rc == 0 and [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
