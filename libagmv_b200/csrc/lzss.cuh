@@ -116,22 +116,36 @@ struct LzDigit {
 // thread are loaded up front (and reused as payload), positions / group starts are loaded eight at a time before
 // any store so that the loads overlap, and every fourth level the next four key bytes are gathered from the
 // bitstream (positions of a group are close to sorted, the 4-byte read stays inside one or two sectors).
+// dynamic shared memory of lz_scatter_k: the tile's elements staged in bucket order so that the global writes of a
+// bucket are contiguous (a warp's store covers consecutive addresses instead of up to 32 different buckets)
+constexpr size_t LZ_SCATTER_SMEM = (size_t)LZ_TILE * 12 + LZ_TILE;
+
 __global__ void __launch_bounds__(LZ_THREADS) lz_scatter_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ pos_in,
                                                            const uint32_t* __restrict__ gs_in, const uint32_t* __restrict__ dig_in,
                                                            uint32_t* __restrict__ pos_out, uint32_t* __restrict__ gs_out,
                                                            uint32_t* __restrict__ dig_out, uint32_t L, uint32_t n, uint32_t ntiles,
                                                            const uint32_t* __restrict__ tile_off) {
+    extern __shared__ __align__(16) uint8_t lz_dyn[];
+    uint32_t* s_pos = reinterpret_cast<uint32_t*>(lz_dyn);
+    uint32_t* s_gs = s_pos + LZ_TILE;
+    uint32_t* s_dig = s_gs + LZ_TILE;
+    uint8_t* s_d = reinterpret_cast<uint8_t*>(s_dig + LZ_TILE);
     __shared__ uint32_t wc[LZ_WARPS][256];
-    __shared__ uint32_t goff[256];
+    __shared__ uint32_t goff[256];    // global index of the tile's first element of each bucket, minus its slot in the tile
+    __shared__ uint32_t lstart[256];  // slot of the tile's first element of each bucket
+    __shared__ uint32_t gtot[8];
     for (int k = threadIdx.x; k < LZ_WARPS * 256; k += LZ_THREADS) (&wc[0][0])[k] = 0;
     const int warp = threadIdx.x >> 5;
-    const uint32_t base = blockIdx.x * LZ_TILE + warp * LZ_WARP_SPAN + lane_id();
+    const uint32_t t0 = blockIdx.x * LZ_TILE;
+    const uint32_t base = t0 + warp * LZ_WARP_SPAN + lane_id();
     const uint32_t sh = 8u * (L & 3u);
-    uint32_t word[LZ_ROUNDS];
+    uint32_t word[LZ_ROUNDS], p[LZ_ROUNDS], g[LZ_ROUNDS];
 #pragma unroll
     for (int r = 0; r < LZ_ROUNDS; r++) {
         uint32_t i = base + r * 32;
         word[r] = i < n ? dig_in[i] : 0u;
+        p[r] = i < n ? pos_in[i] : 0u;
+        g[r] = i < n ? gs_in[i] : 0u;
     }
     __syncthreads();
     uint32_t packed[LZ_ROUNDS];  // digit << 16 | rank inside the warp's span
@@ -152,45 +166,48 @@ __global__ void __launch_bounds__(LZ_THREADS) lz_scatter_k(const uint8_t* __rest
         __syncwarp();
     }
     __syncthreads();
+    uint32_t b_tot = 0, b_inc = 0;  // per bucket (threads 0..255): tile total and its inclusive scan inside a group of 32 buckets
     if (threadIdx.x < 256) {
-        uint32_t run = 0;
         const int d = threadIdx.x;
 #pragma unroll
         for (int w = 0; w < LZ_WARPS; w++) {
             uint32_t t = wc[w][d];
-            wc[w][d] = run;
-            run += t;
+            wc[w][d] = b_tot;
+            b_tot += t;
         }
-        goff[d] = tile_off[d * ntiles + blockIdx.x];
+        b_inc = b_tot;
+#pragma unroll
+        for (int k = 1; k < 32; k <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, b_inc, k); if ((int)lane_id() >= k) b_inc += y; }
+        if (lane_id() == 31) gtot[d >> 5] = b_inc;
     }
     __syncthreads();
+    if (threadIdx.x < 256) {  // slot of the bucket's first element inside the tile: exclusive scan over the 256 buckets
+        uint32_t add = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); w++) add += gtot[w];
+        lstart[threadIdx.x] = add + b_inc - b_tot;
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) goff[threadIdx.x] = tile_off[threadIdx.x * ntiles + blockIdx.x] - lstart[threadIdx.x];
     const bool gather = (L & 3u) == 3u;
 #pragma unroll
-    for (int h = 0; h < LZ_ROUNDS; h += 8) {
-        uint32_t p[8], g[8];
-        static_assert(LZ_ROUNDS % 8 == 0, "rounds are moved eight at a time");
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            uint32_t i = base + (h + r) * 32;
-            p[r] = i < n ? pos_in[i] : 0u;
-            g[r] = i < n ? gs_in[i] : 0u;
+    for (int r = 0; r < LZ_ROUNDS; r++) {
+        uint32_t i = base + r * 32;
+        if (i < n) {
+            const uint32_t d = packed[r] >> 16, rk = packed[r] & 0xffffu;
+            const uint32_t slot = lstart[d] + wc[warp][d] + rk;
+            s_pos[slot] = p[r];
+            s_gs[slot] = g[r];
+            s_dig[slot] = gather ? load4(bs + (p[r] & LZ_POS_MASK) + L + 1) : word[r];
+            s_d[slot] = (uint8_t)d;
         }
-        uint32_t nd[8];
-        if (gather) {
-#pragma unroll
-            for (int r = 0; r < 8; r++) nd[r] = load4(bs + (p[r] & LZ_POS_MASK) + L + 1);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-            uint32_t i = base + (h + r) * 32;
-            if (i < n) {
-                uint32_t d = packed[h + r] >> 16, rk = packed[h + r] & 0xffffu;
-                uint32_t dst = goff[d] + wc[warp][d] + rk;
-                pos_out[dst] = p[r];
-                gs_out[dst] = g[r];
-                dig_out[dst] = gather ? nd[r] : word[h + r];
-            }
-        }
+    }
+    __syncthreads();
+    const uint32_t cnt = min((uint32_t)LZ_TILE, n - t0);
+    for (uint32_t k = threadIdx.x; k < cnt; k += LZ_THREADS) {
+        const uint32_t dst = goff[s_d[k]] + k;
+        pos_out[dst] = s_pos[k];
+        gs_out[dst] = s_gs[k];
+        dig_out[dst] = s_dig[k];
     }
 }
 
@@ -755,7 +772,7 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
             // derives its groups from (frame, 3-byte key)
             uint32_t* gs_dst = Lnew < (uint32_t)LZ_MINLEN ? wk.GS[Lnew] : wk.gs_tmp;
             device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
-            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, LZ_THREADS, 0, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
+            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, LZ_THREADS, LZ_SCATTER_SMEM, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
             if (Lnew < (uint32_t)LZ_MINLEN) {
                 KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{dout, 8u * (Lnew & 3u)}, n, nt, th_next)));
                 continue;
