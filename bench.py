@@ -272,6 +272,7 @@ def run_b200(args):
     # encode-only / decode-only rates (same rules, separate regions)
     enc_ms = timed(encode_step, args.steps)
     dec_ms = timed(lambda: decode_step(stream_np), args.steps)
+    us, cs = ctx.enc_sizes(n_enc)                    # per-frame sizes of the timed workload (read before the e2e leg re-encodes a shorter clip)
 
     # ---- e2e: the same step through the public API with HOST buffers -------------------
     e2e = None
@@ -323,7 +324,6 @@ def run_b200(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
 
     # per-step statistics the algorithmic byte counts are made of
-    us, cs = ctx.enc_sizes(n_enc)
     usize_total, csize_total = float(us.sum()), float(cs.sum())
     n_interp = int((sb >= 0).sum())
     stats = {"P": P, "n_src": n_local, "n_enc": n_enc, "n_interp": n_interp, "usize": usize_total, "csize": csize_total,
