@@ -198,3 +198,15 @@ def ref_decode_raw(data, timing=None):
 
 def sha256(b):
     return hashlib.sha256(b).hexdigest()
+
+
+def oracle_lz77(data, stale=0xA7):
+    """orc_lz77 on `data`; the byte one past the end (read when the last match ends at the buffer end) is `stale`."""
+    lib = oracle()
+    lib.orc_lz77.restype = C.c_uint32
+    lib.orc_lz77.argtypes = [_u8p, C.c_size_t, _u8p, C.POINTER(C.c_size_t)]
+    src = np.concatenate([np.asarray(data, dtype=np.uint8), np.full(8, stale, dtype=np.uint8)])
+    out = np.zeros(len(data) * 4 + 16, dtype=np.uint8)
+    nb = C.c_size_t()
+    csize = lib.orc_lz77(ptr(src, _u8p), len(data), ptr(out, _u8p), C.byref(nb))
+    return csize, out[:nb.value].tobytes()

@@ -48,6 +48,19 @@ MODE_CASES = [
 ]
 
 
+# "next" row N2: the LZ77 entropy coder (stream versions 3 = dual palette, 4 = single palette), all three sequence encoders
+# name, mode, w, h, n_frames, create_n, fps, opt, quality
+LZ77_CASES = [
+    ("lz77_64_III_LOW", "agmv", 64, 64, 12, 11, 24, "III", "LOW"),
+    ("lz77_64_II_LOW", "agmv", 64, 64, 12, 11, 24, "II", "LOW"),
+    ("lz77_96x80_I_MID", "agmv", 96, 80, 24, 23, 30, "I", "MID"),
+    ("lz77_gba240_GBA_I_LOW", "agmv", 240, 160, 24, 23, 16, "GBA_I", "LOW"),
+    ("lz77_video64_III_LOW", "video", 64, 64, 24, 23, 24, "III", "LOW"),
+    ("lz77_full64_ANIM_LOW", "full", 64, 64, 10, 10, 24, "ANIM", "LOW"),
+    ("lz77_320x240_III_LOW", "agmv", 320, 240, 20, 19, 24, "III", "LOW"),
+]
+
+
 def lzss_vectors():
     """Known-answer tests for the exported AGMV_LZSS (src/agmv_encode.c:106-177)."""
     rng = np.random.default_rng(7)
@@ -92,6 +105,42 @@ def ref_lzss(buf):
         out = fh.read()
     os.unlink(path)
     return int(csize), out
+
+
+def ref_lz77(buf, stale=0xA7):
+    """Call the reference's AGMV_LZ77 (src/agmv_encode.c:179-238) on a temp FILE*; data[pos] (read when the last match ends
+    exactly at the end of the buffer) is set to `stale`."""
+    lib = C.CDLL(os.path.join(REF_DIR, "libagmv_ref.so"))
+    libc = C.CDLL(None)
+    libc.fopen.restype = C.c_void_p
+    libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+    libc.fclose.argtypes = [C.c_void_p]
+
+    class BS(C.Structure):
+        _fields_ = [("data", C.POINTER(C.c_uint8)), ("len", C.c_ulong), ("pos", C.c_ulong)]
+
+    lib.AGMV_LZ77.restype = C.c_ulong
+    lib.AGMV_LZ77.argtypes = [C.c_void_p, C.POINTER(BS)]
+    arr = np.concatenate([buf, np.full(32, stale, dtype=np.uint8)])
+    bs = BS(arr.ctypes.data_as(C.POINTER(C.c_uint8)), len(arr), len(buf))
+    path = b"/tmp/_agmv_lz77_golden.bin"
+    f = libc.fopen(path, b"wb")
+    csize = lib.AGMV_LZ77(f, C.byref(bs))
+    libc.fclose(f)
+    with open(path, "rb") as fh:
+        out = fh.read()
+    os.unlink(path)
+    return int(csize), out
+
+
+def lz77_vectors():
+    rng = np.random.default_rng(11)
+    vecs = dict(lzss_vectors())
+    vecs["all_equal_600"] = np.full(600, 0x5E, dtype=np.uint8)          # 255-byte matches, last one ends at the buffer end
+    vecs["ends_in_match"] = np.concatenate([rng.integers(0, 256, 300, dtype=np.uint8)] * 2)   # second half = one long match chain
+    vecs["period7_2k"] = np.tile(np.array([9, 8, 7, 6, 5, 4, 3], dtype=np.uint8), 300)
+    vecs["one_byte"] = np.array([42], dtype=np.uint8)
+    return vecs
 
 
 def main():
@@ -148,7 +197,32 @@ def main():
         print(f"{name}: {len(data)} B, {dec.shape[0]} frames, {time.time() - t0:.1f}s", flush=True)
         json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
 
+    gold.setdefault("encode_lz77", {})
+    for name, mode, w, h, n, create_n, fps, opt, q in LZ77_CASES:
+        if args.only and args.only != name:
+            continue
+        if name in gold["encode_lz77"] and not args.only:
+            continue
+        t0 = time.time()
+        frames = scene_cut_frames(w, h, n) if mode != "agmv" else synth_frames(w, h, n, seed=1234)
+        data = ref_encode(frames, create_n, fps, OPT[opt], QUALITY[q], 2, mode=mode)
+        rc, dec = ref_decode_raw(data)
+        assert rc == 0
+        with open(os.path.join(GOLDEN_DIR, name + ".agmv"), "wb") as f:
+            f.write(data)
+        gold["encode_lz77"][name] = dict(mode=mode, w=w, h=h, n=n, create_n=create_n, fps=fps, opt=opt, quality=q, size=len(data),
+                                         sha256=sha256(data), file=name + ".agmv", version=data[17], decoded_shape=list(dec.shape),
+                                         decoded_frame_sha256=[sha256(dec[k].tobytes()) for k in range(dec.shape[0])])
+        print(f"{name}: {len(data)} B, version {data[17]}, {dec.shape[0]} frames, {time.time() - t0:.1f}s", flush=True)
+        json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
+
     if not args.only:
+        gold.setdefault("lz77", {})
+        for name, buf in lz77_vectors().items():
+            csize, out = ref_lz77(buf)
+            gold["lz77"][name] = dict(n=len(buf), csize=csize, nbytes=len(out), sha256=sha256(out), input_sha256=sha256(buf.tobytes()), stale=0xA7)
+            print(f"lz77 {name}: n={len(buf)} csize={csize} nbytes={len(out)}", flush=True)
+
         for name, buf in lzss_vectors().items():
             csize, out = ref_lzss(buf)
             gold["lzss"][name] = dict(n=len(buf), csize=csize, nbytes=len(out), sha256=sha256(out),

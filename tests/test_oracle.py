@@ -98,3 +98,38 @@ def test_oracle_other_encoders_match_reference_golden(golden, name):
     assert (len(data), sha256(data)) == (g["size"], g["sha256"])
     rc, dec = oracle_decode(data)
     assert rc == 0 and [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+
+
+# ---- "next" row N2: the LZ77 entropy coder (stream versions 3/4) ----
+LZ77_CASES = ["lz77_64_III_LOW", "lz77_64_II_LOW", "lz77_96x80_I_MID", "lz77_gba240_GBA_I_LOW", "lz77_video64_III_LOW",
+              "lz77_full64_ANIM_LOW", "lz77_320x240_III_LOW"]
+
+
+def test_oracle_lz77_known_answers(golden):
+    """orc_lz77 against the reference's AGMV_LZ77 (src/agmv_encode.c:179-238), including the read one past the buffer."""
+    from agmv_testlib import oracle_lz77
+    from golden.make_golden import lz77_vectors
+    for name, buf in lz77_vectors().items():
+        g = golden["lz77"][name]
+        assert sha256(buf.tobytes()) == g["input_sha256"], name
+        csize, out = oracle_lz77(buf, g["stale"])
+        assert (csize, len(out), sha256(out)) == (g["csize"], g["nbytes"], g["sha256"]), name
+
+
+@pytest.mark.parametrize("name", LZ77_CASES)
+def test_oracle_lz77_streams_match_reference_golden(golden, name):
+    from agmv_testlib import LZ77, oracle_encode_mode, scene_cut_frames
+    g = golden["encode_lz77"][name]
+    if g["mode"] == "agmv":
+        frames = synth_frames(g["w"], g["h"], g["n"], seed=1234)
+        data = oracle_encode(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZ77)
+    else:
+        frames = scene_cut_frames(g["w"], g["h"], g["n"])
+        data = oracle_encode_mode(g["mode"], frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZ77)
+    assert data[17] == g["version"]
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"])
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        assert f.read() == data
+    rc, dec = oracle_decode(data)
+    assert rc == 0 and list(dec.shape) == g["decoded_shape"]
+    assert [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
