@@ -164,6 +164,10 @@ int agmvb_test_peek(agmvb_ctx* ctx, int which, void* dst, uint64_t bytes);
  * reference computes them. */
 int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F,
                     uint8_t* out, uint64_t out_cap, uint64_t* out_off, uint32_t* csize, uint32_t* outbits);
+/* AGMV_LZ77 (src/agmv_encode.c:179-238) over F buffers that share one carried bitstream buffer, as consecutive frames of
+ * one handle do; every byte of that buffer starts as persist_fill (the reference: 0). out + out_off[f]: frame f's tokens. */
+int agmvb_test_lz77(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F, int persist_fill,
+                    uint8_t* out, uint64_t out_cap, uint64_t* out_off, uint32_t* csize);
 /* AGMV_FindNearestEntry / AGMV_FindNearestColor over n colours (src/agmv_utils.c:785-895) */
 int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint64_t n, const uint32_t pal0[256],
                         const uint32_t pal1[256], int dual, uint16_t* entries);

@@ -65,6 +65,7 @@ SYMBOLS = {
     "agmvb_profile_read": (C.c_int, [C.c_void_p, _u64p, C.POINTER(C.c_double)]),
     "agmvb_test_peek": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]),
     "agmvb_test_lzss": (C.c_int, [C.c_void_p, _u8p, _u32p, C.c_uint32, _u8p, C.c_uint64, _u64p, _u32p, _u32p]),
+    "agmvb_test_lz77": (C.c_int, [C.c_void_p, _u8p, _u32p, C.c_uint32, C.c_int, _u8p, C.c_uint64, _u64p, _u32p]),
     "agmvb_test_quantize": (C.c_int, [C.c_void_p, _u32p, C.c_uint64, _u32p, _u32p, C.c_int, _u16p]),
     "agmvb_test_assemble": (C.c_int, [C.c_void_p, _u16p, _u16p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, _u8p,
                                       C.c_uint64, _u32p]),
@@ -289,6 +290,20 @@ class Context:
         self._ck(self.lib.agmvb_test_lzss(self.h, _p(data, _u8p), _p(fs, _u32p), len(arrs), _p(out, _u8p), cap, _p(off, _u64p),
                                           _p(cs, _u32p), _p(ob, _u32p)))
         return [(int(cs[k]), out[int(off[k]):int(off[k + 1])].tobytes(), int(ob[k])) for k in range(len(arrs))]
+
+    def test_lz77(self, buffers, persist_fill=0):
+        """buffers: consecutive frames' bitstreams of one handle -> list of (csize, token bytes) as AGMV_LZ77 would produce."""
+        arrs = [np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b for b in buffers]
+        fs = np.zeros(len(arrs) + 1, np.uint32)
+        fs[1:] = np.cumsum([len(a) for a in arrs])
+        data = np.concatenate(arrs + [np.zeros(1, np.uint8)]).astype(np.uint8)
+        cap = int(fs[-1]) * 4 + 64
+        out = np.zeros(cap, np.uint8)
+        off = np.zeros(len(arrs) + 1, np.uint64)
+        cs = np.zeros(len(arrs), np.uint32)
+        self._ck(self.lib.agmvb_test_lz77(self.h, _p(data, _u8p), _p(fs, _u32p), len(arrs), persist_fill, _p(out, _u8p), cap, _p(off, _u64p),
+                                          _p(cs, _u32p)))
+        return [(int(cs[k]), out[int(off[k]):int(off[k + 1])].tobytes()) for k in range(len(arrs))]
 
     def test_quantize(self, colors, pal0, pal1, dual):
         colors = np.ascontiguousarray(colors, np.uint32)

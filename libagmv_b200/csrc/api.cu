@@ -13,6 +13,7 @@
 #include "decode.cuh"
 #include "encode.cuh"
 #include "lzss.cuh"
+#include "lz77.cuh"
 #include "radix.cuh"
 #include "scan.cuh"
 
@@ -71,6 +72,7 @@ struct agmvb_ctx {
     DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small, seqbuf;
     LzWork lz;
     DBuf lzbuf[64];
+    DBuf l77_out, l77_meta, l77_persist;  // LZ77: token words, per-frame arrays, the reference's carried bitstream buffer
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
     void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
@@ -166,6 +168,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
                     &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
+    cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
     for (DecStream& s : ctx->parked) free_stream(s);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -188,7 +191,7 @@ extern "C" int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, i
     if (!ctx) return ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     if (opt < OPT_I || opt > OPT_NDS || quality < Q_HIGH || quality > Q_LOW) FAIL(ERR_ARG, "bad opt/quality");
-    if (compression != COMP_LZSS) FAIL(ERR_UNSUPPORTED, "LZ77 entropy coder (stream versions 3/4) is not built yet (SURVEY 8f N2)");
+    if (compression != COMP_LZSS && compression != COMP_LZ77) FAIL(ERR_ARG, "bad compression %d", compression);
     ctx->src_w = src_w; ctx->src_h = src_h; ctx->opt = opt; ctx->quality = quality; ctx->compression = compression;
     ctx->dual = opt_is_dual(opt); ctx->light = opt_is_light(opt);
     ctx->cw = src_w; ctx->ch = src_h;
@@ -226,6 +229,12 @@ extern "C" int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, i
         CK(cudaMalloc(&ctx->d_map, P * 4));
         CK(cudaMemcpyAsync(ctx->d_map, map.data(), P * 4, cudaMemcpyHostToDevice, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
+    }
+    if (compression == COMP_LZ77) {
+        // CreateAGMV's bitstream buffer (src/agmv_utils.c:338): fresh zero pages, never cleared between frames
+        const size_t pb = (P / 16) * 33 + 64;
+        TRY(ensure(ctx, ctx->l77_persist, pb));
+        CK(cudaMemsetAsync(ctx->l77_persist.p, 0, pb, ctx->st));
     }
     ctx->pal_valid = false;
     ctx->image_bytes = 0;
@@ -442,6 +451,67 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     return OK;
 }
 
+// LZ77 flavour of lz_group (AGMV_LZ77, src/agmv_encode.c:179-238): tokens by lz77_encode_k, chunk framing shared with LZSS
+static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, uint32_t F, uint32_t first_fc) {
+    const uint32_t n = h_fs[F];
+    // per-frame device arrays: fs, wbase, stale_at, total_bits, outbits, csize, chunk_off (F + 2 words each)
+    const size_t stride = (size_t)F + 2;
+    TRY(ensure(ctx, ctx->l77_meta, stride * 7 * 4));
+    TRY(ensure(ctx, ctx->l77_out, ((size_t)n + F + 16) * 4));
+    TRY(ensure_pinned(ctx, stride * 4 * 4));
+    uint32_t* d_fs = ctx->l77_meta.as<uint32_t>();
+    uint32_t *d_wbase = d_fs + stride, *d_stale = d_wbase + stride, *d_bits = d_stale + stride, *d_outbits = d_bits + stride,
+             *d_csize = d_outbits + stride, *d_choff = d_csize + stride;
+    uint32_t* hp = reinterpret_cast<uint32_t*>(ctx->h_pinned);
+    uint32_t *h_w = hp + stride, *h_st = h_w + stride;
+    memcpy(hp, h_fs, (size_t)(F + 1) * 4);
+    // data[pos] of frame f: written by the latest earlier frame that was longer; frames of earlier groups live in l77_persist
+    std::vector<uint32_t> stack;  // frames with strictly decreasing usize towards the top
+    for (uint32_t f = 0; f < F; f++) {
+        const uint32_t us = h_fs[f + 1] - h_fs[f];
+        h_w[f] = h_fs[f] + f;
+        while (!stack.empty() && h_fs[stack.back() + 1] - h_fs[stack.back()] <= us) stack.pop_back();
+        h_st[f] = stack.empty() ? 0xFFFFFFFFu : h_fs[stack.back()] + us;
+        stack.push_back(f);
+    }
+    CK(cudaMemcpyAsync(d_fs, hp, stride * 3 * 4, cudaMemcpyHostToDevice, ctx->st));
+    size_t need = ctx->image_bytes + (size_t)32 * F + (size_t)n * 4 + 64;
+    if (need > ctx->image.cap) {
+        DBuf nb;
+        TRY(ensure(ctx, nb, need + need / 2));
+        if (ctx->image_bytes) CK(cudaMemcpyAsync(nb.p, ctx->image.p, ctx->image_bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        if (ctx->image.p) CK(cudaFree(ctx->image.p));
+        ctx->image = nb;
+    }
+    CK(cudaMemsetAsync(ctx->l77_out.p, 0, ((size_t)n + F + 16) * 4, ctx->st));
+    KL(ctx->lc, KC_LZ_PARSE, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
+                                                                          ctx->l77_out.as<uint32_t>(), d_bits)));
+    KL(ctx->lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, ctx->st>>>(F, ctx->lz.stub_bytes, d_bits, d_outbits, d_csize, d_choff)));
+    dim3 grid(32, F);
+    KL(ctx->lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, ctx->st>>>(d_fs, d_csize, d_choff, d_wbase, ctx->l77_out.as<uint32_t>(), first_fc,
+                                                                          ctx->lz.stub_bytes, ctx->image.as<uint8_t>() + ctx->image_bytes)));
+    // carry the buffer forward: index j now holds the byte of the latest frame longer than j (the stack, bottom = longest)
+    {
+        uint32_t lo = 0;
+        for (size_t k = stack.size(); k-- > 0;) {
+            const uint32_t f = stack[k], us = h_fs[f + 1] - h_fs[f];
+            if (us > lo) CK(cudaMemcpyAsync(ctx->l77_persist.as<uint8_t>() + lo, d_bs + h_fs[f] + lo, us - lo, cudaMemcpyDeviceToDevice, ctx->st));
+            lo = std::max(lo, us);
+        }
+    }
+    uint32_t* hcs = hp + stride * 3;
+    CK(cudaMemcpyAsync(hcs, d_csize, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    TRY(check_launch(ctx, "lz77"));
+    for (uint32_t f = 0; f < F; f++) {
+        ctx->last_usize.push_back(h_fs[f + 1] - h_fs[f]);
+        ctx->last_csize.push_back(hcs[f]);
+        ctx->image_bytes += 24ull + ctx->lz.stub_bytes + hcs[f];
+    }
+    return OK;
+}
+
 static const uint32_t LZ_GROUP_TARGET = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
 
 // classify + assemble n frames whose entries are on the device; runs LZSS group by group
@@ -475,7 +545,8 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
         while (g1 < F && fs[g1 + 1] - fs[g0] <= LZ_GROUP_TARGET) g1++;
         rebased.resize(g1 - g0 + 1);
         for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
-        TRY(lz_group(ctx, ctx->bs.as<uint8_t>() + fs[g0], rebased.data(), g1 - g0, first_fc + g0));
+        if (ctx->compression == COMP_LZ77) TRY(lz77_group(ctx, ctx->bs.as<uint8_t>() + fs[g0], rebased.data(), g1 - g0, first_fc + g0));
+        else TRY(lz_group(ctx, ctx->bs.as<uint8_t>() + fs[g0], rebased.data(), g1 - g0, first_fc + g0));
         g0 = g1;
     }
     return OK;
@@ -837,7 +908,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
         int64_t at = find_next_agfc(file, len, cursor);
         if (at < 0 || (uint64_t)at + 16 > len) FAIL(ERR_HEADER, "frame chunk %u not found", i);
         uint32_t us = get32(file + at + 8), cs = get32(file + at + 12);
-        if (us > 2 * P + 64 || (s.lz77 && (uint64_t)(cs / 4 + 1) * 256 > 2 * P + 64))
+        if (us > 2 * P + 64)
             FAIL(ERR_MEMORY, "frame %u: uncompressed size %u exceeds the reference's bitstream buffer", i, us);
         s.data_off.push_back((uint64_t)at + 16);
         s.usize.push_back(us);
@@ -940,7 +1011,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
     for (uint32_t s = 0; s < S; s++) {
         DecStream& d = ctx->streams[ids[s]];
         for (uint32_t k = 0; k < count; k++) {
-            uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.at(d.next + k)] / 4 + 1) * 256 : d.usize[d.at(d.next + k)];
+            uint64_t e = d.lz77 ? std::min<uint64_t>((uint64_t)(d.csize[d.at(d.next + k)] / 4 + 1) * 256, d.persist_len) : d.usize[d.at(d.next + k)];
             worst = std::max<uint64_t>(worst, e + DEC_SLACK);
         }
     }
@@ -963,7 +1034,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
                 x.file = d.d_file; x.file_len = d.file_len; x.data_off = d.data_off[d.at(g)]; x.ebuf_off = eoff;
                 x.persist = d.d_persist; x.persist_len = d.persist_len; x.usize = d.usize[d.at(g)]; x.csize = d.csize[d.at(g)];
                 x.stream_first = s * cn; x.lz77 = d.lz77; x.dual = d.dual;
-                uint64_t e = d.lz77 ? (uint64_t)(d.csize[d.at(g)] / 4 + 1) * 256 : d.usize[d.at(g)];
+                uint64_t e = d.lz77 ? std::min<uint64_t>((uint64_t)(d.csize[d.at(g)] / 4 + 1) * 256, d.persist_len) : d.usize[d.at(g)];
                 eoff += (e + DEC_SLACK + 15) & ~15ull;
             }
         }
@@ -1277,6 +1348,42 @@ extern "C" int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32
         if (out_off) out_off[f] = o;
         if (csize) csize[f] = ctx->last_csize[f];
         if (outbits) outbits[f] = ob[f];
+        o += nbytes;
+    }
+    if (out_off) out_off[F] = o;
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// AGMV_LZ77 (src/agmv_encode.c:179-238) over F buffers sharing one carried bitstream buffer whose bytes all start as `persist_fill`
+extern "C" int agmvb_test_lz77(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F, int persist_fill, uint8_t* out,
+                               uint64_t out_cap, uint64_t* out_off, uint32_t* csize) {
+    if (!ctx || !frame_start || F == 0) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t n = frame_start[F];
+    uint32_t longest = 0;
+    for (uint32_t f = 0; f < F; f++) longest = std::max(longest, frame_start[f + 1] - frame_start[f]);
+    TRY(ensure(ctx, ctx->bs, (size_t)n + 256));
+    CK(cudaMemsetAsync(ctx->bs.p, 0, (size_t)n + 256, ctx->st));
+    if (n) CK(cudaMemcpyAsync(ctx->bs.p, data, n, cudaMemcpyHostToDevice, ctx->st));
+    TRY(ensure(ctx, ctx->l77_persist, (size_t)longest + 64));
+    CK(cudaMemsetAsync(ctx->l77_persist.p, persist_fill, (size_t)longest + 64, ctx->st));
+    ctx->image_bytes = 0;
+    ctx->last_usize.clear();
+    ctx->last_csize.clear();
+    TRY(lz77_group(ctx, ctx->bs.as<uint8_t>(), frame_start, F, 0));
+    const size_t stride = (size_t)F + 2;
+    std::vector<uint32_t> ob(F), wb(F);
+    CK(cudaMemcpyAsync(wb.data(), ctx->l77_meta.as<uint32_t>() + stride, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(ob.data(), ctx->l77_meta.as<uint32_t>() + stride * 4, (size_t)F * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    uint64_t o = 0;
+    for (uint32_t f = 0; f < F; f++) {
+        uint64_t nbytes = ob[f] / 8;
+        if (o + nbytes > out_cap) FAIL(ERR_ARG, "output buffer too small");
+        if (nbytes) CK(cudaMemcpyAsync(out + o, ctx->l77_out.as<uint32_t>() + wb[f], nbytes, cudaMemcpyDeviceToHost, ctx->st));
+        if (out_off) out_off[f] = o;
+        if (csize) csize[f] = ctx->last_csize[f];
         o += nbytes;
     }
     if (out_off) out_off[F] = o;

@@ -54,18 +54,21 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
     const uint8_t* __restrict__ file = d.file;
     if (d.lz77) {  // 4-byte tokens (src/agmv_decode.c:200-218): rare profile, plain serial walk
         if (lane == 0) {
+            // The reference expands into a 2*W*H byte buffer without a bound check; a stream that would run past it is
+            // outside its defined behaviour: the expansion stops at the buffer's end here.
+            const uint64_t cap = d.persist_len;
             uint64_t rp = d.data_off, bpos = 0;
-            for (uint32_t i = 0; i < d.csize; i += 4) {
+            for (uint32_t i = 0; i < d.csize && bpos < cap; i += 4) {
                 uint32_t b0 = rp < d.file_len ? file[rp] : 0u; rp++;
                 uint32_t b1 = rp < d.file_len ? file[rp] : 0u; rp++;
                 uint32_t len = rp < d.file_len ? file[rp] : 0u; rp++;
                 uint8_t lit = rp < d.file_len ? file[rp] : 0u; rp++;
                 const uint64_t off = b0 | b1 << 8, p = bpos;
-                for (uint32_t k = 0; k < len; k++) {
+                for (uint32_t k = 0; k < len && bpos < cap; k++) {
                     uint64_t s = p - off + k;
                     if (s < bpos) { e[bpos] = e[s]; bpos++; }
                 }
-                e[bpos++] = lit;
+                if (bpos < cap) e[bpos++] = lit;
             }
             bpos_out[f] = (uint32_t)bpos;
             consumed_out[f] = (uint32_t)(rp - d.data_off);

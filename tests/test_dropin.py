@@ -101,10 +101,13 @@ def _libc():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["syn96x80_III_LOW", "gba240_GBA_I_LOW", "syn64_II_LOW"])
+@pytest.mark.parametrize("name", ["syn96x80_III_LOW", "gba240_GBA_I_LOW", "syn64_II_LOW", "lz77_64_II_LOW", "lz77_96x80_I_MID"])
 def test_encode_agmv_dropin_bytes(golden, name):
     """examples/simple_video/simple_video.c, line for line: CreateAGMV + AGMV_EncodeAGMV on a BMP directory."""
-    g = golden["encode"][name]
+    lz77 = name.startswith("lz77")
+    g = dict(golden["encode_lz77" if lz77 else "encode"][name])
+    g.setdefault("seed", 1234)
+    comp = 2 if lz77 else LZSS
     lib = _dropin()
     frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
     cwd = os.getcwd()
@@ -113,7 +116,7 @@ def test_encode_agmv_dropin_bytes(golden, name):
         os.chdir(td)
         try:
             h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
-            lib.AGMV_EncodeAGMV(h, b"o.agmv", b".", b"f", 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            lib.AGMV_EncodeAGMV(h, b"o.agmv", b".", b"f", 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], comp)
             data = open("o.agmv", "rb").read()
             if g["opt"].startswith("GBA"):
                 assert os.path.exists("GBA_GEN_AGMV.h")
@@ -125,10 +128,11 @@ def test_encode_agmv_dropin_bytes(golden, name):
 
 
 @pytest.mark.gpu
-def test_decode_agmv_dropin_exports(golden):
+@pytest.mark.parametrize("name", ["syn64_III_LOW", "lz77_64_II_LOW"])
+def test_decode_agmv_dropin_exports(golden, name):
     """AGMV_DecodeAGMV writes ./quick_export_<k>.bmp; pixel content must equal the reference's frames and,
     where the reference binary is present, the files must be byte-identical to its own export."""
-    g = golden["encode"]["syn64_III_LOW"]
+    g = golden["encode_lz77" if name.startswith("lz77") else "encode"][name]
     path = os.path.join(GOLDEN_DIR, g["file"])
     lib = _dropin()
     cwd = os.getcwd()
@@ -147,21 +151,24 @@ def test_decode_agmv_dropin_exports(golden):
             mine = {f: open(f, "rb").read() for f in bmps}
         finally:
             os.chdir(cwd)
+        # the export counter is process-global in the reference (extern/agidl/src/agidl_img_export.c:18): take the files in order
+        order = sorted(bmps, key=lambda f: int(f[len("quick_export_"):-4]))
         for k in range(len(bmps)):
-            d = mine[f"quick_export_{k + 1}.bmp"]
+            d = mine[order[k]]
             px = np.frombuffer(d[54:], dtype=np.uint8).reshape(g["h"], g["w"], 3).astype(np.uint32)
             frame = px[..., 2] << 16 | px[..., 1] << 8 | px[..., 0]
             assert sha256(frame.astype(np.uint32).tobytes()) == g["decoded_frame_sha256"][k]
         if have_ref():
             subprocess.run([os.path.join(REF_DIR, "ref_decode"), "export", path], cwd=td2, check=True, capture_output=True)
-            for f, d in mine.items():
-                assert open(os.path.join(td2, f), "rb").read() == d, f
+            for k, f in enumerate(order):
+                assert open(os.path.join(td2, f"quick_export_{k + 1}.bmp"), "rb").read() == mine[f], f
 
 
 @pytest.mark.gpu
-def test_decode_frame_chunk_dropin_streaming(golden):
+@pytest.mark.parametrize("name", ["gba240_GBA_I_LOW", "lz77_gba240_GBA_I_LOW"])
+def test_decode_frame_chunk_dropin_streaming(golden, name):
     """AGMV_PlayAGMV's loop (src/agmv_playback.c:102-115): find the next 'AGFC', AGMV_DecodeFrameChunk, repeat."""
-    g = golden["encode"]["gba240_GBA_I_LOW"]
+    g = golden["encode_lz77" if name.startswith("lz77") else "encode"][name]
     path = os.path.join(GOLDEN_DIR, g["file"])
     raw = open(path, "rb").read()
     lib, libc = _dropin(), _libc()
@@ -187,15 +194,18 @@ def test_decode_frame_chunk_dropin_streaming(golden):
 
 
 @pytest.mark.gpu
-def test_encode_frame_dropin_per_frame(golden):
-    """AGMV_EncodeFrame frame by frame (palettes taken from the reference's stream) reproduces the reference's chunks."""
-    g = golden["encode"]["syn64_III_LOW"]
+@pytest.mark.parametrize("comp", [LZSS, 2])
+def test_encode_frame_dropin_per_frame(golden, comp):
+    """AGMV_EncodeFrame frame by frame (palettes taken from the reference's stream) reproduces the reference's chunks,
+    with either entropy coder (LZ77 carries its bitstream buffer from frame to frame)."""
+    g = dict(golden["encode"]["syn64_III_LOW"] if comp == LZSS else golden["encode_lz77"]["lz77_64_III_LOW"])
+    g.setdefault("seed", 1234)
     ref = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
     lib, libc = _dropin(), _libc()
     frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"]).reshape(g["n"], -1)
     h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
     a = h.contents
-    a.opt, a.compression = OPT["III"], LZSS
+    a.opt, a.compression = OPT["III"], comp
     pal = np.frombuffer(ref[38:38 + 1536], dtype=np.uint8).reshape(512, 3).astype(np.uint64)
     for i in range(256):
         a.header.palette0[i] = int(pal[i, 0] << 16 | pal[i, 1] << 8 | pal[i, 2])

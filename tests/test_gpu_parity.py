@@ -348,3 +348,87 @@ def test_other_sequence_encoders_match_reference_golden(ctx, golden, name):
     g0 = golden["encode"]["syn64_III_LOW"]
     d0, _ = ctx.encode_sequence(synth_frames(64, 64, 12), 11, 24, OPT["III"], QUALITY["LOW"], LZSS)
     assert sha256(d0.tobytes()) == g0["sha256"]
+
+
+# ---- the LZ77 entropy coder (stream versions 3/4) ------------------------------
+LZ77_CASES = ["lz77_64_III_LOW", "lz77_64_II_LOW", "lz77_96x80_I_MID", "lz77_gba240_GBA_I_LOW", "lz77_video64_III_LOW",
+              "lz77_full64_ANIM_LOW", "lz77_320x240_III_LOW"]
+
+
+def test_lz77_known_answers(ctx, golden):
+    """lz77_encode_k against the reference's AGMV_LZ77 on the golden buffers (incl. the read one past the buffer end)."""
+    from golden.make_golden import lz77_vectors
+    for name, buf in lz77_vectors().items():
+        g = golden["lz77"][name]
+        if len(buf) == 0:
+            continue  # the C-ABI takes at least one byte per call; the empty frame is covered by the multi-frame test
+        (csize, out), = ctx.test_lz77([buf], persist_fill=g["stale"])
+        assert (csize, len(out), sha256(out)) == (g["csize"], g["nbytes"], g["sha256"]), name
+
+
+def test_lz77_frames_share_the_carried_buffer(ctx):
+    """Consecutive frames of one handle: a match that ends at the end of a frame's bitstream takes its 'next literal' from
+    whatever an earlier, longer frame left behind (src/agmv_encode.c:218-224). Checked against the oracle fed with the
+    same carried buffer."""
+    from agmv_testlib import oracle_lz77
+    rng = np.random.default_rng(5)
+    bufs = []
+    for k, n in enumerate([900, 400, 650, 0, 120, 1300, 1299, 30, 2000, 7]):
+        if n == 0:
+            bufs.append(np.zeros(0, np.uint8))
+            continue
+        half = rng.integers(0, 4, max(1, n // 2), dtype=np.uint8)
+        b = np.concatenate([half, half])[:n]            # second half repeats the first: the last match ends at the buffer end
+        if len(b) < n:
+            b = np.concatenate([b, rng.integers(0, 4, n - len(b), dtype=np.uint8)])
+        bufs.append(b.astype(np.uint8))
+    got = ctx.test_lz77(bufs, persist_fill=0)
+    carried = np.zeros(4096, np.uint8)
+    for k, b in enumerate(bufs):
+        stale = int(carried[len(b)])
+        csize, out = oracle_lz77(b, stale)
+        assert got[k] == (csize, out), f"frame {k} (n={len(b)}, stale={stale})"
+        carried[:len(b)] = b
+
+
+def test_lz77_random_against_oracle(ctx):
+    from agmv_testlib import oracle_lz77
+    rng = np.random.default_rng(9)
+    bufs = [rng.integers(0, 3, 30000, dtype=np.uint8), rng.integers(0, 256, 5000, dtype=np.uint8),
+            np.repeat(rng.integers(0, 256, 300, dtype=np.uint8), rng.integers(1, 700, 300))[:90000].astype(np.uint8)]
+    for b in bufs:
+        (csize, out), = ctx.test_lz77([b], persist_fill=0x11)
+        assert (csize, out) == oracle_lz77(b, 0x11)
+
+
+@pytest.mark.parametrize("name", LZ77_CASES)
+def test_lz77_streams_match_reference_golden(ctx, golden, name):
+    """All three sequence encoders with AGMV_LZ77_COMPRESSION: bytes == the reference's, and the GPU decoder reproduces the
+    reference's frames from the reference's stream."""
+    from agmv_testlib import LZ77, scene_cut_frames
+    g = golden["encode_lz77"][name]
+    if g["mode"] == "agmv":
+        frames = synth_frames(g["w"], g["h"], g["n"], seed=1234)
+        data, n_enc = ctx.encode_sequence(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZ77)
+    else:
+        frames = scene_cut_frames(g["w"], g["h"], g["n"])
+        data, n_enc = ctx.encode_mode(g["mode"], frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZ77)
+    assert data[17] == g["version"]
+    assert (len(data), sha256(data.tobytes())) == (g["size"], g["sha256"])
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        ref_stream = f.read()
+    dec = ctx.decode_all(ref_stream)
+    assert list(dec.shape) == g["decoded_shape"]
+    assert [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+
+
+def test_lz77_720p_against_oracle(ctx):
+    """A larger LZ77 case (1280x720, bitstreams of ~200 KB: windows slide, lengths reach 255) against the oracle."""
+    from agmv_testlib import LZ77
+    frames = synth_frames(1280, 720, 8, seed=77)
+    want = oracle_encode(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    data, n_enc = ctx.encode_sequence(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    assert data.tobytes() == want
+    rc, ref_frames = oracle_decode(want)
+    assert rc == 0
+    assert np.array_equal(ctx.decode_all(want), ref_frames)
