@@ -485,7 +485,7 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
         ctx->image = nb;
     }
     CK(cudaMemsetAsync(ctx->l77_out.p, 0, ((size_t)n + F + 16) * 4, ctx->st));
-    KL(ctx->lc, KC_LZ_PARSE, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
+    KL(ctx->lc, KC_LZ77, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
                                                                           ctx->l77_out.as<uint32_t>(), d_bits)));
     KL(ctx->lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, ctx->st>>>(F, ctx->lz.stub_bytes, d_bits, d_outbits, d_csize, d_choff)));
     dim3 grid(32, F);
@@ -542,7 +542,9 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
     std::vector<uint32_t> rebased;
     for (uint32_t g0 = 0; g0 < F;) {
         uint32_t g1 = g0 + 1;
-        while (g1 < F && fs[g1 + 1] - fs[g0] <= LZ_GROUP_TARGET) g1++;
+        // LZ77 keeps 4 B of workspace per position and wants every frame of the batch in flight at once (one CTA per frame)
+        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : LZ_GROUP_TARGET;
+        while (g1 < F && fs[g1 + 1] - fs[g0] <= target) g1++;
         rebased.resize(g1 - g0 + 1);
         for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
         if (ctx->compression == COMP_LZ77) TRY(lz77_group(ctx, ctx->bs.as<uint8_t>() + fs[g0], rebased.data(), g1 - g0, first_fc + g0));

@@ -21,6 +21,7 @@ namespace agmvb {
 constexpr int L77_THREADS = 512;
 constexpr int L77_MAXLEN = 255;
 constexpr uint32_t L77_WINDOW = 65535;
+constexpr int L77_GROUPS = (65535 + 15 + 16 + 16 * L77_THREADS - 1) / (16 * L77_THREADS);  // 16-byte groups of the window per thread
 
 __device__ __forceinline__ uint32_t l77_load4(const uint8_t* __restrict__ p) {  // unaligned little-endian word
     const uintptr_t a = reinterpret_cast<uintptr_t>(p);
@@ -62,21 +63,60 @@ __global__ void __launch_bounds__(L77_THREADS) lz77_encode_k(const uint8_t* __re
         if (tid == 0) cap_q = 0xFFFFFFFFu;
         __syncthreads();
         const uint32_t lo = i > L77_WINDOW ? i - L77_WINDOW : 0u;
-        const uint8_t val = (uint8_t)own[0];
+        const uint32_t val4 = (own[0] & 255u) * 0x01010101u;
+        const uint32_t own0 = own[0];
         uint32_t blen = 0, bq = 0;
-        for (uint32_t q = lo + tid; q < i; q += L77_THREADS) {
-            if (q > *reinterpret_cast<volatile uint32_t*>(&cap_q)) break;  // an earlier start already has the longest possible match
-            if (data[q] != val) continue;
-            // match length, a word at a time; bytes at or past i + mx never count
-            uint32_t j = 0;
-            while (j < mx) {
-                const uint32_t x = l77_load4(data + q + j) ^ own[j >> 2];
-                if (x) { j += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
-                j += 4;
+        // first-byte filter, 16 starts per load: the window is cut into 16-byte groups (aligned in memory), group g goes to
+        // thread g mod L77_THREADS, all of a thread's loads are issued before the first use
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(data + lo) & ~(uintptr_t)15;
+        const uint4* __restrict__ grp = reinterpret_cast<const uint4*>(a0);
+        const uint32_t head = (uint32_t)(reinterpret_cast<uintptr_t>(data + lo) - a0);
+        const uint32_t total = head + (i - lo);             // bytes from a0 up to (not including) position i
+        const uint32_t ngroups = (total + 15u) >> 4;        // <= 4097
+        uint4 v[L77_GROUPS];
+#pragma unroll
+        for (int k = 0; k < L77_GROUPS; k++) {
+            const uint32_t g = (uint32_t)tid + (uint32_t)k * L77_THREADS;
+            v[k] = g < ngroups ? grp[g] : make_uint4(~val4, ~val4, ~val4, ~val4);
+        }
+        bool done = false;
+#pragma unroll
+        for (int k = 0; k < L77_GROUPS; k++) {
+            const uint32_t g = (uint32_t)tid + (uint32_t)k * L77_THREADS;
+            if (g >= ngroups || done) continue;
+            const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+            uint32_t m = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t t = __vcmpeq4(w[c], val4) & 0x01010101u;
+                t = (t | t >> 7 | t >> 14 | t >> 21) & 15u;
+                m |= t << (4 * c);
             }
-            j = min(j, mx);
-            if (j > blen) { blen = j; bq = q; }
-            if (j == mx) { atomicMin(&cap_q, q); break; }
+            const uint32_t off0 = g << 4;                   // offset of the group's first byte from a0
+            if (off0 < head) m &= 0xFFFFu << (head - off0);
+            if (off0 + 16u > total) m &= 0xFFFFu >> (off0 + 16u - total);
+            while (m) {
+                const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+                m &= m - 1u;
+                const uint32_t q = lo + (off0 + b - head);
+                if (q > *reinterpret_cast<volatile uint32_t*>(&cap_q)) { done = true; break; }  // an earlier start already has the cap
+                // a start can only beat this thread's best if it also matches at index blen
+                if (blen > 0 && blen < mx && data[q + blen] != (uint8_t)(own[blen >> 2] >> (8 * (blen & 3)))) continue;
+                uint32_t j = 0;
+                uint32_t x = l77_load4(data + q) ^ own0;
+                if (x) j = (uint32_t)(__ffs((int)x) - 1) >> 3;
+                else {
+                    j = 4;
+                    while (j < mx) {
+                        x = l77_load4(data + q + j) ^ own[j >> 2];
+                        if (x) { j += (uint32_t)(__ffs((int)x) - 1) >> 3; break; }
+                        j += 4;
+                    }
+                }
+                j = min(j, mx);
+                if (j > blen) { blen = j; bq = q; }
+                if (j == mx) { atomicMin(&cap_q, q); done = true; break; }
+            }
         }
         // CTA-wide: longest, then earliest
         unsigned long long key = ((unsigned long long)blen << 32) | (uint32_t)(~bq);
@@ -98,7 +138,7 @@ __global__ void __launch_bounds__(L77_THREADS) lz77_encode_k(const uint8_t* __re
                 if (i + len < n) nxt = data[i + len];
                 else nxt = stale_at[f] != 0xFFFFFFFFu ? bs[stale_at[f]] : persist[n];
                 word = (i - q) | len << 16 | (uint32_t)nxt << 24;
-            } else word = (uint32_t)val << 24;
+            } else word = (own[0] & 255u) << 24;
             tok[T] = word;
             s_len = len;
         }
