@@ -276,40 +276,84 @@ def run_b200(args):
     us, cs = ctx.enc_sizes(n_enc)                    # per-frame sizes of the timed workload (read before the e2e leg re-encodes a shorter clip)
 
     # ---- e2e: the same step through the public API with HOST buffers -------------------
+    # Every sequence goes host -> encode -> host stream -> decode -> host frames through agmvb_encode_sequence /
+    # agmvb_dec_open / agmvb_dec_frames. A sequence cannot overlap its own transfers with its own compute (the palette
+    # needs every frame before the first one can be encoded), so throughput comes from running `--e2e-streams`
+    # independent sequences at a time, one host thread + context (own CUDA stream) each: one sequence's upload
+    # overlaps another's kernels and download, as a service encoding several clips would run it.
     e2e = None
     if not args.no_e2e:
+        import threading
         e2e_frames = min(n_local, args.e2e_frames)
+        n_streams = max(1, args.e2e_streams)
+        # pinned host memory: frames in + frames out + stream per sequence in flight; stay within a quarter of this rank's share
+        try:
+            import psutil
+            budget = psutil.virtual_memory().available / max(1, world) / 4
+        except Exception:
+            budget = 16e9
+        while n_streams * e2e_frames * P * 4 * 1.9 > budget and (n_streams > 1 or e2e_frames > 64):
+            if n_streams > 1:
+                n_streams -= 1
+            else:
+                e2e_frames //= 2
         sa_e, sb_e = pdifs_schedule(e2e_frames, light)
-        host_frames = torch.empty((e2e_frames, H, W), dtype=torch.int32, pin_memory=True)
-        host_frames.copy_(frames[:e2e_frames])
-        out_host = torch.empty(4096 + e2e_frames * (P // 2), dtype=torch.uint8, pin_memory=True)
-        dec_host = torch.empty((len(sa_e), H, W), dtype=torch.int32, pin_memory=True)
-        out_np = out_host.numpy()
-        h2d = d2h = 0
+        iters = args.e2e_iters if args.e2e_iters > 0 else max(2, args.steps)
 
-        def e2e_step():
-            nonlocal h2d, d2h
-            data, ne = ctx.encode_sequence(host_frames.numpy().view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, COMP, out=out_np)
-            sid, w, h, n = ctx.dec_open(data)
-            ctx.dec_frames(sid, n, w, h, host_ptr=dec_host.data_ptr())
-            ctx.dec_close(sid)
-            h2d = e2e_frames * P * 4 + len(data)
-            d2h = len(data) + n * P * 4
+        class Worker:
+            def __init__(self, k):
+                self.ctx = ctx if k == 0 else libagmv_b200.Context(local)
+                self.host_frames = torch.empty((e2e_frames, H, W), dtype=torch.int32, pin_memory=True)
+                self.host_frames.copy_(frames[:e2e_frames])
+                self.out_host = torch.empty(4096 + e2e_frames * (P // 2), dtype=torch.uint8, pin_memory=True)
+                self.dec_host = torch.empty((len(sa_e), H, W), dtype=torch.int32, pin_memory=True)
+                self.h2d = self.d2h = 0
+                self.err = None
 
-        e2e_step()
+            def step(self):
+                c = self.ctx
+                data, ne = c.encode_sequence(self.host_frames.numpy().view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, COMP,
+                                             out=self.out_host.numpy())
+                sid, w, h, n = c.dec_open(data)
+                c.dec_frames(sid, n, w, h, host_ptr=self.dec_host.data_ptr())
+                c.dec_close(sid)
+                self.h2d = e2e_frames * P * 4 + len(data)
+                self.d2h = len(data) + n * P * 4
+
+            def run(self, k):
+                try:
+                    torch.cuda.set_device(local)
+                    for _ in range(k):
+                        self.step()
+                except Exception as e:  # surfaced after join
+                    self.err = e
+
+        workers = [Worker(k) for k in range(n_streams)]
+        for wk in workers:
+            wk.step()                                   # warm every context's workspaces
         barrier()
         t0 = time.perf_counter()
-        for _ in range(max(1, args.steps // 2)):
-            e2e_step()
+        threads = [threading.Thread(target=wk.run, args=(iters,)) for wk in workers]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
         barrier()
         dt = time.perf_counter() - t0
+        for wk in workers:
+            if wk.err is not None:
+                raise wk.err
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": e2e_frames * world * max(1, args.steps // 2) / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "frames_per_step": e2e_frames,
-               "note": "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers, host wall clock"}
+        seqs = n_streams * iters
+        e2e = {"value": e2e_frames * world * seqs / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(wk.h2d for wk in workers)),
+               "d2h_bytes_per_step": int(sum(wk.d2h for wk in workers)), "frames_per_step": e2e_frames * n_streams,
+               "concurrent_sequences": n_streams,
+               "note": f"{n_streams} independent {e2e_frames}-frame sequences at a time per GPU (one host thread + context each): "
+                       "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers, host wall clock"}
+        workers = None
 
     if rank != 0:
         if world > 1:
@@ -481,6 +525,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2000, help="source frames per GPU (BASELINE config 3: 2000)")
     ap.add_argument("--compression", default="lzss", choices=["lzss", "lz77"], help="entropy coder (BASELINE config 3: lzss; lz77 = SURVEY 8f N2)")
     ap.add_argument("--e2e-frames", type=int, default=512)
+    ap.add_argument("--e2e-streams", type=int, default=3, help="independent sequences in flight per GPU in the e2e leg")
+    ap.add_argument("--e2e-iters", type=int, default=0, help="sequences per worker in the e2e leg (default max(2, steps))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
