@@ -299,26 +299,36 @@ def run_b200(args):
                 e2e_frames //= 2
         sa_e, sb_e = pdifs_schedule(e2e_frames, light)
         iters = args.e2e_iters if args.e2e_iters > 0 else max(2, args.steps)
+        bpp = 3 if args.e2e_pixels == "bgr24" else 4
 
         class Worker:
             def __init__(self, k):
                 self.ctx = ctx if k == 0 else libagmv_b200.Context(local)
-                self.host_frames = torch.empty((e2e_frames, H, W), dtype=torch.int32, pin_memory=True)
-                self.host_frames.copy_(frames[:e2e_frames])
+                # host pixels in the reference's own frame format: the packed B,G,R rows of 24-bit BMP files (AGMVB_PIX_BGR24)
+                self.ctx.set_host_format(1 if bpp == 3 else 0)
+                self.host_frames = torch.empty((e2e_frames, H, W, bpp) if bpp == 3 else (e2e_frames, H, W),
+                                               dtype=torch.uint8 if bpp == 3 else torch.int32, pin_memory=True)
+                if bpp == 3:
+                    src = frames[:e2e_frames].view(torch.uint8).view(e2e_frames, H, W, 4)[..., :3]
+                    self.host_frames.copy_(src)
+                else:
+                    self.host_frames.copy_(frames[:e2e_frames])
                 self.out_host = torch.empty(4096 + e2e_frames * (P // 2), dtype=torch.uint8, pin_memory=True)
-                self.dec_host = torch.empty((len(sa_e), H, W), dtype=torch.int32, pin_memory=True)
+                self.dec_host = torch.empty((len(sa_e), H, W, bpp) if bpp == 3 else (len(sa_e), H, W),
+                                            dtype=torch.uint8 if bpp == 3 else torch.int32, pin_memory=True)
                 self.h2d = self.d2h = 0
                 self.err = None
 
             def step(self):
                 c = self.ctx
-                data, ne = c.encode_sequence(self.host_frames.numpy().view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, COMP,
+                hf = self.host_frames.numpy()
+                data, ne = c.encode_sequence(hf if bpp == 3 else hf.view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, COMP,
                                              out=self.out_host.numpy())
                 sid, w, h, n = c.dec_open(data)
                 c.dec_frames(sid, n, w, h, host_ptr=self.dec_host.data_ptr())
                 c.dec_close(sid)
-                self.h2d = e2e_frames * P * 4 + len(data)
-                self.d2h = len(data) + n * P * 4
+                self.h2d = e2e_frames * P * bpp + len(data)
+                self.d2h = len(data) + n * P * bpp
 
             def run(self, k):
                 try:
@@ -350,9 +360,11 @@ def run_b200(args):
         seqs = n_streams * iters
         e2e = {"value": e2e_frames * world * seqs / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(wk.h2d for wk in workers)),
                "d2h_bytes_per_step": int(sum(wk.d2h for wk in workers)), "frames_per_step": e2e_frames * n_streams,
-               "concurrent_sequences": n_streams,
+               "concurrent_sequences": n_streams, "host_pixels": args.e2e_pixels,
                "note": f"{n_streams} independent {e2e_frames}-frame sequences at a time per GPU (one host thread + context each): "
-                       "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers, host wall clock"}
+                       "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers "
+                       + ("(packed 24-bit BMP pixel rows in and out, AGMVB_PIX_BGR24)" if bpp == 3 else "(u32 pixels)") + ", host wall clock"}
+        ctx.set_host_format(0)
         workers = None
 
     if rank != 0:
@@ -525,7 +537,8 @@ def main():
     ap.add_argument("--frames", type=int, default=2000, help="source frames per GPU (BASELINE config 3: 2000)")
     ap.add_argument("--compression", default="lzss", choices=["lzss", "lz77"], help="entropy coder (BASELINE config 3: lzss; lz77 = SURVEY 8f N2)")
     ap.add_argument("--e2e-frames", type=int, default=512)
-    ap.add_argument("--e2e-streams", type=int, default=3, help="independent sequences in flight per GPU in the e2e leg")
+    ap.add_argument("--e2e-streams", type=int, default=4, help="independent sequences in flight per GPU in the e2e leg")
+    ap.add_argument("--e2e-pixels", default="bgr24", choices=["bgr24", "u32"], help="host pixel format of the e2e leg")
     ap.add_argument("--e2e-iters", type=int, default=0, help="sequences per worker in the e2e leg (default max(2, steps))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -48,6 +48,13 @@ const char* agmvb_last_error(const agmvb_ctx* ctx);
 uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx);
 /* wait for everything queued on the context's stream */
 int agmvb_sync(agmvb_ctx* ctx);
+/* Pixel format of HOST frame buffers (on_device == 0): every `frames` argument of the encoder entry points and the host
+ * `out` of agmvb_dec_frames. AGMVB_PIX_U32 (default): one uint32 0x00RRGGBB per pixel. AGMVB_PIX_BGR24: packed B,G,R bytes,
+ * row-major, no padding - exactly the pixel rows of the 24-bit BMP files the reference reads (AGIDL_LoadBMP) and writes
+ * (AGIDL_QuickExport); a quarter fewer bytes across PCIe, unpacked / packed on the device. Device buffers are always u32. */
+#define AGMVB_PIX_U32 0
+#define AGMVB_PIX_BGR24 1
+int agmvb_set_host_format(agmvb_ctx* ctx, int fmt);
 
 /* ---- encoder: the pieces of AGMV_EncodeAGMV (src/agmv_encode.c:2270-3657) --- */
 /* Start a sequence: source size, profile, quality, entropy coder. GBA / NDS

@@ -32,6 +32,7 @@ SYMBOLS = {
     "agmvb_last_error": (C.c_char_p, [C.c_void_p]),
     "agmvb_kernel_launches": (C.c_uint64, [C.c_void_p]),
     "agmvb_sync": (C.c_int, [C.c_void_p]),
+    "agmvb_set_host_format": (C.c_int, [C.c_void_p, C.c_int]),
     "agmvb_enc_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int]),
     "agmvb_enc_histogram": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int]),
     "agmvb_enc_histogram_ptr": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _u32p]),
@@ -129,10 +130,19 @@ class Context:
     def sync(self):
         self._ck(self.lib.agmvb_sync(self.h))
 
+    def set_host_format(self, fmt):
+        """0 = uint32 0x00RRGGBB host pixels (default), 1 = packed B,G,R bytes (BMP pixel rows)."""
+        self._ck(self.lib.agmvb_set_host_format(self.h, fmt))
+        self.host_fmt = fmt
+
     # ---- encoder ----------------------------------------------------------
     def encode_sequence(self, frames, create_n, fps, opt, quality, compression=LZSS, device_ptr=None, shape=None, out=None):
         """AGMV_EncodeAGMV on in-memory frames. frames: (n,h,w) uint32 host array, or pass device_ptr + shape."""
-        if device_ptr is None:
+        if device_ptr is None and getattr(self, "host_fmt", 0) == 1:
+            frames = np.ascontiguousarray(frames, dtype=np.uint8)   # (n, h, w, 3) packed B,G,R
+            n, h, w, _ = frames.shape
+            src, on_dev = frames.ctypes.data, 0
+        elif device_ptr is None:
             frames = np.ascontiguousarray(frames, dtype=np.uint32)
             n, h, w = frames.shape
             src, on_dev = frames.ctypes.data, 0
@@ -233,7 +243,7 @@ class Context:
             return None
         out = None
         if host_ptr is None:
-            out = np.empty((count, h, w), dtype=np.uint32)
+            out = np.empty((count, h, w, 3), dtype=np.uint8) if getattr(self, "host_fmt", 0) == 1 else np.empty((count, h, w), dtype=np.uint32)
             host_ptr = out.ctypes.data
         self._ck(self.lib.agmvb_dec_frames(self.h, sid, count, C.c_void_p(host_ptr), 0))
         return out

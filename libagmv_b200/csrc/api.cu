@@ -72,6 +72,8 @@ struct agmvb_ctx {
     DBuf stage, entries, rec, boff, bs, fs, image, srcpairs, entpairs, scanws, small, seqbuf;
     LzWork lz;
     DBuf lzbuf[64];
+    int host_fmt = 0;   // pixel format of HOST frame buffers: 0 = u32 0x00RRGGBB, 1 = packed B,G,R bytes (a BMP's pixel rows)
+    DBuf raw24;         // staging for packed 24-bit pixels
     DBuf l77_out, l77_meta, l77_persist;  // LZ77: token words, per-frame arrays, the reference's carried bitstream buffer
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
@@ -96,6 +98,17 @@ struct agmvb_ctx {
         int _rc = (expr);         \
         if (_rc != OK) return _rc; \
     } while (0)
+
+// Bulk host<->device copies go out in pieces: a copy engine serves its queue in order, so one multi-GB transfer would hold
+// up the small parameter copies of every other context (stream) sharing the device for its whole duration.
+static cudaError_t copy_pieces(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+    const size_t piece = 32ull << 20;
+    for (size_t o = 0; o < bytes; o += piece) {
+        cudaError_t e = cudaMemcpyAsync(static_cast<uint8_t*>(dst) + o, static_cast<const uint8_t*>(src) + o, std::min(piece, bytes - o), kind, st);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
 
 static int ensure(agmvb_ctx* ctx, DBuf& b, size_t bytes) {
     if (b.cap >= bytes && b.p) return OK;
@@ -168,7 +181,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
                     &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
-    cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p);
+    cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p); cudaFree(ctx->raw24.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
     for (DecStream& s : ctx->parked) free_stream(s);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -181,6 +194,66 @@ extern "C" uint64_t agmvb_kernel_launches(const agmvb_ctx* ctx) { return ctx ? c
 extern "C" int agmvb_sync(agmvb_ctx* ctx) {
     if (!ctx) return ERR_ARG;
     CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// ---- host pixel formats ------------------------------------------------------------------------
+// The reference's frames come from (and go to) 24-bit BMP files; handing the packed B,G,R rows across PCIe instead of
+// 4-byte pixels moves a quarter fewer bytes, and the unpack / pack runs at HBM speed on the device.
+__global__ void __launch_bounds__(256) unpack_bgr24_k(const uint8_t* __restrict__ src, uint64_t npx, uint32_t* __restrict__ dst) {
+    // four pixels (12 bytes = three aligned words) per thread
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p0 = g * 4;
+    if (p0 >= npx) return;
+    if (p0 + 4 <= npx) {
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(src) + g * 3;
+        const uint32_t a = w[0], b = w[1], c = w[2];
+        uint4 o;
+        o.x = a & 0xFFFFFFu;
+        o.y = (a >> 24) | (b & 0xFFFFu) << 8;
+        o.z = (b >> 16) | (c & 0xFFu) << 16;
+        o.w = c >> 8;
+        *reinterpret_cast<uint4*>(dst + p0) = o;   // byte order B,G,R == 0x00RRGGBB little-endian
+    } else {
+        for (uint64_t p = p0; p < npx; p++) dst[p] = (uint32_t)src[3 * p] | (uint32_t)src[3 * p + 1] << 8 | (uint32_t)src[3 * p + 2] << 16;
+    }
+}
+__global__ void __launch_bounds__(256) pack_bgr24_k(const uint32_t* __restrict__ src, uint64_t npx, uint8_t* __restrict__ dst) {
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t p0 = g * 4;
+    if (p0 >= npx) return;
+    if (p0 + 4 <= npx) {
+        const uint4 v = *reinterpret_cast<const uint4*>(src + p0);
+        uint32_t* w = reinterpret_cast<uint32_t*>(dst) + g * 3;
+        w[0] = (v.x & 0xFFFFFFu) | v.y << 24;
+        w[1] = ((v.y >> 8) & 0xFFFFu) | v.z << 16;
+        w[2] = ((v.z >> 16) & 0xFFu) | v.w << 8;
+    } else {
+        for (uint64_t p = p0; p < npx; p++) { dst[3 * p] = (uint8_t)src[p]; dst[3 * p + 1] = (uint8_t)(src[p] >> 8); dst[3 * p + 2] = (uint8_t)(src[p] >> 16); }
+    }
+}
+
+extern "C" int agmvb_set_host_format(agmvb_ctx* ctx, int fmt) {
+    if (!ctx || (fmt != 0 && fmt != 1)) return ERR_ARG;
+    ctx->host_fmt = fmt;
+    return OK;
+}
+
+// count host frames (fpx pixels each) starting at frame `first` of the caller's buffer -> d_dst as u32 pixels
+static int upload_frames(agmvb_ctx* ctx, const uint32_t* host_frames, uint64_t first, uint64_t count, uint64_t fpx, uint32_t* d_dst) {
+    if (ctx->host_fmt == 0) {
+        CK(copy_pieces(d_dst, host_frames + first * fpx, count * fpx * 4, cudaMemcpyHostToDevice, ctx->st));
+        return OK;
+    }
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(host_frames) + first * fpx * 3;
+    // through a bounded staging buffer so that a long sequence does not need a second full-size copy on the device
+    const uint64_t chunk = std::max<uint64_t>(1, (512ull << 20) / (fpx * 3));
+    TRY(ensure(ctx, ctx->raw24, std::min(chunk, count) * fpx * 3 + 16));
+    for (uint64_t f0 = 0; f0 < count; f0 += chunk) {
+        const uint64_t nf = std::min(chunk, count - f0), npx = nf * fpx;
+        CK(copy_pieces(ctx->raw24.p, src + f0 * fpx * 3, npx * 3, cudaMemcpyHostToDevice, ctx->st));
+        KL(ctx->lc, KC_MISC, (unpack_bgr24_k<<<(unsigned)cdiv(cdiv(npx, 4), 256), 256, 0, ctx->st>>>(ctx->raw24.as<uint8_t>(), npx, d_dst + f0 * fpx)));
+    }
     return OK;
 }
 
@@ -271,7 +344,7 @@ extern "C" int agmvb_enc_histogram(agmvb_ctx* ctx, const uint32_t* frames, uint6
     TRY(ensure(ctx, ctx->stage, std::min(chunk_frames, n_frames) * fpx * 4));
     for (uint64_t f0 = 0; f0 < n_frames; f0 += chunk_frames) {
         uint64_t nf = std::min(chunk_frames, n_frames - f0);
-        CK(cudaMemcpyAsync(ctx->stage.p, frames + f0 * fpx, nf * fpx * 4, cudaMemcpyHostToDevice, ctx->st));
+        TRY(upload_frames(ctx, frames, f0, nf, fpx, ctx->stage.as<uint32_t>()));
         TRY(hist_launch(ctx, ctx->stage.as<uint32_t>(), nf * fpx));
         CK(cudaStreamSynchronize(ctx->st));  // the staging buffer is reused
     }
@@ -588,7 +661,7 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
             uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
             TRY(ensure(ctx, ctx->stage, uniq.size() * SP * 4));
             for (size_t u = 0; u < uniq.size(); u++)
-                CK(cudaMemcpyAsync(ctx->stage.as<uint32_t>() + u * SP, frames + (size_t)uniq[u] * SP, SP * 4, cudaMemcpyHostToDevice, ctx->st));
+                TRY(upload_frames(ctx, frames, (uint64_t)uniq[u], 1, SP, ctx->stage.as<uint32_t>() + u * SP));
             auto slot = [&](int32_t idx) { return (size_t)(std::lower_bound(uniq.begin(), uniq.end(), idx) - uniq.begin()); };
             for (uint32_t k = 0; k < F; k++) {
                 sp[k].a = ctx->stage.as<uint32_t>() + slot(src_a[q0 + k]) * SP;
@@ -637,7 +710,7 @@ extern "C" int agmvb_frame_similarity(agmvb_ctx* ctx, const uint32_t* frames, ui
     const uint32_t* base = frames;
     if (!on_device) {
         TRY(ensure(ctx, ctx->stage, n_frames_in_buffer * SP * 4));
-        CK(cudaMemcpyAsync(ctx->stage.p, frames, n_frames_in_buffer * SP * 4, cudaMemcpyHostToDevice, ctx->st));
+        TRY(upload_frames(ctx, frames, 0, n_frames_in_buffer, SP, ctx->stage.as<uint32_t>()));
         base = ctx->stage.as<uint32_t>();
     }
     std::vector<SrcPair> sp(n_pairs);
@@ -666,7 +739,7 @@ extern "C" int agmvb_enc_fetch(agmvb_ctx* ctx, uint8_t* image, uint64_t cap, uin
     if (!ctx) return ERR_ARG;
     if (image) {
         if (cap < ctx->image_bytes) FAIL(ERR_ARG, "image buffer too small: %llu < %llu", (unsigned long long)cap, (unsigned long long)ctx->image_bytes);
-        if (ctx->image_bytes) CK(cudaMemcpyAsync(image, ctx->image.p, ctx->image_bytes, cudaMemcpyDeviceToHost, ctx->st));
+        if (ctx->image_bytes) CK(copy_pieces(image, ctx->image.p, ctx->image_bytes, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));
     }
     if (usize) memcpy(usize, ctx->last_usize.data(), ctx->last_usize.size() * 4);
@@ -722,7 +795,7 @@ static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames
         CK(cudaMemGetInfo(&free_b, &total_b));
         if (bytes + (8ull << 30) < free_b + ctx->seqbuf.cap) {
             TRY(ensure(ctx, ctx->seqbuf, bytes));
-            CK(cudaMemcpyAsync(ctx->seqbuf.p, frames, bytes, cudaMemcpyHostToDevice, ctx->st));
+            TRY(upload_frames(ctx, frames, 0, n_src, (uint64_t)w * h, ctx->seqbuf.as<uint32_t>()));
             frames = ctx->seqbuf.as<uint32_t>();
             on_device = 1;
         }
@@ -935,7 +1008,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
         s.persist_len = (uint32_t)(2 * P + 64);
         CK(cudaMalloc(&s.d_persist, s.persist_len));
     }
-    CK(cudaMemcpyAsync(s.d_file, file, len, cudaMemcpyHostToDevice, ctx->st));
+    CK(copy_pieces(s.d_file, file, len, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(s.d_file + len, 0, 64, ctx->st));
     CK(cudaMemcpyAsync(s.d_pal, pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(s.d_img, 0, P * 4, ctx->st));      // defined start state: zero pages
@@ -1157,14 +1230,21 @@ extern "C" int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint
     if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) FAIL(ERR_ARG, "bad stream handle");
     if (on_device) { uint32_t* o = out; return dec_batch_impl(ctx, &stream, 1, count, &o, nullptr); }
     const size_t P = (size_t)ctx->streams[stream].w * ctx->streams[stream].h;
-    // host destination: decode into device staging, at most ~1 GB at a time
-    const uint32_t chunk = (uint32_t)std::max<size_t>(4, ((1ull << 30) / (P * 4)) & ~3ull);
+    // host destination: decode into device staging, at most ~4 GB at a time (the expansion kernel is a warp per frame:
+    // its latency is paid once per chunk, so chunks should hold as many frames as is reasonable)
+    const uint32_t chunk = (uint32_t)std::max<size_t>(4, ((4ull << 30) / (P * 4)) & ~3ull);
     for (uint32_t c0 = 0; c0 < count; c0 += chunk) {
         uint32_t cn = std::min(chunk, count - c0);
         TRY(ensure(ctx, ctx->d_out, (size_t)cn * P * 4));
         uint32_t* o = ctx->d_out.as<uint32_t>();
         TRY(dec_batch_impl(ctx, &stream, 1, cn, &o, nullptr));
-        CK(cudaMemcpyAsync(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (ctx->host_fmt == 0) CK(copy_pieces(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
+        else {
+            const uint64_t npx = (uint64_t)cn * P;
+            TRY(ensure(ctx, ctx->raw24, npx * 3 + 16));
+            KL(ctx->lc, KC_MISC, (pack_bgr24_k<<<(unsigned)cdiv(cdiv(npx, 4), 256), 256, 0, ctx->st>>>(o, npx, ctx->raw24.as<uint8_t>())));
+            CK(copy_pieces(reinterpret_cast<uint8_t*>(out) + (size_t)c0 * P * 3, ctx->raw24.p, npx * 3, cudaMemcpyDeviceToHost, ctx->st));
+        }
         CK(cudaStreamSynchronize(ctx->st));
     }
     return OK;

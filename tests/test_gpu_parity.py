@@ -432,3 +432,35 @@ def test_lz77_720p_against_oracle(ctx):
     rc, ref_frames = oracle_decode(want)
     assert rc == 0
     assert np.array_equal(ctx.decode_all(want), ref_frames)
+
+
+def test_bgr24_host_frames_equal_u32_path(ctx, golden):
+    """AGMVB_PIX_BGR24: packed BMP pixel rows in, packed rows out - same stream bytes and same pixels as the u32 path."""
+    g = golden["encode"]["syn96x80_III_LOW"]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    bgr = np.stack([frames & 255, (frames >> 8) & 255, (frames >> 16) & 255], axis=-1).astype(np.uint8)
+    ctx.set_host_format(1)
+    try:
+        data, n_enc = ctx.encode_sequence(bgr, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+        assert sha256(data.tobytes()) == g["sha256"]
+        sid, w, h, n = ctx.dec_open(data.tobytes())
+        out = ctx.dec_frames(sid, n, w, h)
+        ctx.dec_close(sid)
+    finally:
+        ctx.set_host_format(0)
+    assert out.shape == (n, h, w, 3)
+    px = out.astype(np.uint32)
+    dec = px[..., 0] | px[..., 1] << 8 | px[..., 2] << 16
+    assert [sha256(dec[k].tobytes()) for k in range(n)] == g["decoded_frame_sha256"]
+    # the piecewise entry points (streamed histogram) take the packed format as well: same palette either way
+    pals = []
+    for fmt, buf in ((1, bgr), (0, np.ascontiguousarray(frames))):
+        ctx.set_host_format(fmt)
+        try:
+            ctx.enc_begin(g["w"], g["h"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            ctx.enc_histogram(buf.ctypes.data, g["n"], False)
+            ctx.enc_build_palette()
+            pals.append(ctx.enc_get_palette())
+        finally:
+            ctx.set_host_format(0)
+    assert np.array_equal(pals[0][0], pals[1][0]) and np.array_equal(pals[0][1], pals[1][1])
