@@ -151,7 +151,8 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
     }
     ctx->lc.st = ctx->st;
     if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess ||
-        cudaFuncSetAttribute(lz_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SCATTER_SMEM) != cudaSuccess) {
+        cudaFuncSetAttribute(lz_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SCATTER_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(lz_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) {
         delete ctx;
         return ERR_CUDA;
     }

@@ -34,7 +34,8 @@ namespace agmvb {
 
 constexpr int LZ_LEVELS = 15;
 constexpr uint32_t LZ_POS_MASK = 0x0FFFFFFFu;  // A[] words: position in the low 28 bits, min(15, bytes left in the frame) in the top 4
-constexpr uint32_t LZ_MAX_BATCH = 1u << 28;
+constexpr uint32_t LZ_MAX_BATCH = 1u << 27;
+constexpr uint32_t LZ_RES = 1u << 27;          // match_rec: level << 28 | LZ_RES | offset = already resolved (lz_small_k); else level << 28 | group start
 // work layout of the level kernels: 4096-element tiles (same tiling as radix.cuh / scan.cuh), 512 threads x 8 rounds
 constexpr int LZ_THREADS = 512, LZ_WARPS = 16, LZ_ROUNDS = 8, LZ_WARP_SPAN = 256, LZ_TILE = 4096;
 constexpr uint32_t LZ_ALIVE = 0x80000000u;     // GS / gs_tmp words: bit 31 = "a match of this level's length exists for the element"
@@ -374,6 +375,299 @@ __global__ void lz_bestlen_k(const uint32_t* __restrict__ match_rec, uint32_t n,
 }
 
 // =====================================================================================================
+// Levels 4..15 for SMALL groups, entirely in shared memory.
+//
+// After level 3 the array is cut into groups (same frame, same first 3 bytes); every later level only splits groups,
+// so a group is an independent sub-problem. Groups of at most SG_C elements - 75-100 % of all positions on the bench
+// workload - are finished by one CTA without touching HBM again: CTA w owns the groups that START in
+// [w*SG_W, (w+1)*SG_W) (they end before (w+1)*SG_W + SG_C, so SG_W + SG_C slots hold them), compacts them into shared memory and
+// runs the same refinement as the global kernels (stable counting sort by the next key byte, heads = old-group change
+// or bucket start, running max, exists = predecessor within the window) twelve times. When a position's match stops
+// growing it is resolved on the spot: the earliest in-window member of its last group is a binary search in the
+// previous arrangement (still in shared memory), so match_rec receives the final (length, offset) and lz_pack_k has
+// nothing to search. Larger groups (long runs, mostly) are compacted and go through the global level kernels.
+// =====================================================================================================
+constexpr int SG_C = 512;                // largest group finished in shared memory
+constexpr int SG_W = 1536;               // window of group starts per CTA
+constexpr int SG_K = SG_W + SG_C;        // slots per CTA
+constexpr int SG_THREADS = 256, SG_WARPS = SG_THREADS / 32, SG_ROUNDS = SG_K / SG_THREADS, SG_SPAN = SG_ROUNDS * 32;
+constexpr size_t SG_SMEM = (size_t)SG_K * (4 + 4) * 2 + (size_t)SG_K * 2 * 2 + (size_t)SG_K * 2;  // pos, kw (x2), gid (x2), src
+static_assert(SG_K == SG_THREADS * SG_ROUNDS && SG_K <= 4096, "one slot per thread and round; local indices fit 12 bits");
+
+__device__ __forceinline__ uint32_t sg_lower_bound(const uint32_t* __restrict__ pos, uint32_t lo, uint32_t hi, uint32_t target) {
+    // first k in [lo, hi) with (pos[k] & LZ_POS_MASK) >= target; the caller guarantees that one exists
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((pos[mid] & LZ_POS_MASK) >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// is the level-3 group that starts at index g larger than SG_C?
+__device__ __forceinline__ bool sg_group_is_large(const uint32_t* __restrict__ gs3, uint32_t n, uint32_t g) {
+    return g + (uint32_t)SG_C < n && (gs3[g + SG_C] & LZ_GS_MASK) == g;
+}
+struct LargeFlag {
+    const uint32_t* gs3;
+    uint32_t n;
+    __device__ uint32_t operator()(uint32_t i) const { return sg_group_is_large(gs3, n, gs3[i] & LZ_GS_MASK) ? 1u : 0u; }
+};
+// elements of large groups, in order, with group starts renumbered; prefix = exclusive scan of LargeFlag
+__global__ void __launch_bounds__(256) lz_compact_large_k(const uint32_t* __restrict__ a3, const uint32_t* __restrict__ gs3,
+                                                          const uint32_t* __restrict__ dig, const uint32_t* __restrict__ prefix, uint32_t n,
+                                                          uint32_t* __restrict__ a_out, uint32_t* __restrict__ gs_out, uint32_t* __restrict__ dig_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t gw = gs3[i], g = gw & LZ_GS_MASK;
+    if (!sg_group_is_large(gs3, n, g)) return;
+    const uint32_t o = prefix[i];
+    a_out[o] = a3[i];
+    gs_out[o] = prefix[g] | (gw & LZ_ALIVE);
+    dig_out[o] = dig[i];
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 4) lz_small_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ a3,
+                                                         const uint32_t* __restrict__ gs3, uint32_t* __restrict__ match_rec) {
+    extern __shared__ __align__(16) uint8_t lz_dyn[];
+    uint32_t* const pos_all = reinterpret_cast<uint32_t*>(lz_dyn);            // [2][SG_K]
+    uint32_t* const kw_all = pos_all + 2 * SG_K;                              // [2][SG_K]
+    uint16_t* const gid_all = reinterpret_cast<uint16_t*>(kw_all + 2 * SG_K);  // [2][SG_K]
+    uint16_t* const src = gid_all + 2 * SG_K;                                  // [SG_K]
+    __shared__ uint32_t n_list;
+    __shared__ uint32_t wc[SG_WARPS][256];
+    __shared__ uint32_t lstart[256];
+    __shared__ uint32_t gtot[8];
+    __shared__ uint32_t bm[SG_K / 32];
+    __shared__ uint32_t wtot[SG_WARPS];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t w0 = blockIdx.x * (uint32_t)SG_W;
+    const uint32_t sbase = (uint32_t)warp * SG_SPAN + lane;   // slot of round r: sbase + 32 r
+
+    // ---- load the window, keep the small groups that start in it ----
+    uint32_t pw[SG_ROUNDS], gw[SG_ROUNDS];
+#pragma unroll
+    for (int r = 0; r < SG_ROUNDS; r++) {
+        const uint32_t s = sbase + r * 32, idx = w0 + s;
+        gw[r] = idx < n ? gs3[idx] : 0xFFFFFFFFu;
+        pw[r] = idx < n ? a3[idx] : 0u;
+        pos_all[SG_K + s] = gw[r];
+    }
+    __syncthreads();
+    uint32_t keep = 0;  // bit r
+    uint32_t lidx[SG_ROUNDS];
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            const uint32_t s = sbase + r * 32, idx = w0 + s, g = gw[r] & LZ_GS_MASK;
+            bool v = idx < n && g >= w0 && g < w0 + (uint32_t)SG_W;
+            if (v) v = g + (uint32_t)SG_C >= n || (pos_all[SG_K + g + SG_C - w0] & LZ_GS_MASK) != g;
+            const unsigned bal = __ballot_sync(0xffffffffu, v);
+            lidx[r] = run + __popc(bal & lanemask_lt());
+            run += __popc(bal);
+            keep |= (uint32_t)v << r;
+        }
+        if (lane == 0) wtot[warp] = run;
+    }
+    __syncthreads();
+    uint32_t wpre = 0, K = 0;
+#pragma unroll
+    for (int w = 0; w < SG_WARPS; w++) { const uint32_t t = wtot[w]; if (w < warp) wpre += t; K += t; }
+    if (K == 0) return;
+#pragma unroll
+    for (int r = 0; r < SG_ROUNDS; r++) {
+        lidx[r] += wpre;
+        if ((keep >> r) & 1u) src[sbase + r * 32] = (uint16_t)lidx[r];   // slot -> local index (read below for the group heads)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SG_ROUNDS; r++) {
+        if ((keep >> r) & 1u) {
+            const uint32_t i = lidx[r], g = gw[r] & LZ_GS_MASK;
+            pos_all[i] = pw[r];
+            gid_all[i] = (uint16_t)(src[g - w0] | (gw[r] >> 31) << 15);
+            kw_all[i] = load4(bs + (pw[r] & LZ_POS_MASK) + 3);
+        }
+    }
+    __syncthreads();
+
+    // The elements are dealt out in equal contiguous spans (R rounds of 32 per warp). An element that has no match at the
+    // current length and whose successor in its group is farther than the window (or missing) can never be anyone's
+    // match source again - every later member of any sub-group is at least as far away - so it leaves the working set
+    // at the next sort: K shrinks from level to level.
+    __shared__ uint32_t s_knew;
+    int cur = 0;
+    for (uint32_t lvl = 3; lvl < (uint32_t)LZ_LEVELS; lvl++) {   // level lvl -> lvl + 1, key byte index lvl
+        uint32_t* const posc = pos_all + cur * SG_K;  uint32_t* const posn = pos_all + (cur ^ 1) * SG_K;
+        uint32_t* const kwc = kw_all + cur * SG_K;    uint32_t* const kwn = kw_all + (cur ^ 1) * SG_K;
+        uint16_t* const gidc = gid_all + cur * SG_K;  uint16_t* const gidn = gid_all + (cur ^ 1) * SG_K;
+        const int R = (int)((K + SG_THREADS - 1) / SG_THREADS);
+        const uint32_t jbase = (uint32_t)warp * (uint32_t)(R * 32) + lane;
+        if (tid == 0) n_list = 0;
+        for (int k = tid; k < SG_WARPS * 256; k += SG_THREADS) (&wc[0][0])[k] = 0;
+        if (tid < SG_K / 32) bm[tid] = 0;
+        const bool regather = lvl > 3 && ((lvl - 3) & 3u) == 0;
+        const uint32_t sh = 8u * ((lvl - 3) & 3u);
+        uint32_t p[SG_ROUNDS], kk[SG_ROUNDS], packed[SG_ROUNDS];
+        uint16_t gg[SG_ROUNDS];
+        uint32_t stay = 0;  // bit r: the element takes part in the next arrangement
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            if (r >= R) break;
+            const uint32_t j = jbase + r * 32;
+            if (j < K) {
+                p[r] = posc[j];
+                gg[r] = gidc[j];
+                bool st = gg[r] >> 15;
+                if (!st && j + 1 < K) {
+                    const uint32_t gn = gidc[j + 1], pn = posc[j + 1];
+                    st = ((gn ^ gg[r]) & 0x7FFFu) == 0 && (pn & LZ_POS_MASK) - (p[r] & LZ_POS_MASK) <= (uint32_t)LZ_WINDOW;
+                }
+                stay |= (uint32_t)st << r;
+                kk[r] = !st ? 0u : (regather ? load4(bs + (p[r] & LZ_POS_MASK) + lvl) : kwc[j]);
+            } else { p[r] = 0; gg[r] = 0; kk[r] = 0; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            if (r >= R) break;
+            const bool valid = (stay >> r) & 1u;
+            const uint32_t key = valid ? (kk[r] >> sh) & 255u : 256u + lane;
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = wc[warp][key];
+                wc[warp][key] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            packed[r] = (key << 16) | (old + __popc(peers & lanemask_lt()));
+            __syncwarp();
+        }
+        __syncthreads();
+        uint32_t b_tot = 0, b_inc = 0;
+        if (tid < 256) {
+#pragma unroll
+            for (int w = 0; w < SG_WARPS; w++) {
+                const uint32_t t = wc[w][tid];
+                wc[w][tid] = b_tot;
+                b_tot += t;
+            }
+            b_inc = b_tot;
+#pragma unroll
+            for (int k = 1; k < 32; k <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, b_inc, k); if (lane >= k) b_inc += y; }
+            if (lane == 31) gtot[tid >> 5] = b_inc;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t add = 0;
+            for (int w = 0; w < (tid >> 5); w++) add += gtot[w];
+            const uint32_t ls = add + b_inc - b_tot;
+            lstart[tid] = ls;
+            if (b_tot) atomicOr(&bm[ls >> 5], 1u << (ls & 31));   // the first element of a key-byte bucket heads a group
+            if (tid == 255) s_knew = ls + b_tot;
+        }
+        __syncthreads();
+        const uint32_t Kn = s_knew;
+        if (Kn == 0) break;
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            if (r >= R) break;
+            if ((stay >> r) & 1u) {
+                const uint32_t d = packed[r] >> 16, rk = packed[r] & 0xffffu;
+                const uint32_t slot = lstart[d] + wc[warp][d] + rk;
+                posn[slot] = p[r];
+                kwn[slot] = kk[r];
+                gidn[slot] = gg[r];
+                src[slot] = (uint16_t)(jbase + r * 32);
+            }
+        }
+        __syncthreads();
+        // ---- groups of the new arrangement (Kn elements) ----
+        const int Rn = (int)((Kn + SG_THREADS - 1) / SG_THREADS);
+        const uint32_t nbase = (uint32_t)warp * (uint32_t)(Rn * 32) + lane;
+        uint32_t v[SG_ROUNDS], pprev[SG_ROUNDS];
+        {
+            uint32_t carry = 0;
+#pragma unroll
+            for (int r = 0; r < SG_ROUNDS; r++) {
+                if (r >= Rn) break;
+                const uint32_t j = nbase + r * 32;
+                const bool valid = j < Kn;
+                p[r] = valid ? posn[j] : 0u;
+                gg[r] = valid ? gidn[j] : (uint16_t)0;
+                const uint32_t gp = (valid && j > 0) ? gidn[j - 1] : 0u;
+                pprev[r] = (valid && j > 0) ? posn[j - 1] : 0u;
+                const bool hd = valid && (j == 0 || ((gg[r] ^ gp) & 0x7FFFu) != 0 || ((bm[j >> 5] >> (j & 31)) & 1u));
+                const unsigned hm = __ballot_sync(0xffffffffu, hd);
+                const unsigned upto = hm & (0xffffffffu >> (31 - lane));
+                const uint32_t rbase = j - lane;
+                v[r] = upto ? rbase + (31 - __clz(upto)) : carry;
+                carry = hm ? rbase + (31 - __clz(hm)) : carry;
+            }
+            if (lane == 0) wtot[warp] = carry;
+        }
+        __syncthreads();
+        uint32_t pre = 0;
+        for (int w = 0; w < warp; w++) pre = max(pre, wtot[w]);
+        const uint32_t Lnew = lvl + 1;
+        int any_alive = 0;
+        uint16_t ng[SG_ROUNDS];
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            if (r >= Rn) break;
+            const uint32_t j = nbase + r * 32;
+            ng[r] = 0;
+            bool died = false, full = false;
+            uint32_t g = 0;
+            if (j < Kn) {
+                g = max(pre, v[r]);
+                const uint32_t pp = p[r] & LZ_POS_MASK;
+                const bool exists = g != j && pp - (pprev[r] & LZ_POS_MASK) <= (uint32_t)LZ_WINDOW && Lnew <= (p[r] >> 28);
+                died = !exists && (gg[r] >> 15);
+                full = exists && Lnew == (uint32_t)LZ_LEVELS;
+                ng[r] = (uint16_t)(g | (exists ? 0x8000u : 0u));
+                any_alive |= exists;
+            }
+            // a match that stops growing here (or reaches 15) is resolved after the loop, densely: the searches of the few
+            // lanes that need one would otherwise stall the whole warp at every level
+            const unsigned act = __ballot_sync(0xffffffffu, died || full);
+            if (act) {
+                const int leader = __ffs(act) - 1;
+                uint32_t base_slot = 0;
+                if (lane == leader) base_slot = atomicAdd(&n_list, (uint32_t)__popc(act));
+                base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+                if (died || full) kwc[base_slot + __popc(act & lanemask_lt())] = j | g << 12 | (full ? 1u << 24 : 0u);   // kwc is free after the scatter
+            }
+        }
+        __syncthreads();
+        for (uint32_t e = tid; e < n_list; e += SG_THREADS) {
+            const uint32_t rec = kwc[e], j = rec & 0xFFFu, g = (rec >> 12) & 0xFFFu;
+            const uint32_t pp = posn[j] & LZ_POS_MASK;
+            const uint32_t target = pp > (uint32_t)LZ_WINDOW ? pp - (uint32_t)LZ_WINDOW : 0u;
+            if (rec >> 24) {   // 15 bytes match: earliest in-window member of the level-15 group (this arrangement)
+                const uint32_t k = sg_lower_bound(posn, g, j, target);
+                match_rec[pp] = Lnew << 28 | LZ_RES | (pp - (posn[k] & LZ_POS_MASK));
+            } else {           // the match stops at length lvl: earliest in-window member of the level-lvl group (previous arrangement)
+                const uint32_t i = src[j], go = gidn[j] & 0x7FFFu;
+                const uint32_t k = sg_lower_bound(posc, go, i, target);
+                match_rec[pp] = lvl << 28 | LZ_RES | (pp - (posc[k] & LZ_POS_MASK));
+            }
+        }
+        __syncthreads();   // every neighbour's old group id has been read
+#pragma unroll
+        for (int r = 0; r < SG_ROUNDS; r++) {
+            if (r >= Rn) break;
+            const uint32_t j = nbase + r * 32;
+            if (j < Kn) gidn[j] = ng[r];
+        }
+        if (!__syncthreads_or(any_alive)) break;   // nobody can grow any further
+        K = Kn;
+        cur ^= 1;
+    }
+}
+
+// =====================================================================================================
 // Fused level kernel: group phase of level `lvl` + stable scatter by key byte `lvl`, one pass over the data.
 //
 // The three-kernel formulation above (scatter / group reduce / group apply, plus offset scans) reads and writes
@@ -613,7 +907,7 @@ struct LzVisit {
 
 // ---- token emission ----------------------------------------------------------
 __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs, uint32_t F,
-                                                 const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum, APtrs A,
+                                                 const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum, APtrs A, uint32_t na,
                                                  const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
     const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
     const uint32_t i = fs[f] + blockIdx.x * blockDim.x + threadIdx.x;
@@ -622,14 +916,18 @@ __global__ void __launch_bounds__(256) lz_pack_k(const uint8_t* __restrict__ bs,
     if (rel == EMPTY32) return;
     const uint32_t rec = match_rec[i];
     uint32_t l = rec >> 28, v, nb;
-    if (l >= (uint32_t)LZ_MINLEN) {
+    if (l >= (uint32_t)LZ_MINLEN && (rec & LZ_RES)) {   // resolved by lz_small_k
+        v = ((rec & 0xFFFFu) << 1) | (l << 17);
+        nb = 21;
+    } else if (l >= (uint32_t)LZ_MINLEN) {
         const uint32_t* a = A.a[l];
         const uint32_t* g = A.gs[l];
-        const uint32_t glo = rec & LZ_POS_MASK;  // start of i's level-l group in A[l]; positions ascend inside the group
+        const uint32_t glo = rec & (LZ_RES - 1u);  // start of i's level-l group in A[l]; positions ascend inside the group
         const uint32_t target = i > (uint32_t)LZ_WINDOW ? i - (uint32_t)LZ_WINDOW : 0u;
         // first j >= glo with f(j) = (j outside the group) || (a[j] >= target). f is monotone, and the answer lies inside
         // the group because i itself is a member with a[.] = i >= target. Gallop for an upper bound, then bisect.
-        auto f = [&](uint32_t j) { return j >= n || (g[j] & LZ_GS_MASK) != glo || (a[j] & LZ_POS_MASK) >= target; };
+        // (na = number of elements of the level arrays: only the large groups get that far)
+        auto f = [&](uint32_t j) { return j >= na || (g[j] & LZ_GS_MASK) != glo || (a[j] & LZ_POS_MASK) >= target; };
         // Positions inside a group increase by at least 1 per index, so U = glo + (target - a[glo]) already satisfies f;
         // in a dense run (the common large group) it is the exact answer: probe U-1 first. Otherwise gallop up from
         // the group start (small or sparse groups end within a few probes), then bisect.
@@ -728,6 +1026,9 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
                               uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
     cudaStream_t st = lc.st;
     const uint32_t nthreads = 256;
+    uint32_t n_large = n;                       // elements of the level arrays A[3..15] (large groups only; everything in the fused variant)
+    const uint32_t* level3_a = wk.A[LZ_MINLEN];
+    const uint32_t* level3_gs = wk.GS[LZ_MINLEN];
     uint32_t cover = (n + 1 > F + 1 ? n + 1 : F + 1);
     KL(lc, KC_LZ_INIT, (lz_init_k<<<cdiv(cover, nthreads), nthreads, 0, st>>>(bs, n, fs, F, wk.A[0], wk.GS[0], wk.dig4[0], wk.match_rec, wk.bitcum, wk.wbase)));
     if (n > 0) {
@@ -761,38 +1062,63 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
                                                                                                    gout, dout, wk.bstart, chain)));
             }
         } else {
-        KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{wk.dig4[0], 0u}, n, nt, wk.tile_hist[0])));
-        for (uint32_t L = 0; L < (uint32_t)LZ_LEVELS; L++) {
-            uint32_t* din = wk.dig4[L & 1];
-            uint32_t* dout = wk.dig4[(L & 1) ^ 1];
-            uint32_t* th = wk.tile_hist[L & 1];          // counts of this level's key byte
-            uint32_t* th_next = wk.tile_hist[(L & 1) ^ 1];
-            const uint32_t Lnew = L + 1;
-            // levels 1 and 2 never carry a match: no group phase, the frame start rides along as the group; level 3 then
-            // derives its groups from (frame, 3-byte key)
-            uint32_t* gs_dst = Lnew < (uint32_t)LZ_MINLEN ? wk.GS[Lnew] : wk.gs_tmp;
-            device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
-            KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, LZ_THREADS, LZ_SCATTER_SMEM, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
-            if (Lnew < (uint32_t)LZ_MINLEN) {
-                KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{dout, 8u * (Lnew & 3u)}, n, nt, th_next)));
-                continue;
-            }
-            if (Lnew == (uint32_t)LZ_MINLEN) {
+            // ---- levels 1..3 over every position (levels 1 and 2 never carry a match: no group phase, the frame start rides
+            //      along as the group; level 3 derives its groups from (frame, 3-byte key)) ----
+            KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{wk.dig4[0], 0u}, n, nt, wk.tile_hist[0])));
+            for (uint32_t L = 0; L < (uint32_t)LZ_MINLEN; L++) {
+                uint32_t* din = wk.dig4[L & 1];
+                uint32_t* dout = wk.dig4[(L & 1) ^ 1];
+                uint32_t* th = wk.tile_hist[L & 1];
+                uint32_t* th_next = wk.tile_hist[(L & 1) ^ 1];
+                const uint32_t Lnew = L + 1;
+                uint32_t* gs_dst = Lnew < (uint32_t)LZ_MINLEN ? wk.GS[Lnew] : wk.gs_tmp;
+                device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * nt, wk.scan_ws, lc, KC_RX_SCAN);
+                KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<nt, LZ_THREADS, LZ_SCATTER_SMEM, st>>>(bs, wk.A[L], wk.GS[L], din, wk.A[Lnew], gs_dst, dout, L, n, nt, th)));
+                if (Lnew < (uint32_t)LZ_MINLEN) {
+                    KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<nt, RX_THREADS, 0, st>>>(LzDigit{dout, 8u * (Lnew & 3u)}, n, nt, th_next)));
+                    continue;
+                }
                 KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
                 KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
-                                                                                               wk.match_rec, Lnew, dout, th_next)));
-                continue;
-            }
-            KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, dout, wk.scan_ws)));
-            KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, nt)));
-            if (Lnew < (uint32_t)LZ_LEVELS)
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                 wk.match_rec, Lnew, dout, th_next)));
-            else
-                KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
-                                                                                                 wk.match_rec, Lnew, dout, th_next)));
-        }
+            }
+            // ---- small groups: levels 4..15 in shared memory, matches resolved to (length, offset) ----
+            KL(lc, KC_LZ_SMALL, (lz_small_k<<<cdiv(n, (uint32_t)SG_W), SG_THREADS, SG_SMEM, st>>>(bs, n, wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], wk.match_rec)));
+            // ---- large groups: compact them (A[1] / GS[1] are free again) and run the global levels on what is left ----
+            uint32_t* dig3 = wk.dig4[LZ_MINLEN & 1];          // key words in level-3 order
+            uint32_t* digc = wk.dig4[(LZ_MINLEN & 1) ^ 1];
+            uint32_t* prefix = wk.gs_tmp;
+            device_scan<SumOp, true>(LargeFlag{wk.GS[LZ_MINLEN], n}, StoreU32{prefix}, n, wk.scan_ws, lc, KC_LZ_GROUP);
+            cudaMemcpyAsync(&n_large, wk.scan_ws + cdiv(n, (uint32_t)SCAN_TILE), 4, cudaMemcpyDeviceToHost, st);
+            cudaStreamSynchronize(st);
+            if (n_large > 0) {
+                const uint32_t m = n_large, mt = cdiv(m, RX_TILE);
+                KL(lc, KC_LZ_GROUP, (lz_compact_large_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], dig3, prefix, n, wk.A[1], wk.GS[1], digc)));
+                level3_a = wk.A[1];
+                level3_gs = wk.GS[1];
+                // dig parity is flipped from here on: level L reads dig4[(L & 1) ^ 1]
+                KL(lc, KC_RX_HIST, (radix_hist_k<LzDigit><<<mt, RX_THREADS, 0, st>>>(LzDigit{digc, 8u * (LZ_MINLEN & 3u)}, m, mt, wk.tile_hist[LZ_MINLEN & 1])));
+                for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_LEVELS; L++) {
+                    uint32_t* din = wk.dig4[(L & 1) ^ 1];
+                    uint32_t* dout = wk.dig4[L & 1];
+                    uint32_t* th = wk.tile_hist[L & 1];          // counts of this level's key byte
+                    uint32_t* th_next = wk.tile_hist[(L & 1) ^ 1];
+                    const uint32_t Lnew = L + 1;
+                    const uint32_t* a_in = L == (uint32_t)LZ_MINLEN ? level3_a : wk.A[L];
+                    const uint32_t* g_in = L == (uint32_t)LZ_MINLEN ? level3_gs : wk.GS[L];
+                    device_scan<SumOp, true>(LoadU32{th}, StoreU32{th}, 256u * mt, wk.scan_ws, lc, KC_RX_SCAN);
+                    KL(lc, KC_RX_SCATTER, (lz_scatter_k<<<mt, LZ_THREADS, LZ_SCATTER_SMEM, st>>>(bs, a_in, g_in, din, wk.A[Lnew], wk.gs_tmp, dout, L, m, mt, th)));
+                    KL(lc, KC_LZ_GROUP, (lz_group_reduce_k<false><<<mt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, mt, m, dout, wk.scan_ws)));
+                    KL(lc, KC_LZ_GROUP, (scan_partials_k<MaxOp><<<1, 1024, 0, st>>>(wk.scan_ws, mt)));
+                    if (Lnew < (uint32_t)LZ_LEVELS)
+                        KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, true><<<mt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, mt, m, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                                        wk.match_rec, Lnew, dout, th_next)));
+                    else
+                        KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<mt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, mt, m, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
+                                                                                                         wk.match_rec, Lnew, dout, th_next)));
+                }
+            }
         }
         KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));
     }
@@ -802,8 +1128,10 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         APtrs ap;
         for (int l = 0; l <= LZ_LEVELS; l++) { ap.a[l] = wk.A[l]; ap.gs[l] = wk.GS[l]; }
+        ap.a[LZ_MINLEN] = level3_a;
+        ap.gs[LZ_MINLEN] = level3_gs;
         dim3 pgrid(cdiv(max_usize, nthreads), F);
-        KL(lc, KC_LZ_PACK, (lz_pack_k<<<pgrid, nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, wk.wbase, wk.out_words)));
+        KL(lc, KC_LZ_PACK, (lz_pack_k<<<pgrid, nthreads, 0, st>>>(bs, n, fs, F, wk.match_rec, wk.bitcum, ap, n_large, wk.wbase, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
