@@ -151,6 +151,29 @@ def fps_field(n_src, create_n, fps, light):
 # --------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------
+_ALL_CPUS = None
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank's host threads (and so its pinned allocations) on the CPU cores next to its GPU: with several GPUs on
+    one node the e2e leg is host-memory bound, and buffers on the far socket cost a second hop per transfer."""
+    global _ALL_CPUS
+    try:
+        import pynvml
+        _ALL_CPUS = os.sched_getaffinity(0)
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0".encode())
+        n = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {i for i in range(n) if (mask[i // 64] >> (i % 64)) & 1} & _ALL_CPUS
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            log(f"rank on GPU {local}: bound to {len(cpus)} of {len(_ALL_CPUS)} cores")
+    except Exception as e:  # affinity is an optimisation only
+        log(f"no NUMA binding: {e}")
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -162,6 +185,7 @@ def run_b200(args):
     if world != args.gpus:
         log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
@@ -451,6 +475,7 @@ ALG_BYTES = {
     "emit": lambda s: 2.0 * s["P"] * s["n_enc"] + s["usize"],
     "rx_scatter": lambda s: s["usize"] * s["lz_levels"],
     "lz_group": lambda s: s["usize"] * s["lz_levels"] * 3 + s["usize"],
+    "lz_small": lambda s: s["usize"],
     "lz_pack": lambda s: s["usize"] + s["csize"],
     "lz77": lambda s: s["usize"] + s["csize"],
     "expand": lambda s: s["csize"] + s["usize"],
@@ -460,6 +485,8 @@ ALG_BYTES = {
 ALG_RULE = {
     "rx_scatter": "K4 reads usize and writes csize once; each of the 15 refinement scatters is charged one pass over the bitstream (usize bytes) per launch",
     "lz_group": "per launch (reduce / partials / apply, 15 levels): one pass over the bitstream bytes (usize / launch on average)",
+    "lz_small": "K4 levels 4..15 of the small groups, in shared memory: charged one pass over the bitstream (usize bytes) per launch; "
+                "it reads 16 B per position (position + group words, each window twice), gathers 12 key bytes and writes one 4-byte match record",
     "expand": "D2: csize in + usize out",
     "lz77": "K4 (LZ77 flavour): usize in + csize out",
     "reconstruct": "D3: usize in + 4*W*H out per frame",
@@ -492,6 +519,8 @@ def cpu_clip_roundtrip(n_src, procs, use_ref):
 
 
 def cpu_baseline(args, bounded_seconds=25):
+    if _ALL_CPUS:
+        os.sched_setaffinity(0, _ALL_CPUS)   # the CPU legs use every host core, not just the ones next to GPU 0
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_src = 8
