@@ -74,7 +74,7 @@ struct agmvb_ctx {
     DBuf lzbuf[64];
     int host_fmt = 0;   // pixel format of HOST frame buffers: 0 = u32 0x00RRGGBB, 1 = packed B,G,R bytes (a BMP's pixel rows)
     DBuf raw24;         // staging for packed 24-bit pixels
-    DBuf l77_out, l77_meta, l77_persist;  // LZ77: token words, per-frame arrays, the reference's carried bitstream buffer
+    DBuf l77_out, l77_meta, l77_persist, l77_a1, l77_a2, l77_inv, l77_hist, l77_scan, l77_tab;  // LZ77: token words, per-frame arrays, the reference's carried bitstream buffer
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
     void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
@@ -183,6 +183,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
     cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p); cudaFree(ctx->raw24.p);
+    cudaFree(ctx->l77_a1.p); cudaFree(ctx->l77_a2.p); cudaFree(ctx->l77_inv.p); cudaFree(ctx->l77_hist.p); cudaFree(ctx->l77_scan.p); cudaFree(ctx->l77_tab.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
     for (DecStream& s : ctx->parked) free_stream(s);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
@@ -559,8 +560,34 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
         ctx->image = nb;
     }
     CK(cudaMemsetAsync(ctx->l77_out.p, 0, ((size_t)n + F + 16) * 4, ctx->st));
-    KL(ctx->lc, KC_LZ77, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
+    static const bool window_scan = getenv("AGMVB_LZ77_SCAN") && atoi(getenv("AGMVB_LZ77_SCAN")) != 0;
+    if (window_scan || n == 0) {
+        KL(ctx->lc, KC_LZ77, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
                                                                           ctx->l77_out.as<uint32_t>(), d_bits)));
+    } else {
+        // candidate lists: positions sorted by (byte 1, byte 0, position), slice tables per 2-byte and per 1-byte prefix
+        const uint32_t nt = cdiv(n, RX_TILE);
+        TRY(ensure(ctx, ctx->l77_a1, (size_t)n * 4 + 16));
+        TRY(ensure(ctx, ctx->l77_a2, (size_t)n * 4 + 16));
+        TRY(ensure(ctx, ctx->l77_inv, (size_t)n * 4 + 16));
+        TRY(ensure(ctx, ctx->l77_hist, (size_t)256 * nt * 4));
+        TRY(ensure(ctx, ctx->l77_scan, ((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 4) * 4));
+        TRY(ensure(ctx, ctx->l77_tab, (size_t)(260 + 2 * 65536) * 4));
+        uint32_t *a1 = ctx->l77_a1.as<uint32_t>(), *a2 = ctx->l77_a2.as<uint32_t>(), *th = ctx->l77_hist.as<uint32_t>();
+        uint32_t *b1 = ctx->l77_tab.as<uint32_t>(), *b2s = b1 + 260, *b2e = b2s + 65536;
+        CK(cudaMemsetAsync(b1, 0, (size_t)(260 + 2 * 65536) * 4, ctx->st));
+        radix_pass(L77Byte0{d_bs}, L77Move0{a1}, n, th, ctx->l77_scan.as<uint32_t>(), ctx->lc);
+        KL(ctx->lc, KC_LZ77, (l77_b1_k<<<1, 256, 0, ctx->st>>>(th, nt, n, b1)));
+        radix_pass(L77Byte1{d_bs, a1}, L77Move1{a1, a2}, n, th, ctx->l77_scan.as<uint32_t>(), ctx->lc);
+        KL(ctx->lc, KC_LZ77, (l77_buckets_k<<<cdiv(n, 256u), 256, 0, ctx->st>>>(d_bs, a2, n, b2s, b2e, ctx->l77_inv.as<uint32_t>())));
+        // frames in flight per launch (measured: the more the better - 1497 frames in one launch 270 ms, in waves of 592 586 ms)
+        static const uint32_t wave = getenv("AGMVB_LZ77_WAVE") ? (uint32_t)std::max(1, atoi(getenv("AGMVB_LZ77_WAVE"))) : (1u << 20);
+        for (uint32_t f0 = 0; f0 < F; f0 += wave) {
+            const uint32_t nf = std::min(wave, F - f0);
+            KL(ctx->lc, KC_LZ77, (lz77_bucket_encode_k<<<nf, T77, 0, ctx->st>>>(d_bs, d_fs + f0, a1, a2, b1, b2s, b2e, ctx->l77_inv.as<uint32_t>(), d_stale + f0,
+                                                                            ctx->l77_persist.as<uint8_t>(), d_wbase + f0, ctx->l77_out.as<uint32_t>(), d_bits + f0)));
+        }
+    }
     KL(ctx->lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, ctx->st>>>(F, ctx->lz.stub_bytes, d_bits, d_outbits, d_csize, d_choff)));
     dim3 grid(32, F);
     KL(ctx->lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, ctx->st>>>(d_fs, d_csize, d_choff, d_wbase, ctx->l77_out.as<uint32_t>(), first_fc,
@@ -642,7 +669,10 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
     for (uint32_t k = 0; k < n_enc; k++)
         if (src_a[k] < 0 || (uint64_t)src_a[k] >= n_frames_in_buffer || (src_b[k] >= 0 && (uint64_t)src_b[k] >= n_frames_in_buffer))
             FAIL(ERR_ARG, "frame index out of range at encoded frame %u", k);
-    const uint32_t QB = (uint32_t)std::max<size_t>(4, std::min<size_t>(256, (768ull << 20) / (P * 2)));  // frames per quantise batch
+    // frames per quantise batch. LZ77 parses one frame per CTA, serially: it wants every frame of the call in flight at once
+    // (entries 2 B/px + bitstream <= 2.1 B/px per frame: ~17 GB for 2000 1080p frames)
+    const uint32_t QB = ctx->compression == COMP_LZ77 ? (uint32_t)std::max<size_t>(4, std::min<size_t>(4096, (24ull << 30) / (P * 5)))
+                                                      : (uint32_t)std::max<size_t>(4, std::min<size_t>(256, (768ull << 20) / (P * 2)));
     std::vector<SrcPair> sp;
     std::vector<EntPair> ep;
     for (uint32_t q0 = 0; q0 < n_enc; q0 += QB) {

@@ -15,6 +15,7 @@
 #pragma once
 #include "common.cuh"
 #include "scan.cuh"
+#include "radix.cuh"
 
 namespace agmvb {
 
@@ -30,6 +31,31 @@ __device__ __forceinline__ uint32_t l77_load4(const uint8_t* __restrict__ p) {  
     const uint32_t lo = w[0];
     if (sh == 0) return lo;
     return __funnelshift_r(lo, w[1], sh);
+}
+
+// match length of cand[0..] against the token's own bytes (own: words in shared memory, zero padded, at least
+// L77_OWN_WORDS long), capped at mx. Eight words per step, all loads of a step in flight together: a 255-byte match takes
+// 8 dependent steps instead of 64.
+constexpr int L77_OWN_WORDS = L77_MAXLEN / 4 + 10;
+__device__ __forceinline__ uint32_t l77_lcp(const uint8_t* __restrict__ cand, const uint32_t* own, uint32_t mx) {
+    uint32_t j = 0;
+    while (j < mx) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(cand + j);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        const uint32_t sh = (uint32_t)(a & 3) * 8;
+        uint32_t v[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) v[k] = w[k];
+        uint32_t first = 32;   // bytes matched inside this step
+#pragma unroll
+        for (int k = 7; k >= 0; k--) {
+            const uint32_t x = __funnelshift_r(v[k], v[k + 1], sh) ^ own[(j >> 2) + k];
+            if (x) first = 4u * k + ((uint32_t)(__ffs((int)x) - 1) >> 3);
+        }
+        j += first;
+        if (first < 32) break;
+    }
+    return min(j, mx);
 }
 
 // fs: F+1 frame starts inside bs. stale_at[f]: absolute index into bs of the byte the reference would find at data[pos]
@@ -144,6 +170,210 @@ __global__ void __launch_bounds__(L77_THREADS) lz77_encode_k(const uint8_t* __re
         }
         __syncthreads();
         i += s_len + 1;   // a literal token advances by one as well
+        T++;
+    }
+    if (tid == 0) total_bits[f] = T * 32u;
+}
+
+// =====================================================================================================
+// Faster variant: candidates from sorted bucket lists instead of a window scan.
+//
+// Two stable counting-sort passes (radix.cuh) order the positions of the whole batch by (byte 1, byte 0, position):
+// every 2-byte prefix owns a contiguous, position-sorted slice of A2 (bucket table b2), every first byte a slice of A1.
+// For a token at position P the starts that match at least two bytes are the entries of P's bucket that lie in
+// [max(frame start, P-65535), P): two cooperative searches bound them, and only they are extended (in ascending order,
+// a CTA-wide chunk at a time, so "first longest" is "first chunk that raises the maximum, smallest start inside it";
+// a candidate is extended only if it also matches at index best). If there is none, the answer is length 1 at the
+// first entry of the first byte's slice inside the window, or a literal.
+// =====================================================================================================
+constexpr int T77 = 128;
+constexpr int L77_U = 4;      // starts per thread and chunk
+
+struct L77Byte0 { const uint8_t* bs; __device__ uint32_t operator()(uint32_t i) const { return bs[i]; } };
+struct L77Byte1 { const uint8_t* bs; const uint32_t* a1; __device__ uint32_t operator()(uint32_t i) const { return bs[a1[i] + 1]; } };
+struct L77Move0 { uint32_t* out; __device__ void operator()(uint32_t s, uint32_t d) const { out[d] = s; } };
+struct L77Move1 { const uint32_t* in; uint32_t* out; __device__ void operator()(uint32_t s, uint32_t d) const { out[d] = in[s]; } };
+
+// slice boundaries of the 2-byte buckets in A2 (tables zeroed by the caller: start == end == 0 means empty)
+__global__ void __launch_bounds__(256) l77_buckets_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ a2, uint32_t n,
+                                                     uint32_t* __restrict__ b2s, uint32_t* __restrict__ b2e, uint32_t* __restrict__ inv2) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = a2[i];
+    inv2[p] = i;   // where position p sits in A2: everything before it in its bucket starts earlier
+    const uint32_t k = (uint32_t)bs[p] | (uint32_t)bs[p + 1] << 8;
+    uint32_t kp = 0x10000u, kn = 0x10000u;
+    if (i > 0) { const uint32_t q = a2[i - 1]; kp = (uint32_t)bs[q] | (uint32_t)bs[q + 1] << 8; }
+    if (i + 1 < n) { const uint32_t q = a2[i + 1]; kn = (uint32_t)bs[q] | (uint32_t)bs[q + 1] << 8; }
+    if (k != kp) b2s[k] = i;
+    if (k != kn) b2e[k] = i + 1;
+}
+// first-byte slices of A1 from the scanned tile histogram of the first pass (entry [d * ntiles] = first index of byte d)
+__global__ void l77_b1_k(const uint32_t* __restrict__ tile_hist, uint32_t ntiles, uint32_t n, uint32_t* __restrict__ b1) {
+    const uint32_t d = threadIdx.x;
+    if (d < 256) b1[d] = tile_hist[d * ntiles];
+    if (d == 0) b1[256] = n;
+}
+
+// first index in [lo, hi) of the ascending array a with a[idx] >= target (hi if none); all T77 threads call it together
+__device__ __forceinline__ uint32_t l77_coop_lower_bound(const uint32_t* __restrict__ a, uint32_t lo, uint32_t hi, uint32_t target,
+                                                         uint32_t* wfirst) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (lo < hi) {
+        const uint32_t m = hi - lo;
+        const uint32_t step = (m + T77 - 1) / T77;
+        const uint32_t last = lo + min((uint32_t)(tid + 1) * step, m) - 1u;     // probe: the last element of this thread's piece
+        const bool have = (uint32_t)tid * step < m;
+        const bool pred = have && a[last] >= target;
+        const unsigned bal = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0) wfirst[warp] = bal ? (uint32_t)(warp * 32 + __ffs(bal) - 1) : 0xFFFFFFFFu;
+        __syncthreads();
+        uint32_t tf = 0xFFFFFFFFu;
+#pragma unroll
+        for (int w = 0; w < T77 / 32; w++) tf = min(tf, wfirst[w]);
+        __syncthreads();
+        if (tf == 0xFFFFFFFFu) return hi;
+        const uint32_t nlo = lo + tf * step, nhi = lo + min((tf + 1) * step, m);   // a[nhi - 1] >= target
+        if (step == 1) return nlo;
+        lo = nlo;
+        hi = nhi - 1;        // the answer is in [nlo, nhi - 1]; if nothing in [nlo, nhi - 1) qualifies it is nhi - 1
+        if (lo == hi) return lo;
+        // search [lo, hi) and fall back to hi (= nhi - 1, known to qualify)
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(T77) lz77_bucket_encode_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs,
+                                                            const uint32_t* __restrict__ a1, const uint32_t* __restrict__ a2,
+                                                            const uint32_t* __restrict__ b1, const uint32_t* __restrict__ b2s,
+                                                            const uint32_t* __restrict__ b2e, const uint32_t* __restrict__ inv2,
+                                                            const uint32_t* __restrict__ stale_at,
+                                                            const uint8_t* __restrict__ persist, const uint32_t* __restrict__ wbase,
+                                                            uint32_t* __restrict__ out, uint32_t* __restrict__ total_bits) {
+    __shared__ uint32_t own[L77_OWN_WORDS];
+    __shared__ unsigned long long wbest[T77 / 32];
+    __shared__ uint32_t wfirst[T77 / 32];
+    const uint32_t f = blockIdx.x;
+    const uint32_t F0 = fs[f], n = fs[f + 1] - F0;
+    const uint8_t* __restrict__ data = bs + F0;
+    uint32_t* __restrict__ tok = out + wbase[f];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t i = 0, T = 0;
+    while (i < n) {
+        const uint32_t mx = min((uint32_t)L77_MAXLEN, n - i);
+        if (tid < L77_OWN_WORDS) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t k = (uint32_t)tid * 4 + j;
+                if (k < mx) w |= (uint32_t)data[i + k] << (8 * j);
+            }
+            own[tid] = w;
+        }
+        __syncthreads();
+        const uint32_t P = F0 + i;
+        const uint32_t LO = (i > L77_WINDOW) ? P - L77_WINDOW : F0;
+        const uint32_t own0 = own[0];
+        uint32_t blen = 0, bq = 0;   // CTA-uniform
+        if (mx >= 2) {
+            const uint32_t key = own0 & 0xFFFFu;
+            const uint32_t s = b2s[key];
+            const uint32_t c1 = inv2[P];            // P's own slot: the starts before it in the bucket are exactly the earlier ones
+            // first start inside the window: walk back from c1 in strides of 32 (one probe per thread covers 4096 starts),
+            // then resolve inside the stride; wider windows of candidates fall back to the full search
+            uint32_t c0;
+            {
+                const uint32_t back = (uint32_t)(tid + 1) * 32u;
+                const bool inb = c1 >= s + back;                         // slot c1 - back exists in the bucket
+                const bool below = inb && a2[c1 - back] < LO;            // ... and lies before the window
+                const unsigned bal = __ballot_sync(0xffffffffu, below);
+                if (lane == 0) wfirst[warp] = bal ? (uint32_t)(warp * 32 + __ffs(bal) - 1) : 0xFFFFFFFFu;
+                __syncthreads();
+                uint32_t tf = 0xFFFFFFFFu;
+#pragma unroll
+                for (int w = 0; w < T77 / 32; w++) tf = min(tf, wfirst[w]);
+                __syncthreads();
+                uint32_t lo, hi;   // answer in [lo, hi]: a2[lo - 1] < LO (or lo == s), a2[hi] >= LO (or hi == c1)
+                if (tf != 0xFFFFFFFFu) { lo = c1 - (tf + 1u) * 32u + 1u; hi = c1 - tf * 32u; }
+                else if (c1 - s <= (uint32_t)T77 * 32u) { lo = s; hi = c1 - min(c1 - s, ((c1 - s) / 32u) * 32u); }
+                else { lo = s; hi = c1 - (uint32_t)T77 * 32u; }
+                c0 = l77_coop_lower_bound(a2, lo, hi, LO, wfirst);
+            }
+            // A start can only be the answer if its match is at least as long as ANY other start's. The most recent starts
+            // tend to match longest: measure them first (length only) and let the ordered scan discard, with one byte load,
+            // every start that does not reach that length.
+            uint32_t floor_len = 2;
+            if (c1 - c0 > (uint32_t)(T77 * L77_U)) {
+                const uint32_t idx = c1 - T77 + tid;
+                uint32_t j = l77_lcp(bs + a2[idx], own, mx);
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) j = max(j, __shfl_xor_sync(0xffffffffu, j, d));
+                if (lane == 0) wfirst[warp] = j;
+                __syncthreads();
+#pragma unroll
+                for (int w = 0; w < T77 / 32; w++) floor_len = max(floor_len, wfirst[w]);
+                __syncthreads();
+            }
+            for (uint32_t base = c0; base < c1; base += T77 * L77_U) {
+                uint32_t q[L77_U], jj[L77_U];
+                bool go[L77_U];
+                // a start matters if it reaches floor_len and is strictly longer than the best of the earlier starts
+                const uint32_t need = max(floor_len, blen + 1u);   // minimum useful length (blen + 1 > mx cannot happen: the loop ends at mx)
+#pragma unroll
+                for (int u = 0; u < L77_U; u++) {
+                    const uint32_t idx = base + (uint32_t)u * T77 + tid;
+                    go[u] = idx < c1;
+                    q[u] = go[u] ? a2[idx] : 0u;
+                }
+#pragma unroll
+                for (int u = 0; u < L77_U; u++)
+                    if (go[u] && need > 2) go[u] = bs[q[u] + need - 1] == (uint8_t)(own[(need - 1) >> 2] >> (8 * ((need - 1) & 3)));
+                unsigned long long k2 = 0;
+#pragma unroll
+                for (int u = 0; u < L77_U; u++) {
+                    jj[u] = 0;
+                    if (go[u]) {
+                        jj[u] = l77_lcp(bs + q[u], own, mx);
+                    }
+                    const unsigned long long ku = ((unsigned long long)jj[u] << 32) | (uint32_t)(~q[u]);
+                    k2 = ku > k2 ? ku : k2;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k2, d);
+                    k2 = o > k2 ? o : k2;
+                }
+                if (lane == 0) wbest[warp] = k2;
+                __syncthreads();
+                unsigned long long bb = 0;
+#pragma unroll
+                for (int w = 0; w < T77 / 32; w++) bb = wbest[w] > bb ? wbest[w] : bb;
+                __syncthreads();
+                if ((uint32_t)(bb >> 32) > blen) { blen = (uint32_t)(bb >> 32); bq = ~(uint32_t)bb; }
+                if (blen == mx) break;
+            }
+        }
+        if (blen == 0) {   // no start matches two bytes (or only one byte is left): the earliest start with the same first byte
+            const uint32_t v0 = own0 & 255u;
+            const uint32_t s = b1[v0], e = b1[v0 + 1];
+            const uint32_t c = l77_coop_lower_bound(a1, s, e, LO, wfirst);
+            if (c < e) {
+                const uint32_t q = a1[c];
+                if (q < P) { blen = 1; bq = q; }
+            }
+        }
+        if (tid == 0) {
+            uint32_t word;
+            if (blen > 0) {
+                uint8_t nxt;
+                if (i + blen < n) nxt = data[i + blen];
+                else nxt = stale_at[f] != 0xFFFFFFFFu ? bs[stale_at[f]] : persist[n];
+                word = (P - bq) | blen << 16 | (uint32_t)nxt << 24;
+            } else word = (own0 & 255u) << 24;
+            tok[T] = word;
+        }
+        __syncthreads();   // own[] is rewritten by the next token
+        i += blen + 1;
         T++;
     }
     if (tid == 0) total_bits[f] = T * 32u;
