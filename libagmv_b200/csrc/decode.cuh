@@ -52,26 +52,53 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
     const DecFrame d = fr[f];
     uint8_t* e = ebuf + d.ebuf_off;
     const uint8_t* __restrict__ file = d.file;
-    if (d.lz77) {  // 4-byte tokens (src/agmv_decode.c:200-218): rare profile, plain serial walk
-        if (lane == 0) {
-            // The reference expands into a 2*W*H byte buffer without a bound check; a stream that would run past it is
-            // outside its defined behaviour: the expansion stops at the buffer's end here.
-            const uint64_t cap = d.persist_len;
-            uint64_t rp = d.data_off, bpos = 0;
-            for (uint32_t i = 0; i < d.csize && bpos < cap; i += 4) {
-                uint32_t b0 = rp < d.file_len ? file[rp] : 0u; rp++;
-                uint32_t b1 = rp < d.file_len ? file[rp] : 0u; rp++;
-                uint32_t len = rp < d.file_len ? file[rp] : 0u; rp++;
-                uint8_t lit = rp < d.file_len ? file[rp] : 0u; rp++;
-                const uint64_t off = b0 | b1 << 8, p = bpos;
-                for (uint32_t k = 0; k < len && bpos < cap; k++) {
-                    uint64_t s = p - off + k;
-                    if (s < bpos) { e[bpos] = e[s]; bpos++; }
-                }
-                if (bpos < cap) e[bpos++] = lit;
+    if (d.lz77) {
+        // 4-byte tokens (src/agmv_decode.c:200-218): for (i = 0; i < csize; i += 4) { offset, length, literal }. The tokens are a
+        // serial chain, but each one's bytes are independent of each other: byte k of a match comes from
+        // p - off + (k mod off), which lies below the token's start p. 32 tokens are fetched per step (one per lane), then
+        // every token is copied by the whole warp. Offsets the reference's unsigned arithmetic treats specially (0, or
+        // larger than the data so far) take the literal byte-by-byte walk on lane 0.
+        // The reference expands into a 2*W*H byte buffer without a bound check; a stream that would run past it is
+        // outside its defined behaviour: the expansion stops at the buffer's end here.
+        const uint32_t cap = d.persist_len;
+        const uint32_t ntok = (d.csize + 3u) / 4u;
+        uint32_t bpos = 0, done_tok = 0;
+        for (uint32_t t0 = 0; t0 < ntok && bpos < cap; t0 += 32) {
+            uint32_t tw = 0;
+            if (t0 + lane < ntok) {
+                const uint64_t rp = d.data_off + (uint64_t)(t0 + lane) * 4;
+#pragma unroll
+                for (int j = 0; j < 4; j++) tw |= (rp + j < d.file_len ? (uint32_t)file[rp + j] : 0u) << (8 * j);   // fread past EOF leaves 0
             }
-            bpos_out[f] = (uint32_t)bpos;
-            consumed_out[f] = (uint32_t)(rp - d.data_off);
+            const uint32_t nb = min(32u, ntok - t0);
+            for (uint32_t k = 0; k < nb && bpos < cap; k++) {
+                const uint32_t w = __shfl_sync(0xffffffffu, tw, (int)k);
+                const uint32_t off = w & 0xFFFFu, len = (w >> 16) & 255u;
+                const uint8_t lit = (uint8_t)(w >> 24);
+                const uint32_t p = bpos;
+                if (off >= 1 && off <= p) {
+                    const uint32_t nc = min(len, cap - bpos);
+                    for (uint32_t kk = lane; kk < nc; kk += 32) e[p + kk] = e[p - off + (kk % off)];
+                    bpos += nc;
+                } else if (len > 0 && off != 0) {   // off > p: the first off - p bytes wrap below zero and are skipped
+                    if (lane == 0) {
+                        uint32_t bp = bpos;
+                        for (uint32_t kk = 0; kk < len && bp < cap; kk++) {
+                            const uint64_t sidx = (uint64_t)p - off + kk;   // unsigned wrap on purpose
+                            if (sidx < bp) { e[bp] = e[sidx]; bp++; }
+                        }
+                        bpos = bp;
+                    }
+                    bpos = __shfl_sync(0xffffffffu, bpos, 0);
+                }
+                if (bpos < cap) { if (lane == 0) e[bpos] = lit; bpos++; }
+                done_tok = t0 + k + 1;
+                __syncwarp();
+            }
+        }
+        if (lane == 0) {
+            bpos_out[f] = bpos;
+            consumed_out[f] = done_tok * 4u;
         }
         return;
     }
