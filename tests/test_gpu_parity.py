@@ -464,3 +464,21 @@ def test_bgr24_host_frames_equal_u32_path(ctx, golden):
         finally:
             ctx.set_host_format(0)
     assert np.array_equal(pals[0][0], pals[1][0]) and np.array_equal(pals[0][1], pals[1][1])
+
+
+def test_lz77_1080p_prefix_and_scale_properties(ctx):
+    """LZ77 at the bench resolution: an 8-frame 1080p prefix byte-identical to the oracle, and a 64-frame sequence (all
+    frames of the call parsed in one launch) whose GPU-decoded frames equal the oracle's decode of the GPU stream."""
+    from agmv_testlib import LZ77
+    frames = synth_frames(1920, 1080, 8, seed=1234)
+    want = oracle_encode(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    data, _ = ctx.encode_sequence(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    assert data.tobytes() == want
+    frames = synth_frames(1920, 1080, 64, seed=99)
+    data, n_enc = ctx.encode_sequence(frames, 63, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    assert data[17] == 3 and n_enc == 45
+    rc, ref_frames = oracle_decode(data.tobytes())
+    assert rc == 0
+    assert np.array_equal(ctx.decode_all(data.tobytes()), ref_frames)
+    again, _ = ctx.encode_sequence(frames, 63, 24, OPT["III"], QUALITY["LOW"], LZ77)
+    assert again.tobytes() == data.tobytes()
