@@ -142,6 +142,12 @@ int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint32_t* out, 
 int agmvb_dec_batch(agmvb_ctx* ctx, const int* streams, uint32_t n_streams, uint32_t count,
                     uint32_t* const* outs, uint64_t* checksums);
 int agmvb_dec_close(agmvb_ctx* ctx, int stream);
+/* Seek: what AGMV_SkipTo / AGMV_SkipBackwards do to the handle (src/agmv_playback.c:81-100) - the next
+ * frame decoded is frame_index, with frame_count = frame_index; the chunk offsets come from the index built by
+ * agmvb_dec_open (the reference's AGMV_ParseAGMV offset_table, src/agmv_utils.c:219-243). Decoder state (pixels,
+ * I-frame snapshot, expanded-bitstream leftovers) is NOT rewound, as in the reference: seek to an I-frame
+ * (frame_index % 4 == 0) for a clean picture. */
+int agmvb_dec_seek(agmvb_ctx* ctx, int stream, uint32_t frame_index);
 /* Streaming entry: one AGMV_DecodeFrameChunk (src/agmv_decode.c:145-410) at a time, for callers that own the
  * FILE* (AGMV_PlayAGMV, src/agmv_playback.c:102-115). agmvb_dec_open_raw takes what AGMV_DecodeHeader left in
  * the handle (size, version, palettes); agmvb_dec_chunk takes the bytes after the 16-byte 'AGFC' header

@@ -57,6 +57,7 @@ SYMBOLS = {
     "agmvb_dec_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int]),
     "agmvb_dec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
     "agmvb_dec_close": (C.c_int, [C.c_void_p, C.c_int]),
+    "agmvb_dec_seek": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "agmvb_dec_open_raw": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, C.POINTER(C.c_int)]),
     "agmvb_dec_chunk": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p]),
     "agmvb_synth_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
@@ -256,6 +257,10 @@ class Context:
         ck = np.zeros((len(sids), count), np.uint64) if checksums else None
         self._ck(self.lib.agmvb_dec_batch(self.h, ids, len(sids), count, outs, _p(ck, _u64p) if checksums else None))
         return ck
+
+    def dec_seek(self, sid, frame_index):
+        """AGMV_SkipTo without I-frame rounding: the next frame decoded is frame_index; decoder state is not rewound."""
+        self._ck(self.lib.agmvb_dec_seek(self.h, sid, frame_index))
 
     def dec_close(self, sid):
         self._ck(self.lib.agmvb_dec_close(self.h, sid))

@@ -1090,6 +1090,18 @@ extern "C" int agmvb_dec_close(agmvb_ctx* ctx, int stream) {
     return OK;
 }
 
+// AGMV_SkipTo (src/agmv_playback.c:94-100) without the rounding to an I-frame: the next decoded frame is `frame_index`,
+// decoded with frame_count = frame_index; pixels, I-frame snapshot and bitstream leftovers stay what the last decoded
+// frame made them, exactly as in the reference, whose seek only moves the file cursor and sets frame_count.
+extern "C" int agmvb_dec_seek(agmvb_ctx* ctx, int stream, uint32_t frame_index) {
+    if (!ctx || stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) return ERR_ARG;
+    DecStream& d = ctx->streams[stream];
+    if (d.raw) FAIL(ERR_ARG, "chunk-fed streams are positioned by the caller (frame_count argument of agmvb_dec_chunk)");
+    if (frame_index >= d.n_frames) FAIL(ERR_ARG, "frame %u of %u", frame_index, d.n_frames);
+    d.next = frame_index;
+    return OK;
+}
+
 constexpr uint32_t DEC_RING = 8;
 
 // Decode the next `count` frames of each listed stream (all of one size).

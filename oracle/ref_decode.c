@@ -15,6 +15,13 @@
  *                                 appended to OUT as W*H little-endian 32-bit
  *                                 0x00RRGGBB words (OUT "-" = no dump, timing only).
  *                                 Audio chunks are skipped by the chunk scan.
+ *   ref_decode seek FILE OUT PLAN same handle, but the frames are visited in the order given by PLAN
+ *                                 (comma-separated frame indices): AGMV_ParseAGMV fills agmv->offset_table
+ *                                 (src/agmv_utils.c:219-243), and whenever the next index is not the
+ *                                 successor of the previous one the driver does what AGMV_SkipTo does
+ *                                 (src/agmv_playback.c:94-100, without rounding to an I-frame):
+ *                                 fseek(offset_table[k]) and frame_count = k. Pixel, I-frame and bitstream
+ *                                 buffers keep whatever the last decoded frame left in them.
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -68,6 +75,36 @@ int main(int argc, char** argv) {
     uint32_t* narrow = (uint32_t*)malloc(px * 4);
     unsigned long n = AGMV_GetNumberOfFrames(agmv), i;
     double dec = 0.0;
+    if (!strcmp(argv[1], "seek")) {
+        if (argc < 5) return 2;
+        AGMV_ParseAGMV(f, agmv);
+        long prev = -2;
+        unsigned long done = 0;
+        char* tok = strtok(argv[4], ",");
+        while (tok) {
+            long k = atol(tok);
+            if (k < 0 || (unsigned long)k >= n) { err = MEMORY_CORRUPTION_ERR; break; }
+            if (k != prev + 1) {
+                fseek(f, agmv->offset_table[k], SEEK_SET);
+                agmv->frame_count = k;
+            }
+            AGMV_FindNextFrameChunk(f);
+            err = AGMV_DecodeFrameChunk(f, agmv);
+            if (err != NO_ERR) break;
+            if (out) {
+                size_t q;
+                for (q = 0; q < px; q++) narrow[q] = (uint32_t)agmv->frame->img_data[q];
+                fwrite(narrow, 4, px, out);
+            }
+            prev = k;
+            done++;
+            tok = strtok(NULL, ",");
+        }
+        if (out) fclose(out);
+        fclose(f);
+        printf("rc %d frames %lu w %lu h %lu\n", err, done, agmv->header.width, agmv->header.height);
+        return 0;
+    }
     for (i = 0; i < n; i++) {
         double t0 = now();
         AGMV_FindNextFrameChunk(f);

@@ -210,3 +210,16 @@ def oracle_lz77(data, stale=0xA7):
     nb = C.c_size_t()
     csize = lib.orc_lz77(ptr(src, _u8p), len(data), ptr(out, _u8p), C.byref(nb))
     return csize, out[:nb.value].tobytes()
+
+
+def ref_decode_seek(data, plan):
+    """Reference decode visiting frames in the order of `plan` (oracle/ref_decode.c seek mode). Returns (rc, frames)."""
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "i.agmv"), "wb") as f:
+            f.write(data)
+        res = subprocess.run([os.path.join(REF_DIR, "ref_decode"), "seek", "i.agmv", "o.raw", ",".join(str(k) for k in plan)], cwd=td,
+                             check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        tok = res.stdout.decode().split()
+        rc, n, w, h = int(tok[1]), int(tok[3]), int(tok[5]), int(tok[7])
+        raw = np.fromfile(os.path.join(td, "o.raw"), dtype=np.uint32)
+        return rc, raw.reshape(n, h, w)

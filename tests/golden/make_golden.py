@@ -61,6 +61,15 @@ LZ77_CASES = [
 ]
 
 
+# "next" row N3: seeking. stream (golden file), visiting order of the frames
+SEEK_CASES = [
+    ("gba240_GBA_I_LOW.agmv", [0, 1, 8, 9, 10, 4, 5, 6, 7, 3, 16, 17, 0, 1]),
+    ("syn96x80_III_LOW.agmv", [0, 1, 2, 3, 12, 13, 14, 5, 6, 8, 9, 2]),
+    ("lz77_320x240_III_LOW.agmv", [4, 5, 6, 0, 1, 9, 10, 11, 8]),
+    ("syn64_II_LOW.agmv", [3, 4, 0, 5]),
+]
+
+
 def lzss_vectors():
     """Known-answer tests for the exported AGMV_LZSS (src/agmv_encode.c:106-177)."""
     rng = np.random.default_rng(7)
@@ -217,6 +226,14 @@ def main():
         json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
 
     if not args.only:
+        from agmv_testlib import ref_decode_seek
+        gold["seek"] = {}
+        for fn, plan in SEEK_CASES:
+            data = open(os.path.join(GOLDEN_DIR, fn), "rb").read()
+            rc, dec = ref_decode_seek(data, plan)
+            assert rc == 0 and dec.shape[0] == len(plan)
+            gold["seek"][fn] = dict(plan=plan, frame_sha256=[sha256(dec[k].tobytes()) for k in range(len(plan))])
+            print(f"seek {fn}: {len(plan)} frames", flush=True)
         gold.setdefault("lz77", {})
         for name, buf in lz77_vectors().items():
             csize, out = ref_lz77(buf)

@@ -259,3 +259,40 @@ def test_other_encoders_dropin_bytes(golden, name):
         finally:
             os.chdir(cwd)
     assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fn", ["gba240_GBA_I_LOW.agmv", "lz77_320x240_III_LOW.agmv"])
+def test_seek_dropin_like_skipto(golden, fn):
+    """What AGMV_SkipTo does with the reference's own agmv_utils.o in the link (src/agmv_playback.c:94-100): fseek to the
+    chunk, set frame_count, then AGMV_DecodeFrameChunk - served by the drop-in, frames equal to the reference's."""
+    g = golden["seek"][fn]
+    path = os.path.join(GOLDEN_DIR, fn)
+    raw = open(path, "rb").read()
+    offs, p = [], raw.find(b"AGFC")
+    while p >= 0:   # AGMV_ParseAGMV's offset_table: one entry per 'AGFC'
+        offs.append(p)
+        cs = int.from_bytes(raw[p + 12:p + 16], "little")
+        p = raw.find(b"AGFC", p + 16 + cs)
+    lib, libc = _dropin(), _libc()
+    f = libc.fopen(path.encode(), b"rb")
+    h = lib.CreateAGMV(0, int.from_bytes(raw[8:12], "little"), int.from_bytes(raw[12:16], "little"), 16)  # buffers sized for the stream
+    assert lib.AGMV_DecodeHeader(f, h) == 0
+    a = h.contents
+    a.frame.contents.width = a.iframe.contents.width = a.header.width
+    a.frame.contents.height = a.iframe.contents.height = a.header.height
+    a.frame_count = 0
+    P = int(a.header.width * a.header.height)
+    prev = -2
+    for k, want in zip(g["plan"], g["frame_sha256"]):
+        if k != prev + 1:
+            libc.fseek(f, offs[k], 0)
+            a.frame_count = k
+        else:
+            libc.fseek(f, raw.find(b"AGFC", libc.ftell(f)), 0)   # AGMV_FindNextFrameChunk
+        assert lib.AGMV_DecodeFrameChunk(f, h) == 0, lib.AGMV_B200_LastError()
+        px = np.ctypeslib.as_array(a.frame.contents.img_data, shape=(P,)).astype(np.uint32)
+        assert sha256(px.tobytes()) == want, k
+        prev = k
+    libc.fclose(f)
+    lib.DestroyAGMV(h)

@@ -133,3 +133,18 @@ def test_oracle_lz77_streams_match_reference_golden(golden, name):
     rc, dec = oracle_decode(data)
     assert rc == 0 and list(dec.shape) == g["decoded_shape"]
     assert [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_seek_goldens_are_what_the_reference_produces(golden):
+    """The seek vectors are re-derived from the unmodified reference (oracle/ref_decode.c seek mode), and
+    visiting the frames in order reproduces the plain decode."""
+    from agmv_testlib import ref_decode_seek
+    for fn, g in golden["seek"].items():
+        data = open(os.path.join(GOLDEN_DIR, fn), "rb").read()
+        rc, dec = ref_decode_seek(data, g["plan"])
+        assert rc == 0 and [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["frame_sha256"], fn
+    g = golden["encode"]["syn96x80_III_LOW"]
+    data = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
+    rc, dec = ref_decode_seek(data, list(range(g["decoded_shape"][0])))
+    assert rc == 0 and [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
