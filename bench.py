@@ -476,6 +476,7 @@ ALG_BYTES = {
     "rx_scatter": lambda s: s["usize"] * s["lz_levels"],
     "lz_group": lambda s: s["usize"] * s["lz_levels"] * 3 + s["usize"],
     "lz_small": lambda s: s["usize"],
+    "lz_tiny": lambda s: s["usize"],
     "lz_pack": lambda s: s["usize"] + s["csize"],
     "lz77": lambda s: s["usize"] + s["csize"],
     "expand": lambda s: s["csize"] + s["usize"],

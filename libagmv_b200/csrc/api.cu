@@ -1009,7 +1009,6 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     const size_t P = (size_t)W * H;
     // chunk index
     uint64_t cursor = 38 + pal_bytes;
-    bool need_exact_cursor = false;
     for (uint32_t i = 0; i < nfr; i++) {
         int64_t at = find_next_agfc(file, len, cursor);
         if (at < 0 || (uint64_t)at + 16 > len) FAIL(ERR_HEADER, "frame chunk %u not found", i);
@@ -1029,7 +1028,6 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
             if (aa >= 0 && (uint64_t)aa + 8 <= len) cursor = (uint64_t)aa + 8 + get32(file + aa + 4);
         }
     }
-    (void)need_exact_cursor;
     if (!unpark_stream(ctx, s, len, P)) {
         s.file_cap = len + len / 8 + 4096;
         CK(cudaMalloc(&s.d_file, s.file_cap));

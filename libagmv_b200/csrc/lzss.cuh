@@ -426,6 +426,52 @@ __global__ void __launch_bounds__(256) lz_compact_large_k(const uint32_t* __rest
     dig_out[o] = dig[i];
 }
 
+// ---- tiny groups: all pairs ---------------------------------------------------------------------------
+// A level-3 group of at most SG_TINY positions needs no refinement at all: a position's longest match is the largest
+// common prefix with any earlier member inside the window, a handful of comparisons. One thread per position walks its
+// group backwards (most recent member first) while the members are within 65535 bytes; ">=" on the length leaves the
+// EARLIEST start among the longest, as the reference's ascending scan with ">" does.
+constexpr int SG_TINY = 128;
+__device__ __forceinline__ bool sg_group_is_tiny(const uint32_t* __restrict__ gs3, uint32_t n, uint32_t g) {
+    return g + (uint32_t)SG_TINY >= n || (gs3[g + SG_TINY] & LZ_GS_MASK) != g;
+}
+__device__ __forceinline__ void sg_key12(const uint8_t* __restrict__ p, uint32_t k[3]) {  // bytes 3..14 after position p
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p + 3);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3];
+    k[0] = __funnelshift_r(w0, w1, sh);
+    k[1] = __funnelshift_r(w1, w2, sh);
+    k[2] = __funnelshift_r(w2, w3, sh);
+}
+__global__ void __launch_bounds__(256) lz_tiny_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ a3,
+                                                 const uint32_t* __restrict__ gs3, uint32_t* __restrict__ match_rec) {
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const uint32_t gw = gs3[idx];
+    if (!(gw & LZ_ALIVE)) return;                       // no earlier member within the window: no match of length 3
+    const uint32_t g = gw & LZ_GS_MASK;
+    if (!sg_group_is_tiny(gs3, n, g)) return;
+    const uint32_t pw = a3[idx], p = pw & LZ_POS_MASK, cap = pw >> 28;   // cap = min(15, bytes left in the frame) >= 3 here
+    uint32_t ky[3];
+    sg_key12(bs + p, ky);
+    uint32_t best = 0, bestx = 0;
+    for (uint32_t k = idx; k-- > g;) {
+        const uint32_t x = a3[k] & LZ_POS_MASK;
+        if (p - x > (uint32_t)LZ_WINDOW) break;
+        uint32_t kx[3];
+        sg_key12(bs + x, kx);
+        uint32_t l = 12;
+        const uint32_t d2 = kx[2] ^ ky[2], d1 = kx[1] ^ ky[1], d0 = kx[0] ^ ky[0];
+        if (d2) l = 8 + ((uint32_t)(__ffs((int)d2) - 1) >> 3);
+        if (d1) l = 4 + ((uint32_t)(__ffs((int)d1) - 1) >> 3);
+        if (d0) l = (uint32_t)(__ffs((int)d0) - 1) >> 3;
+        l = min(l + 3u, cap);
+        if (l >= best) { best = l; bestx = x; }
+    }
+    match_rec[p] = best << 28 | LZ_RES | (p - bestx);
+}
+
 __global__ void __launch_bounds__(SG_THREADS, 4) lz_small_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ a3,
                                                          const uint32_t* __restrict__ gs3, uint32_t* __restrict__ match_rec) {
     extern __shared__ __align__(16) uint8_t lz_dyn[];
@@ -461,7 +507,8 @@ __global__ void __launch_bounds__(SG_THREADS, 4) lz_small_k(const uint8_t* __res
         for (int r = 0; r < SG_ROUNDS; r++) {
             const uint32_t s = sbase + r * 32, idx = w0 + s, g = gw[r] & LZ_GS_MASK;
             bool v = idx < n && g >= w0 && g < w0 + (uint32_t)SG_W;
-            if (v) v = g + (uint32_t)SG_C >= n || (pos_all[SG_K + g + SG_C - w0] & LZ_GS_MASK) != g;
+            if (v) v = g + (uint32_t)SG_C >= n || (pos_all[SG_K + g + SG_C - w0] & LZ_GS_MASK) != g;          // not large
+            if (v) v = g + (uint32_t)SG_TINY < n && (pos_all[SG_K + g + SG_TINY - w0] & LZ_GS_MASK) == g;      // not tiny (lz_tiny_k)
             const unsigned bal = __ballot_sync(0xffffffffu, v);
             lidx[r] = run + __popc(bal & lanemask_lt());
             run += __popc(bal);
@@ -1083,7 +1130,8 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
                 KL(lc, KC_LZ_GROUP, (lz_group_apply_k<true, false><<<nt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, nt, n, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                 wk.match_rec, Lnew, dout, th_next)));
             }
-            // ---- small groups: levels 4..15 in shared memory, matches resolved to (length, offset) ----
+            // ---- tiny groups: all pairs; small groups: levels 4..15 in shared memory; both resolve to (length, offset) ----
+            KL(lc, KC_LZ_TINY, (lz_tiny_k<<<cdiv(n, 256u), 256, 0, st>>>(bs, n, wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], wk.match_rec)));
             KL(lc, KC_LZ_SMALL, (lz_small_k<<<cdiv(n, (uint32_t)SG_W), SG_THREADS, SG_SMEM, st>>>(bs, n, wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], wk.match_rec)));
             // ---- large groups: compact them (A[1] / GS[1] are free again) and run the global levels on what is left ----
             uint32_t* dig3 = wk.dig4[LZ_MINLEN & 1];          // key words in level-3 order
