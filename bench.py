@@ -298,6 +298,8 @@ def run_b200(args):
     enc_ms = timed(encode_step, args.steps)
     dec_ms = timed(lambda: decode_step(stream_np), args.steps)
     us, cs = ctx.enc_sizes(n_enc)                    # per-frame sizes of the timed workload (read before the e2e leg re-encodes a shorter clip)
+    dec_out.untyped_storage().resize_(0)             # the decoded frames of the timed workload are not needed any more (12.4 GB)
+    torch.cuda.empty_cache()
 
     # ---- e2e: the same step through the public API with HOST buffers -------------------
     # Every sequence goes host -> encode -> host stream -> decode -> host frames through agmvb_encode_sequence /
@@ -362,32 +364,58 @@ def run_b200(args):
                 except Exception as e:  # surfaced after join
                     self.err = e
 
-        workers = [Worker(k) for k in range(n_streams)]
-        for wk in workers:
-            wk.step()                                   # warm every context's workspaces
-        barrier()
-        t0 = time.perf_counter()
-        threads = [threading.Thread(target=wk.run, args=(iters,)) for wk in workers]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        barrier()
-        dt = time.perf_counter() - t0
-        for wk in workers:
-            if wk.err is not None:
-                raise wk.err
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        seqs = n_streams * iters
-        e2e = {"value": e2e_frames * world * seqs / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(wk.h2d for wk in workers)),
-               "d2h_bytes_per_step": int(sum(wk.d2h for wk in workers)), "frames_per_step": e2e_frames * n_streams,
-               "concurrent_sequences": n_streams, "host_pixels": args.e2e_pixels,
-               "note": f"{n_streams} independent {e2e_frames}-frame sequences at a time per GPU (one host thread + context each): "
-                       "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers "
-                       + ("(packed 24-bit BMP pixel rows in and out, AGMVB_PIX_BGR24)" if bpp == 3 else "(u32 pixels)") + ", host wall clock"}
+        # build and warm the workers; if a rank runs out of (device or pinned) memory every rank halves the number of sequences
+        # in flight together and tries again
+        workers = None
+        while True:
+            ok = 1
+            try:
+                workers = [Worker(k) for k in range(n_streams)]
+                for wk in workers:
+                    wk.step()                               # warm every context's workspaces
+            except Exception as e:
+                log(f"e2e with {n_streams} sequences in flight failed on rank {rank}: {e}")
+                ok = 0
+            if world > 1:
+                t = torch.tensor([ok], dtype=torch.int32, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                ok = int(t.item())
+            if ok:
+                break
+            for wk in workers or []:
+                if wk.ctx is not ctx:
+                    wk.ctx.close()
+            workers = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            if n_streams == 1:
+                break
+            n_streams = max(1, n_streams // 2)
+        if workers:
+            barrier()
+            t0 = time.perf_counter()
+            threads = [threading.Thread(target=wk.run, args=(iters,)) for wk in workers]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+            barrier()
+            dt = time.perf_counter() - t0
+            for wk in workers:
+                if wk.err is not None:
+                    raise wk.err
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            seqs = n_streams * iters
+            e2e = {"value": e2e_frames * world * seqs / dt, "unit": UNIT, "h2d_bytes_per_step": int(sum(wk.h2d for wk in workers)),
+                   "d2h_bytes_per_step": int(sum(wk.d2h for wk in workers)), "frames_per_step": e2e_frames * n_streams,
+                   "concurrent_sequences": n_streams, "host_pixels": args.e2e_pixels,
+                   "note": f"{n_streams} independent {e2e_frames}-frame sequences at a time per GPU (one host thread + context each): "
+                           "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers "
+                           + ("(packed 24-bit BMP pixel rows in and out, AGMVB_PIX_BGR24)" if bpp == 3 else "(u32 pixels)") + ", host wall clock"}
         ctx.set_host_format(0)
         workers = None
 

@@ -52,6 +52,7 @@ inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
         if (_e != cudaSuccess) {                                                             \
             snprintf(ctx->err, sizeof ctx->err, "%s:%d %s: %s", __FILE__, __LINE__, #expr,   \
                      cudaGetErrorString(_e));                                                \
+            (void)cudaGetLastError(); /* reported through the return code: do not leave it for the next CUDA user */ \
             return ERR_CUDA;                                                                 \
         }                                                                                    \
     } while (0)
