@@ -24,7 +24,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct"]
-CLASS_OF = {"scatter": "rx_scatter", "group": "lz_group", "small": "lz_small", "expand": "expand", "quantize": "quantize", "hist": "hist", "recon": "reconstruct",
+CLASS_OF = {"scatter": "rx_scatter", "group": "lz_group", "small": "lz_small", "tiny": "lz_tiny", "expand": "expand", "quantize": "quantize", "hist": "hist", "recon": "reconstruct",
             "pack": "lz_pack", "classify": "classify", "index": "index"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 

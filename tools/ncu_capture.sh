@@ -12,6 +12,7 @@ cap() { # name regex skip count
 cap scatter lz_scatter_k 6 2
 cap group lz_group_apply_k 4 2
 cap small lz_small_k 1 1
+cap tiny lz_tiny_k 1 1
 cap greduce lz_group_reduce_k 4 1
 cap expand expand_mrr_k 0 1
 cap quantize quantize_k 1 1
