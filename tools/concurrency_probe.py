@@ -5,7 +5,7 @@ import os, sys, threading, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import libagmv_b200
-W, H, N = 1920, 1080, 512
+W, H, N = 1920, 1080, int(os.environ.get("PROBE_FRAMES", "512"))
 P = W * H
 dev = torch.device("cuda", 0)
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 4
