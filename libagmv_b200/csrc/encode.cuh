@@ -189,12 +189,13 @@ __device__ __forceinline__ uint32_t lut_entry(uint32_t c, bool valid, uint16_t* 
     while (m) {
         int leader = __ffs(m) - 1;
         uint32_t cc = __shfl_sync(0xffffffffu, c, leader);
-        int r = (cc >> 16) & 255, g = (cc >> 8) & 255, b = cc & 255;
+        // |c - p|^2 = c.c + p.p - 2 c.p on the packed bytes (top byte 0 on both sides): exact in 32 bits, two dp4a per entry
+        const uint32_t cdot = __dp4a(cc, cc, 0u);
         uint32_t best = 0xFFFFFFFFu;
         for (int j = lane_id(); j < npal; j += 32) {
-            uint32_t p = spal[j];
-            int dr = r - (int)((p >> 16) & 255), dg = g - (int)((p >> 8) & 255), db = b - (int)(p & 255);
-            uint32_t key = (uint32_t)(dr * dr + dg * dg + db * db) * 512u + (uint32_t)j;
+            const uint32_t p = spal[j];
+            const uint32_t d = cdot + __dp4a(p, p, 0u) - 2u * __dp4a(cc, p, 0u);
+            const uint32_t key = d * 512u + (uint32_t)j;
             best = key < best ? key : best;
         }
 #pragma unroll
