@@ -555,6 +555,7 @@ def cpu_baseline(args, bounded_seconds=25):
     n_src = 8
     dt, frames, ok, outs = cpu_clip_roundtrip(n_src, procs, use_ref=False)
     return {"value": frames / dt if ok else None, "unit": UNIT, "cores": procs, "kind": "port",
+            "per_core": (frames / dt / procs) if ok else None,
             "sample": f"{procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), oracle port encode + decode, "
                       f"{dt:.1f} s wall",
             "note": "oracle/agmv_oracle.c (qsort instead of the reference's O(n^2) bubble sort, memoised quantiser): faster than the "
