@@ -512,3 +512,65 @@ def test_seek_matches_reference(ctx, golden, fn):
     finally:
         ctx.dec_close(sid)
     assert got == g["frame_sha256"]
+
+
+def _lz_structured_buffers():
+    """Buffers aimed at the three K4 paths and their hand-over points: level-3 groups of controlled sizes around the
+    all-pairs limit (128), the shared-memory limit (512) and far above it; long runs and their tails; short periods;
+    repeats just inside / outside the 65535-byte window; a match that is cut by the end of the buffer."""
+    rng = np.random.default_rng(2024)
+    bufs = []
+
+    def filler(k):  # bytes that never form the prefixes used below (values >= 64)
+        return rng.integers(64, 256, k, dtype=np.uint8)
+
+    # one prefix occurring exactly `count` times with assorted continuations, the rest filler
+    for count, gap in ((127, 40), (128, 37), (129, 35), (511, 90), (512, 80), (513, 70), (3000, 21), (700, 150)):
+        parts = []
+        for k in range(count):
+            tail = rng.integers(0, 6, rng.integers(0, 14), dtype=np.uint8)      # small alphabet: continuations often agree
+            parts += [np.array([1, 2, 3], np.uint8), tail, filler(rng.integers(1, gap))]
+        bufs.append(np.concatenate(parts))
+    # runs of one byte with every tail length, separated by short and by long stretches, one run ending the buffer
+    parts = []
+    for k in range(400):
+        parts += [np.full(rng.integers(3, 60), 0x5E, np.uint8), filler(rng.integers(1, 9))]
+    parts += [np.full(5000, 0x5E, np.uint8), filler(3), np.full(70000, 0x5E, np.uint8), filler(2), np.full(40, 0x5E, np.uint8)]
+    bufs.append(np.concatenate(parts))
+    # period 2 and period 3 stretches (FILL records of one colour look like this), mixed with the run byte
+    parts = []
+    for k in range(300):
+        parts += [np.tile(np.array([0x4E, 7], np.uint8), rng.integers(2, 40)), np.tile(np.array([0x4E, 9, 0x5E], np.uint8), rng.integers(1, 12)),
+                  np.full(rng.integers(1, 20), 0x5E, np.uint8), filler(rng.integers(0, 5))]
+    bufs.append(np.concatenate(parts))
+    # the same 40-byte phrase 65530..65540 bytes apart: the window edge decides between a match and literals
+    phrase = rng.integers(0, 256, 40, dtype=np.uint8)
+    parts = [phrase]
+    for d in (65530, 65535, 65536, 65540, 65534):
+        parts += [filler(d - 40), phrase]
+    bufs.append(np.concatenate(parts))
+    # motif soup: group sizes spread over several orders of magnitude
+    motifs = [rng.integers(0, 8, 24, dtype=np.uint8) for _ in range(30)]
+    parts, tot = [], 0
+    while tot < 200000:
+        if rng.random() < 0.75:
+            m = motifs[rng.integers(0, len(motifs))][:rng.integers(3, 25)]
+        else:
+            m = rng.integers(0, 256, rng.integers(1, 6), dtype=np.uint8)
+        parts.append(m)
+        tot += len(m)
+    bufs.append(np.concatenate(parts))
+    return [np.ascontiguousarray(b, dtype=np.uint8) for b in bufs]
+
+
+def test_lzss_group_size_paths_against_oracle(ctx):
+    """lz_tiny_k / lz_small_k / the global levels and lz_pack_k's search, each on inputs built to land there - one buffer
+    per call, and all of them as the frames of one batch (groups are per frame)."""
+    bufs = _lz_structured_buffers()
+    want = [oracle_lzss(b) for b in bufs]
+    for b, w in zip(bufs, want):
+        (cs, out, bits), = ctx.test_lzss([b])
+        assert (cs, bits) == (w[0], w[2]) and out == w[1], f"buffer of {len(b)} bytes"
+    got = ctx.test_lzss(bufs)
+    for k, (g, w) in enumerate(zip(got, want)):
+        assert (g[0], g[2]) == (w[0], w[2]) and g[1] == w[1], f"frame {k} of the batch"
