@@ -574,3 +574,18 @@ def test_lzss_group_size_paths_against_oracle(ctx):
     got = ctx.test_lzss(bufs)
     for k, (g, w) in enumerate(zip(got, want)):
         assert (g[0], g[2]) == (w[0], w[2]) and g[1] == w[1], f"frame {k} of the batch"
+
+
+def test_lz77_structured_inputs_against_oracle(ctx):
+    """The same structured inputs through the LZ77 coder: as single buffers, and as consecutive frames of one handle
+    (the byte after a frame's end comes from the carried buffer, src/agmv_encode.c:218-224)."""
+    from agmv_testlib import oracle_lz77
+    bufs = _lz_structured_buffers()
+    for b in bufs:
+        (cs, out), = ctx.test_lz77([b], persist_fill=0x33)
+        assert (cs, out) == oracle_lz77(b, 0x33), f"buffer of {len(b)} bytes"
+    got = ctx.test_lz77(bufs, persist_fill=0)
+    carried = np.zeros(max(len(b) for b in bufs) + 8, np.uint8)
+    for k, b in enumerate(bufs):
+        assert got[k] == oracle_lz77(b, int(carried[len(b)])), f"frame {k} of the batch"
+        carried[:len(b)] = b
