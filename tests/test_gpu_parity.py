@@ -589,3 +589,33 @@ def test_lz77_structured_inputs_against_oracle(ctx):
     for k, b in enumerate(bufs):
         assert got[k] == oracle_lz77(b, int(carried[len(b)])), f"frame {k} of the batch"
         carried[:len(b)] = b
+
+
+@pytest.mark.parametrize("name", ["lz77_64_III_LOW", "lz77_gba240_GBA_I_LOW", "lz77_64_II_LOW"])
+def test_decode_damaged_lz77_offsets_like_the_reference(ctx, golden, name):
+    """LZ77 tokens with damaged distance / literal bytes (lengths intact, so the expansion never outgrows the reference's
+    buffer): distance 0 copies nothing, a distance beyond the data so far skips its first bytes and then copies from index
+    0 (unsigned arithmetic, src/agmv_decode.c:200-218); frames come out short and later frames see stale bytes."""
+    g = golden["encode_lz77"][name]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        clean = f.read()
+    rng = np.random.default_rng(777)
+    checked = 0
+    for trial in range(30):
+        data = bytearray(clean)
+        for start, cs in _chunk_ranges(clean):
+            if cs < 16 or rng.random() < 0.3:
+                continue
+            for _ in range(int(rng.integers(1, 6))):
+                tok = int(rng.integers(0, cs // 4))
+                which = int(rng.choice([0, 1, 3]))
+                val = int(rng.choice([0, 0, 255, int(rng.integers(0, 256))]))
+                data[start + 4 * tok + which] = val
+        data = bytes(data)
+        rc, exp = oracle_decode(data)
+        if rc != 0:
+            continue
+        got = ctx.decode_all(data)
+        assert np.array_equal(got, exp), f"trial {trial}"
+        checked += 1
+    assert checked >= 20
