@@ -619,3 +619,16 @@ def test_decode_damaged_lz77_offsets_like_the_reference(ctx, golden, name):
         assert np.array_equal(got, exp), f"trial {trial}"
         checked += 1
     assert checked >= 20
+
+
+def test_small_and_odd_frame_sizes_against_oracle(ctx):
+    """Frames of a single 4x4 block, a single block row, widths that are not multiples of 8 or 16; dual- and single-palette,
+    LIGHT and HEAVY schedules (tests/test_oracle.py holds the oracle to the live reference on the same cases)."""
+    for w, h, n in [(4, 4, 8), (8, 4, 12), (36, 20, 16), (132, 12, 9)]:
+        for opt, q in (("III", "LOW"), ("I", "LOW"), ("II", "MID")):
+            frames = synth_frames(w, h, n, seed=5)
+            want = oracle_encode(frames, n - 1, 24, OPT[opt], QUALITY[q], LZSS)
+            data, _ = ctx.encode_sequence(frames, n - 1, 24, OPT[opt], QUALITY[q], LZSS)
+            assert data.tobytes() == want, (w, h, opt, q)
+            rc, exp = oracle_decode(want)
+            assert rc == 0 and np.array_equal(ctx.decode_all(want), exp), (w, h, opt, q)

@@ -148,3 +148,21 @@ def test_seek_goldens_are_what_the_reference_produces(golden):
     data = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
     rc, dec = ref_decode_seek(data, list(range(g["decoded_shape"][0])))
     assert rc == 0 and [sha256(dec[k].tobytes()) for k in range(dec.shape[0])] == g["decoded_frame_sha256"]
+
+
+SMALL_SIZES = [(4, 4, 8), (8, 4, 12), (36, 20, 16), (132, 12, 9)]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_oracle_small_and_odd_frame_sizes_match_live_reference():
+    """One block per frame, one block row, widths that are not multiples of 8 or 16: the oracle against the unmodified
+    reference, bytes and decoded frames (the GPU test of the same name checks the CUDA path against the oracle)."""
+    for w, h, n in (SMALL_SIZES[0], SMALL_SIZES[3]):          # the reference needs ~6 s per LOW-quality run (bubble sort)
+        for opt, q in (("III", "LOW"), ("II", "LOW")):
+            frames = synth_frames(w, h, n, seed=5)
+            mine = oracle_encode(frames, n - 1, 24, OPT[opt], QUALITY[q], LZSS)
+            ref = ref_encode(frames, n - 1, 24, OPT[opt], QUALITY[q], LZSS)
+            assert mine == ref, (w, h, opt, q)
+            rc, dec = oracle_decode(ref)
+            rc2, dec2 = ref_decode_raw(ref)
+            assert rc == rc2 == 0 and np.array_equal(dec, dec2), (w, h, opt, q)
