@@ -70,6 +70,32 @@ SEEK_CASES = [
 ]
 
 
+# AGMV_EncodeAGMV over a frame range that does not start at 1 (start_frame / end_frame arguments): name -> first, last source frame
+RANGE_CASES = {"start3_64_III_LOW": (3, 16, "III", "LOW", 13), "start2_64_I_LOW": (2, 15, "I", "LOW", 13)}
+
+
+def make_range_cases(gold):
+    """16 synthetic 64x64 frames written as f1..f16.bmp, the reference run on f<start>..f<end> (oracle/ref_encode.c)."""
+    import subprocess
+    import tempfile
+    from agmv_testlib import write_bmps
+    w, h, n = 64, 64, 16
+    fr = synth_frames(w, h, n, seed=1234)
+    gold["encode_ranges"] = {}
+    for name, (start, end, opt, q, create_n) in RANGE_CASES.items():
+        with tempfile.TemporaryDirectory() as td:
+            write_bmps(fr, td, "f", 1)
+            subprocess.run([os.path.join(REF_DIR, "ref_encode"), "o.agmv", ".", "f", str(start), str(end), str(w), str(h), "24", str(OPT[opt]),
+                            str(QUALITY[q]), "1", str(create_n), "agmv"], cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            data = open(os.path.join(td, "o.agmv"), "rb").read()
+        rc, dec = ref_decode_raw(data)
+        assert rc == 0
+        with open(os.path.join(GOLDEN_DIR, name + ".agmv"), "wb") as f:
+            f.write(data)
+        gold["encode_ranges"][name] = dict(w=w, h=h, n=n, seed=1234, start=start, end=end, opt=opt, quality=q, create_n=create_n, fps=24,
+                                           size=len(data), sha256=sha256(data), file=name + ".agmv", decoded_shape=list(dec.shape))
+
+
 def lzss_vectors():
     """Known-answer tests for the exported AGMV_LZSS (src/agmv_encode.c:106-177)."""
     rng = np.random.default_rng(7)
@@ -226,6 +252,7 @@ def main():
         json.dump(gold, open(jpath, "w"), indent=1, sort_keys=True)
 
     if not args.only:
+        make_range_cases(gold)
         from agmv_testlib import ref_decode_seek
         gold["seek"] = {}
         for fn, plan in SEEK_CASES:

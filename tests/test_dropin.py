@@ -296,3 +296,23 @@ def test_seek_dropin_like_skipto(golden, fn):
         prev = k
     libc.fclose(f)
     lib.DestroyAGMV(h)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["start3_64_III_LOW", "start2_64_I_LOW"])
+def test_encode_agmv_dropin_frame_range(golden, name):
+    """AGMV_EncodeAGMV with start_frame > 1: the BMP directory holds f1..f16, frames start..end are encoded."""
+    g = golden["encode_ranges"][name]
+    lib = _dropin()
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        write_bmps(frames, td, "f", 1)
+        os.chdir(td)
+        try:
+            h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
+            lib.AGMV_EncodeAGMV(h, b"o.agmv", b".", b"f", 1, g["start"], g["end"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            data = open("o.agmv", "rb").read()
+        finally:
+            os.chdir(cwd)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()

@@ -166,3 +166,12 @@ def test_oracle_small_and_odd_frame_sizes_match_live_reference():
             rc, dec = oracle_decode(ref)
             rc2, dec2 = ref_decode_raw(ref)
             assert rc == rc2 == 0 and np.array_equal(dec, dec2), (w, h, opt, q)
+
+
+@pytest.mark.parametrize("name", ["start3_64_III_LOW", "start2_64_I_LOW"])
+def test_oracle_frame_range_not_starting_at_one(golden, name):
+    """AGMV_EncodeAGMV(start_frame > 1): the reference on f<start>..f<end> equals the oracle on that slice of the frames."""
+    g = golden["encode_ranges"][name]
+    frames = synth_frames(g["w"], g["h"], g["n"], seed=g["seed"])[g["start"] - 1:g["end"]]
+    data = oracle_encode(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"])
