@@ -453,7 +453,11 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         uint32_t nt = cdiv(cap, RX_TILE);
         TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[0]));
         TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[1]));
-        TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + cdiv(cap, SCAN_TILE) + 8) * 4, (void**)&w.scan_ws));
+        TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2 * (size_t)cdiv(cap, SCAN_TILE) + 16) * 4, (void**)&w.scan_ws));
+        // optional: resolve the large three-equal-byte groups from run tables (exact; pays off for long runs - on the bench
+        // workload, whose runs average a few dozen bytes, it measured 236 vs 224 ms per step, so it is off by default)
+        w.runs = getenv("AGMVB_LZ_RUNS") ? atoi(getenv("AGMVB_LZ_RUNS")) != 0 : false;
+        if (w.runs) TRY(grab((size_t)cap * 4, (void**)&w.run_ws));
         w.cap_n = cap;
     }
     size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 16;

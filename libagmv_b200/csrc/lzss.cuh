@@ -62,6 +62,8 @@ struct LzWork {
     uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
     uint32_t* tile_hist[2] = {};         // key-byte counts / offsets per (digit, tile), double buffered across levels
     uint32_t* scan_ws = nullptr;
+    uint32_t* run_ws = nullptr;          // run tables of the large three-equal-byte groups (cap_n words)
+    bool runs = false;                   // AGMVB_LZ_RUNS: resolve those groups from run tables instead of the global levels
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
     uint32_t* seg_len = nullptr;         // cap_frames
@@ -1064,6 +1066,141 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
     }
 }
 
+// =====================================================================================================
+// Large groups whose key is three equal bytes (long runs): run tables instead of sorting.
+// (tools/run_path_prototype.py states the rule and checks it against the brute-force search.)
+//
+// For a member y of such a group let r(y) be the length of the run of that byte starting at y. A candidate x matches
+// min(r(x), r(y)) bytes unless r(x) == r(y), in which case the bytes after the two runs decide. So
+//   * the group's members are cut into runs (consecutive positions): start position and length per run, plus, for every
+//     v = 4..15, the sorted list of the runs at least v long;
+//   * y's match is min(r(y), 15, bytes left, largest r in the window), its start the earliest window member with at least
+//     that r - the member of a run with r >= v that comes first is max(run start, window start), so both are answered
+//     per run, by binary search, without touching the members (rg_match_k);
+//   * only members with r(y) <= 14 (the last twelve of every run) can do better, through a candidate with the same r whose
+//     continuation also matches: they alone stay in the compacted array that goes through the global levels, and
+//     rg_match_k keeps that result when it is longer than r(y).
+// A run of R members thus contributes 12 elements to the sorted passes instead of R.
+// =====================================================================================================
+struct RunView {
+    const uint32_t* a3;
+    const uint32_t* gs3;
+    const uint32_t* dig3;   // key words (bytes 0..3) in level-3 order
+    uint32_t* mi;           // exclusive count of members; after rg_build_k bit 31 = "is a member" (the key words are gone by then)
+    const uint32_t* rsx;    // exclusive count of run starts
+    const uint32_t* rs;     // per run: position of its first member
+    const uint32_t* rmi;    // per run: member index of its first member (rmi[K] = number of members)
+    uint32_t n;
+    bool late;              // after the global levels: dig3 has been overwritten, use the flag in mi
+    __device__ bool member(uint32_t i) const {
+        if (late) return mi[i] >> 31;
+        const uint32_t d = dig3[i];
+        return ((d ^ (d >> 8)) & 0xFFFFu) == 0 && sg_group_is_large(gs3, n, gs3[i] & LZ_GS_MASK);
+    }
+    __device__ bool run_start(uint32_t i) const {
+        if (!member(i)) return false;
+        if (i == (gs3[i] & LZ_GS_MASK)) return true;
+        return (a3[i] & LZ_POS_MASK) != (a3[i - 1] & LZ_POS_MASK) + 1u;
+    }
+    __device__ uint32_t run_of(uint32_t i) const { return rsx[i] + (run_start(i) ? 1u : 0u) - 1u; }   // i must be a member
+    __device__ uint32_t run_len(uint32_t k) const { return rmi[k + 1] - rmi[k] + 2u; }               // bytes of the run
+};
+struct RunMemberFlag { RunView v; __device__ uint32_t operator()(uint32_t i) const { return v.member(i) ? 1u : 0u; } };
+struct RunStartFlag { RunView v; __device__ uint32_t operator()(uint32_t i) const { return v.run_start(i) ? 1u : 0u; } };
+struct RunLenFlag { const uint32_t* rmi; uint32_t len; __device__ uint32_t operator()(uint32_t k) const { return rmi[k + 1] - rmi[k] + 2u >= len ? 1u : 0u; } };
+
+__global__ void __launch_bounds__(256) rg_build_k(RunView v, uint32_t* __restrict__ rs, uint32_t* __restrict__ rmi, uint32_t n_members, uint32_t n_runs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) rmi[n_runs] = n_members;
+    if (i >= v.n || !v.member(i)) return;
+    const uint32_t m = v.mi[i];
+    if (v.run_start(i)) {
+        const uint32_t k = v.rsx[i];
+        rs[k] = v.a3[i] & LZ_POS_MASK;
+        rmi[k] = m;
+    }
+    v.mi[i] = m | 0x80000000u;
+}
+__global__ void __launch_bounds__(256) rg_list_k(const uint32_t* __restrict__ rmi, uint32_t n_runs, uint32_t len, const uint32_t* __restrict__ prefix,
+                                                 uint32_t* __restrict__ list) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_runs && rmi[k + 1] - rmi[k] + 2u >= len) list[prefix[k]] = k;
+}
+// what goes through the global levels: the large groups, minus the run members that the run tables settle (r >= 15)
+struct LargeKeepFlag {
+    RunView v;
+    __device__ uint32_t operator()(uint32_t i) const {
+        if (!sg_group_is_large(v.gs3, v.n, v.gs3[i] & LZ_GS_MASK)) return 0u;
+        if (!v.member(i)) return 1u;
+        const uint32_t k = v.run_of(i);
+        const uint32_t r = v.rs[k] + v.run_len(k) - (v.a3[i] & LZ_POS_MASK);
+        return r < (uint32_t)LZ_MAXLEN ? 1u : 0u;
+    }
+};
+__global__ void __launch_bounds__(256) rg_compact_k(RunView v, const uint32_t* __restrict__ prefix, uint32_t* __restrict__ a_out,
+                                                    uint32_t* __restrict__ gs_out, uint32_t* __restrict__ dig_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n || !LargeKeepFlag{v}(i)) return;
+    const uint32_t gw = v.gs3[i], o = prefix[i];
+    a_out[o] = v.a3[i];
+    gs_out[o] = prefix[gw & LZ_GS_MASK] | (gw & LZ_ALIVE);   // the group's first kept element (the start itself may be gone)
+    dig_out[o] = v.dig3[i];
+}
+
+// earliest member x of the group with lo <= x < y and r(x) >= len; k = y's run, kf = the group's first run. EMPTY32 if none.
+__device__ __forceinline__ uint32_t rg_earliest(const RunView& v, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ lcnt, uint32_t kcap,
+                                                uint32_t lo, uint32_t y, uint32_t k, uint32_t kf, uint32_t len) {
+    // last run of [kf, k] that starts at or before lo (kf if none does)
+    uint32_t a = kf, b = k + 1;
+    while (b - a > 1) {
+        const uint32_t mid = (a + b) >> 1;
+        if (v.rs[mid] <= lo) a = mid; else b = mid;
+    }
+    const uint32_t klo = a;
+    {
+        const uint32_t s = v.rs[klo], e = s + v.run_len(klo);
+        const uint32_t first = max(s, lo);
+        if (klo == k) return (first < y && e - first >= len) ? first : EMPTY32;
+        if (first + 3u <= e && e - first >= len) return first;     // first is still a member (first <= e - 3)
+    }
+    // runs klo+1 .. k-1 lie inside the window entirely
+    if (len <= 3u) {
+        if (klo + 1 < k) return v.rs[klo + 1];
+    } else {
+        const uint32_t* list = lists + (size_t)(len - 4u) * kcap;
+        uint32_t lo_i = 0, hi_i = lcnt[len - 4u];
+        while (lo_i < hi_i) {
+            const uint32_t mid = (lo_i + hi_i) >> 1;
+            if (list[mid] >= klo + 1) hi_i = mid; else lo_i = mid + 1;
+        }
+        if (lo_i < lcnt[len - 4u] && list[lo_i] < k) return v.rs[list[lo_i]];
+    }
+    // y's own run: its members before y all have a larger r than y
+    const uint32_t s = v.rs[k];
+    return s < y ? s : EMPTY32;
+}
+
+__global__ void __launch_bounds__(256) rg_match_k(RunView v, const uint32_t* __restrict__ lists, const uint32_t* __restrict__ lcnt, uint32_t kcap,
+                                                  uint32_t* __restrict__ match_rec) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= v.n || !v.member(i)) return;
+    const uint32_t gw = v.gs3[i];
+    if (!(gw & LZ_ALIVE)) return;                                   // no earlier member within the window
+    const uint32_t pw = v.a3[i], y = pw & LZ_POS_MASK, cap = pw >> 28;
+    const uint32_t k = v.run_of(i), kf = v.rsx[gw & LZ_GS_MASK];
+    const uint32_t r = v.rs[k] + v.run_len(k) - y;
+    if (r < (uint32_t)LZ_MAXLEN && (match_rec[y] >> 28) > r) return;   // a same-r candidate matched past the run (global levels)
+    const uint32_t lo = y > (uint32_t)LZ_WINDOW ? y - (uint32_t)LZ_WINDOW : 0u;
+    for (uint32_t len = min(min(r, (uint32_t)LZ_MAXLEN), cap); len >= (uint32_t)LZ_MINLEN; len--) {
+        const uint32_t x = rg_earliest(v, lists, lcnt, kcap, lo, y, k, kf, len);
+        if (x != EMPTY32) {
+            match_rec[y] = len << 28 | LZ_RES | (y - x);
+            return;
+        }
+    }
+    match_rec[y] = 0;   // (not reached for an alive member; clears a partial record of the global levels otherwise)
+}
+
 // Host driver. bs: batch bitstream (n bytes + >=16 bytes of readable padding);
 // fs: device array of F+1 frame starts (fs[0]=0, fs[F]=n); wk.segs / wk.seg_len
 // describe the same frames for the parse (filled by the caller, ntile tiles in
@@ -1137,12 +1274,47 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
             uint32_t* dig3 = wk.dig4[LZ_MINLEN & 1];          // key words in level-3 order
             uint32_t* digc = wk.dig4[(LZ_MINLEN & 1) ^ 1];
             uint32_t* prefix = wk.gs_tmp;
-            device_scan<SumOp, true>(LargeFlag{wk.GS[LZ_MINLEN], n}, StoreU32{prefix}, n, wk.scan_ws, lc, KC_LZ_GROUP);
+            // run tables of the large three-equal-byte groups (A[2] / GS[2] are free: member and run-start counts)
+            RunView rv{wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], dig3, wk.A[2], wk.GS[2], nullptr, nullptr, n, false};
+            uint32_t n_runs = 0, n_members = 0, kcap = 0;
+            uint32_t *lists = nullptr, *lcnt = nullptr;
+            bool use_runs = false;
+            if (wk.runs) {
+                const uint32_t st_tiles = cdiv(n, (uint32_t)SCAN_TILE);
+                device_scan<SumOp, true>(RunMemberFlag{rv}, StoreU32{wk.A[2]}, n, wk.scan_ws, lc, KC_LZ_GROUP);
+                cudaMemcpyAsync(&n_members, wk.scan_ws + st_tiles, 4, cudaMemcpyDeviceToHost, st);
+                device_scan<SumOp, true>(RunStartFlag{rv}, StoreU32{wk.GS[2]}, n, wk.scan_ws + st_tiles + 2, lc, KC_LZ_GROUP);
+                cudaMemcpyAsync(&n_runs, wk.scan_ws + st_tiles + 2 + st_tiles, 4, cudaMemcpyDeviceToHost, st);
+                cudaStreamSynchronize(st);
+                // worth it only for long runs, and the tables have to fit: rs, rmi, 12 lists, 16 counters
+                kcap = n_runs + 8;
+                use_runs = n_runs > 0 && (uint64_t)n_runs * 16u <= n_members && (uint64_t)kcap * 14u + 32u <= wk.cap_n;
+            }
+            if (use_runs) {
+                uint32_t* rs = wk.run_ws;
+                uint32_t* rmi = rs + kcap;
+                lcnt = rmi + kcap;
+                lists = lcnt + 16;
+                rv.rs = rs;
+                rv.rmi = rmi;
+                KL(lc, KC_LZ_GROUP, (rg_build_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(rv, rs, rmi, n_members, n_runs)));
+                for (uint32_t len = 4; len <= (uint32_t)LZ_MAXLEN; len++) {
+                    uint32_t* pre = wk.tile_hist[0];   // n_runs <= n / 16 words: fits the tile histogram buffer
+                    uint32_t* ws = wk.scan_ws;
+                    device_scan<SumOp, true>(RunLenFlag{rmi, len}, StoreU32{pre}, n_runs, ws, lc, KC_LZ_GROUP);
+                    cudaMemcpyAsync(lcnt + (len - 4), ws + cdiv(n_runs, (uint32_t)SCAN_TILE), 4, cudaMemcpyDeviceToDevice, st);
+                    KL(lc, KC_LZ_GROUP, (rg_list_k<<<cdiv(n_runs, nthreads), nthreads, 0, st>>>(rmi, n_runs, len, pre, lists + (size_t)(len - 4) * kcap)));
+                }
+                device_scan<SumOp, true>(LargeKeepFlag{rv}, StoreU32{prefix}, n, wk.scan_ws, lc, KC_LZ_GROUP);
+            } else {
+                device_scan<SumOp, true>(LargeFlag{wk.GS[LZ_MINLEN], n}, StoreU32{prefix}, n, wk.scan_ws, lc, KC_LZ_GROUP);
+            }
             cudaMemcpyAsync(&n_large, wk.scan_ws + cdiv(n, (uint32_t)SCAN_TILE), 4, cudaMemcpyDeviceToHost, st);
             cudaStreamSynchronize(st);
             if (n_large > 0) {
                 const uint32_t m = n_large, mt = cdiv(m, RX_TILE);
-                KL(lc, KC_LZ_GROUP, (lz_compact_large_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], dig3, prefix, n, wk.A[1], wk.GS[1], digc)));
+                if (use_runs) KL(lc, KC_LZ_GROUP, (rg_compact_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(rv, prefix, wk.A[1], wk.GS[1], digc)));
+                else KL(lc, KC_LZ_GROUP, (lz_compact_large_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.A[LZ_MINLEN], wk.GS[LZ_MINLEN], dig3, prefix, n, wk.A[1], wk.GS[1], digc)));
                 level3_a = wk.A[1];
                 level3_gs = wk.GS[1];
                 // dig parity is flipped from here on: level L reads dig4[(L & 1) ^ 1]
@@ -1166,6 +1338,10 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
                         KL(lc, KC_LZ_GROUP, (lz_group_apply_k<false, false><<<mt, LZ_THREADS, 0, st>>>(wk.gs_tmp, th, mt, m, wk.scan_ws, wk.A[Lnew], wk.GS[Lnew],
                                                                                                          wk.match_rec, Lnew, dout, th_next)));
                 }
+            }
+            if (use_runs) {
+                rv.late = true;
+                KL(lc, KC_LZ_GROUP, (rg_match_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(rv, lists, lcnt, kcap, wk.match_rec)));
             }
         }
         KL(lc, KC_LZ_GROUP, (lz_bestlen_k<<<cdiv(n, nthreads), nthreads, 0, st>>>(wk.match_rec, n, wk.bestlen)));
