@@ -120,6 +120,28 @@ int agmvb_frame_similarity(agmvb_ctx* ctx, const uint32_t* frames, uint64_t n_fr
 /* Whether agmvb_enc_frames appends the empty 'AGAC' chunk after every frame chunk (AGMV_EncodeAGMV does, the per-frame
  * AGMV_EncodeFrame and the other two encoders do not). Default on. */
 int agmvb_enc_set_audio_stub(agmvb_ctx* ctx, int on);
+/* ---- audio chunk codec -------------------------------------------------------- */
+/* The audio track of the handle about to be encoded, as AGMV_WavToAudioTrack leaves it (src/agmv_utils.c:1035-1087):
+ * audio_size samples of 16-bit (uint16_t) or 8-bit PCM in host memory plus the header fields. Uploads the track and runs
+ * AGMV_CompressAudio (src/agmv_encode.c:659-705: every 16-bit sample becomes one byte - the closest of a square, a rounded
+ * square and a shifted code; 8-bit samples are copied) on the device, where the result stays. The next
+ * agmvb_encode_sequence / agmvb_encode_full writes the header's audio fields and one 'AGAC' chunk of
+ * (u32)(audio_size / (f32)frames) bytes after every frame chunk (AGMV_EncodeAudioChunk, :707-717; frames = the adjusted
+ * frame count of :2296-2353 for AGMV_EncodeAGMV, end - start for AGMV_EncodeFullAGMV) and consumes the track.
+ * pcm == NULL or audio_size == 0 clears it. The track survives agmvb_enc_begin. */
+int agmvb_enc_set_audio(agmvb_ctx* ctx, const void* pcm, uint64_t audio_size, int bits_per_sample, uint32_t sample_rate,
+                        uint32_t channels, uint32_t total_duration);
+/* For callers that drive agmvb_enc_frames themselves: from now on frame number g (first_frame_count + k) is followed by
+ * 'AGAC' chunk_size and atsample[g * chunk_size .. +chunk_size) (bytes past the end of the track read as 0; the reference
+ * reads past its allocation there). agmvb_enc_set_audio_stub switches back to empty / no audio chunks. */
+int agmvb_enc_set_audio_chunk(agmvb_ctx* ctx, uint32_t chunk_size);
+/* the companded track (audio_size bytes), e.g. for AGMV_EncodeAudioChunk calls of the per-frame API */
+int agmvb_enc_get_atsample(agmvb_ctx* ctx, uint8_t* out, uint64_t cap);
+/* AGMV_CompressAudio / the sample loop of AGMV_DecodeAudioChunk (src/agmv_decode.c:431-451: even byte b -> b*b, odd byte
+ * -> b << 8, i.e. AGMV_SQR_TABLE / AGMV_SHIFT_TABLE) on n samples, host buffers. */
+int agmvb_audio_compress(agmvb_ctx* ctx, const void* pcm, uint64_t n, int bits_per_sample, uint8_t* atsample);
+int agmvb_audio_expand(agmvb_ctx* ctx, const uint8_t* atsample, uint64_t n, int bits_per_sample, void* pcm);
+
 /* Header only (AGMV_EncodeHeader, src/agmv_encode.c:21-94) with the current palette. */
 int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps, uint8_t* out, uint64_t cap, uint64_t* len);
 
@@ -141,6 +163,10 @@ int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint32_t* out, 
  * n_streams*count) receives a 64-bit position-weighted sum per frame. */
 int agmvb_dec_batch(agmvb_ctx* ctx, const int* streams, uint32_t n_streams, uint32_t count,
                     uint32_t* const* outs, uint64_t* checksums);
+/* The audio half of AGMV_DecodeAGMV (src/agmv_decode.c:572-587): every 'AGAC' chunk of an open stream, decoded by
+ * AGMV_DecodeAudioChunk's rule into pcm (uint16_t samples for 16-bit tracks, bytes for 8-bit ones; host). *n_samples =
+ * audio_track->start_point after the last chunk. pcm == NULL only queries the sizes. Independent of the frame cursor. */
+int agmvb_dec_audio(agmvb_ctx* ctx, int stream, void* pcm, uint64_t cap_samples, uint64_t* n_samples, int* bits_per_sample);
 int agmvb_dec_close(agmvb_ctx* ctx, int stream);
 /* Seek: what AGMV_SkipTo / AGMV_SkipBackwards do to the handle (src/agmv_playback.c:81-100) - the next
  * frame decoded is frame_index, with frame_count = frame_index; the chunk offsets come from the index built by

@@ -114,6 +114,13 @@ void AGMV_EncodeFullAGMV(AGMV* agmv, const char* filename, const char* dir, cons
                          u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
                          AGMV_COMPRESSION compression);
 
+/* audio chunk codec: include/agmv_encode.h (AGMV_CompressAudio, AGMV_EncodeAudioChunk), include/agmv_decode.h
+ * (AGMV_DecodeAudioChunk), include/agmv_utils.h (AGMV_ExportAudioType; WAV only here, weak). The sample maps run on the GPU. */
+void AGMV_CompressAudio(AGMV* agmv);
+void AGMV_EncodeAudioChunk(FILE* file, AGMV* agmv);
+int AGMV_DecodeAudioChunk(FILE* file, AGMV* agmv);
+void AGMV_ExportAudioType(FILE* audio, AGMV* agmv, AGMV_AUDIO_TYPE audio_type);
+
 /* decode: include/agmv_decode.h:21-22,26 */
 int AGMV_DecodeHeader(FILE* file, AGMV* agmv);
 int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv);

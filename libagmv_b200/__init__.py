@@ -53,6 +53,12 @@ SYMBOLS = {
                                     C.c_int, C.c_void_p, C.c_uint64, _u64p, _u32p]),
     "agmvb_frame_similarity": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, _i32p, _i32p, C.c_uint32, _u64p]),
     "agmvb_enc_set_audio_stub": (C.c_int, [C.c_void_p, C.c_int]),
+    "agmvb_enc_set_audio": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "agmvb_enc_set_audio_chunk": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "agmvb_enc_get_atsample": (C.c_int, [C.c_void_p, _u8p, C.c_uint64]),
+    "agmvb_audio_compress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, _u8p]),
+    "agmvb_audio_expand": (C.c_int, [C.c_void_p, _u8p, C.c_uint64, C.c_int, C.c_void_p]),
+    "agmvb_dec_audio": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64, _u64p, C.POINTER(C.c_int)]),
     "agmvb_dec_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int), _u32p, _u32p, _u32p]),
     "agmvb_dec_frames": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_void_p, C.c_int]),
     "agmvb_dec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), _u64p]),
@@ -264,6 +270,46 @@ class Context:
 
     def dec_close(self, sid):
         self._ck(self.lib.agmvb_dec_close(self.h, sid))
+
+    # ---- audio chunk codec ---------------------------------------
+    def enc_set_audio(self, pcm, sample_rate, channels, total_duration):
+        """The handle's audio track (what AGMV_WavToAudioTrack sets): uint16 or uint8 samples. None clears it."""
+        if pcm is None:
+            self._ck(self.lib.agmvb_enc_set_audio(self.h, None, 0, 16, 0, 0, 0))
+            return
+        pcm = np.ascontiguousarray(pcm)
+        bits = {np.dtype(np.uint16): 16, np.dtype(np.uint8): 8}[pcm.dtype]
+        self._ck(self.lib.agmvb_enc_set_audio(self.h, C.c_void_p(pcm.ctypes.data), pcm.size, bits, sample_rate, channels, total_duration))
+
+    def enc_set_audio_chunk(self, chunk_size):
+        self._ck(self.lib.agmvb_enc_set_audio_chunk(self.h, chunk_size))
+
+    def enc_get_atsample(self, n):
+        out = np.empty(n, np.uint8)
+        self._ck(self.lib.agmvb_enc_get_atsample(self.h, _p(out, _u8p), n))
+        return out
+
+    def audio_compress(self, pcm):
+        pcm = np.ascontiguousarray(pcm)
+        bits = {np.dtype(np.uint16): 16, np.dtype(np.uint8): 8}[pcm.dtype]
+        out = np.empty(pcm.size, np.uint8)
+        self._ck(self.lib.agmvb_audio_compress(self.h, C.c_void_p(pcm.ctypes.data), pcm.size, bits, _p(out, _u8p)))
+        return out
+
+    def audio_expand(self, atsample, bits=16):
+        atsample = np.ascontiguousarray(atsample, dtype=np.uint8)
+        out = np.empty(atsample.size, np.uint16 if bits == 16 else np.uint8)
+        self._ck(self.lib.agmvb_audio_expand(self.h, _p(atsample, _u8p), atsample.size, bits, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def dec_audio(self, sid):
+        """Every audio chunk of an open stream, decoded (AGMV_DecodeAudioChunk): uint16 or uint8 samples."""
+        n, bits = C.c_uint64(), C.c_int()
+        self._ck(self.lib.agmvb_dec_audio(self.h, sid, None, 0, C.byref(n), C.byref(bits)))
+        out = np.empty(n.value, np.uint16 if bits.value == 16 else np.uint8)
+        if n.value:
+            self._ck(self.lib.agmvb_dec_audio(self.h, sid, C.c_void_p(out.ctypes.data), n.value, C.byref(n), C.byref(bits)))
+        return out
 
     def decode_all(self, data):
         sid, w, h, n = self.dec_open(data)

@@ -7,8 +7,10 @@
  * (if the GPU layer fails, the encode functions report to stderr and the decode functions
  * return MEMORY_CORRUPTION_ERR, the only channel the reference API offers - SURVEY.md 8b).
  *
- * Out of scope here: audio tracks (#16) and image formats other than BMP
- * (#18, AGIDL).
+ * The audio chunk codec is served too: a handle's track (AGMV_WavToAudioTrack) is companded on the GPU
+ * and interleaved by the sequence encoders, AGMV_DecodeAGMV expands the track on the GPU and writes quick_export.wav.
+ * Out of scope here: WAV / AIFF import and AIFF export (agmv_utils.c, host file I/O - link the
+ * reference's agmv_utils.o for them) and image formats other than BMP (#18, AGIDL).
  */
 #include "agmv_dropin.h"
 
@@ -255,6 +257,32 @@ void AGMV_EncodeFrame(FILE* file, AGMV* agmv, u32* img_data) {
     free(px); free(ent); free(img);
 }
 
+/* the handle's audio track (AGMV_WavToAudioTrack, src/agmv_utils.c:1035-1087) -> GPU layer; AGMV_CompressAudio runs there */
+static int track_to_gpu(agmvb_ctx* c, AGMV* agmv) {
+    if (agmv->header.audio_size == 0) return agmvb_enc_set_audio(c, NULL, 0, 16, 0, 0, 0);
+    const void* pcm = agmv->header.bits_per_sample == 16 ? (const void*)agmv->audio_track->pcm : (const void*)agmv->audio_track->pcm8;
+    return agmvb_enc_set_audio(c, pcm, (uint64_t)agmv->header.audio_size, (int)agmv->header.bits_per_sample, (uint32_t)agmv->header.sample_rate,
+                               (uint32_t)agmv->header.num_of_channels, (uint32_t)agmv->header.total_audio_duration);
+}
+
+/* src/agmv_encode.c:659-705: fills agmv->audio_chunk->atsample (allocated by the caller, audio_size bytes) - on the GPU */
+void AGMV_CompressAudio(AGMV* agmv) {
+    agmvb_ctx* c = ctx_get();
+    if (!c || agmv->header.audio_size == 0) return;
+    const void* pcm = agmv->header.bits_per_sample == 16 ? (const void*)agmv->audio_track->pcm : (const void*)agmv->audio_track->pcm8;
+    int rc = agmvb_audio_compress(c, pcm, (uint64_t)agmv->header.audio_size, (int)agmv->header.bits_per_sample, agmv->audio_chunk->atsample);
+    if (rc) fail(rc, "AGMV_CompressAudio");
+}
+
+/* src/agmv_encode.c:707-717 (container framing only) */
+void AGMV_EncodeAudioChunk(FILE* file, AGMV* agmv) {
+    const u32 size = agmv->audio_chunk->size;
+    fwrite("AGAC", 1, 4, file);
+    w32(file, size);
+    fwrite(agmv->audio_chunk->atsample + agmv->audio_track->start_point, 1, (size_t)size, file);
+    agmv->audio_track->start_point += size;
+}
+
 /* src/agmv_encode.c:2270-3657, BMP input */
 void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame,
                      u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
@@ -267,7 +295,6 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
         DestroyAGMV(agmv);
         return;
     }
-    if (agmv->header.audio_size != 0) fprintf(stderr, "libagmv_dropin: audio track ignored (audio codec is out of scope); empty AGAC chunks are written\n");
     agmv->opt = opt;
     agmv->compression = compression;
     agmv->leniency = 0;
@@ -293,6 +320,9 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
     char path[512];
     int rc = agmvb_enc_begin(c, (uint32_t)width, (uint32_t)height, (int)opt, (int)quality, (int)compression);
     if (!rc) rc = agmvb_enc_set_audio_stub(c, 1); /* AGMV_EncodeAudioChunk after every frame: 'AGAC' 0 when there is no audio */
+    if (!rc) rc = track_to_gpu(c, agmv);          /* AGMV_CompressAudio (:2667) */
+    if (!rc && agmv->header.audio_size != 0)      /* audio_chunk->size = audio_size / (f32)adjusted frames (:2661-2663) */
+        rc = agmvb_enc_set_audio_chunk(c, (uint32_t)(u32)(agmv->header.audio_size / (f32)adjusted));
     g_enc.valid = 0;
     /* frames are streamed from disk twice, like the reference: once for the histogram, once for the encode */
     const u32 CH = 64; /* source frames per upload; a multiple of 16 keeps LIGHT groups and GOPs whole */
@@ -357,6 +387,8 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
     w32(file, (u32)round(agmv->header.frames_per_second * rate));
     fclose(file);
     free(buf); free(sa); free(sb); free(img);
+    agmvb_enc_set_audio(c, NULL, 0, 16, 0, 0, 0);
+    agmvb_enc_set_audio_stub(c, 1);
     DestroyAGMV(agmv); /* the reference consumes the caller's handle (:3625) */
 
     if (opt == AGMV_OPT_GBA_I || opt == AGMV_OPT_GBA_II || opt == AGMV_OPT_GBA_III) { /* :3627-3656 */
@@ -427,7 +459,10 @@ static void encode_whole(int video, AGMV* agmv, const char* filename, const char
         else snprintf(path, sizeof path, "%s/%s%lu.bmp", dir, basename, start_frame + k);
         if (load_bmp(path, width, height, buf + (size_t)k * SP)) rc = AGMVB_ERR_FILE;
     }
-    uint64_t cap = 4096 + (uint64_t)n_src * (SP * 3 + 64), len = 0;
+    const uint64_t track_bytes = (!video && agmv && agmv->header.total_audio_duration != 0) ? (uint64_t)agmv->header.audio_size : 0;
+    if (!rc && track_bytes) rc = track_to_gpu(c, agmv); /* AGMV_EncodeFullAGMV interleaves the track only when it has a duration (:4022-4029) */
+    else if (!rc) rc = agmvb_enc_set_audio(c, NULL, 0, 16, 0, 0, 0);
+    uint64_t cap = 4096 + (uint64_t)n_src * (SP * 3 + 64 + 8) + track_bytes, len = 0;
     uint8_t* out = (uint8_t*)malloc(cap);
     uint32_t nenc = 0;
     if (!rc) {
@@ -552,9 +587,79 @@ int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
     return NO_ERR;
 }
 
-/* src/agmv_decode.c:527-647 (video frames; the audio track is skipped) */
+/* src/agmv_decode.c:412-453: one 'AGAC' chunk, expanded on the GPU into audio_track->pcm / pcm8 at start_point */
+int AGMV_DecodeAudioChunk(FILE* file, AGMV* agmv) {
+    if (fread(agmv->audio_chunk->fourcc, 1, 4, file) != 4) { }
+    agmv->audio_chunk->size = r32(file);
+    if (memcmp(agmv->audio_chunk->fourcc, "AGAC", 4)) return INVALID_HEADER_FORMATTING_ERR;
+    const size_t size = (size_t)agmv->audio_chunk->size;
+    if (size == 0) return NO_ERR;
+    agmvb_ctx* c = ctx_get();
+    if (!c) return MEMORY_CORRUPTION_ERR;
+    uint8_t* b = (uint8_t*)malloc(size);
+    size_t got = fread(b, 1, size, file);
+    if (got < size) memset(b + got, 0xFF, size - got); /* AGIDL_ReadByte at the end of the file: EOF stored in a u8 */
+    const int bits = agmv->header.bits_per_sample == 16 ? 16 : 8;
+    void* dst = bits == 16 ? (void*)(agmv->audio_track->pcm + agmv->audio_track->start_point) : (void*)(agmv->audio_track->pcm8 + agmv->audio_track->start_point);
+    int rc = agmvb_audio_expand(c, b, (uint64_t)size, bits, dst);
+    free(b);
+    if (rc) { fail(rc, "AGMV_DecodeAudioChunk"); return MEMORY_CORRUPTION_ERR; }
+    agmv->audio_track->start_point += size;
+    return NO_ERR;
+}
+
+/* src/agmv_utils.c:1403-1435, the WAV case (weak: the reference's agmv_utils.o brings AIFF / AIFC as well) */
+WEAK void AGMV_ExportAudioType(FILE* audio, AGMV* agmv, AGMV_AUDIO_TYPE audio_type) {
+    if (audio_type != AGMV_AUDIO_WAV) fprintf(stderr, "libagmv_dropin: AIFF export is agmv_utils.c's (link the reference's agmv_utils.o); writing WAV\n");
+    const u32 bytes = agmv->header.bits_per_sample == 16 ? agmv->header.audio_size * 2 : agmv->header.audio_size;
+    fwrite("RIFF", 1, 4, audio);
+    w32(audio, bytes);
+    fwrite("WAVEfmt ", 1, 8, audio);
+    w32(audio, 16);
+    w16(audio, 1);
+    w16(audio, agmv->header.num_of_channels);
+    w32(audio, agmv->header.sample_rate);
+    w32(audio, 75600);
+    w16(audio, (agmv->header.num_of_channels * agmv->header.bits_per_sample) / 8);
+    w16(audio, agmv->header.bits_per_sample);
+    fwrite("data", 1, 4, audio);
+    w32(audio, bytes);
+    if (agmv->header.bits_per_sample == 16) fwrite(agmv->audio_track->pcm, 2, (size_t)agmv->header.audio_size, audio);
+    else fwrite(agmv->audio_track->pcm8, 1, (size_t)agmv->header.audio_size, audio);
+}
+
+/* src/agmv_decode.c:572-618: the whole track in one GPU call, then quick_export.wav / .aiff. Samples the stream's chunks
+ * do not cover (audio_size - size * frames of them) are zero here; the reference leaves them uninitialised. */
+static int export_track(agmvb_ctx* c, int stream, const uint8_t* hdr, AGMV_AUDIO_TYPE audio_type) {
+    AGMV a;
+    AGMV_AUDIO_TRACK tr;
+    memset(&a, 0, sizeof a.header);
+    a.header.total_audio_duration = hdr[22] | hdr[23] << 8 | hdr[24] << 16 | (u32)hdr[25] << 24;
+    a.header.sample_rate = hdr[26] | hdr[27] << 8 | hdr[28] << 16 | (u32)hdr[29] << 24;
+    a.header.audio_size = hdr[30] | hdr[31] << 8 | hdr[32] << 16 | (u32)hdr[33] << 24;
+    a.header.num_of_channels = (u16)(hdr[34] | hdr[35] << 8);
+    a.header.bits_per_sample = (u16)(hdr[36] | hdr[37] << 8);
+    if (a.header.total_audio_duration == 0) return 0;
+    uint64_t n = 0;
+    int bits = 16;
+    int rc = agmvb_dec_audio(c, stream, NULL, 0, &n, &bits);
+    if (rc) return rc;
+    const uint64_t cap = n > a.header.audio_size ? n : a.header.audio_size;
+    void* pcm = calloc((size_t)cap + 1, 2);
+    rc = agmvb_dec_audio(c, stream, pcm, cap, &n, &bits);
+    if (!rc) {
+        tr.pcm = (u16*)pcm; tr.pcm8 = (u8*)pcm; tr.start_point = n; tr.total_audio_duration = 0;
+        a.audio_track = &tr;
+        const int aiff = audio_type == AGMV_AUDIO_AIFF || audio_type == AGMV_AUDIO_AIFC;
+        FILE* f = fopen(aiff ? "quick_export.aiff" : "quick_export.wav", "wb");
+        if (f) { AGMV_ExportAudioType(f, &a, aiff ? audio_type : AGMV_AUDIO_WAV); fclose(f); }
+    }
+    free(pcm);
+    return rc;
+}
+
+/* src/agmv_decode.c:527-647 */
 int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type) {
-    (void)audio_type;
     FILE* f = fopen(filename, "rb");
     if (!f) return FILE_NOT_FOUND_ERR;
     fseek(f, 0, SEEK_END);
@@ -568,6 +673,8 @@ int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_typ
     int stream = -1;
     uint32_t w = 0, h = 0, n = 0;
     int rc = agmvb_dec_open(c, data, (uint64_t)size, &stream, &w, &h, &n);
+    uint8_t hdr[38];
+    memcpy(hdr, data, size >= 38 ? 38 : 0);
     free(data);
     if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
     const size_t P = (size_t)w * h;
@@ -579,6 +686,7 @@ int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_typ
         if (!rc && img_type == AGMV_IMG_BMP) for (uint32_t k = 0; k < nf; k++) quick_export_bmp(px + (size_t)k * P, w, h);
     }
     free(px);
+    if (!rc) rc = export_track(c, stream, hdr, audio_type);
     agmvb_dec_close(c, stream);
     if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
     return NO_ERR;

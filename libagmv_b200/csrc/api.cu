@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "audio.cuh"
 #include "common.cuh"
 #include "decode.cuh"
 #include "encode.cuh"
@@ -35,6 +36,9 @@ struct DecStream {
     uint64_t file_len = 0;
     std::vector<uint64_t> data_off;
     std::vector<uint32_t> usize, csize;
+    std::vector<uint64_t> audio_off;   // per frame: file offset of the 'AGAC' chunk's sample bytes (streams with an audio track)
+    std::vector<uint32_t> audio_len;
+    uint32_t audio_bits = 16;
     uint32_t* d_pal = nullptr;      // 512
     uint32_t* d_img = nullptr;      // P: pixels after the last decoded frame
     uint32_t* d_ifr = nullptr;      // P: I-frame snapshot
@@ -77,6 +81,10 @@ struct agmvb_ctx {
     DBuf l77_out, l77_meta, l77_persist, l77_a1, l77_a2, l77_inv, l77_hist, l77_scan, l77_tab;  // LZ77: token words, per-frame arrays, the reference's carried bitstream buffer
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
+    // audio track of the sequence being encoded: the header fields AGMV_WavToAudioTrack sets and the companded bytes
+    DBuf at_pcm, at_sample, at_idx;
+    uint64_t at_size = 0;      // header.audio_size (samples); 0 = no track
+    uint32_t at_bits = 16, at_rate = 0, at_channels = 0, at_duration = 0;
     void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
     size_t h_pinned_cap = 0;
 
@@ -182,6 +190,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
                     &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
+    cudaFree(ctx->at_pcm.p); cudaFree(ctx->at_sample.p); cudaFree(ctx->at_idx.p);
     cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p); cudaFree(ctx->raw24.p);
     cudaFree(ctx->l77_a1.p); cudaFree(ctx->l77_a2.p); cudaFree(ctx->l77_inv.p); cudaFree(ctx->l77_hist.p); cudaFree(ctx->l77_scan.p); cudaFree(ctx->l77_tab.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
@@ -495,7 +504,7 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     memcpy(hp, h_fs, (size_t)(F + 1) * 4);
     TRY(ensure(ctx, ctx->fs, (size_t)(F + 2) * 4));
     CK(cudaMemcpyAsync(ctx->fs.p, hp, (size_t)(F + 1) * 4, cudaMemcpyHostToDevice, ctx->st));
-    size_t need = ctx->image_bytes + (size_t)32 * F + (((size_t)n * 9) >> 3) + 64;
+    size_t need = ctx->image_bytes + (size_t)(24 + ctx->lz.stub_bytes) * F + (((size_t)n * 9) >> 3) + 64;
     if (need > ctx->image.cap) {  // grow, keeping what is already there
         DBuf nb;
         TRY(ensure(ctx, nb, need + need / 2));
@@ -554,7 +563,7 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
         stack.push_back(f);
     }
     CK(cudaMemcpyAsync(d_fs, hp, stride * 3 * 4, cudaMemcpyHostToDevice, ctx->st));
-    size_t need = ctx->image_bytes + (size_t)32 * F + (size_t)n * 4 + 64;
+    size_t need = ctx->image_bytes + (size_t)(24 + ctx->lz.stub_bytes) * F + (size_t)n * 4 + 64;
     if (need > ctx->image.cap) {
         DBuf nb;
         TRY(ensure(ctx, nb, need + need / 2));
@@ -595,7 +604,8 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
     KL(ctx->lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, ctx->st>>>(F, ctx->lz.stub_bytes, d_bits, d_outbits, d_csize, d_choff)));
     dim3 grid(32, F);
     KL(ctx->lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, ctx->st>>>(d_fs, d_csize, d_choff, d_wbase, ctx->l77_out.as<uint32_t>(), first_fc,
-                                                                          ctx->lz.stub_bytes, ctx->image.as<uint8_t>() + ctx->image_bytes)));
+                                                                          ctx->lz.stub_bytes, ctx->image.as<uint8_t>() + ctx->image_bytes,
+                                                                          ctx->lz.audio_chunk, ctx->lz.audio, ctx->lz.audio_size)));
     // carry the buffer forward: index j now holds the byte of the latest frame longer than j (the stack, bottom = longest)
     {
         uint32_t lo = 0;
@@ -732,6 +742,93 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
 extern "C" int agmvb_enc_set_audio_stub(agmvb_ctx* ctx, int on) {
     if (!ctx) return ERR_ARG;
     ctx->lz.stub_bytes = on ? 8u : 0u;
+    ctx->lz.audio_chunk = 0;
+    ctx->lz.audio = nullptr;
+    ctx->lz.audio_size = 0;
+    return OK;
+}
+
+// ===========================================================================
+// audio chunk codec
+// ===========================================================================
+static int audio_grid(uint64_t n16) { return (int)std::min<uint64_t>(std::max<uint64_t>(cdiv(n16, 256), 1), 148ull * 8); }
+
+// AGMV_CompressAudio (src/agmv_encode.c:659-705): 16-bit samples are companded to one byte each, 8-bit samples are copied
+static int audio_compress_dev(agmvb_ctx* ctx, const void* pcm, uint64_t n, int bits) {
+    TRY(ensure(ctx, ctx->at_sample, n + 16));
+    if (bits == 16) {
+        TRY(ensure(ctx, ctx->at_pcm, n * 2 + 32));
+        CK(copy_pieces(ctx->at_pcm.p, pcm, n * 2, cudaMemcpyHostToDevice, ctx->st));
+        KL(ctx->lc, KC_AUDIO, (audio_compress16_k<<<audio_grid(n >> 4), 256, 0, ctx->st>>>(ctx->at_pcm.as<uint16_t>(), n, ctx->at_sample.as<uint8_t>())));
+        TRY(check_launch(ctx, "audio_compress16"));
+    } else {
+        CK(copy_pieces(ctx->at_sample.p, pcm, n, cudaMemcpyHostToDevice, ctx->st));
+    }
+    return OK;
+}
+
+extern "C" int agmvb_enc_set_audio(agmvb_ctx* ctx, const void* pcm, uint64_t audio_size, int bits_per_sample, uint32_t sample_rate,
+                                   uint32_t channels, uint32_t total_duration) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->at_size = 0;
+    ctx->lz.audio_chunk = 0; ctx->lz.audio = nullptr; ctx->lz.audio_size = 0;
+    if (ctx->lz.stub_bytes > 8) ctx->lz.stub_bytes = 8;
+    if (!pcm || audio_size == 0) return OK;
+    if (bits_per_sample != 16 && bits_per_sample != 8) FAIL(ERR_ARG, "bits per sample must be 8 or 16");
+    TRY(audio_compress_dev(ctx, pcm, audio_size, bits_per_sample));
+    CK(cudaStreamSynchronize(ctx->st));  // pcm is the caller's
+    ctx->at_size = audio_size; ctx->at_bits = (uint32_t)bits_per_sample; ctx->at_rate = sample_rate; ctx->at_channels = channels;
+    ctx->at_duration = total_duration;
+    return OK;
+}
+
+extern "C" int agmvb_enc_set_audio_chunk(agmvb_ctx* ctx, uint32_t chunk_size) {
+    if (!ctx) return ERR_ARG;
+    if (!ctx->at_size) FAIL(ERR_ARG, "no audio track: call agmvb_enc_set_audio first");
+    ctx->lz.audio = ctx->at_sample.as<uint8_t>();
+    ctx->lz.audio_size = ctx->at_size;
+    ctx->lz.audio_chunk = chunk_size;
+    ctx->lz.stub_bytes = 8 + chunk_size;
+    return OK;
+}
+
+extern "C" int agmvb_enc_get_atsample(agmvb_ctx* ctx, uint8_t* out, uint64_t cap) {
+    if (!ctx || !out) return ERR_ARG;
+    if (!ctx->at_size || cap < ctx->at_size) FAIL(ERR_ARG, "no audio track, or buffer smaller than %llu bytes", (unsigned long long)ctx->at_size);
+    CK(cudaSetDevice(ctx->device));
+    CK(copy_pieces(out, ctx->at_sample.p, ctx->at_size, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+extern "C" int agmvb_audio_compress(agmvb_ctx* ctx, const void* pcm, uint64_t n, int bits_per_sample, uint8_t* atsample) {
+    if (!ctx || (n && (!pcm || !atsample)) || (bits_per_sample != 16 && bits_per_sample != 8)) return ERR_ARG;
+    if (n == 0) return OK;
+    if (ctx->at_size) FAIL(ERR_ARG, "a sequence's audio track is loaded: clear it with agmvb_enc_set_audio(ctx, NULL, 0, ...) first");
+    CK(cudaSetDevice(ctx->device));
+    TRY(audio_compress_dev(ctx, pcm, n, bits_per_sample));
+    CK(copy_pieces(atsample, ctx->at_sample.p, n, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// the sample loop of AGMV_DecodeAudioChunk (src/agmv_decode.c:431-451)
+extern "C" int agmvb_audio_expand(agmvb_ctx* ctx, const uint8_t* atsample, uint64_t n, int bits_per_sample, void* pcm) {
+    if (!ctx || (n && (!pcm || !atsample)) || (bits_per_sample != 16 && bits_per_sample != 8)) return ERR_ARG;
+    if (n == 0) return OK;
+    CK(cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->at_idx, n + 16));
+    CK(copy_pieces(ctx->at_idx.p, atsample, n, cudaMemcpyHostToDevice, ctx->st));
+    if (bits_per_sample == 16) {
+        TRY(ensure(ctx, ctx->d_out, n * 2 + 32));
+        KL(ctx->lc, KC_AUDIO, (audio_expand16_k<<<audio_grid(n >> 4), 256, 0, ctx->st>>>(ctx->at_idx.as<uint8_t>(), n, ctx->d_out.as<uint16_t>())));
+        TRY(check_launch(ctx, "audio_expand16"));
+        CK(copy_pieces(pcm, ctx->d_out.p, n * 2, cudaMemcpyDeviceToHost, ctx->st));
+    } else {
+        CK(copy_pieces(pcm, ctx->at_idx.p, n, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
     return OK;
 }
 
@@ -806,6 +903,13 @@ extern "C" int agmvb_enc_header(agmvb_ctx* ctx, uint32_t n_frames, uint32_t fps,
     out[17] = (uint8_t)((ctx->compression == COMP_LZSS ? 0 : 2) + (ctx->dual ? 1 : 2));  // src/agmv_utils.c:487-545
     put32(out + 18, fps);
     out[36] = 16;  // bits per sample
+    if (ctx->at_size) {  // the handle carries an audio track (AGMV_WavToAudioTrack, src/agmv_utils.c:1070-1083)
+        put32(out + 22, ctx->at_duration);
+        put32(out + 26, ctx->at_rate);
+        put32(out + 30, (uint32_t)ctx->at_size);
+        out[34] = (uint8_t)ctx->at_channels; out[35] = (uint8_t)(ctx->at_channels >> 8);
+        out[36] = (uint8_t)ctx->at_bits;
+    }
     uint8_t* p = out + 38;
     for (int i = 0; i < (ctx->dual ? 512 : 256); i++) {
         uint32_t c = ctx->h_pal[i];
@@ -822,7 +926,7 @@ static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames
                                 uint64_t* out_len, uint32_t* n_encoded) {
     if (!ctx || !frames || !out || n_src < 2) return ERR_ARG;
     TRY(agmvb_enc_begin(ctx, w, h, opt, quality, compression));
-    ctx->lz.stub_bytes = mode == SEQ_AGMV ? 8u : 0u;  // only AGMV_EncodeAGMV interleaves (empty) audio chunks
+    agmvb_enc_set_audio_stub(ctx, mode == SEQ_AGMV);  // only AGMV_EncodeAGMV interleaves (empty) audio chunks
     if (!on_device) {
         // both passes read every frame: upload once when the sequence fits comfortably, else stream it twice
         size_t free_b = 0, total_b = 0;
@@ -878,18 +982,24 @@ static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames
             if (i + 4 >= end) break;
         }
     }
+    uint32_t adjusted = end - start;
+    switch (opt) {  // :2296-2353
+        case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
+        case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
+        default: adjusted = (uint32_t)(adjusted * 0.75); break;
+    }
+    if (ctx->at_size && mode != SEQ_VIDEO) {
+        // audio_chunk->size = audio_size / (f32)frames (:2661-2663 with the adjusted count, :4024-4025 with end - start);
+        // AGMV_EncodeFullAGMV writes audio chunks only for handles with a track (:4072-4076)
+        const float per_frame = (float)ctx->at_size / (float)(mode == SEQ_AGMV ? adjusted : end - start);
+        TRY(agmvb_enc_set_audio_chunk(ctx, (uint32_t)per_frame));
+    }
     uint64_t hdr_len = 0, img = 0;
     TRY(agmvb_enc_header(ctx, create_n, fps, out, cap, &hdr_len));
     TRY(agmvb_enc_frames(ctx, frames, n_src, on_device, sa.data(), sb.data(), (uint32_t)sa.size(), 0, &img));
     if (hdr_len + img > cap) FAIL(ERR_ARG, "output buffer too small: need %llu", (unsigned long long)(hdr_len + img));
     TRY(agmvb_enc_fetch(ctx, out + hdr_len, cap - hdr_len, nullptr, nullptr));
     if (mode == SEQ_AGMV) {  // back-patch (:3615-3620)
-        uint32_t adjusted = end - start;
-        switch (opt) {  // :2296-2353
-            case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
-            case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
-            default: adjusted = (uint32_t)(adjusted * 0.75); break;
-        }
         put32(out + 4, (uint32_t)sa.size());
         float rate = (float)adjusted / (create_n + 1);
         put32(out + 18, (uint32_t)round(fps * rate));
@@ -898,7 +1008,8 @@ static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames
         float rate = (float)sa.size() / create_n;
         put32(out + 18, (uint32_t)round(fps * rate));
     }
-    ctx->lz.stub_bytes = 8;
+    agmvb_enc_set_audio_stub(ctx, 1);
+    ctx->at_size = 0;  // the reference consumes the handle, track included (:3625)
     if (out_len) *out_len = hdr_len + img;
     if (n_encoded) *n_encoded = (uint32_t)sa.size();
     return OK;
@@ -1029,9 +1140,10 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
             int64_t aa = -1;
             if (q + 4 <= len && !memcmp(file + q, "AGAC", 4)) aa = (int64_t)q;
             else for (uint64_t r = q + 4; r + 4 <= len; r++) if (!memcmp(file + r, "AGAC", 4)) { aa = (int64_t)r; break; }
-            if (aa >= 0 && (uint64_t)aa + 8 <= len) cursor = (uint64_t)aa + 8 + get32(file + aa + 4);
+            if (aa >= 0 && (uint64_t)aa + 8 <= len) { cursor = (uint64_t)aa + 8 + get32(file + aa + 4); s.audio_off.push_back((uint64_t)aa + 8); s.audio_len.push_back(get32(file + aa + 4)); }
         }
     }
+    s.audio_bits = (uint32_t)bps;
     if (!unpark_stream(ctx, s, len, P)) {
         s.file_cap = len + len / 8 + 4096;
         CK(cudaMalloc(&s.d_file, s.file_cap));
@@ -1056,7 +1168,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     CK(cudaStreamSynchronize(ctx->st));
     if (hits != nfr && !s.lz77) {
         // rare slow path: replay the token stream on the host to learn the exact cursor after every frame
-        s.data_off.clear(); s.usize.clear(); s.csize.clear();
+        s.data_off.clear(); s.usize.clear(); s.csize.clear(); s.audio_off.clear(); s.audio_len.clear();
         cursor = 38 + pal_bytes;
         for (uint32_t i = 0; i < nfr; i++) {
             int64_t at = find_next_agfc(file, len, cursor);
@@ -1069,7 +1181,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
                 int64_t aa = -1;
                 if (cursor + 4 <= len && !memcmp(file + cursor, "AGAC", 4)) aa = (int64_t)cursor;
                 else for (uint64_t r = cursor + 4; r + 4 <= len; r++) if (!memcmp(file + r, "AGAC", 4)) { aa = (int64_t)r; break; }
-                if (aa >= 0 && (uint64_t)aa + 8 <= len) cursor = (uint64_t)aa + 8 + get32(file + aa + 4);
+                if (aa >= 0 && (uint64_t)aa + 8 <= len) { cursor = (uint64_t)aa + 8 + get32(file + aa + 4); s.audio_off.push_back((uint64_t)aa + 8); s.audio_len.push_back(get32(file + aa + 4)); }
             }
         }
     }
@@ -1082,6 +1194,43 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     if (w) *w = W;
     if (h) *h = H;
     if (n_frames) *n_frames = nfr;
+    return OK;
+}
+
+// The audio half of AGMV_DecodeAGMV's loop (src/agmv_decode.c:572-587): every 'AGAC' chunk that follows a frame chunk, in
+// order, expanded (16-bit tracks) or copied (8-bit) to audio_track->pcm / pcm8 at the running start_point. One launch for
+// the whole track; the chunk positions come from the index agmvb_dec_open built.
+extern "C" int agmvb_dec_audio(agmvb_ctx* ctx, int stream, void* pcm, uint64_t cap_samples, uint64_t* n_samples, int* bits_per_sample) {
+    if (!ctx || stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open || ctx->streams[stream].raw) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    DecStream& d = ctx->streams[stream];
+    const size_t nc = d.audio_off.size();
+    uint64_t total = 0;
+    uint32_t maxlen = 0;
+    std::vector<uint64_t> dst(nc);
+    for (size_t c = 0; c < nc; c++) { dst[c] = total; total += d.audio_len[c]; maxlen = std::max(maxlen, d.audio_len[c]); }
+    if (n_samples) *n_samples = total;
+    if (bits_per_sample) *bits_per_sample = (int)d.audio_bits;
+    if (!pcm || total == 0) return OK;  // size query, or a stream without a track
+    if (cap_samples < total) FAIL(ERR_ARG, "audio track has %llu samples", (unsigned long long)total);
+    const size_t bytes = total * (d.audio_bits == 16 ? 2 : 1);
+    TRY(ensure(ctx, ctx->d_out, bytes + 32));
+    TRY(ensure(ctx, ctx->at_idx, nc * 20 + 64));
+    uint8_t* base = ctx->at_idx.as<uint8_t>();
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(base);
+    uint64_t* d_dst = d_off + nc;
+    uint32_t* d_len = reinterpret_cast<uint32_t*>(d_dst + nc);
+    CK(cudaMemcpyAsync(d_off, d.audio_off.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d_dst, dst.data(), nc * 8, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d_len, d.audio_len.data(), nc * 4, cudaMemcpyHostToDevice, ctx->st));
+    for (size_t c0 = 0; c0 < nc; c0 += 32768) {
+        dim3 grid(std::min<uint32_t>(std::max<uint32_t>(cdiv(maxlen, 256), 1), 64), (uint32_t)std::min<size_t>(32768, nc - c0));
+        KL(ctx->lc, KC_AUDIO, (audio_track_k<<<grid, 256, 0, ctx->st>>>(d.d_file, d.file_len, d_off + c0, d_len + c0, d_dst + c0, (int)d.audio_bits,
+                                                                      ctx->d_out.as<uint16_t>(), ctx->d_out.as<uint8_t>())));
+    }
+    TRY(check_launch(ctx, "audio_track"));
+    CK(copy_pieces(pcm, ctx->d_out.p, bytes, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));  // dst / the index vectors are host memory of this call
     return OK;
 }
 

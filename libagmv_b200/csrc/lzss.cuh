@@ -74,6 +74,9 @@ struct LzWork {
     uint32_t* csize = nullptr;           // cap_frames
     uint32_t* chunk_off = nullptr;       // cap_frames + 1
     uint32_t stub_bytes = 8;             // empty 'AGAC' chunk after every frame chunk (AGMV_EncodeAGMV); 0 for the other encoders
+    uint32_t audio_chunk = 0;            // bytes of audio per frame (stub_bytes = 8 + audio_chunk while a track is interleaved)
+    const uint8_t* audio = nullptr;      // companded track on the device (AGMV_CompressAudio's atsample)
+    uint64_t audio_size = 0;
 };
 
 struct APtrs { const uint32_t* a[LZ_LEVELS + 1]; const uint32_t* gs[LZ_LEVELS + 1]; };
@@ -1045,7 +1048,8 @@ __global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, uint32_t stub,
 __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restrict__ fs, const uint32_t* __restrict__ csize,
                                                          const uint32_t* __restrict__ chunk_off, const uint32_t* __restrict__ wbase,
                                                          const uint32_t* __restrict__ out_words, uint32_t first_frame_count,
-                                                         uint32_t stub, uint8_t* __restrict__ image) {
+                                                         uint32_t stub, uint8_t* __restrict__ image, uint32_t audio_chunk = 0,
+                                                         const uint8_t* __restrict__ audio = nullptr, uint64_t audio_size = 0) {
     const uint32_t f = blockIdx.y;
     const uint32_t cs = csize[f], len = 24u + stub + cs, usize = fs[f + 1] - fs[f];
     const uint8_t* pay = reinterpret_cast<const uint8_t*>(out_words + wbase[f]);
@@ -1059,8 +1063,15 @@ __global__ void __launch_bounds__(256) lz_write_chunks_k(const uint32_t* __restr
         } else if (b < 16 + cs) v = pay[b - 16];
         else if (b < 24 + cs) v = 0xFF;
         else {
+            // AGMV_EncodeAudioChunk (:707-717): 'AGAC', size, then size bytes from atsample[start_point++]; frame number g of the
+            // sequence starts at g * size. Reads past the track (the reference walks off its malloc) are defined as 0.
             const uint32_t k = b - 24 - cs;
-            v = k < 4 ? (uint8_t)(0x43414741u /* "AGAC" */ >> (k * 8)) : 0;
+            if (k < 4) v = (uint8_t)(0x43414741u /* "AGAC" */ >> (k * 8));
+            else if (k < 8) v = (uint8_t)(audio_chunk >> ((k - 4) * 8));
+            else {
+                const uint64_t idx = (uint64_t)(first_frame_count + f) * audio_chunk + (k - 8);
+                v = idx < audio_size ? audio[idx] : 0;
+            }
         }
         dst[b] = v;
     }
@@ -1359,7 +1370,8 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);
-    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, wk.stub_bytes, image)));
+    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, wk.stub_bytes, image,
+                                                                 wk.audio_chunk, wk.audio, wk.audio_size)));
 }
 
 }  // namespace agmvb

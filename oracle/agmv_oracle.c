@@ -710,3 +710,38 @@ int orc_decode_agmv(const uint8_t* file, size_t len, uint32_t* frames_out, size_
     free(img); free(ifr); free(buf);
     return rc;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * N4: audio chunk codec
+ * ------------------------------------------------------------------------------------------------ */
+/* src/agmv_encode.c:15-29 (roundUpEven / roundUpOdd on a u8: 255 wraps to 0) */
+static uint8_t up_even(uint8_t v) { while (v % 2 != 0) v++; return v; }
+static uint8_t up_odd(uint8_t v) { while (v % 2 == 0) v++; return v; }
+/* src/agmv_encode.c:31-36 */
+static float orc_round(float x) { return x >= 0.0 ? floor(x + 0.5) : ceil(x - 0.5); }
+
+/* src/agmv_encode.c:666-697. The one conversion the C standard leaves open - (u8)256.0f for samples above 65280, where
+ * round(sqrt) is 256 - is written the way the reference's x86-64 build evaluates it (truncate to int, keep the low byte). */
+void orc_audio_compress16(const uint16_t* pcm, size_t n, uint8_t* atsample) {
+    for (size_t i = 0; i < n; i++) {
+        int samp = pcm[i];
+        uint8_t ssqrt1 = (uint8_t)sqrt(samp);
+        uint8_t ssqrt2 = (uint8_t)(int)orc_round(sqrt(samp));
+        uint8_t shift = (uint8_t)(samp >> 8);
+        ssqrt1 = up_even(ssqrt1);
+        ssqrt2 = up_even(ssqrt2);
+        shift = up_odd(shift);
+        int resamp1 = ssqrt1 * ssqrt1, resamp2 = ssqrt2 * ssqrt2, resamp3 = shift << 8;
+        uint32_t dist1 = abs(resamp1 - samp), dist2 = abs(resamp2 - samp), dist3 = abs(resamp3 - samp);
+        uint32_t dist = dist1 < dist3 ? dist1 : dist3; /* :683-684: the min with dist2 is overwritten */
+        atsample[i] = dist == dist1 ? ssqrt1 : (dist == dist2 ? ssqrt2 : shift);
+    }
+}
+
+/* src/agmv_decode.c:433-438 with AGMV_SQR_TABLE[b] = b*b and AGMV_SHIFT_TABLE[b] = 256*b (:21-89) */
+void orc_audio_expand16(const uint8_t* atsample, size_t n, uint16_t* pcm) {
+    for (size_t i = 0; i < n; i++) {
+        unsigned b = atsample[i];
+        pcm[i] = (uint16_t)(b % 2 == 0 ? b * b : b * 256);
+    }
+}

@@ -75,6 +75,12 @@ long orc_encode_frames(const uint32_t* frames, int w, int h, const int32_t* src_
 int orc_decode_agmv(const uint8_t* file, size_t len, uint32_t* frames_out, size_t cap_px,
                     int* w, int* h, int* n_frames);
 
+/* "next" row N4: the audio chunk codec. orc_audio_compress16 = AGMV_CompressAudio's 16-bit branch (src/agmv_encode.c:659-705),
+ * orc_audio_expand16 = the sample loop of AGMV_DecodeAudioChunk (src/agmv_decode.c:431-445). Pinned against the unmodified
+ * reference on all 65 536 sample values and all 256 codes (tests/golden/audio_*.bin). */
+void orc_audio_compress16(const uint16_t* pcm, size_t n, uint8_t* atsample);
+void orc_audio_expand16(const uint8_t* atsample, size_t n, uint16_t* pcm);
+
 #ifdef __cplusplus
 }
 #endif

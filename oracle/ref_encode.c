@@ -7,6 +7,8 @@
  *
  *   ref_encode OUT DIR BASE START END W H FPS OPT QUALITY COMPRESSION CREATE_N [MODE]
  *   MODE: agmv (default) = AGMV_EncodeAGMV, video = AGMV_EncodeVideo, full = AGMV_EncodeFullAGMV
+ *   environment REF_WAV=file.wav: AGMV_WavToAudioTrack(file.wav, agmv) between CreateAGMV and the encode call, as in
+ *   examples/simple_video_and_audio/simple_video_and_audio.c:20-22 (agmv and full modes)
  *
  * mirrors the call sequence of the reference's own examples
  * (examples/simple_video/simple_video.c: CreateAGMV then AGMV_EncodeAGMV).
@@ -37,6 +39,7 @@ int main(int argc, char** argv) {
         AGMV_EncodeVideo(out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps, (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
     } else {
         AGMV* agmv = CreateAGMV(create_n, w, h, fps);
+        if (getenv("REF_WAV")) AGMV_WavToAudioTrack(getenv("REF_WAV"), agmv);
         if (!strcmp(mode, "full"))
             AGMV_EncodeFullAGMV(agmv, out, dir, base, AGMV_IMG_BMP, start, end, w, h, fps, (AGMV_OPT)opt, (AGMV_QUALITY)quality, (AGMV_COMPRESSION)comp);
         else

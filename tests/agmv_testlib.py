@@ -64,6 +64,8 @@ def oracle():
         lib.orc_decode_agmv.restype = C.c_int
         lib.orc_decode_agmv.argtypes = [_u8p, C.c_size_t, _u32p, C.c_size_t,
                                         C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.orc_audio_compress16.argtypes = [_u16p, C.c_size_t, _u8p]
+        lib.orc_audio_expand16.argtypes = [_u8p, C.c_size_t, _u16p]
         _oracle = lib
     return _oracle
 
@@ -159,15 +161,20 @@ def have_ref():
     return os.path.exists(os.path.join(REF_DIR, "ref_encode")) and os.path.exists(os.path.join(REF_DIR, "ref_decode"))
 
 
-def ref_encode(frames, create_n, fps, opt, quality, compression=LZSS, workdir=None, timing=None, mode="agmv"):
-    """Run the reference encoder on BMP files of `frames` (frames 1..n). Returns .agmv bytes."""
+def ref_encode(frames, create_n, fps, opt, quality, compression=LZSS, workdir=None, timing=None, mode="agmv", audio=None):
+    """Run the reference encoder on BMP files of `frames` (frames 1..n). Returns .agmv bytes.
+    audio = (pcm, sample_rate, channels): written as a WAV file and loaded with AGMV_WavToAudioTrack first."""
     n, h, w = frames.shape
     with tempfile.TemporaryDirectory(dir=workdir) as td:
         # the reference formats paths into char[60] (src/agmv_encode.c:2372): keep them short
         write_bmps(frames, td, "f", 1)
+        env = dict(os.environ)
+        if audio is not None:
+            write_wav(os.path.join(td, "a.wav"), *audio)
+            env["REF_WAV"] = "a.wav"
         res = subprocess.run([os.path.join(REF_DIR, "ref_encode"), "o.agmv", ".", "f", "1", str(n), str(w), str(h),
                               str(fps), str(opt), str(quality), str(compression), str(create_n), mode],
-                             cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+                             cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, env=env)
         if timing is not None:
             for line in res.stderr.decode().splitlines():
                 if line.startswith("ref_encode_seconds"):
@@ -223,3 +230,109 @@ def ref_decode_seek(data, plan):
         rc, n, w, h = int(tok[1]), int(tok[3]), int(tok[5]), int(tok[7])
         raw = np.fromfile(os.path.join(td, "o.raw"), dtype=np.uint32)
         return rc, raw.reshape(n, h, w)
+
+
+# ---- audio chunk codec ---------------------------------------------------------------
+def oracle_audio_compress16(pcm):
+    pcm = np.ascontiguousarray(pcm, dtype=np.uint16)
+    out = np.empty(pcm.size, np.uint8)
+    oracle().orc_audio_compress16(ptr(pcm, _u16p), pcm.size, ptr(out, _u8p))
+    return out
+
+
+def oracle_audio_expand16(at):
+    at = np.ascontiguousarray(at, dtype=np.uint8)
+    out = np.empty(at.size, np.uint16)
+    oracle().orc_audio_expand16(ptr(at, _u8p), at.size, ptr(out, _u16p))
+    return out
+
+
+def synth_pcm(n, bits=16, seed=7):
+    """Deterministic synthetic track: a swept tone around mid-scale, a quiet noise floor, bursts reaching both rails."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64)
+    x = 0.6 * np.sin(t * (0.01 + t / n * 0.2)) + 0.05 * rng.standard_normal(n)
+    x[n // 3:n // 3 + n // 20] *= 3.0
+    full = (1 << bits) - 1
+    v = np.clip(np.rint((x * 0.5 + 0.5) * full), 0, full)
+    v[:min(n, 8)] = [0, 1, full, full - 1, 255, 256, 65280 & full, 65281 & full][:min(n, 8)]
+    return v.astype(np.uint16 if bits == 16 else np.uint8)
+
+
+def write_wav(path, pcm, sample_rate, channels):
+    """The 44-byte header AGMV_WavToAudioTrack reads (src/agmv_utils.c:1043-1056). The reference takes the RIFF chunk size
+    at offset 4 as the number of sample BYTES (audio_size = chunk_size / 2 for 16-bit), so that field is written as
+    exactly the data size - with the usual 36 + data the reference's track would end in 18 uninitialised samples."""
+    pcm = np.ascontiguousarray(pcm)
+    bits = pcm.dtype.itemsize * 8
+    data = pcm.tobytes()
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, channels, sample_rate,
+                sample_rate * channels * bits // 8, channels * bits // 8, bits) + b"data" + struct.pack("<I", len(data)))
+        f.write(data)
+
+
+def audio_duration(pcm, sample_rate, channels):
+    """header.total_audio_duration as AGMV_WavToAudioTrack computes it (src/agmv_utils.c:1070)."""
+    return pcm.nbytes // (sample_rate * channels * pcm.dtype.itemsize)
+
+
+def ref_audio(kind, arr):
+    """kind 'compress': uint16 samples -> bytes through the reference's AGMV_CompressAudio; 'expand': the reverse
+    through AGMV_DecodeAudioChunk."""
+    with tempfile.TemporaryDirectory() as td:
+        np.ascontiguousarray(arr).tofile(os.path.join(td, "i.bin"))
+        subprocess.run([os.path.join(REF_DIR, "ref_audio"), kind, "i.bin", "o.bin"], cwd=td, check=True, stdout=subprocess.DEVNULL)
+        return np.fromfile(os.path.join(td, "o.bin"), dtype=np.uint8 if kind == "compress" else np.uint16)
+
+
+def ref_audio_track(data):
+    """The reference's decode loop for a stream with audio (frames + audio chunks). Returns (rc, samples)."""
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "i.agmv"), "wb") as f:
+            f.write(data)
+        res = subprocess.run([os.path.join(REF_DIR, "ref_audio"), "track", "i.agmv", "o.bin"], cwd=td, check=True, stdout=subprocess.PIPE)
+        tok = res.stdout.decode().split()
+        rc = int(tok[1])
+        if len(tok) < 6:
+            return rc, None
+        return rc, np.fromfile(os.path.join(td, "o.bin"), dtype=np.uint16 if int(tok[5]) == 16 else np.uint8)
+
+
+def audio_chunk_size(audio_size, n_src, opt, mode="agmv"):
+    """audio_chunk->size = audio_size / (f32)frames (src/agmv_encode.c:2661-2663 adjusted count, :4024-4025 end - start)."""
+    adj = n_src - 1
+    if mode == "agmv":
+        if opt in (OPT["I"], OPT["ANIM"], OPT["GBA_I"], OPT["GBA_II"]):
+            adj //= 2
+        elif opt == OPT["GBA_III"]:
+            adj = int(np.float32(adj) * np.float32(0.75))
+        else:
+            adj = int(adj * 0.75)
+    return int(np.float32(audio_size) / np.float32(adj))
+
+
+def mux_audio(stream, atsample, chunk, pcm, sample_rate, channels, mode="agmv"):
+    """Expected stream with an audio track, built from the same stream without one: header audio fields
+    (src/agmv_encode.c:41-49) and 'AGAC' chunk | chunk bytes after every frame chunk (AGMV_EncodeAudioChunk, :707-717),
+    frame g taking atsample[g*chunk : (g+1)*chunk]."""
+    import struct
+    s = bytes(stream)
+    dual = s[17] in (1, 3)
+    o = 38 + 768 * (2 if dual else 1)
+    out = bytearray(s[:o])
+    out[22:38] = struct.pack("<IIIHH", audio_duration(pcm, sample_rate, channels), sample_rate, pcm.size, channels, pcm.dtype.itemsize * 8)
+    g = 0
+    while o < len(s):
+        assert s[o:o + 4] == b"AGFC"
+        ln = 24 + int.from_bytes(s[o + 12:o + 16], "little")
+        out += s[o:o + ln]
+        o += ln
+        if mode == "agmv":
+            assert s[o:o + 8] == b"AGAC\0\0\0\0"
+            o += 8
+        piece = bytes(atsample[g * chunk:(g + 1) * chunk])
+        out += b"AGAC" + struct.pack("<I", chunk) + piece + bytes(chunk - len(piece))  # past the track: defined as 0 (the reference over-reads)
+        g += 1
+    return bytes(out)
