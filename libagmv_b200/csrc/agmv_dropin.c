@@ -110,6 +110,8 @@ WEAK void DestroyAGMV(AGMV* a) {
 /* ------------------------------------------------------------------------------------ */
 static void w32(FILE* f, u32 v) { uint32_t x = (uint32_t)v; fwrite(&x, 4, 1, f); }
 static void w16(FILE* f, u32 v) { uint16_t x = (uint16_t)v; fwrite(&x, 2, 1, f); }
+/* AGMV_ReadFourCC: four fgetc calls, so the end of the file reads as 0xFF bytes and never as the previous chunk's tag */
+static void read_fourcc(FILE* f, char* fourcc) { for (int i = 0; i < 4; i++) fourcc[i] = (char)fgetc(f); }
 static u32 r32(FILE* f) { uint32_t x = 0; if (fread(&x, 1, 4, f) != 4) { /* short read leaves what arrived */ } return x; }
 static u32 r16(FILE* f) { uint16_t x = 0; if (fread(&x, 1, 2, f) != 2) { } return x; }
 static u32 r8(FILE* f) { uint8_t x = 0; if (fread(&x, 1, 1, f) != 1) { } return x; }
@@ -557,7 +559,7 @@ static int bound_stream(agmvb_ctx* c, AGMV* agmv, int* stream) {
 /* src/agmv_decode.c:145-410 */
 int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
     agmv->bitstream->pos = 0;
-    if (fread(agmv->frame_chunk->fourcc, 1, 4, file) != 4) { }
+    read_fourcc(file, agmv->frame_chunk->fourcc);
     agmv->frame_chunk->frame_num = r32(file);
     agmv->frame_chunk->uncompressed_size = r32(file);
     agmv->frame_chunk->compressed_size = r32(file);
@@ -589,7 +591,7 @@ int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
 
 /* src/agmv_decode.c:412-453: one 'AGAC' chunk, expanded on the GPU into audio_track->pcm / pcm8 at start_point */
 int AGMV_DecodeAudioChunk(FILE* file, AGMV* agmv) {
-    if (fread(agmv->audio_chunk->fourcc, 1, 4, file) != 4) { }
+    read_fourcc(file, agmv->audio_chunk->fourcc);
     agmv->audio_chunk->size = r32(file);
     if (memcmp(agmv->audio_chunk->fourcc, "AGAC", 4)) return INVALID_HEADER_FORMATTING_ERR;
     const size_t size = (size_t)agmv->audio_chunk->size;

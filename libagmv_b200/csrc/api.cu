@@ -82,7 +82,7 @@ struct agmvb_ctx {
     uint64_t image_bytes = 0;
     std::vector<uint32_t> last_usize, last_csize;
     // audio track of the sequence being encoded: the header fields AGMV_WavToAudioTrack sets and the companded bytes
-    DBuf at_pcm, at_sample, at_idx;
+    DBuf at_pcm, at_sample, at_idx, at_lut;
     uint64_t at_size = 0;      // header.audio_size (samples); 0 = no track
     uint32_t at_bits = 16, at_rate = 0, at_channels = 0, at_duration = 0;
     void* h_pinned = nullptr;  // small pinned scratch for async size read-backs
@@ -190,7 +190,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
                     &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
-    cudaFree(ctx->at_pcm.p); cudaFree(ctx->at_sample.p); cudaFree(ctx->at_idx.p);
+    cudaFree(ctx->at_pcm.p); cudaFree(ctx->at_sample.p); cudaFree(ctx->at_idx.p); cudaFree(ctx->at_lut.p);
     cudaFree(ctx->l77_out.p); cudaFree(ctx->l77_meta.p); cudaFree(ctx->l77_persist.p); cudaFree(ctx->raw24.p);
     cudaFree(ctx->l77_a1.p); cudaFree(ctx->l77_a2.p); cudaFree(ctx->l77_inv.p); cudaFree(ctx->l77_hist.p); cudaFree(ctx->l77_scan.p); cudaFree(ctx->l77_tab.p);
     for (DecStream& s : ctx->streams) if (s.open) free_stream(s);
@@ -759,7 +759,19 @@ static int audio_compress_dev(agmvb_ctx* ctx, const void* pcm, uint64_t n, int b
     if (bits == 16) {
         TRY(ensure(ctx, ctx->at_pcm, n * 2 + 32));
         CK(copy_pieces(ctx->at_pcm.p, pcm, n * 2, cudaMemcpyHostToDevice, ctx->st));
-        KL(ctx->lc, KC_AUDIO, (audio_compress16_k<<<audio_grid(n >> 4), 256, 0, ctx->st>>>(ctx->at_pcm.as<uint16_t>(), n, ctx->at_sample.as<uint8_t>())));
+        static const uint64_t lut_from = getenv("AGMVB_AUDIO_LUT_FROM") ? strtoull(getenv("AGMVB_AUDIO_LUT_FROM"), nullptr, 10) : (1ull << 20);
+        if (n >= lut_from) {  // long track: the 64 KB answer table in shared memory (one persistent CTA pair per SM)
+            if (!ctx->at_lut.p) {
+                TRY(ensure(ctx, ctx->at_lut, 65536));
+                KL(ctx->lc, KC_AUDIO, (audio_lut_k<<<256, 256, 0, ctx->st>>>(ctx->at_lut.as<uint8_t>())));
+                CK(cudaFuncSetAttribute(audio_compress16_lut_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+            }
+            const int grid = (int)std::min<uint64_t>(std::max<uint64_t>(cdiv(n >> 4, AUDIO_LUT_THREADS), 1), 148ull * 2);
+            KL(ctx->lc, KC_AUDIO, (audio_compress16_lut_k<<<grid, AUDIO_LUT_THREADS, 65536, ctx->st>>>(ctx->at_pcm.as<uint16_t>(), n, ctx->at_lut.as<uint8_t>(),
+                                                                                                       ctx->at_sample.as<uint8_t>())));
+        } else {
+            KL(ctx->lc, KC_AUDIO, (audio_compress16_k<<<audio_grid(n >> 4), 256, 0, ctx->st>>>(ctx->at_pcm.as<uint16_t>(), n, ctx->at_sample.as<uint8_t>())));
+        }
         TRY(check_launch(ctx, "audio_compress16"));
     } else {
         CK(copy_pieces(ctx->at_sample.p, pcm, n, cudaMemcpyHostToDevice, ctx->st));

@@ -47,13 +47,45 @@ __global__ void __launch_bounds__(256) audio_compress16_k(const uint16_t* __rest
         for (uint64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) at[i] = (uint8_t)audio_compress_sample(pcm[i]);
 }
 
+// The same map through a table: all 65 536 answers (audio_lut_k, once per context, 64 KB) staged into shared memory by every
+// CTA of a persistent grid, then one shared-memory byte load per sample instead of ~45 ALU / SFU instructions - the ALU pipe
+// is what bounds audio_compress16_k (ncu: 71 % ALU, 28 % of HBM peak). Used for tracks long enough to amortise the staging.
+__global__ void __launch_bounds__(256) audio_lut_k(uint8_t* __restrict__ lut) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < 65536u) lut[s] = (uint8_t)audio_compress_sample(s);
+}
+
+constexpr int AUDIO_LUT_THREADS = 512;
+__global__ void __launch_bounds__(AUDIO_LUT_THREADS) audio_compress16_lut_k(const uint16_t* __restrict__ pcm, uint64_t n, const uint8_t* __restrict__ lut,
+                                                                           uint8_t* __restrict__ at) {
+    extern __shared__ uint4 lut_s4[];
+    const uint8_t* t = reinterpret_cast<const uint8_t*>(lut_s4);
+    for (int i = threadIdx.x; i < 4096; i += AUDIO_LUT_THREADS) lut_s4[i] = __ldg(reinterpret_cast<const uint4*>(lut) + i);
+    __syncthreads();
+    const uint64_t n16 = n >> 4, stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint4* in = reinterpret_cast<const uint4*>(pcm);
+    uint4* out = reinterpret_cast<uint4*>(at);
+    auto code4 = [&](uint32_t w0, uint32_t w1) { return (uint32_t)t[w0 & 0xFFFFu] | (uint32_t)t[w0 >> 16] << 8 | (uint32_t)t[w1 & 0xFFFFu] << 16 | (uint32_t)t[w1 >> 16] << 24; };
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; i + stride < n16; i += 2 * stride) {  // two independent 32-byte reads in flight per thread
+        const uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1), c = __ldg(in + 2 * (i + stride)), d = __ldg(in + 2 * (i + stride) + 1);
+        out[i] = make_uint4(code4(a.x, a.y), code4(a.z, a.w), code4(b.x, b.y), code4(b.z, b.w));
+        out[i + stride] = make_uint4(code4(c.x, c.y), code4(c.z, c.w), code4(d.x, d.y), code4(d.z, d.w));
+    }
+    if (i < n16) {
+        const uint4 a = __ldg(in + 2 * i), b = __ldg(in + 2 * i + 1);
+        out[i] = make_uint4(code4(a.x, a.y), code4(a.z, a.w), code4(b.x, b.y), code4(b.z, b.w));
+    }
+    if (blockIdx.x == 0)
+        for (uint64_t k = (n16 << 4) + threadIdx.x; k < n; k += blockDim.x) at[k] = t[pcm[k]];
+}
+
 // atsample -> pcm (u16)
 __global__ void __launch_bounds__(256) audio_expand16_k(const uint8_t* __restrict__ at, uint64_t n, uint16_t* __restrict__ pcm) {
     const uint64_t n16 = n >> 4;
     const uint4* in = reinterpret_cast<const uint4*>(at);
     uint4* out = reinterpret_cast<uint4*>(pcm);
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint4 a = __ldg(in + i);
+    auto put = [&](uint64_t i, const uint4 a) {
         const uint32_t w[4] = {a.x, a.y, a.z, a.w};
         uint32_t o[8];
 #pragma unroll
@@ -61,9 +93,16 @@ __global__ void __launch_bounds__(256) audio_expand16_k(const uint8_t* __restric
             o[2 * q] = audio_expand_sample(w[q] & 255u) | audio_expand_sample((w[q] >> 8) & 255u) << 16;
             o[2 * q + 1] = audio_expand_sample((w[q] >> 16) & 255u) | audio_expand_sample(w[q] >> 24) << 16;
         }
-        out[2 * i] = make_uint4(o[0], o[1], o[2], o[3]);
-        out[2 * i + 1] = make_uint4(o[4], o[5], o[6], o[7]);
+        __stcs(out + 2 * i, make_uint4(o[0], o[1], o[2], o[3]));
+        __stcs(out + 2 * i + 1, make_uint4(o[4], o[5], o[6], o[7]));
+    };
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {  // four independent reads in flight per thread
+        const uint4 a = __ldg(in + i), b = __ldg(in + i + stride), c = __ldg(in + i + 2 * stride), d = __ldg(in + i + 3 * stride);
+        put(i, a); put(i + stride, b); put(i + 2 * stride, c); put(i + 3 * stride, d);
     }
+    for (; i < n16; i += stride) put(i, __ldg(in + i));
     if (blockIdx.x == 0)
         for (uint64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) pcm[i] = (uint16_t)audio_expand_sample(at[i]);
 }

@@ -96,7 +96,7 @@ def test_compress_every_sample_value(ctx, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 4097, 1_000_003])
+@pytest.mark.parametrize("n", [1, 15, 16, 17, 31, 4097, 1_000_003, 3_000_017])  # the last one takes the shared-memory table kernel
 def test_compress_and_expand_ragged_lengths(ctx, n):
     rng = np.random.default_rng(n)
     pcm = rng.integers(0, 65536, n, dtype=np.uint16)
@@ -297,7 +297,7 @@ def test_dropin_per_chunk_audio_api(golden):
         assert b"".join(raw[k * 1508 + 8:(k + 1) * 1508] for k in range(4)) == want.tobytes()
         # decode the four chunks back into the track
         back = (C.c_uint16 * pcm.size)()
-        keep = tr.pcm
+        keep = C.cast(tr.pcm, C.c_void_p).value   # the address, not a view of the field
         tr.pcm, tr.start_point = C.cast(back, C.POINTER(C.c_uint16)), 0
         f = libc.fopen(path, b"rb")
         for _ in range(4):
@@ -306,6 +306,6 @@ def test_dropin_per_chunk_audio_api(golden):
         libc.fclose(f)
         assert tr.start_point == 6000
         assert np.array_equal(np.frombuffer(back, dtype=np.uint16), oracle_audio_expand16(want))
-        tr.pcm = keep
+        tr.pcm = C.cast(C.c_void_p(keep), C.POINTER(C.c_uint16))
     ch.atsample = None
     lib.DestroyAGMV(h)
