@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
                                                              uint32_t* __restrict__ bpos_out, uint32_t* __restrict__ consumed_out) {
     __shared__ uint32_t win[EX_WARPS][EX_WIN + 3];
     __shared__ uint32_t tk_o[EX_WARPS][32];
+    __shared__ __align__(16) uint8_t stp[EX_WARPS][EX_WIN * 32];   // per bit of the staged window: length of a token starting there (9 / 21)
     const int warp = threadIdx.x >> 5, lane = lane_id();
     const uint32_t f = blockIdx.x * EX_WARPS + warp;
     if (f >= F) return;
@@ -117,6 +118,15 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
             win[warp][k] = w;
         }
         __syncwarp();
+        // Token length for a token starting at every bit of the window (flag bit 1: literal, 9 bits; 0: match, 21 bits), so that
+        // the serial walk below is one shared-memory byte load and one add per token. Four bits -> one 32-bit store; lanes write
+        // consecutive words.
+        for (int it = 0; it < EX_WIN / 4; it++) {
+            const int k = it * 4 + (lane >> 3), q = lane & 7;
+            const uint32_t nib = (win[warp][k] >> (4 * q)) & 15u;
+            reinterpret_cast<uint32_t*>(stp[warp])[k * 8 + q] = 0x15151515u - 12u * ((nib & 1u) | (nib & 2u) << 7 | (nib & 4u) << 14 | (nib & 8u) << 21);
+        }
+        __syncwarp();
         const uint64_t wbit0 = win_word0 << 5;
         const uint32_t limit = (uint32_t)((nbits - wbit0) < (uint64_t)(EX_WIN * 32) ? (nbits - wbit0) : (uint64_t)(EX_WIN * 32));  // tokens must start below it
         bool window_left = true;
@@ -126,20 +136,10 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
             const uint32_t rel0 = (uint32_t)(bitp - wbit0);
             if (lane == 0) {
                 uint32_t rel = rel0;
-                uint32_t wi = rel >> 5;
-                uint64_t r = (((uint64_t)win[warp][wi + 1] << 32) | win[warp][wi]) >> (rel & 31);
-                int avail = 64 - (int)(rel & 31);
+                const uint8_t* st = stp[warp];
                 while (ntok < 32 && rel < limit) {
                     tk_o[warp][ntok++] = rel;
-                    const uint32_t step = 21u - 12u * ((uint32_t)r & 1u);
-                    rel += step;
-                    r >>= step;
-                    avail -= (int)step;
-                    if (avail < 21) {
-                        wi = rel >> 5;
-                        r = (((uint64_t)win[warp][wi + 1] << 32) | win[warp][wi]) >> (rel & 31);
-                        avail = 64 - (int)(rel & 31);
-                    }
+                    rel += st[rel];
                 }
             }
             ntok = __shfl_sync(0xffffffffu, ntok, 0);
