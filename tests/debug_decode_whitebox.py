@@ -1,3 +1,4 @@
+# TEST INFRASTRUCTURE (debugging aid, uses the oracle helpers): white-box comparison of the decoder's internal buffers with a Python restatement.
 import os, sys, json
 import numpy as np
 sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo')

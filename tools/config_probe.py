@@ -6,7 +6,7 @@
   c5  batched decode of S independent 1080p streams (each a config-3-style encode of 64 source frames -> 45 encoded
       frames, seeds 1000+s; D distinct streams, each opened S/D times - opens are independent decoder states):
       all streams advance together, one reconstruct launch per frame step for every stream (agmvb_dec_batch), frames/s;
-      checked against the single-stream decoder (per-frame checksums) and, for one stream, against the oracle decoder.
+      checked against the single-stream decoder (per-frame checksums), which tests/ hold to the oracle.
 
     python tools/config_probe.py [--c4-frames 256] [--c5-streams 512] [--c5-distinct 64] [--skip c4|c5]
 
@@ -21,7 +21,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 import libagmv_b200  # noqa: E402
 
 OPT_III, HIGH, LZSS = 3, 1, 1
@@ -134,15 +133,12 @@ def main():
             single = ctx.decode_all(streams[s])
             assert np.array_equal(checksum_np(single), ck[s]), f"batched decode of stream {s} differs from the single-stream decoder"
             ok_single += 1
-        from agmv_testlib import oracle_decode
-        rc, odec = oracle_decode(streams[0].tobytes())
-        assert rc == 0 and np.array_equal(checksum_np(odec), ck[0]), "batched decode differs from the oracle decoder"
         total = S * n_fr
         sbytes = sum(len(streams[s % D]) for s in range(S))
         res["c5"] = dict(workload=f"{S} streams ({D} distinct, seeds 1000+s) x {n_fr} frames 1920x1080, OPT_III/HIGH/LZSS, batched decode, 1 GPU",
                          frames=total, open_upload_decode_ms=all_ms, decode_only_ms=only_ms, fps_with_open_and_upload=total / all_ms * 1e3,
                          fps_decode_only=total / only_ms * 1e3, decode_only_compulsory_gbs=(4.0 * W * H * total + sbytes) / only_ms / 1e6,
-                         checked=f"replicas equal; {ok_single} streams vs single-stream decoder; stream 0 vs oracle decoder")
+                         checked=f"replicas equal; {ok_single} streams vs the single-stream decoder (itself held to the oracle in tests/)")
     print(json.dumps(res))
     ctx.close()
 
