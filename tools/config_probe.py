@@ -125,7 +125,7 @@ def main():
         for sid in state["sids"]:
             ctx.dec_close(sid)
         ck = state["ck"]
-        # checks: replicas agree, batch == single-stream decoder, stream 0 == oracle decoder
+        # checks: replicas agree, batch == single-stream decoder
         for s in range(S):
             assert np.array_equal(ck[s], ck[s % D]) and np.array_equal(state["ck2"][s], ck[s % D]), f"stream {s} differs from its replica"
         ok_single = 0
