@@ -80,6 +80,11 @@ AUDIO_CASES = [
     ("aud64_I_LOW_pcm8", "agmv", 64, 64, 12, 11, 24, "I", "LOW", 1, 8, 24000, 8000, 2),
     ("aud_full64_ANIM_LOW", "full", 64, 64, 10, 10, 24, "ANIM", "LOW", 1, 16, 22050, 11025, 2),
     ("aud_lz77_64_III_LOW", "agmv", 64, 64, 12, 11, 24, "III", "LOW", 2, 16, 20000, 8000, 1),
+    # every branch of the adjusted frame count the chunk size is divided by (src/agmv_encode.c:2296-2353)
+    ("aud_gba240_GBA_I_LOW", "agmv", 240, 160, 24, 23, 16, "GBA_I", "LOW", 1, 16, 30000, 8000, 1),
+    ("aud_gba240_GBA_III_LOW", "agmv", 240, 160, 24, 23, 16, "GBA_III", "LOW", 1, 16, 30011, 8000, 1),
+    ("aud_nds240_NDS_LOW", "agmv", 240, 160, 24, 23, 16, "NDS", "LOW", 1, 8, 29999, 8000, 2),
+    ("aud_lz77_64_II_LOW_pcm8", "agmv", 64, 64, 20, 19, 24, "II", "LOW", 2, 8, 21001, 8000, 1),
 ]
 
 

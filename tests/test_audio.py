@@ -1,8 +1,8 @@
 """The audio chunk codec: AGMV_CompressAudio / AGMV_EncodeAudioChunk / AGMV_DecodeAudioChunk.
 
 CPU part: the oracle's restatement against the known answers of the unmodified reference - every 16-bit sample value
-through AGMV_CompressAudio, every code through AGMV_DecodeAudioChunk, four golden streams with a track (16- and 8-bit,
-mono and stereo, AGMV_EncodeAGMV and AGMV_EncodeFullAGMV, both entropy coders).
+through AGMV_CompressAudio, every code through AGMV_DecodeAudioChunk, eight golden streams with a track (16- and 8-bit,
+mono and stereo, AGMV_EncodeAGMV and AGMV_EncodeFullAGMV, both entropy coders, every profile family).
 GPU part (-m gpu): the kernels behind the C-ABI and the drop-in API against the same vectors and the oracle.
 """
 import ctypes as C
@@ -16,7 +16,9 @@ import libagmv_b200
 from agmv_testlib import (GOLDEN_DIR, OPT, QUALITY, audio_chunk_size, have_ref, mux_audio, oracle_audio_compress16, oracle_audio_expand16,
                           oracle_encode, oracle_encode_mode, ref_audio, ref_audio_track, sha256, synth_frames, synth_pcm, write_bmps)
 
-STREAMS = ["aud64_III_LOW", "aud64_I_LOW_pcm8", "aud_full64_ANIM_LOW", "aud_lz77_64_III_LOW"]
+STREAMS = ["aud64_III_LOW", "aud64_I_LOW_pcm8", "aud_full64_ANIM_LOW", "aud_lz77_64_III_LOW",
+           # one per branch of the adjusted frame count the chunk size divides by (GBA_I: / 2, GBA_III: * 0.75f, NDS / II: * 0.75)
+           "aud_gba240_GBA_I_LOW", "aud_gba240_GBA_III_LOW", "aud_nds240_NDS_LOW", "aud_lz77_64_II_LOW_pcm8"]
 
 
 def _table(golden):
