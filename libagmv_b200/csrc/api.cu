@@ -1351,8 +1351,12 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         OrbitTables tb;
         tb.exit_tab = ctx->d_oexit.as<uint8_t>(); tb.w_tab = ctx->d_ow.as<uint16_t>(); tb.entry_tab = ctx->d_oentry.as<uint8_t>();
         tb.cumbase = ctx->d_ocum.as<uint32_t>(); tb.final_pos = ctx->d_ofinal.as<uint32_t>(); tb.final_cum = tb.final_pos + F;
-        KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
-                                                                                        ctx->d_consumed.as<uint32_t>())));
+        static const bool expand_pc = getenv("AGMVB_EXPAND_PC") ? atoi(getenv("AGMVB_EXPAND_PC")) != 0 : false;
+        if (expand_pc)  // two warps per frame: parser + copier (decode.cuh)
+            KL(ctx->lc, KC_EXPAND, (expand_pc_k<<<F, 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>())));
+        else
+            KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
+                                                                                            ctx->d_consumed.as<uint32_t>())));
         KL(ctx->lc, KC_STALE, (stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>())));
         {
             dim3 sgrid(std::min<uint32_t>(max_tiles * 4, 1024), F);
