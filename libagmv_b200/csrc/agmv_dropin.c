@@ -599,6 +599,7 @@ int AGMV_DecodeAudioChunk(FILE* file, AGMV* agmv) {
     agmvb_ctx* c = ctx_get();
     if (!c) return MEMORY_CORRUPTION_ERR;
     uint8_t* b = (uint8_t*)malloc(size);
+    if (!b) return MEMORY_CORRUPTION_ERR; /* a damaged size field */
     size_t got = fread(b, 1, size, file);
     if (got < size) memset(b + got, 0xFF, size - got); /* AGIDL_ReadByte at the end of the file: EOF stored in a u8 */
     const int bits = agmv->header.bits_per_sample == 16 ? 16 : 8;
