@@ -1351,10 +1351,10 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         OrbitTables tb;
         tb.exit_tab = ctx->d_oexit.as<uint8_t>(); tb.w_tab = ctx->d_ow.as<uint16_t>(); tb.entry_tab = ctx->d_oentry.as<uint8_t>();
         tb.cumbase = ctx->d_ocum.as<uint32_t>(); tb.final_pos = ctx->d_ofinal.as<uint32_t>(); tb.final_cum = tb.final_pos + F;
-        static const int expand_pc = getenv("AGMVB_EXPAND_PC") ? atoi(getenv("AGMVB_EXPAND_PC")) : 0;   // 1: with the copier's fence, 2: without
+        static const int expand_pc = getenv("AGMVB_EXPAND_PC") ? atoi(getenv("AGMVB_EXPAND_PC")) : 0;   // 1: SC fences on both sides, 2: none on the copier, 3: none on the copier + release-only fence on the parser (not yet measured)
         if (expand_pc)  // two warps per frame: parser + copier (decode.cuh)
             KL(ctx->lc, KC_EXPAND, (expand_pc_k<<<F, 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>(),
-                                                                     expand_pc == 1 ? 1 : 0)));
+                                                                     expand_pc == 1 ? 1 : (expand_pc == 3 ? 2 : 0))));
         else
             KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
                                                                                             ctx->d_consumed.as<uint32_t>())));

@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(64) expand_pc_k(const DecFrame* __restrict__ f
             // The slot must have been read before the parser may refill it. A fence guarantees that but also waits for the
             // previous chunk's global stores; without it (copier_fence == 0, experimental) the order rests on the warp issuing
             // its shared-memory loads before the barrier arrive, and the values being consumed by the vote below.
-            if (copier_fence) __threadfence_block();
+            if (copier_fence & 1) __threadfence_block();
             else if (__any_sync(0xffffffffu, (o ^ dd ^ m ^ last) == 0x9E3779B9u && last > 1u)) return;   // never true: last is 0 or 1
             __syncwarp();
             pc_bar_arrive(3 + slot);
@@ -387,7 +387,10 @@ __global__ void __launch_bounds__(64) expand_pc_k(const DecFrame* __restrict__ f
             ch_d[slot][lane] = dd;
             ch_m[slot][lane] = (active ? 1u : 0u) | (lit ? 2u : 0u) | l << 2 | ((w >> 1) & 255u) << 8;
             if (lane == 0) ch_last[slot] = more ? 0u : 1u;
-            __threadfence_block();
+            // publish the slot: __threadfence_block() is a MEMBAR.SC.CTA in SASS (sequentially consistent, every chunk);
+            // copier_fence & 2 selects the lighter release-only fence (experimental, not yet measured)
+            if (copier_fence & 2) asm volatile("fence.acq_rel.cta;" ::: "memory");
+            else __threadfence_block();
             __syncwarp();
             pc_bar_arrive(1 + slot);
             slot ^= 1u;
