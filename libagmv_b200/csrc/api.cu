@@ -431,6 +431,8 @@ extern "C" int agmvb_enc_get_iframe_entries(agmvb_ctx* ctx, uint16_t* entries) {
 static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
     LzWork& w = ctx->lz;
     const uint32_t cap_before = w.cap_n;
+    static const bool legacy = getenv("AGMVB_LZ_LEGACY") && atoi(getenv("AGMVB_LZ_LEGACY")) != 0;
+    w.legacy = legacy;
     if (n + 64 > w.cap_n || !w.bestlen) {
         uint32_t cap = std::max<uint32_t>(n + n / 4 + 4096, 1u << 20);
         int k = 0;
@@ -441,32 +443,35 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
             return OK;
         };
         TRY(grab(cap, (void**)&w.bestlen));
-        for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
-        for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));
-        TRY(grab((size_t)cap * 4, (void**)&w.gs_tmp));
-        TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[0]));
-        TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[1]));
-        TRY(grab((size_t)(LZ_LEVELS + 1) * 257 * 4, (void**)&w.bstart));
-        TRY(grab(256 * 4, (void**)&w.bytehist));
-        {
-            const size_t ct = cdiv(cap, LZ_TILE) + 1;
-            TRY(grab((ct * 257 + 4) * 4, (void**)&w.chain_mem));
-        }
-        // single-pass level kernel (decoupled look-back): exact, but measured slower than the three-kernel levels on B200
-        // (203 vs 186 ms per config-3 step); kept selectable for further work
-        w.fused = getenv("AGMVB_LZ_FUSED") ? atoi(getenv("AGMVB_LZ_FUSED")) != 0 : false;
-        TRY(grab((size_t)cap * 4, (void**)&w.dig4[0]));
-        TRY(grab((size_t)cap * 4, (void**)&w.dig4[1]));
         TRY(grab((size_t)cap * 4, (void**)&w.match_rec));
         TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
-        uint32_t nt = cdiv(cap, RX_TILE);
-        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[0]));
-        TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[1]));
-        TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2 * (size_t)cdiv(cap, SCAN_TILE) + 16) * 4, (void**)&w.scan_ws));
-        // optional: resolve the large three-equal-byte groups from run tables (exact; pays off for long runs - on the bench
-        // workload, whose runs average a few dozen bytes, it measured 236 vs 224 ms per step, so it is off by default)
-        w.runs = getenv("AGMVB_LZ_RUNS") ? atoi(getenv("AGMVB_LZ_RUNS")) != 0 : false;
-        if (w.runs) TRY(grab((size_t)cap * 4, (void**)&w.run_ws));
+        if (!legacy) {
+            // occurrence-chain match finder (lzchain.cuh): 19 B per position
+            TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
+            TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
+            TRY(grab((size_t)cap * 2, (void**)&w.rsd));
+        } else {
+            for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
+            for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));
+            TRY(grab((size_t)cap * 4, (void**)&w.gs_tmp));
+            TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[0]));
+            TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[1]));
+            TRY(grab((size_t)(LZ_LEVELS + 1) * 257 * 4, (void**)&w.bstart));
+            TRY(grab(256 * 4, (void**)&w.bytehist));
+            {
+                const size_t ct = cdiv(cap, LZ_TILE) + 1;
+                TRY(grab((ct * 257 + 4) * 4, (void**)&w.chain_mem));
+            }
+            w.fused = getenv("AGMVB_LZ_FUSED") ? atoi(getenv("AGMVB_LZ_FUSED")) != 0 : false;
+            TRY(grab((size_t)cap * 4, (void**)&w.dig4[0]));
+            TRY(grab((size_t)cap * 4, (void**)&w.dig4[1]));
+            uint32_t nt = cdiv(cap, RX_TILE);
+            TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[0]));
+            TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[1]));
+            TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2 * (size_t)cdiv(cap, SCAN_TILE) + 16) * 4, (void**)&w.scan_ws));
+            w.runs = getenv("AGMVB_LZ_RUNS") ? atoi(getenv("AGMVB_LZ_RUNS")) != 0 : false;
+            if (w.runs) TRY(grab((size_t)cap * 4, (void**)&w.run_ws));
+        }
         w.cap_n = cap;
     }
     size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 16;
@@ -525,6 +530,14 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     }
     CK(cudaMemcpyAsync(ctx->lz.segs, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->lz.seg_len, slen.data(), F * 4, cudaMemcpyHostToDevice, ctx->st));
+    std::vector<LzcItem> items;
+    if (!ctx->lz.legacy) {   // (frame, range) work items of the serial hash-link kernel
+        lzc_build_items(h_fs, F, items);
+        TRY(ensure(ctx, ctx->lzbuf[60], (items.size() + 1) * sizeof(LzcItem)));
+        ctx->lz.items = ctx->lzbuf[60].as<LzcItem>();
+        ctx->lz.n_items = (uint32_t)items.size();
+        if (!items.empty()) CK(cudaMemcpyAsync(ctx->lz.items, items.data(), items.size() * sizeof(LzcItem), cudaMemcpyHostToDevice, ctx->st));
+    }
     lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, ntile, max_usize, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
     CK(cudaStreamSynchronize(ctx->st));  // segs / slen are stack vectors
     TRY(check_launch(ctx, "lzss"));
@@ -627,7 +640,8 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
     return OK;
 }
 
-static const uint32_t LZ_GROUP_TARGET = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
+static const uint32_t LZ_GROUP_TARGET_LEGACY = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
+static const uint32_t LZ_GROUP_TARGET = 448u << 20;        // chain path: 19 B of workspace per position (~8.5 GB)
 
 // classify + assemble n frames whose entries are on the device; runs LZSS group by group
 static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_t F, uint32_t first_fc) {
@@ -658,7 +672,8 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
     for (uint32_t g0 = 0; g0 < F;) {
         uint32_t g1 = g0 + 1;
         // LZ77 keeps 4 B of workspace per position and wants every frame of the batch in flight at once (one CTA per frame)
-        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : LZ_GROUP_TARGET;
+        static const bool lz_legacy = getenv("AGMVB_LZ_LEGACY") && atoi(getenv("AGMVB_LZ_LEGACY")) != 0;
+        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : (lz_legacy ? LZ_GROUP_TARGET_LEGACY : LZ_GROUP_TARGET);
         while (g1 < F && fs[g1 + 1] - fs[g0] <= target) g1++;
         rebased.resize(g1 - g0 + 1);
         for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
@@ -685,8 +700,16 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
             FAIL(ERR_ARG, "frame index out of range at encoded frame %u", k);
     // frames per quantise batch. LZ77 parses one frame per CTA, serially: it wants every frame of the call in flight at once
     // (entries 2 B/px + bitstream <= 2.1 B/px per frame: ~17 GB for 2000 1080p frames)
-    const uint32_t QB = ctx->compression == COMP_LZ77 ? (uint32_t)std::max<size_t>(4, std::min<size_t>(4096, (24ull << 30) / (P * 5)))
-                                                      : (uint32_t)std::max<size_t>(4, std::min<size_t>(256, (768ull << 20) / (P * 2)));
+    // The assembled bitstream of a batch is addressed with 32-bit offsets (block offsets, frame starts): a block record is at
+    // most 33 bytes, so F * B * 33 must stay below 2^32 whatever the content.
+    const size_t B33 = (P / 16) * 33 + 1;
+    const size_t qb_off = std::max<size_t>(1, (size_t)0xFFFFFFFFull / B33);
+    if (qb_off < 4 && n_enc > qb_off) FAIL(ERR_UNSUPPORTED, "frame of %u x %u pixels: bitstream offsets do not fit 32 bits", W, H);
+    static const size_t qb_env = getenv("AGMVB_QB") ? (size_t)std::max(1, atoi(getenv("AGMVB_QB"))) : 0;
+    size_t qb = ctx->compression == COMP_LZ77 ? std::max<size_t>(4, std::min<size_t>(4096, (24ull << 30) / (P * 5)))
+                                              : std::max<size_t>(4, std::min<size_t>(1024, (4096ull << 20) / (P * 2)));
+    if (qb_env) qb = qb_env;
+    const uint32_t QB = (uint32_t)std::min(qb, qb_off);
     std::vector<SrcPair> sp;
     std::vector<EntPair> ep;
     for (uint32_t q0 = 0; q0 < n_enc; q0 += QB) {

@@ -29,6 +29,8 @@
 #include "orbit.cuh"
 #include "radix.cuh"
 #include "scan.cuh"
+#include <vector>
+#include "lzchain.cuh"
 
 namespace agmvb {
 
@@ -64,6 +66,11 @@ struct LzWork {
     uint32_t* scan_ws = nullptr;
     uint32_t* run_ws = nullptr;          // run tables of the large three-equal-byte groups (cap_n words)
     bool runs = false;                   // AGMVB_LZ_RUNS: resolve those groups from run tables instead of the global levels
+    bool legacy = false;                 // AGMVB_LZ_LEGACY=1: the radix-refinement match finder below instead of lzchain.cuh
+    uint32_t* lw[2] = {};                // chain path: link words, ping-pong (lw[1] doubles as the hash-level links)
+    uint16_t* rsd = nullptr;             // chain path: distance of every position to the start of its byte run
+    LzcItem* items = nullptr;            // chain path: (frame, range) work items of lzc_hashlink_k
+    uint32_t n_items = 0, cap_items = 0;
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
     uint32_t* seg_len = nullptr;         // cap_frames
@@ -1212,6 +1219,35 @@ __global__ void __launch_bounds__(256) rg_match_k(RunView v, const uint32_t* __r
     match_rec[y] = 0;   // (not reached for an alive member; clears a partial record of the global levels otherwise)
 }
 
+// Host driver of the chain path (lzchain.cuh). Same contract as lzss_encode_batch below.
+inline void lzss_encode_batch_chain(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n, uint32_t ntile, uint32_t max_usize,
+                                    uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
+    cudaStream_t st = lc.st;
+    KL(lc, KC_LZ_INIT, (lzc_wbase_k<<<cdiv(F + 1, 256), 256, 0, st>>>(fs, F, wk.wbase)));
+    const uint32_t* lw15 = wk.lw[0];
+    if (n > 0) {
+        cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
+        const uint32_t nb = cdiv(n, LZC_THREADS);
+        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, fs, wk.items, wk.lw[1], wk.rsd)));
+        KL(lc, KC_LZ_LINK, (lzc_link3_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen)));
+        int cur = 0;
+        for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
+            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen)));
+        lw15 = wk.lw[cur];
+    }
+    orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
+    if (n > 0) {
+        size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
+        cudaMemsetAsync(wk.out_words, 0, words * 4, st);
+        dim3 pgrid(cdiv(max_usize, 256u), F);
+        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, 256, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
+    }
+    KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
+    dim3 grid(32, F);
+    KL(lc, KC_LZ_CHUNK, (lz_write_chunks_k<<<grid, 256, 0, st>>>(fs, wk.csize, wk.chunk_off, wk.wbase, wk.out_words, first_frame_count, wk.stub_bytes, image,
+                                                                 wk.audio_chunk, wk.audio, wk.audio_size)));
+}
+
 // Host driver. bs: batch bitstream (n bytes + >=16 bytes of readable padding);
 // fs: device array of F+1 frame starts (fs[0]=0, fs[F]=n); wk.segs / wk.seg_len
 // describe the same frames for the parse (filled by the caller, ntile tiles in
@@ -1219,6 +1255,7 @@ __global__ void __launch_bounds__(256) rg_match_k(RunView v, const uint32_t* __r
 // image written to `image` (capacity >= 32*F + 9n/8 + 8).
 inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs, uint32_t F, uint32_t n, uint32_t ntile, uint32_t max_usize,
                               uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
+    if (!wk.legacy) { lzss_encode_batch_chain(wk, bs, fs, F, n, ntile, max_usize, first_frame_count, image, lc); return; }
     cudaStream_t st = lc.st;
     const uint32_t nthreads = 256;
     uint32_t n_large = n;                       // elements of the level arrays A[3..15] (large groups only; everything in the fused variant)
