@@ -641,7 +641,7 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
 }
 
 static const uint32_t LZ_GROUP_TARGET_LEGACY = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
-static const uint32_t LZ_GROUP_TARGET = 448u << 20;        // chain path: 19 B of workspace per position (~8.5 GB)
+static const uint32_t LZ_GROUP_TARGET = 1000u << 20;       // chain path: 19 B of workspace per position (<= 19 GB)
 
 // classify + assemble n frames whose entries are on the device; runs LZSS group by group
 static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_t F, uint32_t first_fc) {

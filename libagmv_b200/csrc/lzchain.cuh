@@ -97,39 +97,174 @@ __device__ __forceinline__ uint32_t lzc_frame_of(const uint32_t* __restrict__ fs
     }
     return lo;
 }
-// bytes left in p's frame; the block's first position is searched once, the others walk forward from it
-__device__ __forceinline__ uint32_t lzc_rem(const uint32_t* __restrict__ fs, uint32_t F, uint32_t p, uint32_t n) {
-    __shared__ uint32_t s_f;
-    if (threadIdx.x == 0) s_f = lzc_frame_of(fs, F, min(blockIdx.x * blockDim.x, n - 1));
-    __syncthreads();
-    if (p >= n) return 0;
-    uint32_t f = s_f;
-    while (fs[f + 1] <= p) f++;
-    return fs[f + 1] - p;
-}
+
+// ---- the walking kernels ---------------------------------------------------------------------------------------
+// A walk is a chain of dependent gathers whose length varies from position to position (most end at the first hop, a
+// few per cent must cross their whole window), so "one thread walks one position to the end" leaves most lanes of a warp
+// waiting for the slowest one. Both kernels therefore work in two phases on a warp's 512 consecutive positions:
+//   1. a coalesced sweep that takes every position's FIRST hop (four independent rounds in flight) and finishes the
+//      positions it settles; the others are queued (shared memory, 2 B each);
+//   2. the queue is drained with lane refill: a lane whose walk ends takes the next queued position at once, so every
+//      hop instruction has (almost) all lanes doing useful work.
+constexpr int LZC_ROUNDS = 16;
+constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per warp
+constexpr int LZC_WARPS = LZC_THREADS / 32;
+constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block
+constexpr int LZC_MLP = 4;                            // rounds of phase 1 in flight together
 
 __global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
                                                            const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
                                                            uint32_t* __restrict__ lw3, uint8_t* __restrict__ bestlen) {
-    const uint32_t p = blockIdx.x * LZC_THREADS + threadIdx.x;
-    const uint32_t rem = lzc_rem(fs, F, p, n);
-    if (p >= n) return;
-    const uint32_t d3 = lzc_link3(bs, lwh, rsd, p, rem);
-    lw3[p] = d3 | (uint32_t)bs[p + 3] << 16;
-    if (!d3) bestlen[p] = 0;
+    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t cbase = blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK;
+    if (cbase >= n) return;
+    uint32_t f0 = 0;
+    if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
+    f0 = __shfl_sync(0xffffffffu, f0, 0);
+    auto cap_of = [&](uint32_t p) {   // min(15, bytes left in p's frame)
+        uint32_t f = f0;
+        while (fs[f + 1] <= p) f++;
+        return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
+    };
+    uint32_t qn = 0;
+    for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+        uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane;
+            w[j] = 0; b23[j] = 0; cap[j] = 0;
+            if (p < n) { w[j] = lwh[p]; b23[j] = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8; cap[j] = cap_of(p); }
+        }
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+            wk[j] = 0; k2[j] = 0;
+            if (cap[j] >= 3u && dist) { wk[j] = lwh[p - dist]; k2[j] = bs[p - dist + 2]; }
+        }
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+            bool pend = false;
+            if (p < n) {
+                uint32_t nd = 0;
+                if (cap[j] >= 3u && dist) {
+                    if ((wk[j] >> 16) == (w[j] >> 16) && k2[j] == (b23[j] & 0xFFu)) nd = dist;
+                    else pend = true;
+                }
+                if (!pend) {
+                    lw3[p] = lzc_word(nd, b23[j] >> 8, b23[j] & 0xFFu, cap[j]);
+                    if (!nd) bestlen[p] = 0;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pend);
+            if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)((r0 + j) * 32 + lane);
+            qn += __popc(bal);
+        }
+    }
+    __syncwarp();
+    uint32_t qi = 0, b23c = 0;
+    bool busy = false;
+    LzcLink3Walk wlk;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (qi < qn && idle) {
+            const uint32_t my = qi + __popc(idle & lanemask_lt());
+            if (!busy && my < qn) {
+                const uint32_t p = cbase + q[warp][my];
+                const uint32_t cp = cap_of(p);
+                b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
+                wlk.start(p, lwh[p], b23c & 0xFFu, cp);
+                busy = true;
+            }
+            qi += __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy) {
+            const int r = wlk.hop(bs, lwh, rsd);
+            if (r != LZC_GO) {
+                const uint32_t nd = r == LZC_FOUND ? wlk.acc : 0u;
+                lw3[wlk.p] = lzc_word(nd, (b23c >> 8) & 0xFFu, b23c & 0xFFu, b23c >> 16);
+                if (!nd) bestlen[wlk.p] = 0;
+                busy = false;
+            }
+        }
+    }
 }
 
-__global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n, uint32_t L,
-                                                           const uint32_t* __restrict__ lw, const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next,
+__global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
+                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next,
                                                            uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen) {
-    const uint32_t p = blockIdx.x * LZC_THREADS + threadIdx.x;
-    const uint32_t rem = lzc_rem(fs, F, p, n);
-    if (p >= n) return;
-    uint32_t rec = 0;
-    const uint32_t nd = lzc_level(bs, lw, rsd, p, rem, L, &rec);
-    lw_next[p] = nd | (uint32_t)bs[p + L + 1] << 16;
-    if (rec) { match_rec[p] = rec; bestlen[p] = (uint8_t)L; }
-    else if (nd && L + 1 == (uint32_t)LZ_MAXLEN) bestlen[p] = (uint8_t)LZ_MAXLEN;
+    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t cbase = blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK;
+    if (cbase >= n) return;
+    const bool top = L + 1u == (uint32_t)LZ_MAXLEN;
+    uint32_t qn = 0;
+    for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+        uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane;
+            w[j] = 0; nb[j] = 0;
+            if (p < n) { w[j] = lw[p]; nb[j] = bs[p + L + 1]; }
+        }
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+            wk[j] = 0;
+            if (dist) wk[j] = lw[p - dist];
+        }
+#pragma unroll
+        for (int j = 0; j < LZC_MLP; j++) {
+            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+            const uint32_t c = (w[j] >> 16) & 0xFFu, cap = (w[j] >> 24) & 0xFu;
+            bool pend = false;
+            if (p < n) {
+                uint32_t nd = 0;
+                if (dist) {
+                    if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) nd = dist;
+                    else pend = true;
+                }
+                if (!pend) {
+                    lw_next[p] = lzc_word(nd, nb[j], c, cap);
+                    if (nd && top) bestlen[p] = (uint8_t)LZ_MAXLEN;
+                }
+            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pend);
+            if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)((r0 + j) * 32 + lane);
+            qn += __popc(bal);
+        }
+    }
+    __syncwarp();
+    uint32_t qi = 0, nbc = 0;
+    bool busy = false;
+    LzcLevelWalk wlk;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (qi < qn && idle) {
+            const uint32_t my = qi + __popc(idle & lanemask_lt());
+            if (!busy && my < qn) {
+                const uint32_t p = cbase + q[warp][my];
+                const uint32_t w = lw[p];
+                nbc = (uint32_t)bs[p + L + 1] | ((w >> 24) & 0xFu) << 8;
+                wlk.start(p, w, L);
+                busy = true;
+            }
+            qi += __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy) {
+            const int r = wlk.hop(lw, rsd);
+            if (r != LZC_GO) {
+                const uint32_t nd = r == LZC_FOUND ? wlk.acc : 0u;
+                lw_next[wlk.p] = lzc_word(nd, nbc & 0xFFu, wlk.c, nbc >> 8);
+                if (r == LZC_END) { match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last; bestlen[wlk.p] = (uint8_t)L; }
+                else if (top) bestlen[wlk.p] = (uint8_t)LZ_MAXLEN;
+                busy = false;
+            }
+        }
+    }
 }
 
 __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ wbase) {
@@ -137,29 +272,63 @@ __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_
     if (i <= F) wbase[i] = (uint32_t)(((uint64_t)fs[i] * 9u) >> 5) + 3u * i;
 }
 
-// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165)
-__global__ void __launch_bounds__(256) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint8_t* __restrict__ bestlen,
-                                                  const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum,
-                                                  const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
-                                                  const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
-    const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
-    const uint32_t i = fs[f] + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= fs[f + 1]) return;
-    const uint32_t rel = bitcum[i];
-    if (rel == EMPTY32) return;
-    const uint32_t l = bestlen[i];
-    uint32_t v, nb;
-    if (l >= (uint32_t)LZ_MINLEN) {
-        const uint32_t off = l == (uint32_t)LZ_MAXLEN ? lzc_chain_end(lw15, rsd, i) : match_rec[i] & 0xFFFFu;
-        v = (off << 1) | (l << 17);
-        nb = 21;
-    } else {
-        v = 1u | ((uint32_t)bs[i] << 1);
-        nb = 9;
-    }
-    const uint32_t w = wbase[f] + (rel >> 5), sh = rel & 31;
+// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165). Same two phases as the
+// walking kernels: literals and matches shorter than 15 bytes are emitted in the sweep, the 15-byte matches of the parse
+// (the only positions whose earliest start is still unknown) walk their level-15 chain to its end with lane refill.
+__device__ __forceinline__ void lzc_emit(uint32_t* __restrict__ out_words, uint32_t wb, uint32_t rel, uint32_t v, uint32_t nb) {
+    const uint32_t w = wb + (rel >> 5), sh = rel & 31;
     atomicOr(&out_words[w], v << sh);
     if (sh + nb > 32) atomicOr(&out_words[w + 1], v >> (32 - sh));
+}
+__global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint8_t* __restrict__ bestlen,
+                                                          const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum,
+                                                          const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
+                                                          const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
+    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
+    const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t cbase = fs[f] + blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK, end = fs[f + 1];
+    if (cbase >= end) return;
+    const uint32_t wb = wbase[f];
+    uint32_t qn = 0;
+#pragma unroll 4
+    for (int r = 0; r < LZC_ROUNDS; r++) {
+        const uint32_t i = cbase + r * 32 + lane;
+        bool pend = false;
+        if (i < end) {
+            const uint32_t rel = bitcum[i];
+            if (rel != EMPTY32) {
+                const uint32_t l = bestlen[i];
+                if (l == (uint32_t)LZ_MAXLEN) pend = true;
+                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((match_rec[i] & 0xFFFFu) << 1) | (l << 17), 21);
+                else lzc_emit(out_words, wb, rel, 1u | ((uint32_t)bs[i] << 1), 9);
+            }
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, pend);
+        if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)(r * 32 + lane);
+        qn += __popc(bal);
+    }
+    __syncwarp();
+    uint32_t qi = 0;
+    bool busy = false;
+    LzcEndWalk wlk;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (qi < qn && idle) {
+            const uint32_t my = qi + __popc(idle & lanemask_lt());
+            if (!busy && my < qn) {
+                const uint32_t p = cbase + q[warp][my];
+                wlk.start(p, lw15[p]);   // a 15-byte match: the link is never 0
+                busy = true;
+            }
+            qi += __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy && wlk.hop(lw15, rsd) != LZC_GO) {
+            lzc_emit(out_words, wb, bitcum[wlk.p], (wlk.last << 1) | ((uint32_t)LZ_MAXLEN << 17), 21);
+            busy = false;
+        }
+    }
 }
 
 }  // namespace agmvb

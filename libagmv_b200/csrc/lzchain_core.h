@@ -18,14 +18,14 @@
 //
 // So no position is ever sorted or moved: a level is one streaming pass (4 B in, 4 B out per position) plus a few
 // gathers into the previous 64 KB of the same array, which sit in L1 / L2. The level-3 links come from a hashed
-// "previous occurrence" table (lzchain.cuh: lzc_hashlink_k) refined by lzc_link3 below.
+// "previous occurrence" table (lzchain.cuh: lzc_hashlink_k) refined by LzcLink3Walk below.
 //
 // Byte runs are the one input on which a chain walk degenerates (every position of a long run is on the chain of every
 // other one). They are skipped exactly: when the walk stands on an element k whose link is 1, k-1 .. runstart(k) all carry
 // the same L-gram (all one byte b) and the same byte L (b again), so if b is not the byte looked for none of them can
 // end the walk, and the walk continues from the run's first position.
 //
-// This header is plain C++ (no CUDA types): the kernels in lzchain.cuh call these functions per thread, and
+// This header is plain C++ (no CUDA types): the kernels in lzchain.cuh drive these state machines one hop at a time, and
 // tests/lzchain_host_check.cpp compiles them for the host to check the logic against a brute-force search.
 #pragma once
 #include <stddef.h>
@@ -33,8 +33,10 @@
 
 #ifdef __CUDACC__
 #define LZC_HD __host__ __device__ __forceinline__
+#define LZC_HDM __host__ __device__ __forceinline__
 #else
 #define LZC_HD static inline
+#define LZC_HDM inline
 #endif
 
 namespace agmvb {
@@ -42,90 +44,101 @@ namespace agmvb {
 constexpr uint32_t LZC_WINDOW = 65535u;     // src/agmv_encode.c:102
 constexpr uint32_t LZC_RESOLVED = 1u << 27; // match_rec: length << 28 | LZC_RESOLVED | offset
 
-// link words: low 16 bits = dist, then key bytes.
+// Link words: low 16 bits = dist, then key bits.
 //   hash level (lzc_hashlink_k): dist to the previous position with the same 3-gram hash | byte0 << 16 | byte1 << 24
-//   level L >= 3:                dist_L | byte[p + L] << 16
+//   level L >= 3:  dist_L | byte[p+L] << 16 | cap << 24 | (byte[p+L] != byte[p+L-1]) << 28,
+//                  cap = min(15, bytes left in the frame from p on): the reference caps a match there (src/agmv_encode.c:121-123)
 LZC_HD uint32_t lzc_hash(uint32_t gram24, int bits) { return (gram24 * 2654435761u) >> (32 - bits); }
+LZC_HD uint32_t lzc_word(uint32_t dist, uint32_t byte_l, uint32_t byte_before, uint32_t cap) {
+    return dist | byte_l << 16 | cap << 24 | (byte_l != byte_before ? 1u << 28 : 0u);
+}
+
+enum { LZC_GO = 0, LZC_FOUND = 1, LZC_END = 2 };
 
 // level 3 from the hash chain: most recent earlier position with the same three bytes, within the window.
-// d, lwh, rsd are batch arrays, p the position, rem = bytes left in p's frame from p on.
-LZC_HD uint32_t lzc_link3(const uint8_t* d, const uint32_t* lwh, const uint16_t* rsd, size_t p, uint32_t rem) {
-    if (rem < 3u) return 0u;
-    const uint32_t w = lwh[p];
-    const uint32_t key01 = w >> 16;
-    const uint8_t b2 = d[p + 2];
-    uint32_t dist = w & 0xFFFFu, acc = 0;
-    while (dist) {
+// Usage: if (start(...)) while ((r = hop(...)) == LZC_GO); r == LZC_FOUND: acc = dist_3.
+struct LzcLink3Walk {
+    uint32_t p, acc, dist, key;   // key = byte0 | byte1 << 8 | byte2 << 16
+    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t byte2, uint32_t cap) {
+        p = p_; acc = 0; dist = w & 0xFFFFu; key = (w >> 16) | byte2 << 16;
+        return cap >= 3u && dist != 0u;
+    }
+    LZC_HDM int hop(const uint8_t* d, const uint32_t* lwh, const uint16_t* rsd) {
         acc += dist;
-        if (acc > LZC_WINDOW) return 0u;
-        const size_t k = p - acc;
-        const uint32_t wk = lwh[k];
-        const uint32_t g01 = wk >> 16;
-        if (g01 == key01 && d[k + 2] == b2) return acc;
+        if (acc > LZC_WINDOW) return LZC_END;
+        const uint32_t k = p - acc, wk = lwh[k], g01 = wk >> 16;
+        if (g01 == (key & 0xFFFFu) && d[k + 2] == (key >> 16)) return LZC_FOUND;
         dist = wk & 0xFFFFu;
         // run skip: k reads b,b,b and so does k-1 (its link is 1): every position back to the run start has the same
         // gram, hence the same hash, and is the next chain element; none of them is p's gram (k was not)
-        if (dist == 1u && (g01 & 0xFFu) == (g01 >> 8) && d[k + 2] == (uint8_t)g01) {
+        if (dist == 1u && (g01 & 0xFFu) == (g01 >> 8) && d[k + 2] == (g01 & 0xFFu)) {
             const uint32_t r = rsd[k];
             if (r) {
-                if (acc + r > LZC_WINDOW) return 0u;
+                if (acc + r > LZC_WINDOW) return LZC_END;
                 acc += r;
                 dist = lwh[p - acc] & 0xFFFFu;
             }
         }
+        return dist ? LZC_GO : LZC_END;
     }
-    return 0u;
-}
+};
 
-// one level: dist_{L+1}[p] from the level-L links. Returns the new distance (0 = no match of length L+1).
-// *rec is set to L << 28 | LZC_RESOLVED | offset when p had a match of length L and has none of length L+1 (its final
-// answer: offset = distance to the EARLIEST level-L occurrence inside the window), and left untouched otherwise.
-LZC_HD uint32_t lzc_level(const uint8_t* d, const uint32_t* lw, const uint16_t* rsd, size_t p, uint32_t rem, uint32_t L, uint32_t* rec) {
-    const uint32_t w = lw[p];
-    uint32_t dist = w & 0xFFFFu;
-    if (!dist) return 0u;
-    const uint32_t c = (w >> 16) & 0xFFu;      // byte L of p
-    const bool can_extend = L + 1u <= rem;     // the reference caps the match at the bytes left in the frame (src/agmv_encode.c:121-123)
-    const uint32_t b = d[p];
-    uint32_t acc = 0, last = 0;
-    while (dist) {
+// one level: dist_{L+1}[p] from the level-L links.
+// r == LZC_FOUND: acc = dist_{L+1}. r == LZC_END: no match of length L+1; `last` = distance to the EARLIEST level-L
+// occurrence inside the window, i.e. the offset of p's final (length L) match.
+struct LzcLevelWalk {
+    uint32_t p, acc, last, dist, c;
+    bool ext, neq;
+    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t L) {
+        p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; c = (w >> 16) & 0xFFu;
+        ext = L + 1u <= ((w >> 24) & 0xFu);
+        neq = (w >> 28) & 1u;
+        return dist != 0u;
+    }
+    LZC_HDM int hop(const uint32_t* lw, const uint16_t* rsd) {
         acc += dist;
-        if (acc > LZC_WINDOW) break;
+        if (acc > LZC_WINDOW) return LZC_END;
         const uint32_t wk = lw[p - acc];
-        if (can_extend && ((wk >> 16) & 0xFFu) == c) return acc;
+        if (ext && ((wk >> 16) & 0xFFu) == c) return LZC_FOUND;
         last = acc;
         dist = wk & 0xFFFFu;
-        if (dist == 1u && (!can_extend || c != b)) {
-            // the element stands inside a run of byte b = p's own first byte (same L-gram); everything back to the run
-            // start is on the chain and carries byte L == b != c
+        if (dist == 1u && (!ext || neq)) {
+            // the element stands inside a run of one byte b (its L-gram, hence p's, is all b, and neq says p's byte L is
+            // not b): everything back to the run start is on the chain and carries byte L == b
             const uint32_t r = rsd[p - acc];
-            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; break; }   // the window ends inside the run: p - 65535 is on the chain
+            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }   // the window ends inside the run: p - 65535 is on the chain
             acc += r;
             last = acc;
             dist = lw[p - acc] & 0xFFFFu;
         }
+        return dist ? LZC_GO : LZC_END;
     }
-    *rec = L << 28 | LZC_RESOLVED | last;
-    return 0u;
-}
+};
 
-// positions whose match reaches 15 bytes: offset of the earliest occurrence of the 15-gram inside the window
-LZC_HD uint32_t lzc_chain_end(const uint32_t* lw15, const uint16_t* rsd, size_t p) {
-    uint32_t dist = lw15[p] & 0xFFFFu, acc = 0, last = 0;
-    while (dist) {
+// positions whose match reaches 15 bytes: `last` ends as the offset of the earliest occurrence of the 15-gram inside the
+// window (the end of the level-15 chain). Usage: start(); while (hop(...) == LZC_GO);
+struct LzcEndWalk {
+    uint32_t p, acc, last, dist;
+    LZC_HDM bool start(uint32_t p_, uint32_t w) { p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; return dist != 0u; }
+    LZC_HDM int hop(const uint32_t* lw15, const uint16_t* rsd) {
         acc += dist;
-        if (acc > LZC_WINDOW) break;
+        if (acc > LZC_WINDOW) return LZC_END;
         last = acc;
         dist = lw15[p - acc] & 0xFFFFu;
-        if (dist == 1u) {
+        if (dist == 1u) {   // inside a run: every position back to its start carries the same 15 bytes
             const uint32_t r = rsd[p - acc];
-            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; break; }
+            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }
             acc += r;
             last = acc;
             dist = lw15[p - acc] & 0xFFFFu;
         }
+        return dist ? LZC_GO : LZC_END;
     }
-    return last;
+};
+LZC_HD uint32_t lzc_chain_end(const uint32_t* lw15, const uint16_t* rsd, uint32_t p) {
+    LzcEndWalk w;
+    if (w.start(p, lw15[p])) while (w.hop(lw15, rsd) == LZC_GO) {}
+    return w.last;
 }
 
 }  // namespace agmvb

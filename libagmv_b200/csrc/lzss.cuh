@@ -1227,20 +1227,20 @@ inline void lzss_encode_batch_chain(LzWork& wk, const uint8_t* bs, const uint32_
     const uint32_t* lw15 = wk.lw[0];
     if (n > 0) {
         cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
-        const uint32_t nb = cdiv(n, LZC_THREADS);
+        const uint32_t nb = cdiv(n, LZC_BCHUNK);
         KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, fs, wk.items, wk.lw[1], wk.rsd)));
-        KL(lc, KC_LZ_LINK, (lzc_link3_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen)));
+        KL(lc, KC_LZ_LINK3, (lzc_link3_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen)));
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
-            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen)));
+            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen)));
         lw15 = wk.lw[cur];
     }
     orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
     if (n > 0) {
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
-        dim3 pgrid(cdiv(max_usize, 256u), F);
-        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, 256, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
+        dim3 pgrid(cdiv(max_usize, (uint32_t)LZC_BCHUNK), F);
+        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);

@@ -48,21 +48,34 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
         }
     }
     for (size_t p = 0; p < n; p++) {
-        const uint32_t d3 = lzc_link3(d.data(), lwh.data(), rsd.data(), p, rem[p]);
-        lw[0][p] = d3 | (uint32_t)d[p + 3] << 16;
+        const uint32_t cap = std::min<uint32_t>(rem[p], 15u);
+        LzcLink3Walk wk;
+        uint32_t d3 = 0;
+        if (wk.start((uint32_t)p, lwh[p], d[p + 2], cap)) {
+            int r;
+            while ((r = wk.hop(d.data(), lwh.data(), rsd.data())) == LZC_GO) {}
+            if (r == LZC_FOUND) d3 = wk.acc;
+        }
+        lw[0][p] = lzc_word(d3, d[p + 3], d[p + 2], cap);
     }
     int cur = 0;
     for (uint32_t L = 3; L < 15; L++) {
         for (size_t p = 0; p < n; p++) {
-            uint32_t rec = 0;
-            const uint32_t nd = lzc_level(d.data(), lw[cur].data(), rsd.data(), p, rem[p], L, &rec);
-            lw[cur ^ 1][p] = nd | (uint32_t)d[p + L + 1] << 16;
-            if (rec) { R.len[p] = (uint8_t)(rec >> 28); R.off[p] = rec & 0xFFFFu; }
+            const uint32_t w = lw[cur][p];
+            LzcLevelWalk wk;
+            uint32_t nd = 0;
+            if (wk.start((uint32_t)p, w, L)) {
+                int r;
+                while ((r = wk.hop(lw[cur].data(), rsd.data())) == LZC_GO) {}
+                if (r == LZC_FOUND) nd = wk.acc;
+                else { R.len[p] = (uint8_t)L; R.off[p] = wk.last; }
+            }
+            lw[cur ^ 1][p] = lzc_word(nd, d[p + L + 1], d[p + L], (w >> 24) & 0xFu);
         }
         cur ^= 1;
     }
     for (size_t p = 0; p < n; p++)
-        if (lw[cur][p] & 0xFFFFu) { R.len[p] = 15; R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), p); }
+        if (lw[cur][p] & 0xFFFFu) { R.len[p] = 15; R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p); }
     return R;
 }
 
