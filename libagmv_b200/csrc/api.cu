@@ -450,6 +450,14 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
             TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
             TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
             TRY(grab((size_t)cap * 2, (void**)&w.rsd));
+            TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
+            int sms = 148;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            int per3 = 5, perl = 6;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k, LZC_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k, LZC_THREADS, 0);
+            w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
+            w.level_blocks = (uint32_t)(sms * std::max(1, perl));
         } else {
             for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
             for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));

@@ -40,51 +40,79 @@ inline void lzc_build_items(const uint32_t* h_fs, uint32_t F, std::vector<LzcIte
     }
 }
 
-__global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const LzcItem* __restrict__ items,
-                                                     uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd) {
+// The bytes of 16 steps (512 positions + 3) are staged in shared memory with coalesced word loads issued one block ahead,
+// so the serial loop never waits for global memory: a step is stage read -> hash -> table read -> match -> table write.
+constexpr int LZC_STAGE_STEPS = 16;
+constexpr int LZC_STAGE_WORDS = 32 * 5;   // 640 bytes >= 32 * 16 + 3 + 3 bytes of misalignment
+
+__global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs,
+                                                     const LzcItem* __restrict__ items, uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd) {
     extern __shared__ uint32_t lzc_tab[];
+    __shared__ uint32_t stage[2][LZC_STAGE_WORDS + 1];
     const LzcItem it = items[blockIdx.x];
     const uint32_t base = fs[it.frame], len = fs[it.frame + 1] - base;
     const uint32_t lane = threadIdx.x;
     for (uint32_t k = lane; k < (1u << LZC_HB); k += 32) lzc_tab[k] = 0;
-    __syncwarp();
-    const uint8_t* d = bs + base;
     uint32_t i0 = it.start > LZC_PREROLL ? it.start - LZC_PREROLL : 0u;
     uint32_t run_start = i0;
-    // bytes i-1 .. i+2 of this lane's position, fetched one step ahead (indices clamped: the values of positions past the
-    // frame end are never used)
-    auto fetch = [&](uint32_t i, uint32_t& w) {
-        const uint32_t a = i > 0 ? i - 1 : 0, lim = len ? len - 1 : 0;
-        const uint32_t pb = d[min(a, lim)], b0 = d[min(i, lim)], b1 = d[min(i + 1, lim)], b2 = d[min(i + 2, lim)];
-        w = pb | b0 << 8 | b1 << 16 | b2 << 24;
+    // readable words of the batch buffer: [word_lo, word_hi] (bs has 16 bytes of padding after its n bytes)
+    const uintptr_t word_lo = reinterpret_cast<uintptr_t>(bs) & ~(uintptr_t)3;
+    const uintptr_t word_hi = (reinterpret_cast<uintptr_t>(bs) + n + 12u) & ~(uintptr_t)3;
+    // block of 16 steps starting at position j0: words from the aligned address at or below byte j0 - 1
+    uint32_t regs[5];
+    auto block_addr = [&](uint32_t j0) {
+        const uintptr_t want = reinterpret_cast<uintptr_t>(bs) + base + j0 - 1u;   // byte before the block's first position
+        const uintptr_t a = want & ~(uintptr_t)3;
+        return a < word_lo ? word_lo : a;
     };
-    uint32_t wnext = 0;
-    fetch(i0 + lane, wnext);
-    for (; i0 < it.end; i0 += 32) {
-        const uint32_t i = i0 + lane, w = wnext;
-        if (i0 + 32 < it.end) fetch(i + 32, wnext);
-        const bool valid = i + 3u <= len && i < it.end;
-        const uint32_t h = lzc_hash(w >> 8, LZC_HB);
-        const uint32_t old = valid ? lzc_tab[h] : 0u;
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? h : (0x80000000u | lane));
-        const unsigned lower = peers & lanemask_lt();
-        uint32_t dist = 0;
-        if (valid) {
-            const bool has = lower || old;
-            const uint32_t q = lower ? i0 + (31u - (uint32_t)__clz(lower)) : old - 1u;
-            if (has && i - q <= LZC_WINDOW) dist = i - q;
-            if ((peers >> lane) == 1u) lzc_tab[h] = i + 1u;   // the group's last lane: most recent position of this hash
+    auto fetch = [&](uint32_t j0) {
+        const uintptr_t a = block_addr(j0);
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            uintptr_t x = a + 4u * (uint32_t)(k * 32 + lane);
+            if (x > word_hi) x = word_hi;
+            regs[k] = *reinterpret_cast<const uint32_t*>(x);
         }
-        const bool brk = i < len && (i == 0 || ((w >> 8) & 0xFFu) != (w & 0xFFu));
-        const unsigned bal = __ballot_sync(0xffffffffu, brk);
-        const unsigned upto = bal & (0xffffffffu >> (31u - lane));
-        const uint32_t rs = upto ? i0 + (31u - (uint32_t)__clz(upto)) : run_start;
-        if (bal) run_start = i0 + (31u - (uint32_t)__clz(bal));
-        if (i >= it.start && i < it.end) {
-            lwh[base + i] = dist | (w >> 8 & 0xFFFFu) << 16;
-            rsd[base + i] = (uint16_t)min(i - rs, 65535u);
-        }
+    };
+    fetch(i0);
+    int buf = 0;
+    for (uint32_t j0 = i0; j0 < it.end; j0 += 32 * LZC_STAGE_STEPS, buf ^= 1) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) stage[buf][k * 32 + lane] = regs[k];
+        if (lane == 0) stage[buf][LZC_STAGE_WORDS] = 0;
         __syncwarp();
+        if (j0 + 32 * LZC_STAGE_STEPS < it.end) fetch(j0 + 32 * LZC_STAGE_STEPS);
+        // byte offset of position j0 - 1 inside the staged words (-1 only for the very first byte of the buffer)
+        const int off0 = (int)(reinterpret_cast<uintptr_t>(bs) + base + j0 - 1u - block_addr(j0));
+        const uint32_t jend = min(j0 + 32 * LZC_STAGE_STEPS, it.end);
+        for (uint32_t s0 = j0; s0 < jend; s0 += 32) {
+            const uint32_t i = s0 + lane;
+            const int o = off0 + (int)(i - j0);
+            // bytes i-1 .. i+2 (o == -1: the buffer's very first position, which has no byte before it)
+            const uint32_t w = o < 0 ? stage[buf][0] << 8 : __funnelshift_r(stage[buf][o >> 2], stage[buf][(o >> 2) + 1], (o & 3) * 8);
+            const bool valid = i + 3u <= len && i < it.end;
+            const uint32_t h = lzc_hash(w >> 8, LZC_HB);
+            const uint32_t old = valid ? lzc_tab[h] : 0u;
+            const unsigned peers = __match_any_sync(0xffffffffu, valid ? h : (0x80000000u | lane));
+            const unsigned lower = peers & lanemask_lt();
+            uint32_t dist = 0;
+            if (valid) {
+                const bool has = lower || old;
+                const uint32_t q = lower ? s0 + (31u - (uint32_t)__clz(lower)) : old - 1u;
+                if (has && i - q <= LZC_WINDOW) dist = i - q;
+                if ((peers >> lane) == 1u) lzc_tab[h] = i + 1u;   // the group's last lane: most recent position of this hash
+            }
+            const bool brk = i < len && (i == 0 || ((w >> 8) & 0xFFu) != (w & 0xFFu));
+            const unsigned bal = __ballot_sync(0xffffffffu, brk);
+            const unsigned upto = bal & (0xffffffffu >> (31u - lane));
+            const uint32_t rs = upto ? s0 + (31u - (uint32_t)__clz(upto)) : run_start;
+            if (bal) run_start = s0 + (31u - (uint32_t)__clz(bal));
+            if (i >= it.start && i < it.end) {
+                lwh[base + i] = dist | (w >> 8 & 0xFFFFu) << 16;
+                rsd[base + i] = (uint16_t)min(i - rs, 65535u);
+            }
+            __syncwarp();
+        }
     }
 }
 
@@ -101,170 +129,199 @@ __device__ __forceinline__ uint32_t lzc_frame_of(const uint32_t* __restrict__ fs
 // ---- the walking kernels ---------------------------------------------------------------------------------------
 // A walk is a chain of dependent gathers whose length varies from position to position (most end at the first hop, a
 // few per cent must cross their whole window), so "one thread walks one position to the end" leaves most lanes of a warp
-// waiting for the slowest one. Both kernels therefore work in two phases on a warp's 512 consecutive positions:
-//   1. a coalesced sweep that takes every position's FIRST hop (four independent rounds in flight) and finishes the
-//      positions it settles; the others are queued (shared memory, 2 B each);
-//   2. the queue is drained with lane refill: a lane whose walk ends takes the next queued position at once, so every
-//      hop instruction has (almost) all lanes doing useful work.
+// - and most warps of a block - waiting for the slowest one. Both kernels are therefore persistent warps that take
+// 512-position chunks from a global counter and work in two interleaved phases:
+//   sweep: a coalesced pass over a chunk that takes every position's FIRST hop (four independent rounds in flight) and
+//          finishes the positions it settles; the others are queued (shared memory, one word each);
+//   drain: the queue is worked off with lane refill - a lane whose walk ends takes the next queued position at once, so
+//          every hop instruction has (almost) all lanes doing useful work. When the queue runs low the warp sweeps its
+//          next chunk while the walks still in progress simply keep their state.
 constexpr int LZC_ROUNDS = 16;
-constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per warp
+constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per chunk
 constexpr int LZC_WARPS = LZC_THREADS / 32;
-constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block
-constexpr int LZC_MLP = 4;                            // rounds of phase 1 in flight together
+constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (lzc_pack_k)
+constexpr int LZC_MLP = 4;                            // rounds of a sweep in flight together
+constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
 
-__global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
-                                                           const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
-                                                           uint32_t* __restrict__ lw3, uint8_t* __restrict__ bestlen) {
-    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t cbase = blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK;
-    if (cbase >= n) return;
-    uint32_t f0 = 0;
-    if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
-    f0 = __shfl_sync(0xffffffffu, f0, 0);
-    auto cap_of = [&](uint32_t p) {   // min(15, bytes left in p's frame)
-        uint32_t f = f0;
-        while (fs[f + 1] <= p) f++;
-        return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
-    };
-    uint32_t qn = 0;
-    for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
-        uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane;
-            w[j] = 0; b23[j] = 0; cap[j] = 0;
-            if (p < n) { w[j] = lwh[p]; b23[j] = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8; cap[j] = cap_of(p); }
-        }
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
-            wk[j] = 0; k2[j] = 0;
-            if (cap[j] >= 3u && dist) { wk[j] = lwh[p - dist]; k2[j] = bs[p - dist + 2]; }
-        }
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
-            bool pend = false;
-            if (p < n) {
-                uint32_t nd = 0;
-                if (cap[j] >= 3u && dist) {
-                    if ((wk[j] >> 16) == (w[j] >> 16) && k2[j] == (b23[j] & 0xFFu)) nd = dist;
-                    else pend = true;
-                }
-                if (!pend) {
-                    lw3[p] = lzc_word(nd, b23[j] >> 8, b23[j] & 0xFFu, cap[j]);
-                    if (!nd) bestlen[p] = 0;
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pend);
-            if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)((r0 + j) * 32 + lane);
-            qn += __popc(bal);
-        }
-    }
-    __syncwarp();
-    uint32_t qi = 0, b23c = 0;
-    bool busy = false;
-    LzcLink3Walk wlk;
+// Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
+//     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
+template <class Op>
+__device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
+    const uint32_t lane = lane_id();
+    uint32_t qn = 0, qi = 0;
+    bool more = true, busy = false;
     for (;;) {
+        if (more && qn - qi < 32u) {   // keep the leftovers, sweep the next chunk
+            const uint32_t left = qn - qi;
+            const uint32_t keep = lane < left ? q[qi + lane] : 0u;
+            __syncwarp();
+            if (lane < left) q[lane] = keep;
+            qn = left;
+            qi = 0;
+            uint32_t ch = 0;
+            if (lane == 0) ch = atomicAdd(counter, 1u);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            const uint64_t cb = (uint64_t)ch * LZC_WCHUNK;
+            if (cb >= n) more = false;
+            else qn += op.sweep((uint32_t)cb, q + qn);
+            __syncwarp();
+            continue;
+        }
         const unsigned idle = __ballot_sync(0xffffffffu, !busy);
         if (qi < qn && idle) {
             const uint32_t my = qi + __popc(idle & lanemask_lt());
-            if (!busy && my < qn) {
-                const uint32_t p = cbase + q[warp][my];
-                const uint32_t cp = cap_of(p);
-                b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
-                wlk.start(p, lwh[p], b23c & 0xFFu, cp);
-                busy = true;
-            }
-            qi += __popc(idle);
+            if (!busy && my < qn) { op.begin(q[my]); busy = true; }
+            qi = min(qn, qi + (uint32_t)__popc(idle));
         }
-        if (!__any_sync(0xffffffffu, busy)) break;
-        if (busy) {
-            const int r = wlk.hop(bs, lwh, rsd);
-            if (r != LZC_GO) {
-                const uint32_t nd = r == LZC_FOUND ? wlk.acc : 0u;
-                lw3[wlk.p] = lzc_word(nd, (b23c >> 8) & 0xFFu, b23c & 0xFFu, b23c >> 16);
-                if (!nd) bestlen[wlk.p] = 0;
-                busy = false;
-            }
+        if (!__any_sync(0xffffffffu, busy)) {
+            if (!more) break;
+            continue;
         }
+        if (busy && op.step()) busy = false;
     }
+}
+
+struct LzcLink3Op {
+    const uint8_t* __restrict__ bs; const uint32_t* __restrict__ fs; uint32_t F, n;
+    const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3; uint8_t* __restrict__ bestlen;
+    LzcLink3Walk wlk;
+    uint32_t b23c;   // byte 2 | byte 3 << 8 | cap << 16 of the position being walked
+    __device__ __forceinline__ uint32_t cap_of(uint32_t f, uint32_t p) const {   // min(15, bytes left in p's frame); f = a frame at or before p's
+        while (fs[f + 1] <= p) f++;
+        return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
+    }
+    __device__ __forceinline__ void put(uint32_t p, uint32_t nd, uint32_t b2, uint32_t b3, uint32_t cap) const {
+        lw3[p] = lzc_word(nd, b3, b2, cap);
+        if (!nd) bestlen[p] = 0;
+    }
+    __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
+        const uint32_t lane = lane_id();
+        uint32_t f0 = 0;
+        if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
+        f0 = __shfl_sync(0xffffffffu, f0, 0);
+        uint32_t qn = 0;
+        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+            uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane;
+                w[j] = 0; b23[j] = 0; cap[j] = 0;
+                if (p < n) { w[j] = lwh[p]; b23[j] = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8; cap[j] = cap_of(f0, p); }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                wk[j] = 0; k2[j] = 0;
+                if (cap[j] >= 3u && dist) { wk[j] = lwh[p - dist]; k2[j] = bs[p - dist + 2]; }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                bool pend = false;
+                if (p < n) {
+                    uint32_t nd = 0;
+                    if (cap[j] >= 3u && dist) {
+                        if ((wk[j] >> 16) == (w[j] >> 16) && k2[j] == (b23[j] & 0xFFu)) nd = dist;
+                        else pend = true;
+                    }
+                    if (!pend) put(p, nd, b23[j] & 0xFFu, b23[j] >> 8, cap[j]);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
+                qn += __popc(bal);
+            }
+        }
+        return qn;
+    }
+    __device__ __forceinline__ void begin(uint32_t p) {
+        const uint32_t cp = cap_of(lzc_frame_of(fs, F, p), p);
+        b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
+        wlk.start(p, lwh[p], b23c & 0xFFu, cp);
+    }
+    __device__ __forceinline__ bool step() {
+        const int r = wlk.hop(bs, lwh, rsd);
+        if (r == LZC_GO) return false;
+        put(wlk.p, r == LZC_FOUND ? wlk.acc : 0u, b23c & 0xFFu, (b23c >> 8) & 0xFFu, b23c >> 16);
+        return true;
+    }
+};
+
+struct LzcLevelOp {
+    const uint8_t* __restrict__ bs; uint32_t n, L;
+    const uint32_t* __restrict__ lw; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw_next;
+    uint32_t* __restrict__ match_rec; uint8_t* __restrict__ bestlen;
+    LzcLevelWalk wlk;
+    uint32_t nbc;   // byte L+1 | cap << 8 of the position being walked
+    __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
+        const uint32_t lane = lane_id();
+        const bool top = L + 1u == (uint32_t)LZ_MAXLEN;
+        uint32_t qn = 0;
+        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+            uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane;
+                w[j] = 0; nb[j] = 0;
+                if (p < n) { w[j] = lw[p]; nb[j] = bs[p + L + 1]; }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                wk[j] = 0;
+                if (dist) wk[j] = lw[p - dist];
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                const uint32_t c = (w[j] >> 16) & 0xFFu, cap = (w[j] >> 24) & 0xFu;
+                bool pend = false;
+                if (p < n) {
+                    uint32_t nd = 0;
+                    if (dist) {
+                        if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) nd = dist;
+                        else pend = true;
+                    }
+                    if (!pend) {
+                        lw_next[p] = lzc_word(nd, nb[j], c, cap);
+                        if (nd && top) bestlen[p] = (uint8_t)LZ_MAXLEN;
+                    }
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
+                qn += __popc(bal);
+            }
+        }
+        return qn;
+    }
+    __device__ __forceinline__ void begin(uint32_t p) {
+        const uint32_t w = lw[p];
+        nbc = (uint32_t)bs[p + L + 1] | ((w >> 24) & 0xFu) << 8;
+        wlk.start(p, w, L);
+    }
+    __device__ __forceinline__ bool step() {
+        const int r = wlk.hop(lw, rsd);
+        if (r == LZC_GO) return false;
+        lw_next[wlk.p] = lzc_word(r == LZC_FOUND ? wlk.acc : 0u, nbc & 0xFFu, wlk.c, nbc >> 8);
+        if (r == LZC_END) { match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last; bestlen[wlk.p] = (uint8_t)L; }
+        else if (L + 1u == (uint32_t)LZ_MAXLEN) bestlen[wlk.p] = (uint8_t)LZ_MAXLEN;
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
+                                                           const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
+                                                           uint32_t* __restrict__ lw3, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
+    LzcLink3Op op{bs, fs, F, n, lwh, rsd, lw3, bestlen};
+    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
 }
 
 __global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
                                                            const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next,
-                                                           uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen) {
-    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t cbase = blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK;
-    if (cbase >= n) return;
-    const bool top = L + 1u == (uint32_t)LZ_MAXLEN;
-    uint32_t qn = 0;
-    for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
-        uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane;
-            w[j] = 0; nb[j] = 0;
-            if (p < n) { w[j] = lw[p]; nb[j] = bs[p + L + 1]; }
-        }
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
-            wk[j] = 0;
-            if (dist) wk[j] = lw[p - dist];
-        }
-#pragma unroll
-        for (int j = 0; j < LZC_MLP; j++) {
-            const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
-            const uint32_t c = (w[j] >> 16) & 0xFFu, cap = (w[j] >> 24) & 0xFu;
-            bool pend = false;
-            if (p < n) {
-                uint32_t nd = 0;
-                if (dist) {
-                    if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) nd = dist;
-                    else pend = true;
-                }
-                if (!pend) {
-                    lw_next[p] = lzc_word(nd, nb[j], c, cap);
-                    if (nd && top) bestlen[p] = (uint8_t)LZ_MAXLEN;
-                }
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pend);
-            if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)((r0 + j) * 32 + lane);
-            qn += __popc(bal);
-        }
-    }
-    __syncwarp();
-    uint32_t qi = 0, nbc = 0;
-    bool busy = false;
-    LzcLevelWalk wlk;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (qi < qn && idle) {
-            const uint32_t my = qi + __popc(idle & lanemask_lt());
-            if (!busy && my < qn) {
-                const uint32_t p = cbase + q[warp][my];
-                const uint32_t w = lw[p];
-                nbc = (uint32_t)bs[p + L + 1] | ((w >> 24) & 0xFu) << 8;
-                wlk.start(p, w, L);
-                busy = true;
-            }
-            qi += __popc(idle);
-        }
-        if (!__any_sync(0xffffffffu, busy)) break;
-        if (busy) {
-            const int r = wlk.hop(lw, rsd);
-            if (r != LZC_GO) {
-                const uint32_t nd = r == LZC_FOUND ? wlk.acc : 0u;
-                lw_next[wlk.p] = lzc_word(nd, nbc & 0xFFu, wlk.c, nbc >> 8);
-                if (r == LZC_END) { match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last; bestlen[wlk.p] = (uint8_t)L; }
-                else if (top) bestlen[wlk.p] = (uint8_t)LZ_MAXLEN;
-                busy = false;
-            }
-        }
-    }
+                                                           uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
+    LzcLevelOp op{bs, n, L, lw, rsd, lw_next, match_rec, bestlen};
+    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
 }
 
 __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ wbase) {

@@ -71,6 +71,8 @@ struct LzWork {
     uint16_t* rsd = nullptr;             // chain path: distance of every position to the start of its byte run
     LzcItem* items = nullptr;            // chain path: (frame, range) work items of lzc_hashlink_k
     uint32_t n_items = 0, cap_items = 0;
+    uint32_t* counters = nullptr;        // chain path: chunk counters of the persistent kernels (one per launch of a batch)
+    uint32_t link3_blocks = 148 * 5, level_blocks = 148 * 6;   // chain path: resident blocks of the persistent walking kernels
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
     uint32_t* seg_len = nullptr;         // cap_frames
@@ -1227,12 +1229,15 @@ inline void lzss_encode_batch_chain(LzWork& wk, const uint8_t* bs, const uint32_
     const uint32_t* lw15 = wk.lw[0];
     if (n > 0) {
         cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
-        const uint32_t nb = cdiv(n, LZC_BCHUNK);
-        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, fs, wk.items, wk.lw[1], wk.rsd)));
-        KL(lc, KC_LZ_LINK3, (lzc_link3_k<<<nb, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen)));
+        // persistent walking kernels: enough warps to fill the GPU, chunks handed out through one counter per launch
+        const uint32_t nb3 = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.link3_blocks), nb = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.level_blocks);
+        cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
+        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd)));
+        KL(lc, KC_LZ_LINK3, (lzc_link3_k<<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen, wk.counters)));
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
-            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen)));
+            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen,
+                                                                         wk.counters + (L - LZ_MINLEN + 1))));
         lw15 = wk.lw[cur];
     }
     orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
