@@ -186,6 +186,7 @@ struct LzcLink3Op {
     const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3; uint8_t* __restrict__ bestlen;
     LzcLink3Walk wlk;
     uint32_t b23c;   // byte 2 | byte 3 << 8 | cap << 16 of the position being walked
+    uint32_t f_cur = 0, f_prev = 0;   // frames of the first position of the last two chunks swept: the queue only holds positions of those two
     __device__ __forceinline__ uint32_t cap_of(uint32_t f, uint32_t p) const {   // min(15, bytes left in p's frame); f = a frame at or before p's
         while (fs[f + 1] <= p) f++;
         return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
@@ -199,6 +200,8 @@ struct LzcLink3Op {
         uint32_t f0 = 0;
         if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
         f0 = __shfl_sync(0xffffffffu, f0, 0);
+        f_prev = min(f_cur, f0);   // (chunks are handed out in increasing order, but not necessarily to the same warp)
+        f_cur = f0;
         uint32_t qn = 0;
         for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
             uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
@@ -234,7 +237,7 @@ struct LzcLink3Op {
         return qn;
     }
     __device__ __forceinline__ void begin(uint32_t p) {
-        const uint32_t cp = cap_of(lzc_frame_of(fs, F, p), p);
+        const uint32_t cp = cap_of(f_prev, p);
         b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
         wlk.start(p, lwh[p], b23c & 0xFFu, cp);
     }
