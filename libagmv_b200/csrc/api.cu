@@ -160,9 +160,7 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
     ctx->lc.st = ctx->st;
     if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess ||
         cudaFuncSetAttribute(lz_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SCATTER_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(lz_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(lzt_pass_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LztSmem)) != cudaSuccess ||
-        cudaFuncSetAttribute(lzt_pass_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LztSmem)) != cudaSuccess) {
+        cudaFuncSetAttribute(lz_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) {
         delete ctx;
         return ERR_CUDA;
     }
@@ -449,15 +447,17 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
         if (!legacy) {
             // occurrence-chain match finder (lzchain.cuh): 19 B per position
-            TRY(grab((size_t)cap * 2, (void**)&w.dl[0]));
-            TRY(grab((size_t)cap * 2, (void**)&w.dl[1]));
+            TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
+            TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
             TRY(grab((size_t)cap * 2, (void**)&w.rsd));
             TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
-            int sms = 148, per = 4;
+            int sms = 148;
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, lzt_pass_k<1>, LZT_THREADS, sizeof(LztSmem));
-            w.pass_blocks = (uint32_t)(sms * std::max(1, per));
-            TRY(grab((size_t)w.pass_blocks * LZT_ARENA_WORDS * 4, (void**)&w.arena));
+            int per3 = 5, perl = 6;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k, LZC_THREADS, 0);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k, LZC_THREADS, 0);
+            w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
+            w.level_blocks = (uint32_t)(sms * std::max(1, perl));
         } else {
             for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
             for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));

@@ -6,13 +6,13 @@
 //                   8192-entry "last position of this 3-gram hash" table in shared memory -> hash-level links + the
 //                   distance of every position to the start of its byte run. The only serial kernel of the stage: a
 //                   step is one shared-memory round trip, and thousands of ranges are in flight.
-//   lzt_pass_k<0>   hash chain -> level-3 link (most recent earlier occurrence of the 3 bytes).
-//   lzt_pass_k<1>   x12: level L -> L+1. A position whose match stops growing writes its final (length, offset) on the spot.
-//                   Both are the tiled walker below: every gather of a chain walk is served from shared memory.
+//   lzc_link3_k     thread per position: hash chain -> level-3 link (most recent earlier occurrence of the 3 bytes).
+//   lzc_level_k     x12, thread per position: level L -> L+1 (lzc_level). A position whose match stops growing writes its
+//                   final (length, offset) on the spot.
 //   (orbit.cuh)     greedy parse over bestlen[].
-//   lzc_pack_k      token emission; 15-byte matches find their earliest start here (end of their level-15 chain),
-//                   parse-visited positions only.
-// Workspace: 15 bytes per bitstream byte + 4.9 MB per resident block of the tiled kernel.
+//   lzc_pack_k      token emission; 15-byte matches find their earliest start here (lzc_chain_end), parse-visited
+//                   positions only.
+// Workspace: 19 bytes per bitstream byte.
 #pragma once
 #include "common.cuh"
 #include <algorithm>
@@ -32,7 +32,7 @@ struct LzcItem { uint32_t frame, start, end; };            // positions [start, 
 inline void lzc_build_items(const uint32_t* h_fs, uint32_t F, std::vector<LzcItem>& items) {
     items.clear();
     const uint64_t n = h_fs[F];
-    uint64_t range = (n / 2072u + 31u) & ~(uint64_t)31u;
+    uint64_t range = (n / 1776u + 31u) & ~(uint64_t)31u;   // two waves of 6 one-warp blocks per SM
     if (range < LZC_PREROLL) range = LZC_PREROLL;
     for (uint32_t f = 0; f < F; f++) {
         const uint32_t len = h_fs[f + 1] - h_fs[f];
@@ -46,7 +46,7 @@ constexpr int LZC_STAGE_STEPS = 16;
 constexpr int LZC_STAGE_WORDS = 32 * 5;   // 640 bytes >= 32 * 16 + 3 + 3 bytes of misalignment
 
 __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs,
-                                                     const LzcItem* __restrict__ items, uint16_t* __restrict__ dh, uint16_t* __restrict__ rsd) {
+                                                     const LzcItem* __restrict__ items, uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd) {
     extern __shared__ uint32_t lzc_tab[];
     __shared__ uint32_t stage[2][LZC_STAGE_WORDS + 1];
     const LzcItem it = items[blockIdx.x];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__
             const uint32_t rs = upto ? s0 + (31u - (uint32_t)__clz(upto)) : run_start;
             if (bal) run_start = s0 + (31u - (uint32_t)__clz(bal));
             if (i >= it.start && i < it.end) {
-                dh[base + i] = (uint16_t)dist;
+                lwh[base + i] = dist | (w >> 8 & 0xFFFFu) << 16;
                 rsd[base + i] = (uint16_t)min(i - rs, 65535u);
             }
             __syncwarp();
@@ -116,177 +116,210 @@ __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__
     }
 }
 
-// ---- the tiled walker ------------------------------------------------------------------------------------------
-// A chain walk is a string of dependent 2-byte gathers into the 64 KB behind a position. From global memory such gathers
-// cost an L1 wavefront per lane (measured: the level kernels ran at exactly that limit, ~2 cycles per lane-gather); from
-// shared memory they are nearly free. So a block takes one frame at a time and visits its 16384-position tiles from the
-// LAST to the FIRST, holding only the current tile (links + bytes, 48 KB) in shared memory:
-//   * sweep: every position of the tile starts its walk. A first hop that stays inside the tile is checked on the spot
-//     (97 % of the first hops do, and most end the walk); otherwise the walker (12 bytes) is parked in the bin of the tile
-//     its next hop lands in;
-//   * drain: the walkers parked in this tile's bin - the tile's own and those that came down from the four tiles above -
-//     hop inside the tile until they end or leave it downwards (parked again, in a lower bin). Lanes refill from the bin as
-//     their walks end, so walks of very different lengths keep the warp full.
-// Because tiles go downwards, a bin is complete when its tile becomes resident, and every tile is loaded exactly once per
-// level. The bins live in global memory (L2): 5 bins per block, each sized for the worst case (every position of the five
-// tiles that can reach it). Four blocks are resident per SM, so one block's barrier waits hide behind the others' work.
-constexpr int LZT_LOG = 14, LZT_TILE = 1 << LZT_LOG;
-constexpr int LZT_BINS = 5;                                   // resident tile + the 4 below it (4 * 16384 >= 65535)
-constexpr int LZT_THREADS = 256;
-constexpr uint32_t LZT_BINCAP = (uint32_t)LZT_BINS * LZT_TILE;
-constexpr size_t LZT_ARENA_WORDS = (size_t)LZT_BINS * LZT_BINCAP * 3;   // per block: 3 words per parked walker
-constexpr int LZT_RAW = LZT_TILE + 32;                        // bytes of a tile + what a hop reads past its last position
-struct LztSmem {
-    uint4 sd4[LZT_TILE / 8 + 1];     // links of the tile (u16), shifted so that 16-byte chunks of the global array stay aligned
-    uint4 sraw4[LZT_RAW / 16 + 2];   // bytes of the tile, shifted likewise
-    uint32_t cnt[LZT_BINS];          // walkers parked per bin slot
-    uint32_t head;                   // next walker of the bin being drained
-    uint32_t frame;
+// largest f with fs[f] <= i and fs[f+1] > i (empty frames are skipped); i < fs[F]
+__device__ __forceinline__ uint32_t lzc_frame_of(const uint32_t* __restrict__ fs, uint32_t F, uint32_t i) {
+    uint32_t lo = 0, hi = F;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (fs[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- the walking kernels ---------------------------------------------------------------------------------------
+// A walk is a chain of dependent gathers whose length varies from position to position (most end at the first hop, a
+// few per cent must cross their whole window), so "one thread walks one position to the end" leaves most lanes of a warp
+// - and most warps of a block - waiting for the slowest one. Both kernels are therefore persistent warps that take
+// 512-position chunks from a global counter and work in two interleaved phases:
+//   sweep: a coalesced pass over a chunk that takes every position's FIRST hop (four independent rounds in flight) and
+//          finishes the positions it settles; the others are queued (shared memory, one word each);
+//   drain: the queue is worked off with lane refill - a lane whose walk ends takes the next queued position at once, so
+//          every hop instruction has (almost) all lanes doing useful work. When the queue runs low the warp sweeps its
+//          next chunk while the walks still in progress simply keep their state.
+constexpr int LZC_ROUNDS = 16;
+constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per chunk
+constexpr int LZC_WARPS = LZC_THREADS / 32;
+constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (lzc_pack_k)
+constexpr int LZC_MLP = 4;                            // rounds of a sweep in flight together
+constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
+
+// Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
+//     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
+template <class Op>
+__device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
+    const uint32_t lane = lane_id();
+    uint32_t qn = 0, qi = 0;
+    bool more = true, busy = false;
+    for (;;) {
+        if (more && qn - qi < 32u) {   // keep the leftovers, sweep the next chunk
+            const uint32_t left = qn - qi;
+            const uint32_t keep = lane < left ? q[qi + lane] : 0u;
+            __syncwarp();
+            if (lane < left) q[lane] = keep;
+            qn = left;
+            qi = 0;
+            uint32_t ch = 0;
+            if (lane == 0) ch = atomicAdd(counter, 1u);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
+            const uint64_t cb = (uint64_t)ch * LZC_WCHUNK;
+            if (cb >= n) more = false;
+            else qn += op.sweep((uint32_t)cb, q + qn);
+            __syncwarp();
+            continue;
+        }
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (qi < qn && idle) {
+            const uint32_t my = qi + __popc(idle & lanemask_lt());
+            if (!busy && my < qn) { op.begin(q[my]); busy = true; }
+            qi = min(qn, qi + (uint32_t)__popc(idle));
+        }
+        if (!__any_sync(0xffffffffu, busy)) {
+            if (!more) break;
+            continue;
+        }
+        if (busy && op.step()) busy = false;
+    }
+}
+
+struct LzcLink3Op {
+    const uint8_t* __restrict__ bs; const uint32_t* __restrict__ fs; uint32_t F, n;
+    const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3; uint8_t* __restrict__ bestlen;
+    LzcLink3Walk wlk;
+    uint32_t b23c;   // byte 2 | byte 3 << 8 | cap << 16 of the position being walked
+    uint32_t f_cur = 0, f_prev = 0;   // frames of the first position of the last two chunks swept: the queue only holds positions of those two
+    __device__ __forceinline__ uint32_t cap_of(uint32_t f, uint32_t p) const {   // min(15, bytes left in p's frame); f = a frame at or before p's
+        while (fs[f + 1] <= p) f++;
+        return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
+    }
+    __device__ __forceinline__ void put(uint32_t p, uint32_t nd, uint32_t b3, uint32_t cap) const {
+        const uint32_t lev = nd ? lzc_lcp(bs, p, p - nd, cap) : 0u;   // how far the level-3 link holds (lzchain_core.h)
+        lw3[p] = lzc_word(nd, b3, lev, cap);
+        if (!nd) bestlen[p] = 0;
+        else if (lev == (uint32_t)LZ_MAXLEN) bestlen[p] = (uint8_t)LZ_MAXLEN;
+    }
+    __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
+        const uint32_t lane = lane_id();
+        uint32_t f0 = 0;
+        if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
+        f0 = __shfl_sync(0xffffffffu, f0, 0);
+        f_prev = min(f_cur, f0);   // (chunks are handed out in increasing order, but not necessarily to the same warp)
+        f_cur = f0;
+        uint32_t qn = 0;
+        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+            uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane;
+                w[j] = 0; b23[j] = 0; cap[j] = 0;
+                if (p < n) { w[j] = lwh[p]; b23[j] = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8; cap[j] = cap_of(f0, p); }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                wk[j] = 0; k2[j] = 0;
+                if (cap[j] >= 3u && dist) { wk[j] = lwh[p - dist]; k2[j] = bs[p - dist + 2]; }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                bool pend = false;
+                if (p < n) {
+                    uint32_t nd = 0;
+                    if (cap[j] >= 3u && dist) {
+                        if ((wk[j] >> 16) == (w[j] >> 16) && k2[j] == (b23[j] & 0xFFu)) nd = dist;
+                        else pend = true;
+                    }
+                    if (!pend) put(p, nd, b23[j] >> 8, cap[j]);
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
+                qn += __popc(bal);
+            }
+        }
+        return qn;
+    }
+    __device__ __forceinline__ void begin(uint32_t p) {
+        const uint32_t cp = cap_of(f_prev, p);
+        b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
+        wlk.start(p, lwh[p], b23c & 0xFFu, cp);
+    }
+    __device__ __forceinline__ bool step() {
+        const int r = wlk.hop(bs, lwh, rsd);
+        if (r == LZC_GO) return false;
+        put(wlk.p, r == LZC_FOUND ? wlk.acc : 0u, (b23c >> 8) & 0xFFu, b23c >> 16);
+        return true;
+    }
 };
 
-// park walkers: lanes with `push` append w to bin slot `bin` (aggregated per bin: one shared-memory atomic per bin and warp)
-__device__ __forceinline__ void lzt_push(LztSmem& S, uint32_t* __restrict__ arena, bool push, uint32_t bin, const LzcWalker& w) {
-    if (!__ballot_sync(0xffffffffu, push)) return;
-    uint32_t slot = 0;
+struct LzcLevelOp {
+    const uint8_t* __restrict__ bs; uint32_t n, L;
+    const uint32_t* __restrict__ lw; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw_next;
+    uint32_t* __restrict__ match_rec; uint8_t* __restrict__ bestlen;
+    LzcLevelWalk wlk;
+    uint32_t nbc;   // byte L+1 | cap << 8 of the position being walked
+    // a walk that found the (L+1)-gram at distance nd: how far does that link hold?
+    __device__ __forceinline__ void found(uint32_t p, uint32_t nd, uint32_t nb, uint32_t cap) const {
+        const uint32_t lev = lzc_lcp(bs, p, p - nd, cap);
+        lw_next[p] = lzc_word(nd, nb, lev, cap);
+        if (lev == (uint32_t)LZ_MAXLEN) bestlen[p] = (uint8_t)LZ_MAXLEN;
+    }
+    __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
+        const uint32_t lane = lane_id();
+        uint32_t qn = 0;
+        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+            uint32_t w[LZC_MLP], nb[LZC_MLP];
 #pragma unroll
-    for (uint32_t b = 0; b < (uint32_t)LZT_BINS; b++) {
-        const unsigned m = __ballot_sync(0xffffffffu, push && bin == b);
-        if (m) {
-            const int leader = __ffs(m) - 1;
-            uint32_t b0 = 0;
-            if ((int)lane_id() == leader) b0 = atomicAdd(&S.cnt[b], (uint32_t)__popc(m));
-            b0 = __shfl_sync(0xffffffffu, b0, leader);
-            if (push && bin == b) slot = b0 + __popc(m & lanemask_lt());
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane;
+                w[j] = 0; nb[j] = 0;
+                if (p < n) { w[j] = lw[p]; nb[j] = bs[p + L + 1]; }
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu, lev = (w[j] >> 24) & 0xFu;
+                // dist == 0: no match of this length. lev > L: the link holds for the next level as well (copied, no gather).
+                // lev == L: the occurrence it points at differs in byte L (or the cap is reached): walk the chain.
+                const bool pend = p < n && dist && lev <= L;
+                if (p < n && !pend) lw_next[p] = lzc_word(dist, nb[j], dist ? lev : 0u, w[j] >> 28);
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
+                qn += __popc(bal);
+            }
         }
+        return qn;
     }
-    if (push && slot < LZT_BINCAP) {
-        uint32_t* e = arena + ((size_t)bin * LZT_BINCAP + slot) * 3;
-        e[0] = w.p;
-        e[1] = w.acc | w.dist << 16;
-        e[2] = w.key;
+    __device__ __forceinline__ void begin(uint32_t p) {
+        const uint32_t w = lw[p];
+        nbc = (uint32_t)bs[p + L + 1] | (w >> 28) << 8;
+        wlk.start(p, w, L, bs[p + L - 1]);
     }
+    __device__ __forceinline__ bool step() {
+        const int r = wlk.hop(lw, rsd);
+        if (r == LZC_GO) return false;
+        if (r == LZC_FOUND) found(wlk.p, wlk.acc, nbc & 0xFFu, nbc >> 8);
+        else {
+            lw_next[wlk.p] = lzc_word(0u, nbc & 0xFFu, 0u, nbc >> 8);
+            match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last;
+            bestlen[wlk.p] = (uint8_t)L;
+        }
+        return true;
+    }
+};
+
+__global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
+                                                           const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
+                                                           uint32_t* __restrict__ lw3, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
+    LzcLink3Op op{bs, fs, F, n, lwh, rsd, lw3, bestlen};
+    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
 }
 
-// copy `bytes` bytes from global `src` into shared memory in aligned 16-byte chunks; returns the byte offset of src[0] inside
-// dst (src & 15). May read up to 15 bytes before src and 15 after src + bytes (inside the same allocations).
-__device__ __forceinline__ uint32_t lzt_load(uint4* dst, const void* src, uint32_t bytes) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(src);
-    const uint32_t shift = (uint32_t)(a & 15u);
-    const uint4* g = reinterpret_cast<const uint4*>(a - shift);
-    const uint32_t chunks = (shift + bytes + 15u) >> 4;
-    for (uint32_t c = threadIdx.x; c < chunks; c += blockDim.x) dst[c] = g[c];
-    return shift;
-}
-
-// MODE 0: hash links -> level-3 links (L unused). MODE 1: level L -> L+1.
-template <int MODE>
-__global__ void __launch_bounds__(LZT_THREADS) lzt_pass_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t L,
-                                                          const uint16_t* __restrict__ din, const uint16_t* __restrict__ rsd, uint16_t* __restrict__ dout,
-                                                          uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen,
-                                                          uint32_t* __restrict__ arena, uint32_t* __restrict__ counter) {
-    extern __shared__ __align__(16) uint8_t lzt_smem_raw[];
-    LztSmem& S = *reinterpret_cast<LztSmem*>(lzt_smem_raw);
-    uint32_t* const my_arena = arena + (size_t)blockIdx.x * LZT_ARENA_WORDS;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const bool top = MODE == 1 && L + 1u == (uint32_t)LZ_MAXLEN;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) S.frame = atomicAdd(counter, 1u);
-        if (tid < (uint32_t)LZT_BINS) S.cnt[tid] = 0;
-        __syncthreads();
-        const uint32_t f = S.frame;
-        if (f >= F) break;
-        const uint32_t base = fs[f], len = fs[f + 1] - base;
-        const uint16_t* const g_in = din + base;
-        const uint16_t* const g_rsd = rsd + base;
-        const uint8_t* const raw = bs + base;
-        for (uint32_t j = (len + LZT_TILE - 1) >> LZT_LOG; j-- > 0;) {
-            const uint32_t t0 = j << LZT_LOG, cntp = min(len - t0, (uint32_t)LZT_TILE), slot = j % (uint32_t)LZT_BINS;
-            const uint32_t sh_d = lzt_load(S.sd4, g_in + t0, cntp * 2u);
-            const uint32_t sh_r = lzt_load(S.sraw4, raw + t0, cntp + 32u);   // bs is readable 64 bytes past the batch
-            if (tid == 0) S.head = 0;
-            __syncthreads();
-            const uint16_t* const sd = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(S.sd4) + sh_d);
-            const uint8_t* const sraw = reinterpret_cast<const uint8_t*>(S.sraw4) + sh_r;
-            // ---- sweep ----
-            for (uint32_t i0 = 0; i0 < cntp; i0 += LZT_THREADS) {
-                const uint32_t i = i0 + tid;
-                bool push = false;
-                uint32_t bin = 0;
-                LzcWalker w{0u, 0u, 0u, 0u};
-                if (i < cntp) {
-                    const uint32_t p = t0 + i, dist = sd[i], cap = min(len - p, (uint32_t)LZ_MAXLEN);
-                    if (!dist || (MODE == 0 && cap < (uint32_t)LZ_MINLEN)) {
-                        dout[base + p] = 0;
-                        if (MODE == 0) bestlen[base + p] = 0;
-                    } else {
-                        w.p = p;
-                        w.dist = dist;
-                        if (MODE == 0) w.key = (uint32_t)sraw[i] | (uint32_t)sraw[i + 1] << 8 | (uint32_t)sraw[i + 2] << 16;
-                        else w.key = lzc_level_key(sraw[i + L], sraw[i + L - 1], L + 1u <= cap);
-                        const uint32_t k = p - dist;
-                        if (k >= t0) {   // first hop inside the tile: settle it here if it ends the walk
-                            const uint32_t kk = k - t0;
-                            bool hit;
-                            if (MODE == 0) hit = ((uint32_t)sraw[kk] | (uint32_t)sraw[kk + 1] << 8 | (uint32_t)sraw[kk + 2] << 16) == w.key;
-                            else hit = ((w.key >> 8) & 1u) && sraw[kk + L] == (w.key & 0xFFu);
-                            if (hit) {
-                                dout[base + p] = (uint16_t)dist;
-                                if (top) bestlen[base + p] = (uint8_t)LZ_MAXLEN;
-                            } else { push = true; bin = slot; }
-                        } else { push = true; bin = (k >> LZT_LOG) % (uint32_t)LZT_BINS; }
-                    }
-                }
-                lzt_push(S, my_arena, push, bin, w);
-            }
-            __syncthreads();
-            // ---- drain ----
-            const uint32_t total = min(S.cnt[slot], LZT_BINCAP);
-            const uint32_t* const qa = my_arena + (size_t)slot * LZT_BINCAP * 3;
-            bool busy = false, dry = false;
-            LzcWalker w{0u, 0u, 0u, 0u};
-            for (;;) {
-                const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-                if (idle && !dry) {
-                    const int leader = __ffs(idle) - 1;
-                    uint32_t b0 = 0;
-                    if ((int)lane == leader) b0 = atomicAdd(&S.head, (uint32_t)__popc(idle));
-                    b0 = __shfl_sync(0xffffffffu, b0, leader);
-                    const uint32_t e = b0 + __popc(idle & lanemask_lt());
-                    if (!busy && e < total) {
-                        const uint32_t* q = qa + (size_t)e * 3;
-                        const uint32_t x = q[1];
-                        w.p = q[0]; w.acc = x & 0xFFFFu; w.dist = x >> 16; w.key = q[2];
-                        busy = true;
-                    }
-                    dry = b0 + (uint32_t)__popc(idle) >= total;
-                }
-                if (!__any_sync(0xffffffffu, busy)) break;
-                bool push = false;
-                uint32_t bin = 0;
-                if (busy) {
-                    const int r = MODE == 0 ? lzc_link3_hop(w, t0, sd, sraw, g_in, g_rsd) : lzc_level_hop(w, L, t0, sd, sraw, g_in, g_rsd);
-                    if (r == LZC_FOUND) {
-                        dout[base + w.p] = (uint16_t)w.acc;
-                        if (top) bestlen[base + w.p] = (uint8_t)LZ_MAXLEN;
-                        busy = false;
-                    } else if (r == LZC_END) {
-                        dout[base + w.p] = 0;
-                        if (MODE == 0) bestlen[base + w.p] = 0;
-                        else { match_rec[base + w.p] = L << 28 | LZC_RESOLVED | w.acc; bestlen[base + w.p] = (uint8_t)L; }
-                        busy = false;
-                    } else if (r == LZC_LEAVE) {
-                        push = true;
-                        bin = ((w.p - w.acc - w.dist) >> LZT_LOG) % (uint32_t)LZT_BINS;
-                        busy = false;
-                    }
-                }
-                lzt_push(S, my_arena, push, bin, w);
-            }
-            __syncthreads();
-            if (tid == 0) S.cnt[slot] = 0;
-        }
-    }
+__global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
+                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next,
+                                                           uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
+    LzcLevelOp op{bs, n, L, lw, rsd, lw_next, match_rec, bestlen};
+    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
 }
 
 __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ wbase) {
@@ -294,13 +327,9 @@ __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_
     if (i <= F) wbase[i] = (uint32_t)(((uint64_t)fs[i] * 9u) >> 5) + 3u * i;
 }
 
-// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165). Literals and matches
-// shorter than 15 bytes are emitted in a coalesced sweep; the 15-byte matches of the parse (the only positions whose earliest
-// start is still unknown) walk their level-15 chain to its end, queued per warp and drained with lane refill.
-constexpr int LZC_ROUNDS = 16;
-constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per warp
-constexpr int LZC_WARPS = LZC_THREADS / 32;
-constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block
+// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165). Same two phases as the
+// walking kernels: literals and matches shorter than 15 bytes are emitted in the sweep, the 15-byte matches of the parse
+// (the only positions whose earliest start is still unknown) walk their level-15 chain to its end with lane refill.
 __device__ __forceinline__ void lzc_emit(uint32_t* __restrict__ out_words, uint32_t wb, uint32_t rel, uint32_t v, uint32_t nb) {
     const uint32_t w = wb + (rel >> 5), sh = rel & 31;
     atomicOr(&out_words[w], v << sh);
@@ -308,27 +337,26 @@ __device__ __forceinline__ void lzc_emit(uint32_t* __restrict__ out_words, uint3
 }
 __global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint8_t* __restrict__ bestlen,
                                                           const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum,
-                                                          const uint16_t* __restrict__ d15, const uint16_t* __restrict__ rsd,
+                                                          const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
                                                           const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
     __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
     const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
     const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t fbase = fs[f], cbase = blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK, flen = fs[f + 1] - fbase;   // frame-relative chunk
-    if (cbase >= flen) return;
+    const uint32_t cbase = fs[f] + blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK, end = fs[f + 1];
+    if (cbase >= end) return;
     const uint32_t wb = wbase[f];
-    const uint32_t* const bc = bitcum + fbase;
     uint32_t qn = 0;
 #pragma unroll 4
     for (int r = 0; r < LZC_ROUNDS; r++) {
         const uint32_t i = cbase + r * 32 + lane;
         bool pend = false;
-        if (i < flen) {
-            const uint32_t rel = bc[i];
+        if (i < end) {
+            const uint32_t rel = bitcum[i];
             if (rel != EMPTY32) {
-                const uint32_t l = bestlen[fbase + i];
+                const uint32_t l = bestlen[i];
                 if (l == (uint32_t)LZ_MAXLEN) pend = true;
-                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((match_rec[fbase + i] & 0xFFFFu) << 1) | (l << 17), 21);
-                else lzc_emit(out_words, wb, rel, 1u | ((uint32_t)bs[fbase + i] << 1), 9);
+                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((match_rec[i] & 0xFFFFu) << 1) | (l << 17), 21);
+                else lzc_emit(out_words, wb, rel, 1u | ((uint32_t)bs[i] << 1), 9);
             }
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pend);
@@ -338,22 +366,21 @@ __global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restr
     __syncwarp();
     uint32_t qi = 0;
     bool busy = false;
-    LzcWalker w{0u, 0u, 0u, 0u};
+    LzcEndWalk wlk;
     for (;;) {
         const unsigned idle = __ballot_sync(0xffffffffu, !busy);
         if (qi < qn && idle) {
             const uint32_t my = qi + __popc(idle & lanemask_lt());
             if (!busy && my < qn) {
-                w.p = cbase + q[warp][my];
-                w.acc = 0;
-                w.dist = d15[fbase + w.p];   // a 15-byte match: the link is never 0
+                const uint32_t p = cbase + q[warp][my];
+                wlk.start(p, lw15[p]);   // a 15-byte match: the link is never 0
                 busy = true;
             }
             qi += __popc(idle);
         }
         if (!__any_sync(0xffffffffu, busy)) break;
-        if (busy && lzc_end_hop(w, d15 + fbase, rsd + fbase) != LZC_GO) {
-            lzc_emit(out_words, wb, bc[w.p], (w.acc << 1) | ((uint32_t)LZ_MAXLEN << 17), 21);
+        if (busy && wlk.hop(lw15, rsd) != LZC_GO) {
+            lzc_emit(out_words, wb, bitcum[wlk.p], (wlk.last << 1) | ((uint32_t)LZ_MAXLEN << 17), 21);
             busy = false;
         }
     }

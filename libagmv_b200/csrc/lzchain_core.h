@@ -16,19 +16,16 @@
 //   * a position whose walk runs off the window has no longer match; the walk has then visited its whole level-L chain,
 //     and the LAST element it saw is the earliest occurrence inside the window - the start the reference picks.
 //
-// So no position is ever sorted or moved: a level reads one 16-bit link per position and writes one. The level-3 links
-// come from a hashed "previous occurrence" table (lzchain.cuh: lzc_hashlink_k) refined by lzc_link3_hop below.
+// So no position is ever sorted or moved: a level is one streaming pass (4 B in, 4 B out per position) plus a few
+// gathers into the previous 64 KB of the same array, which sit in L1 / L2. The level-3 links come from a hashed
+// "previous occurrence" table (lzchain.cuh: lzc_hashlink_k) refined by LzcLink3Walk below.
 //
 // Byte runs are the one input on which a chain walk degenerates (every position of a long run is on the chain of every
 // other one). They are skipped exactly: when the walk stands on an element k whose link is 1, k-1 .. runstart(k) all carry
 // the same L-gram (all one byte b) and the same byte L (b again), so if b is not the byte looked for none of them can
 // end the walk, and the walk continues from the run's first position.
 //
-// A walk is taken one hop at a time against ONE TILE of the frame held in fast memory (the links and the bytes of
-// positions [t0, t0 + tile)): a hop whose target lies below the tile returns LZC_LEAVE with the walker unchanged, to be
-// resumed when that lower tile is resident (lzchain.cuh processes a frame's tiles from the last to the first).
-//
-// This header is plain C++ (no CUDA types): the kernels in lzchain.cuh drive these functions, and
+// This header is plain C++ (no CUDA types): the kernels in lzchain.cuh drive these state machines one hop at a time, and
 // tests/lzchain_host_check.cpp compiles them for the host to check the logic against a brute-force search.
 #pragma once
 #include <stddef.h>
@@ -36,8 +33,10 @@
 
 #ifdef __CUDACC__
 #define LZC_HD __host__ __device__ __forceinline__
+#define LZC_HDM __host__ __device__ __forceinline__
 #else
 #define LZC_HD static inline
+#define LZC_HDM inline
 #endif
 
 namespace agmvb {
@@ -45,85 +44,132 @@ namespace agmvb {
 constexpr uint32_t LZC_WINDOW = 65535u;     // src/agmv_encode.c:102
 constexpr uint32_t LZC_RESOLVED = 1u << 27; // match_rec: length << 28 | LZC_RESOLVED | offset
 
+// Link words: low 16 bits = dist, then key bits.
+//   hash level (lzc_hashlink_k): dist to the previous position with the same 3-gram hash | byte0 << 16 | byte1 << 24
+//   level L >= 3:  dist_L | byte[p+L] << 16 | lev << 24 | cap << 28
+//     cap = min(15, bytes left in the frame from p on): the reference caps a match there (src/agmv_encode.c:121-123)
+//     lev = min(cap, number of leading bytes p shares with p - dist_L): the occurrence the link points at stays the most
+//           recent one for every length up to lev (a nearer occurrence of a longer gram would be a nearer occurrence of the
+//           shorter one too), so dist_L' == dist_L for all L <= L' <= lev and the position is simply copied through those
+//           levels - no gather, no walk. It is looked at again at level lev, where the bytes differ (or the cap is reached).
+//           On this codec's bitstreams 45-60 % of the positions reach lev = 15 straight from their level-3 link.
 LZC_HD uint32_t lzc_hash(uint32_t gram24, int bits) { return (gram24 * 2654435761u) >> (32 - bits); }
+LZC_HD uint32_t lzc_word(uint32_t dist, uint32_t byte_l, uint32_t lev, uint32_t cap) { return dist | byte_l << 16 | lev << 24 | cap << 28; }
 
-enum { LZC_GO = 0, LZC_FOUND = 1, LZC_END = 2, LZC_LEAVE = 3 };
-
-// A walk in progress. p = position (frame-relative), acc = distance already covered (p - acc is the chain element the walk
-// stands on; acc == 0: still on p itself), dist = link of that element (the next hop), key:
-//   level walk: byte L of p | ext << 8 | neq << 9   (ext: a match of length L+1 fits before the frame end - the reference
-//               caps matches there, src/agmv_encode.c:121-123; neq: byte L of p differs from byte L-1 of p)
-//   link3 walk: the three bytes at p
-struct LzcWalker { uint32_t p, acc, dist, key; };
-
-LZC_HD uint32_t lzc_level_key(uint32_t byte_l, uint32_t byte_before, bool ext) { return byte_l | (ext ? 1u << 8 : 0u) | (byte_l != byte_before ? 1u << 9 : 0u); }
-
-// One hop of a level-L walk. sd / sraw: links and bytes of the resident tile, indexed by (position - t0); sraw reaches 32
-// bytes past the tile. g_dl / g_rsd: the frame's whole link / run-start-distance arrays (used by the run skip only).
-//   LZC_FOUND: w.acc = dist_{L+1}[p].   LZC_END: no match of length L+1; w.acc = offset of the EARLIEST level-L occurrence
-//   inside the window, i.e. of p's final match of length L.   LZC_LEAVE: resume in the tile that holds p - w.acc - w.dist.
-LZC_HD int lzc_level_hop(LzcWalker& w, uint32_t L, uint32_t t0, const uint16_t* sd, const uint8_t* sraw, const uint16_t* g_dl, const uint16_t* g_rsd) {
-    const uint32_t nacc = w.acc + w.dist;
-    if (nacc > LZC_WINDOW) return LZC_END;
-    const uint32_t k = w.p - nacc;
-    if (k < t0) return LZC_LEAVE;
-    w.acc = nacc;
-    const bool ext = (w.key >> 8) & 1u, neq = (w.key >> 9) & 1u;
-    if (ext && sraw[k - t0 + L] == (w.key & 0xFFu)) return LZC_FOUND;
-    w.dist = sd[k - t0];
-    if (w.dist == 1u && (!ext || neq)) {
-        // k stands inside a run of one byte b (its L-gram, hence p's, is all b, and neq says p's byte L is not b):
-        // everything back to the run start is on the chain and carries byte L == b
-        const uint32_t r = g_rsd[k];
-        if (w.acc + r > LZC_WINDOW) { w.acc = LZC_WINDOW; return LZC_END; }   // the window ends inside the run: p - 65535 is on the chain
-        w.acc += r;
-        const uint32_t s = k - r;
-        w.dist = s >= t0 ? sd[s - t0] : g_dl[s];
-    }
-    return w.dist ? LZC_GO : LZC_END;
+// bytes 0..15 at address a (any alignment) as two 64-bit words, from three aligned loads
+LZC_HD void lzc_load16(const uint8_t* a, uint64_t& lo, uint64_t& hi) {
+    const uintptr_t x = reinterpret_cast<uintptr_t>(a);
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(x & ~(uintptr_t)7);
+    const uint32_t sh = (uint32_t)(x & 7u) * 8u;
+    const uint64_t w0 = w[0], w1 = w[1], w2 = w[2];
+    lo = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
+    hi = sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1;
+}
+LZC_HD uint32_t lzc_ctz64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return (uint32_t)(__ffsll((long long)v) - 1);
+#else
+    return (uint32_t)__builtin_ctzll(v);
+#endif
+}
+// min(cap, number of leading bytes d[p..] and d[q..] share), cap <= 15. Reads up to 23 bytes past either position and up to
+// 7 before it (inside the batch buffer and its padding).
+LZC_HD uint32_t lzc_lcp(const uint8_t* d, uint32_t p, uint32_t q, uint32_t cap) {
+    uint64_t a0, a1, b0, b1;
+    lzc_load16(d + p, a0, a1);
+    lzc_load16(d + q, b0, b1);
+    const uint64_t x0 = a0 ^ b0, x1 = a1 ^ b1;
+    const uint32_t l = x0 ? lzc_ctz64(x0) >> 3 : (x1 ? 8u + (lzc_ctz64(x1) >> 3) : 16u);
+    return l < cap ? l : cap;
 }
 
-// One hop of a hash-chain walk towards the most recent earlier position with p's three bytes (level 3).
-//   LZC_FOUND: w.acc = dist_3[p].   LZC_END: none inside the window.
-LZC_HD int lzc_link3_hop(LzcWalker& w, uint32_t t0, const uint16_t* sd, const uint8_t* sraw, const uint16_t* g_dh, const uint16_t* g_rsd) {
-    const uint32_t nacc = w.acc + w.dist;
-    if (nacc > LZC_WINDOW) return LZC_END;
-    const uint32_t k = w.p - nacc;
-    if (k < t0) return LZC_LEAVE;
-    w.acc = nacc;
-    const uint8_t* q = sraw + (k - t0);
-    const uint32_t b0 = q[0], b1 = q[1], b2 = q[2];
-    if ((b0 | b1 << 8 | b2 << 16) == w.key) return LZC_FOUND;
-    w.dist = sd[k - t0];
-    // run skip: k reads b,b,b and so does k-1 (its link is 1): every position back to the run start has the same gram,
-    // hence the same hash, and is the next chain element; none of them is p's gram (k was not)
-    if (w.dist == 1u && b0 == b1 && b1 == b2) {
-        const uint32_t r = g_rsd[k];
-        if (r) {
-            if (w.acc + r > LZC_WINDOW) return LZC_END;
-            w.acc += r;
-            const uint32_t s = k - r;
-            w.dist = s >= t0 ? sd[s - t0] : g_dh[s];
+enum { LZC_GO = 0, LZC_FOUND = 1, LZC_END = 2 };
+
+// level 3 from the hash chain: most recent earlier position with the same three bytes, within the window.
+// Usage: if (start(...)) while ((r = hop(...)) == LZC_GO); r == LZC_FOUND: acc = dist_3.
+struct LzcLink3Walk {
+    uint32_t p, acc, dist, key;   // key = byte0 | byte1 << 8 | byte2 << 16
+    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t byte2, uint32_t cap) {
+        p = p_; acc = 0; dist = w & 0xFFFFu; key = (w >> 16) | byte2 << 16;
+        return cap >= 3u && dist != 0u;
+    }
+    LZC_HDM int hop(const uint8_t* d, const uint32_t* lwh, const uint16_t* rsd) {
+        acc += dist;
+        if (acc > LZC_WINDOW) return LZC_END;
+        const uint32_t k = p - acc, wk = lwh[k], g01 = wk >> 16;
+        if (g01 == (key & 0xFFFFu) && d[k + 2] == (key >> 16)) return LZC_FOUND;
+        dist = wk & 0xFFFFu;
+        // run skip: k reads b,b,b and so does k-1 (its link is 1): every position back to the run start has the same
+        // gram, hence the same hash, and is the next chain element; none of them is p's gram (k was not)
+        if (dist == 1u && (g01 & 0xFFu) == (g01 >> 8) && d[k + 2] == (g01 & 0xFFu)) {
+            const uint32_t r = rsd[k];
+            if (r) {
+                if (acc + r > LZC_WINDOW) return LZC_END;
+                acc += r;
+                dist = lwh[p - acc] & 0xFFFFu;
+            }
         }
+        return dist ? LZC_GO : LZC_END;
     }
-    return w.dist ? LZC_GO : LZC_END;
-}
+};
 
-// positions whose match reaches 15 bytes: one hop towards the end of the level-15 chain; on LZC_END w.acc is the offset
-// of the earliest occurrence of the 15-gram inside the window. (g15 / g_rsd: whole-frame arrays, w.key unused.)
-LZC_HD int lzc_end_hop(LzcWalker& w, const uint16_t* g15, const uint16_t* g_rsd) {
-    const uint32_t nacc = w.acc + w.dist;
-    if (nacc > LZC_WINDOW) return LZC_END;
-    w.acc = nacc;
-    const uint32_t k = w.p - nacc;
-    w.dist = g15[k];
-    if (w.dist == 1u) {   // inside a run: every position back to its start carries the same 15 bytes
-        const uint32_t r = g_rsd[k];
-        if (w.acc + r > LZC_WINDOW) { w.acc = LZC_WINDOW; return LZC_END; }
-        w.acc += r;
-        w.dist = g15[k - r];
+// one level: dist_{L+1}[p] from the level-L links, for a position whose lev == L (see above; positions with lev > L are
+// copied, positions with dist == 0 have no match of length L).
+// r == LZC_FOUND: acc = dist_{L+1}. r == LZC_END: no match of length L+1; `last` = distance to the EARLIEST level-L
+// occurrence inside the window, i.e. the offset of p's final (length L) match.
+struct LzcLevelWalk {
+    uint32_t p, acc, last, dist, c;
+    bool ext, neq;
+    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t L, uint32_t byte_before) {
+        p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; c = (w >> 16) & 0xFFu;
+        ext = L + 1u <= (w >> 28);
+        neq = c != byte_before;   // byte L of p differs from byte L-1 of p
+        return dist != 0u;
     }
-    return w.dist ? LZC_GO : LZC_END;
+    LZC_HDM int hop(const uint32_t* lw, const uint16_t* rsd) {
+        acc += dist;
+        if (acc > LZC_WINDOW) return LZC_END;
+        const uint32_t wk = lw[p - acc];
+        if (ext && ((wk >> 16) & 0xFFu) == c) return LZC_FOUND;
+        last = acc;
+        dist = wk & 0xFFFFu;
+        if (dist == 1u && (!ext || neq)) {
+            // the element stands inside a run of one byte b (its L-gram, hence p's, is all b, and neq says p's byte L is
+            // not b): everything back to the run start is on the chain and carries byte L == b
+            const uint32_t r = rsd[p - acc];
+            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }   // the window ends inside the run: p - 65535 is on the chain
+            acc += r;
+            last = acc;
+            dist = lw[p - acc] & 0xFFFFu;
+        }
+        return dist ? LZC_GO : LZC_END;
+    }
+};
+
+// positions whose match reaches 15 bytes: `last` ends as the offset of the earliest occurrence of the 15-gram inside the
+// window (the end of the level-15 chain). Usage: start(); while (hop(...) == LZC_GO);
+struct LzcEndWalk {
+    uint32_t p, acc, last, dist;
+    LZC_HDM bool start(uint32_t p_, uint32_t w) { p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; return dist != 0u; }
+    LZC_HDM int hop(const uint32_t* lw15, const uint16_t* rsd) {
+        acc += dist;
+        if (acc > LZC_WINDOW) return LZC_END;
+        last = acc;
+        dist = lw15[p - acc] & 0xFFFFu;
+        if (dist == 1u) {   // inside a run: every position back to its start carries the same 15 bytes
+            const uint32_t r = rsd[p - acc];
+            if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }
+            acc += r;
+            last = acc;
+            dist = lw15[p - acc] & 0xFFFFu;
+        }
+        return dist ? LZC_GO : LZC_END;
+    }
+};
+LZC_HD uint32_t lzc_chain_end(const uint32_t* lw15, const uint16_t* rsd, uint32_t p) {
+    LzcEndWalk w;
+    if (w.start(p, lw15[p])) while (w.hop(lw15, rsd) == LZC_GO) {}
+    return w.last;
 }
 
 }  // namespace agmvb

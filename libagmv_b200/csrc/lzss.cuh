@@ -67,13 +67,12 @@ struct LzWork {
     uint32_t* run_ws = nullptr;          // run tables of the large three-equal-byte groups (cap_n words)
     bool runs = false;                   // AGMVB_LZ_RUNS: resolve those groups from run tables instead of the global levels
     bool legacy = false;                 // AGMVB_LZ_LEGACY=1: the radix-refinement match finder below instead of lzchain.cuh
-    uint16_t* dl[2] = {};                // chain path: level links, ping-pong (dl[1] doubles as the hash-level links)
-    uint32_t* arena = nullptr;           // chain path: parked walkers of the tiled passes (LZT_ARENA_WORDS per resident block)
+    uint32_t* lw[2] = {};                // chain path: link words, ping-pong (lw[1] doubles as the hash-level links)
     uint16_t* rsd = nullptr;             // chain path: distance of every position to the start of its byte run
     LzcItem* items = nullptr;            // chain path: (frame, range) work items of lzc_hashlink_k
     uint32_t n_items = 0, cap_items = 0;
     uint32_t* counters = nullptr;        // chain path: chunk counters of the persistent kernels (one per launch of a batch)
-    uint32_t pass_blocks = 148 * 4;      // chain path: resident blocks of the tiled passes
+    uint32_t link3_blocks = 148 * 5, level_blocks = 148 * 6;   // chain path: resident blocks of the persistent walking kernels
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
     uint32_t* seg_len = nullptr;         // cap_frames
@@ -1227,26 +1226,26 @@ inline void lzss_encode_batch_chain(LzWork& wk, const uint8_t* bs, const uint32_
                                     uint32_t first_frame_count, uint8_t* image, LaunchCtx& lc) {
     cudaStream_t st = lc.st;
     KL(lc, KC_LZ_INIT, (lzc_wbase_k<<<cdiv(F + 1, 256), 256, 0, st>>>(fs, F, wk.wbase)));
-    const uint16_t* d15 = wk.dl[0];
+    const uint32_t* lw15 = wk.lw[0];
     if (n > 0) {
         cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
+        // persistent walking kernels: enough warps to fill the GPU, chunks handed out through one counter per launch
+        const uint32_t nb3 = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.link3_blocks), nb = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.level_blocks);
         cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
-        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, n, fs, wk.items, wk.dl[1], wk.rsd)));
-        const uint32_t nb = std::min<uint32_t>(F, wk.pass_blocks);
-        KL(lc, KC_LZ_LINK3, (lzt_pass_k<0><<<nb, LZT_THREADS, sizeof(LztSmem), st>>>(bs, fs, F, 0u, wk.dl[1], wk.rsd, wk.dl[0], wk.match_rec, wk.bestlen,
-                                                                                    wk.arena, wk.counters)));
+        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd)));
+        KL(lc, KC_LZ_LINK3, (lzc_link3_k<<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen, wk.counters)));
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
-            KL(lc, KC_LZ_LEVEL, (lzt_pass_k<1><<<nb, LZT_THREADS, sizeof(LztSmem), st>>>(bs, fs, F, L, wk.dl[cur], wk.rsd, wk.dl[cur ^ 1], wk.match_rec, wk.bestlen,
-                                                                                        wk.arena, wk.counters + (L - LZ_MINLEN + 1))));
-        d15 = wk.dl[cur];
+            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen,
+                                                                         wk.counters + (L - LZ_MINLEN + 1))));
+        lw15 = wk.lw[cur];
     }
     orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
     if (n > 0) {
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         dim3 pgrid(cdiv(max_usize, (uint32_t)LZC_BCHUNK), F);
-        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, d15, wk.rsd, wk.wbase, wk.out_words)));
+        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);

@@ -15,26 +15,26 @@
 using namespace agmvb;
 
 static const int HB = 13;
-static uint32_t TILE = 16384;   // positions per tile (the kernels use 16384; smaller values exercise the tile crossings harder)
 
 struct Result { std::vector<uint8_t> len; std::vector<uint32_t> off; };
 
-// The pipeline as the kernels run it: hash links in position order, then per level every frame's tiles from the last to the
-// first; a walker that leaves the resident tile is parked in the bin of the tile its next hop lands in.
-// fs = starts of the frames inside data (last entry = n).
+// the pipeline as the kernels run it; frames = starts of the frames inside d (last entry = n)
 static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector<uint32_t>& fs) {
     const size_t n = fs.back();
     std::vector<uint8_t> d(data);
-    d.resize(n + 64, 0xA5);
-    std::vector<uint16_t> dh(n), dl[2], rsd(n);
-    dl[0].resize(n); dl[1].resize(n);
+    d.resize(n + 32, 0xA5);
+    std::vector<uint32_t> lwh(n), lw[2];
+    lw[0].resize(n); lw[1].resize(n);
+    std::vector<uint16_t> rsd(n);
     Result R; R.len.assign(n, 0); R.off.assign(n, 0);
+    std::vector<uint32_t> rem(n);
     for (size_t f = 0; f + 1 < fs.size(); f++) {
         const size_t base = fs[f], len = fs[f + 1] - fs[f];
         std::vector<uint32_t> tab((size_t)1 << HB, 0);
         size_t runstart = 0;
         for (size_t i = 0; i < len; i++) {
             const size_t p = base + i;
+            rem[p] = (uint32_t)(len - i);
             if (i == 0 || d[p] != d[p - 1]) runstart = i;
             rsd[p] = (uint16_t)std::min<size_t>(i - runstart, 65535);
             uint32_t dist = 0;
@@ -44,69 +44,54 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
                 if (old && i - (old - 1) <= LZC_WINDOW) dist = (uint32_t)(i - (old - 1));
                 tab[h] = (uint32_t)i + 1;
             }
-            dh[p] = (uint16_t)dist;
+            lwh[p] = dist | (uint32_t)d[p] << 16 | (uint32_t)d[p + 1] << 24;
         }
     }
-    // one tiled pass over every frame: mode 0 = link3 (in: dh, out: dl[0]), mode L >= 3 = level L -> L+1
-    auto pass = [&](uint32_t L, const std::vector<uint16_t>& in, std::vector<uint16_t>& out) {
-        for (size_t f = 0; f + 1 < fs.size(); f++) {
-            const uint32_t base = fs[f], len = fs[f + 1] - fs[f];
-            const uint8_t* raw = d.data() + base;
-            const uint16_t* g_in = in.data() + base;
-            const uint16_t* g_rsd = rsd.data() + base;
-            const uint32_t ntile = (len + TILE - 1) / TILE;
-            std::vector<std::vector<LzcWalker>> bins(ntile);
-            auto finish = [&](const LzcWalker& w, int r) {
-                const uint32_t p = w.p;
-                if (r == LZC_FOUND) { out[base + p] = (uint16_t)w.acc; if (L == 14) { R.len[base + p] = 15; } }
-                else {
-                    out[base + p] = 0;
-                    if (L >= 3) { R.len[base + p] = (uint8_t)L; R.off[base + p] = w.acc; }
-                }
-            };
-            for (uint32_t j = ntile; j-- > 0;) {
-                const uint32_t t0 = j * TILE, tend = std::min(len, t0 + TILE);
-                const uint16_t* sd = g_in + t0;
-                const uint8_t* sraw = raw + t0;
-                // sweep: every position of the tile starts its walk
-                for (uint32_t p = t0; p < tend; p++) {
-                    const uint32_t dist = sd[p - t0], cap = std::min<uint32_t>(15u, len - p);
-                    if (!dist || (L == 0 && cap < 3)) { out[base + p] = 0; continue; }
-                    LzcWalker w{p, 0u, dist, 0u};
-                    if (L == 0) w.key = raw[p] | raw[p + 1] << 8 | raw[p + 2] << 16;
-                    else w.key = lzc_level_key(raw[p + L], raw[p + L - 1], L + 1 <= cap);
-                    const uint32_t k = p - dist;   // dist <= p by construction
-                    bins[k >= t0 ? j : k / TILE].push_back(w);
-                }
-                // drain the tile's bin
-                for (size_t e = 0; e < bins[j].size(); e++) {
-                    LzcWalker w = bins[j][e];
-                    int r;
-                    do r = L == 0 ? lzc_link3_hop(w, t0, sd, sraw, g_in, g_rsd) : lzc_level_hop(w, L, t0, sd, sraw, g_in, g_rsd);
-                    while (r == LZC_GO);
-                    if (r == LZC_LEAVE) {
-                        const uint32_t tk = (w.p - w.acc - w.dist) / TILE;
-                        if (tk >= j || (TILE == 16384 && tk + 4 < j)) { printf("bad leave: tile %u -> %u\n", j, tk); exit(3); }
-                        bins[tk].push_back(w);
-                    } else finish(w, r);
-                }
-                bins[j].clear();
-                bins[j].shrink_to_fit();
-            }
+    for (size_t p = 0; p < n; p++) {
+        const uint32_t cap = std::min<uint32_t>(rem[p], 15u);
+        LzcLink3Walk wk;
+        uint32_t d3 = 0;
+        if (wk.start((uint32_t)p, lwh[p], d[p + 2], cap)) {
+            int r;
+            while ((r = wk.hop(d.data(), lwh.data(), rsd.data())) == LZC_GO) {}
+            if (r == LZC_FOUND) d3 = wk.acc;
         }
-    };
-    pass(0, dh, dl[0]);
+        const uint32_t lev = d3 ? lzc_lcp(d.data(), (uint32_t)p, (uint32_t)p - d3, cap) : 0u;
+        if (lev == 15) R.len[p] = 15;
+        lw[0][p] = lzc_word(d3, d[p + 3], lev, cap);
+    }
     int cur = 0;
-    for (uint32_t L = 3; L < 15; L++, cur ^= 1) pass(L, dl[cur], dl[cur ^ 1]);
-    // 15-byte matches: earliest start = end of the level-15 chain (lzc_pack_k)
-    for (size_t f = 0; f + 1 < fs.size(); f++) {
-        const uint32_t base = fs[f], len = fs[f + 1] - fs[f];
-        for (uint32_t p = 0; p < len; p++) {
-            if (R.len[base + p] != 15) continue;
-            LzcWalker w{p, 0u, dl[cur][base + p], 0u};
-            while (lzc_end_hop(w, dl[cur].data() + base, rsd.data() + base) == LZC_GO) {}
-            R.off[base + p] = w.acc;
+    size_t walks = 0, copies = 0;
+    for (uint32_t L = 3; L < 15; L++) {
+        for (size_t p = 0; p < n; p++) {
+            const uint32_t w = lw[cur][p], cap = w >> 28, lev = (w >> 24) & 0xFu;
+            if ((w & 0xFFFFu) && lev > L) {   // the link holds for the next level too
+                lw[cur ^ 1][p] = lzc_word(w & 0xFFFFu, d[p + L + 1], lev, cap);
+                copies++;
+                continue;
+            }
+            LzcLevelWalk wk;
+            uint32_t nd = 0, nlev = 0;
+            if (wk.start((uint32_t)p, w, L, d[p + L - 1])) {
+                walks++;
+                if (lev != L) { printf("lev %u at level %u (p=%zu)\n", lev, L, p); exit(3); }
+                int r;
+                while ((r = wk.hop(lw[cur].data(), rsd.data())) == LZC_GO) {}
+                if (r == LZC_FOUND) {
+                    nd = wk.acc;
+                    nlev = lzc_lcp(d.data(), (uint32_t)p, (uint32_t)p - nd, cap);
+                    if (nlev <= L) { printf("lcp %u after a match of %u (p=%zu)\n", nlev, L + 1, p); exit(3); }
+                    if (nlev == 15) R.len[p] = 15;
+                } else { R.len[p] = (uint8_t)L; R.off[p] = wk.last; }
+            }
+            lw[cur ^ 1][p] = lzc_word(nd, d[p + L + 1], nlev, cap);
         }
+        cur ^= 1;
+    }
+    if (getenv("LZC_STATS")) printf("  level visits: %zu walks, %zu copies, n=%zu\n", walks, copies, n);
+    for (size_t p = 0; p < n; p++) {
+        if (((lw[cur][p] & 0xFFFFu) != 0) != (R.len[p] == 15)) { printf("level-15 link and bestlen disagree at %zu\n", p); exit(3); }
+        if (R.len[p] == 15) R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p);
     }
     return R;
 }
@@ -139,15 +124,8 @@ static Result brute(const std::vector<uint8_t>& data, const std::vector<uint32_t
 static uint32_t rng_state = 12345;
 static uint32_t rnd() { rng_state = rng_state * 1664525u + 1013904223u; return rng_state >> 8; }
 
-static int check1(const char* name, const std::vector<uint8_t>& data, const std::vector<uint32_t>& fs, const Result& b);
 static int check(const char* name, const std::vector<uint8_t>& data, const std::vector<uint32_t>& fs) {
-    const Result b = brute(data, fs);
-    int bad = 0;
-    for (uint32_t t : {16384u, 1024u}) { TILE = t; bad += check1(name, data, fs, b); }
-    return bad;
-}
-static int check1(const char* name, const std::vector<uint8_t>& data, const std::vector<uint32_t>& fs, const Result& b) {
-    Result a = chain_pipeline(data, fs);
+    Result a = chain_pipeline(data, fs), b = brute(data, fs);
     size_t nm = 0;
     for (size_t p = 0; p < fs.back(); p++) {
         if (a.len[p] != b.len[p] || (b.len[p] && a.off[p] != b.off[p])) {
@@ -157,7 +135,7 @@ static int check1(const char* name, const std::vector<uint8_t>& data, const std:
     }
     size_t matched = 0;
     for (size_t p = 0; p < fs.back(); p++) matched += b.len[p] != 0;
-    printf("%-28s tile=%5u n=%8u frames=%2zu matched=%8zu %s\n", name, TILE, fs.back(), fs.size() - 1, matched, nm ? "MISMATCH" : "ok");
+    printf("%-28s n=%8u frames=%2zu matched=%8zu %s\n", name, fs.back(), fs.size() - 1, matched, nm ? "MISMATCH" : "ok");
     return nm ? 1 : 0;
 }
 
