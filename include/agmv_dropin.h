@@ -125,6 +125,11 @@ void AGMV_ExportAudioType(FILE* audio, AGMV* agmv, AGMV_AUDIO_TYPE audio_type);
 int AGMV_DecodeHeader(FILE* file, AGMV* agmv);
 int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv);
 int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type);
+/* the rest of include/agmv_decode.h:23-25, defined in src/agmv_decode.c:455-525 (frames only), :682-767 (audio track only) and
+ * :649-680 (AIFF sample-rate field; called from the reference's agmv_utils.c:1457,1510, so whoever replaces agmv_decode.o owes it) */
+int AGMV_DecodeVideo(const char* filename, u8 img_type);
+int AGMV_DecodeAudio(const char* filename, AGMV_AUDIO_TYPE audio_type);
+void to_80bitfloat(u32 num, u8 bytes[10]);
 
 /* not part of the reference: last error text of the GPU layer, and the device to use (default 0) */
 const char* AGMV_B200_LastError(void);

@@ -206,18 +206,22 @@ void AGMV_EncodeHeader(FILE* file, AGMV* agmv) {
 }
 
 /* encoder configuration currently loaded in the GPU context (per-frame API) */
-static struct { u32 w, h; int opt, comp, valid; } g_enc = {0, 0, 0, 0, 0};
+static struct { u32 w, h; int opt, comp, valid; const AGMV* owner; } g_enc = {0, 0, 0, 0, 0, NULL};
 
 static int enc_prepare(agmvb_ctx* c, AGMV* agmv) {
     u32 w = agmv->header.width, h = agmv->header.height;
-    if (!g_enc.valid || g_enc.w != w || g_enc.h != h || g_enc.opt != (int)agmv->opt || g_enc.comp != (int)agmv->compression) {
+    /* The state carried from frame to frame (the LZ77 coder's bitstream buffer, the I-frame entries) belongs to ONE handle's
+     * sequence: CreateAGMV hands the reference a zeroed buffer. So the GPU context is set up again whenever another handle
+     * shows up or a handle starts over at frame 0, not only when the configuration changes. */
+    if (!g_enc.valid || g_enc.owner != agmv || agmv->frame_count == 0 || g_enc.w != w || g_enc.h != h || g_enc.opt != (int)agmv->opt ||
+        g_enc.comp != (int)agmv->compression) {
         /* coded size == handle size here: scaling (GBA / NDS) is AGMV_EncodeAGMV's job, the per-frame call gets scaled frames */
         int o = agmv->opt;
         if (o == AGMV_OPT_GBA_I || o == AGMV_OPT_GBA_III || o == AGMV_OPT_NDS) o = AGMV_OPT_III; /* same codec path, no rescale */
         if (o == AGMV_OPT_GBA_II) o = AGMV_OPT_II;
         int rc = agmvb_enc_begin(c, (uint32_t)w, (uint32_t)h, o, AGMVB_HIGH_QUALITY, (int)agmv->compression);
         if (rc) return rc;
-        g_enc.w = w; g_enc.h = h; g_enc.opt = (int)agmv->opt; g_enc.comp = (int)agmv->compression; g_enc.valid = 1;
+        g_enc.w = w; g_enc.h = h; g_enc.opt = (int)agmv->opt; g_enc.comp = (int)agmv->compression; g_enc.valid = 1; g_enc.owner = agmv;
     }
     uint32_t p0[256], p1[256];
     for (int i = 0; i < 256; i++) { p0[i] = (uint32_t)agmv->header.palette0[i]; p1[i] = (uint32_t)agmv->header.palette1[i]; }
@@ -569,12 +573,18 @@ int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
     const u32 usize = agmv->frame_chunk->uncompressed_size, csize = agmv->frame_chunk->compressed_size;
     const size_t P = (size_t)agmv->header.width * agmv->header.height;
     const long data_start = ftell(file);
+    /* csize comes from the file: never allocate past what the file still holds */
+    long here = data_start, end_pos = data_start;
+    if (fseek(file, 0, SEEK_END) == 0) { end_pos = ftell(file); fseek(file, here, SEEK_SET); }
+    size_t left = end_pos > here ? (size_t)(end_pos - here) : 0;
     size_t want = (size_t)csize + 64;
+    if (want > left + 64) want = left + 64;
     uint8_t* pay = (uint8_t*)malloc(want);
+    uint32_t* px = (uint32_t*)malloc(P * 4);
+    if (!pay || !px) { free(pay); free(px); return MEMORY_CORRUPTION_ERR; }
     size_t got = fread(pay, 1, want, file);
     int stream = -1;
     int rc = bound_stream(c, agmv, &stream);
-    uint32_t* px = (uint32_t*)malloc(P * 4);
     uint32_t bpos = 0, consumed = 0;
     if (!rc) rc = agmvb_dec_chunk(c, stream, pay, got, (uint32_t)usize, (uint32_t)csize, (uint32_t)agmv->frame_count, px, &bpos, &consumed);
     if (!rc) {
@@ -585,7 +595,11 @@ int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
         fseek(file, data_start + (long)consumed, SEEK_SET); /* where the reference's bit reader leaves the cursor */
     }
     free(pay); free(px);
-    if (rc) { fail(rc, "AGMV_DecodeFrameChunk"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    if (rc) {
+        fseek(file, data_start, SEEK_SET); /* nothing was consumed */
+        fail(rc, "AGMV_DecodeFrameChunk");
+        return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR;
+    }
     return NO_ERR;
 }
 
@@ -649,6 +663,7 @@ static int export_track(agmvb_ctx* c, int stream, const uint8_t* hdr, AGMV_AUDIO
     if (rc) return rc;
     const uint64_t cap = n > a.header.audio_size ? n : a.header.audio_size;
     void* pcm = calloc((size_t)cap + 1, 2);
+    if (!pcm) return MEMORY_CORRUPTION_ERR; /* a damaged audio_size field */
     rc = agmvb_dec_audio(c, stream, pcm, cap, &n, &bits);
     if (!rc) {
         tr.pcm = (u16*)pcm; tr.pcm8 = (u8*)pcm; tr.start_point = n; tr.total_audio_duration = 0;
@@ -661,14 +676,15 @@ static int export_track(agmvb_ctx* c, int stream, const uint8_t* hdr, AGMV_AUDIO
     return rc;
 }
 
-/* src/agmv_decode.c:527-647 */
-int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type) {
+/* src/agmv_decode.c:527-647 (AGMV_DecodeAGMV), :455-525 (AGMV_DecodeVideo: frames only), :682-767 (AGMV_DecodeAudio: track only) */
+static int decode_file(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type, int frames, int audio, const char* who) {
     FILE* f = fopen(filename, "rb");
     if (!f) return FILE_NOT_FOUND_ERR;
     fseek(f, 0, SEEK_END);
     long size = ftell(f);
     fseek(f, 0, SEEK_SET);
     uint8_t* data = (uint8_t*)malloc((size_t)size + 1);
+    if (!data) { fclose(f); return MEMORY_CORRUPTION_ERR; }
     if (fread(data, 1, (size_t)size, f) != (size_t)size) { }
     fclose(f);
     agmvb_ctx* c = ctx_get();
@@ -679,18 +695,41 @@ int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_typ
     uint8_t hdr[38];
     memcpy(hdr, data, size >= 38 ? 38 : 0);
     free(data);
-    if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
-    const size_t P = (size_t)w * h;
-    const uint32_t CH = 32;
-    uint32_t* px = (uint32_t*)malloc((size_t)CH * P * 4);
-    for (uint32_t f0 = 0; f0 < n && !rc; f0 += CH) {
-        uint32_t nf = n - f0 < CH ? n - f0 : CH;
-        rc = agmvb_dec_frames(c, stream, nf, px, 0);
-        if (!rc && img_type == AGMV_IMG_BMP) for (uint32_t k = 0; k < nf; k++) quick_export_bmp(px + (size_t)k * P, w, h);
+    if (rc) { fail(rc, who); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    if (frames) {
+        const size_t P = (size_t)w * h;
+        const uint32_t CH = 32;
+        uint32_t* px = (uint32_t*)malloc((size_t)CH * P * 4);
+        if (!px) rc = AGMVB_ERR_MEMORY;
+        for (uint32_t f0 = 0; f0 < n && !rc; f0 += CH) {
+            uint32_t nf = n - f0 < CH ? n - f0 : CH;
+            rc = agmvb_dec_frames(c, stream, nf, px, 0);
+            if (!rc && img_type == AGMV_IMG_BMP) for (uint32_t k = 0; k < nf; k++) quick_export_bmp(px + (size_t)k * P, w, h);
+        }
+        free(px);
     }
-    free(px);
-    if (!rc) rc = export_track(c, stream, hdr, audio_type);
+    if (!rc && audio) rc = export_track(c, stream, hdr, audio_type);
     agmvb_dec_close(c, stream);
-    if (rc) { fail(rc, "AGMV_DecodeAGMV"); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
+    if (rc) { fail(rc, who); return rc <= 3 ? rc : MEMORY_CORRUPTION_ERR; }
     return NO_ERR;
+}
+int AGMV_DecodeAGMV(const char* filename, u8 img_type, AGMV_AUDIO_TYPE audio_type) { return decode_file(filename, img_type, audio_type, 1, 1, "AGMV_DecodeAGMV"); }
+int AGMV_DecodeVideo(const char* filename, u8 img_type) { return decode_file(filename, img_type, AGMV_AUDIO_WAV, 1, 0, "AGMV_DecodeVideo"); }
+int AGMV_DecodeAudio(const char* filename, AGMV_AUDIO_TYPE audio_type) { return decode_file(filename, 0, audio_type, 0, 1, "AGMV_DecodeAudio"); }
+
+/* src/agmv_decode.c:649-680: an unsigned integer as the 80-bit IEEE extended float of an AIFF header (sample rate);
+ * the reference's agmv_utils.c (AIFF / AIFC export, :1457,1510) calls it, so a drop-in for agmv_decode.c has to export it.
+ * Sign 0, exponent 16383 + floor(log2 num), mantissa = num with its top bit at bit 63; only bytes 0..5 are written. */
+void to_80bitfloat(u32 num, u8 bytes[10]) {
+    if (num <= 1) { bytes[0] = 0x3F; bytes[1] = 0xFF; bytes[2] = 0x80; return; }
+    bytes[0] = 0x40;
+    if (num >= 0x40000000ul) { bytes[1] = 0x1D; return; }
+    int lead = 0;   /* zero bits below bit 31 before the number's highest set bit, counted from bit 30 down */
+    while (!(num & (0x40000000ul >> lead))) lead++;
+    const unsigned long mant = lead < 31 ? num << (lead + 1) : 0;
+    bytes[1] = (u8)(29 - lead);
+    bytes[2] = (u8)(mant >> 24);
+    bytes[3] = (u8)(mant >> 16);
+    bytes[4] = (u8)(mant >> 8);
+    bytes[5] = (u8)mant;
 }

@@ -142,6 +142,7 @@ constexpr int LZC_WARPS = LZC_THREADS / 32;
 constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (lzc_pack_k)
 constexpr int LZC_MLP = 4;                            // rounds of a sweep in flight together
 constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
+constexpr int LZC_GRAB = 1;                           // chunks a warp takes from the counter at a time
 
 // Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
 //     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
@@ -149,6 +150,8 @@ template <class Op>
 __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
     const uint32_t lane = lane_id();
     uint32_t qn = 0, qi = 0;
+    uint32_t ch = 0, ch_end = 0;   // chunks in hand: taken LZC_GRAB at a time (one counter serves every warp of the GPU, and
+                                   // atomics on one address complete at only a few hundred million per second)
     bool more = true, busy = false;
     for (;;) {
         if (more && qn - qi < 32u) {   // keep the leftovers, sweep the next chunk
@@ -158,10 +161,13 @@ __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restri
             if (lane < left) q[lane] = keep;
             qn = left;
             qi = 0;
-            uint32_t ch = 0;
-            if (lane == 0) ch = atomicAdd(counter, 1u);
-            ch = __shfl_sync(0xffffffffu, ch, 0);
+            if (ch == ch_end) {
+                if (lane == 0) ch = atomicAdd(counter, (uint32_t)LZC_GRAB);
+                ch = __shfl_sync(0xffffffffu, ch, 0);
+                ch_end = ch + LZC_GRAB;
+            }
             const uint64_t cb = (uint64_t)ch * LZC_WCHUNK;
+            ch++;
             if (cb >= n) more = false;
             else qn += op.sweep((uint32_t)cb, q + qn);
             __syncwarp();

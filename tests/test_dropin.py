@@ -316,3 +316,74 @@ def test_encode_agmv_dropin_frame_range(golden, name):
         finally:
             os.chdir(cwd)
     assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()
+
+
+REFERENCE = "/root/reference"
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="needs the reference sources (build container only)")
+def test_integration_link_recipe():
+    """INTEGRATION.md section 1, performed: the reference's own objects WITHOUT agmv_encode.o / agmv_decode.o - agmv_utils.c,
+    agmv_playback.c, all of AGIDL and tools/agmvcli/agmvcli.c, compiled from /root/reference - link against
+    -lagmv_dropin -lagmv_b200 with nothing left undefined (to_80bitfloat, AGMV_DecodeVideo, AGMV_DecodeAudio included)."""
+    libdir = os.path.join(ROOT, "libagmv_b200")
+    srcs = [os.path.join(REFERENCE, "tools/agmvcli/agmvcli.c"), os.path.join(REFERENCE, "src/agmv_utils.c"),
+            os.path.join(REFERENCE, "src/agmv_playback.c")]
+    agidl = os.path.join(REFERENCE, "extern/agidl/src")
+    srcs += [os.path.join(agidl, f) for f in sorted(os.listdir(agidl)) if f.endswith(".c") and f != "main.c"]
+    with tempfile.TemporaryDirectory() as td:
+        exe = os.path.join(td, "agmvcli")
+        r = subprocess.run(["gcc", "-O1", "-w", f"-I{REFERENCE}/extern/agidl/include", f"-I{REFERENCE}/include", "-o", exe] + srcs +
+                           [f"-L{libdir}", "-lagmv_dropin", "-lagmv_b200", "-lm", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
+        # every hot-path symbol the CLI and agmv_utils.o need is resolved by the drop-in, none by a stray reference object
+        und = subprocess.run(["nm", "-u", exe], capture_output=True, text=True, check=True).stdout
+        for sym in ("AGMV_EncodeAGMV", "AGMV_EncodeVideo", "AGMV_DecodeAGMV", "AGMV_DecodeAudioChunk", "to_80bitfloat"):
+            assert sym in und, f"{sym} is not taken from the shared drop-in"
+        # usage text without a script: the binary loads both shared libraries and runs
+        out = subprocess.run([exe], capture_output=True, text=True)
+        assert "AGMVCLI" in out.stdout
+
+
+def _agmvcli():
+    exe = os.path.join(REF_DIR, "agmvcli_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/agmvcli_dropin not built (oracle/Makefile builds it where the reference sources are)")
+    return exe
+
+
+@pytest.mark.gpu
+def test_agmvcli_on_dropin_encode_script(golden):
+    """The reference's CLI (tools/agmvcli/agmvcli.c, unmodified, linked per INTEGRATION.md section 1) run on an .agvs script:
+    '$video ENC ...' without an audio track calls AGMV_EncodeVideo (:168) - bytes equal the reference's golden stream."""
+    from agmv_testlib import scene_cut_frames
+    g = golden["encode_modes"]["video64_III_LOW"]
+    exe = _agmvcli()
+    frames = scene_cut_frames(g["w"], g["h"], g["n"])
+    with tempfile.TemporaryDirectory() as td:
+        write_bmps(frames, td, "f", 1)
+        open(os.path.join(td, "enc.agvs"), "w").write(f"$video ENC o.agmv . f BMP 1 {g['n']} {g['w']} {g['h']} {g['fps']} OPT_III LOW_Q LZSS\n")
+        r = subprocess.run([exe, "enc.agvs"], cwd=td, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        data = open(os.path.join(td, "o.agmv"), "rb").read()
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"])
+
+
+@pytest.mark.gpu
+def test_agmvcli_on_dropin_decode_script(golden):
+    """'$video DEC cur <file> BMP WAV' -> AGMV_DecodeAGMV (:185-190): the exported frames equal the reference's."""
+    g = golden["encode"]["syn64_III_LOW"]
+    exe = _agmvcli()
+    with tempfile.TemporaryDirectory() as td:
+        import shutil
+        shutil.copy(os.path.join(GOLDEN_DIR, g["file"]), os.path.join(td, "s.agmv"))
+        open(os.path.join(td, "dec.agvs"), "w").write("$video DEC cur s.agmv BMP WAV\n")
+        r = subprocess.run([exe, "dec.agvs"], cwd=td, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        bmps = sorted((f for f in os.listdir(td) if f.startswith("quick_export_")), key=lambda f: int(f[len("quick_export_"):-4]))
+        assert len(bmps) == g["decoded_shape"][0]
+        for k, f in enumerate(bmps):
+            d = open(os.path.join(td, f), "rb").read()
+            px = np.frombuffer(d[54:], dtype=np.uint8).reshape(g["h"], g["w"], 3).astype(np.uint32)
+            frame = px[..., 2] << 16 | px[..., 1] << 8 | px[..., 0]
+            assert sha256(frame.astype(np.uint32).tobytes()) == g["decoded_frame_sha256"][k]
