@@ -142,7 +142,6 @@ constexpr int LZC_WARPS = LZC_THREADS / 32;
 constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (lzc_pack_k)
 constexpr int LZC_MLP = 4;                            // rounds of a sweep in flight together
 constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
-constexpr int LZC_GRAB = 1;                           // chunks a warp takes from the counter at a time
 
 // Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
 //     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
@@ -150,8 +149,6 @@ template <class Op>
 __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
     const uint32_t lane = lane_id();
     uint32_t qn = 0, qi = 0;
-    uint32_t ch = 0, ch_end = 0;   // chunks in hand: taken LZC_GRAB at a time (one counter serves every warp of the GPU, and
-                                   // atomics on one address complete at only a few hundred million per second)
     bool more = true, busy = false;
     for (;;) {
         if (more && qn - qi < 32u) {   // keep the leftovers, sweep the next chunk
@@ -161,13 +158,10 @@ __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restri
             if (lane < left) q[lane] = keep;
             qn = left;
             qi = 0;
-            if (ch == ch_end) {
-                if (lane == 0) ch = atomicAdd(counter, (uint32_t)LZC_GRAB);
-                ch = __shfl_sync(0xffffffffu, ch, 0);
-                ch_end = ch + LZC_GRAB;
-            }
+            uint32_t ch = 0;
+            if (lane == 0) ch = atomicAdd(counter, 1u);
+            ch = __shfl_sync(0xffffffffu, ch, 0);
             const uint64_t cb = (uint64_t)ch * LZC_WCHUNK;
-            ch++;
             if (cb >= n) more = false;
             else qn += op.sweep((uint32_t)cb, q + qn);
             __syncwarp();
@@ -197,11 +191,9 @@ struct LzcLink3Op {
         while (fs[f + 1] <= p) f++;
         return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
     }
-    __device__ __forceinline__ void put(uint32_t p, uint32_t nd, uint32_t b3, uint32_t cap) const {
-        const uint32_t lev = nd ? lzc_lcp(bs, p, p - nd, cap) : 0u;   // how far the level-3 link holds (lzchain_core.h)
-        lw3[p] = lzc_word(nd, b3, lev, cap);
+    __device__ __forceinline__ void put(uint32_t p, uint32_t nd, uint32_t b2, uint32_t b3, uint32_t cap) const {
+        lw3[p] = lzc_word(nd, b3, b2, cap);
         if (!nd) bestlen[p] = 0;
-        else if (lev == (uint32_t)LZ_MAXLEN) bestlen[p] = (uint8_t)LZ_MAXLEN;
     }
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
@@ -235,7 +227,7 @@ struct LzcLink3Op {
                         if ((wk[j] >> 16) == (w[j] >> 16) && k2[j] == (b23[j] & 0xFFu)) nd = dist;
                         else pend = true;
                     }
-                    if (!pend) put(p, nd, b23[j] >> 8, cap[j]);
+                    if (!pend) put(p, nd, b23[j] & 0xFFu, b23[j] >> 8, cap[j]);
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, pend);
                 if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
@@ -252,7 +244,7 @@ struct LzcLink3Op {
     __device__ __forceinline__ bool step() {
         const int r = wlk.hop(bs, lwh, rsd);
         if (r == LZC_GO) return false;
-        put(wlk.p, r == LZC_FOUND ? wlk.acc : 0u, (b23c >> 8) & 0xFFu, b23c >> 16);
+        put(wlk.p, r == LZC_FOUND ? wlk.acc : 0u, b23c & 0xFFu, (b23c >> 8) & 0xFFu, b23c >> 16);
         return true;
     }
 };
@@ -263,17 +255,12 @@ struct LzcLevelOp {
     uint32_t* __restrict__ match_rec; uint8_t* __restrict__ bestlen;
     LzcLevelWalk wlk;
     uint32_t nbc;   // byte L+1 | cap << 8 of the position being walked
-    // a walk that found the (L+1)-gram at distance nd: how far does that link hold?
-    __device__ __forceinline__ void found(uint32_t p, uint32_t nd, uint32_t nb, uint32_t cap) const {
-        const uint32_t lev = lzc_lcp(bs, p, p - nd, cap);
-        lw_next[p] = lzc_word(nd, nb, lev, cap);
-        if (lev == (uint32_t)LZ_MAXLEN) bestlen[p] = (uint8_t)LZ_MAXLEN;
-    }
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
+        const bool top = L + 1u == (uint32_t)LZ_MAXLEN;
         uint32_t qn = 0;
         for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
-            uint32_t w[LZC_MLP], nb[LZC_MLP];
+            uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
                 const uint32_t p = cbase + (r0 + j) * 32 + lane;
@@ -282,11 +269,26 @@ struct LzcLevelOp {
             }
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
-                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu, lev = (w[j] >> 24) & 0xFu;
-                // dist == 0: no match of this length. lev > L: the link holds for the next level as well (copied, no gather).
-                // lev == L: the occurrence it points at differs in byte L (or the cap is reached): walk the chain.
-                const bool pend = p < n && dist && lev <= L;
-                if (p < n && !pend) lw_next[p] = lzc_word(dist, nb[j], dist ? lev : 0u, w[j] >> 28);
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                wk[j] = 0;
+                if (dist) wk[j] = lw[p - dist];
+            }
+#pragma unroll
+            for (int j = 0; j < LZC_MLP; j++) {
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                const uint32_t c = (w[j] >> 16) & 0xFFu, cap = (w[j] >> 24) & 0xFu;
+                bool pend = false;
+                if (p < n) {
+                    uint32_t nd = 0;
+                    if (dist) {
+                        if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) nd = dist;
+                        else pend = true;
+                    }
+                    if (!pend) {
+                        lw_next[p] = lzc_word(nd, nb[j], c, cap);
+                        if (nd && top) bestlen[p] = (uint8_t)LZ_MAXLEN;
+                    }
+                }
                 const unsigned bal = __ballot_sync(0xffffffffu, pend);
                 if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
                 qn += __popc(bal);
@@ -296,18 +298,15 @@ struct LzcLevelOp {
     }
     __device__ __forceinline__ void begin(uint32_t p) {
         const uint32_t w = lw[p];
-        nbc = (uint32_t)bs[p + L + 1] | (w >> 28) << 8;
-        wlk.start(p, w, L, bs[p + L - 1]);
+        nbc = (uint32_t)bs[p + L + 1] | ((w >> 24) & 0xFu) << 8;
+        wlk.start(p, w, L);
     }
     __device__ __forceinline__ bool step() {
         const int r = wlk.hop(lw, rsd);
         if (r == LZC_GO) return false;
-        if (r == LZC_FOUND) found(wlk.p, wlk.acc, nbc & 0xFFu, nbc >> 8);
-        else {
-            lw_next[wlk.p] = lzc_word(0u, nbc & 0xFFu, 0u, nbc >> 8);
-            match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last;
-            bestlen[wlk.p] = (uint8_t)L;
-        }
+        lw_next[wlk.p] = lzc_word(r == LZC_FOUND ? wlk.acc : 0u, nbc & 0xFFu, wlk.c, nbc >> 8);
+        if (r == LZC_END) { match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last; bestlen[wlk.p] = (uint8_t)L; }
+        else if (L + 1u == (uint32_t)LZ_MAXLEN) bestlen[wlk.p] = (uint8_t)LZ_MAXLEN;
         return true;
     }
 };

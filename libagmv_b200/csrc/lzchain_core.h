@@ -46,41 +46,11 @@ constexpr uint32_t LZC_RESOLVED = 1u << 27; // match_rec: length << 28 | LZC_RES
 
 // Link words: low 16 bits = dist, then key bits.
 //   hash level (lzc_hashlink_k): dist to the previous position with the same 3-gram hash | byte0 << 16 | byte1 << 24
-//   level L >= 3:  dist_L | byte[p+L] << 16 | lev << 24 | cap << 28
-//     cap = min(15, bytes left in the frame from p on): the reference caps a match there (src/agmv_encode.c:121-123)
-//     lev = min(cap, number of leading bytes p shares with p - dist_L): the occurrence the link points at stays the most
-//           recent one for every length up to lev (a nearer occurrence of a longer gram would be a nearer occurrence of the
-//           shorter one too), so dist_L' == dist_L for all L <= L' <= lev and the position is simply copied through those
-//           levels - no gather, no walk. It is looked at again at level lev, where the bytes differ (or the cap is reached).
-//           On this codec's bitstreams 45-60 % of the positions reach lev = 15 straight from their level-3 link.
+//   level L >= 3:  dist_L | byte[p+L] << 16 | cap << 24 | (byte[p+L] != byte[p+L-1]) << 28,
+//                  cap = min(15, bytes left in the frame from p on): the reference caps a match there (src/agmv_encode.c:121-123)
 LZC_HD uint32_t lzc_hash(uint32_t gram24, int bits) { return (gram24 * 2654435761u) >> (32 - bits); }
-LZC_HD uint32_t lzc_word(uint32_t dist, uint32_t byte_l, uint32_t lev, uint32_t cap) { return dist | byte_l << 16 | lev << 24 | cap << 28; }
-
-// bytes 0..15 at address a (any alignment) as two 64-bit words, from three aligned loads
-LZC_HD void lzc_load16(const uint8_t* a, uint64_t& lo, uint64_t& hi) {
-    const uintptr_t x = reinterpret_cast<uintptr_t>(a);
-    const uint64_t* w = reinterpret_cast<const uint64_t*>(x & ~(uintptr_t)7);
-    const uint32_t sh = (uint32_t)(x & 7u) * 8u;
-    const uint64_t w0 = w[0], w1 = w[1], w2 = w[2];
-    lo = sh ? (w0 >> sh) | (w1 << (64u - sh)) : w0;
-    hi = sh ? (w1 >> sh) | (w2 << (64u - sh)) : w1;
-}
-LZC_HD uint32_t lzc_ctz64(uint64_t v) {
-#ifdef __CUDA_ARCH__
-    return (uint32_t)(__ffsll((long long)v) - 1);
-#else
-    return (uint32_t)__builtin_ctzll(v);
-#endif
-}
-// min(cap, number of leading bytes d[p..] and d[q..] share), cap <= 15. Reads up to 23 bytes past either position and up to
-// 7 before it (inside the batch buffer and its padding).
-LZC_HD uint32_t lzc_lcp(const uint8_t* d, uint32_t p, uint32_t q, uint32_t cap) {
-    uint64_t a0, a1, b0, b1;
-    lzc_load16(d + p, a0, a1);
-    lzc_load16(d + q, b0, b1);
-    const uint64_t x0 = a0 ^ b0, x1 = a1 ^ b1;
-    const uint32_t l = x0 ? lzc_ctz64(x0) >> 3 : (x1 ? 8u + (lzc_ctz64(x1) >> 3) : 16u);
-    return l < cap ? l : cap;
+LZC_HD uint32_t lzc_word(uint32_t dist, uint32_t byte_l, uint32_t byte_before, uint32_t cap) {
+    return dist | byte_l << 16 | cap << 24 | (byte_l != byte_before ? 1u << 28 : 0u);
 }
 
 enum { LZC_GO = 0, LZC_FOUND = 1, LZC_END = 2 };
@@ -113,17 +83,16 @@ struct LzcLink3Walk {
     }
 };
 
-// one level: dist_{L+1}[p] from the level-L links, for a position whose lev == L (see above; positions with lev > L are
-// copied, positions with dist == 0 have no match of length L).
+// one level: dist_{L+1}[p] from the level-L links.
 // r == LZC_FOUND: acc = dist_{L+1}. r == LZC_END: no match of length L+1; `last` = distance to the EARLIEST level-L
 // occurrence inside the window, i.e. the offset of p's final (length L) match.
 struct LzcLevelWalk {
     uint32_t p, acc, last, dist, c;
     bool ext, neq;
-    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t L, uint32_t byte_before) {
+    LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t L) {
         p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; c = (w >> 16) & 0xFFu;
-        ext = L + 1u <= (w >> 28);
-        neq = c != byte_before;   // byte L of p differs from byte L-1 of p
+        ext = L + 1u <= ((w >> 24) & 0xFu);
+        neq = (w >> 28) & 1u;
         return dist != 0u;
     }
     LZC_HDM int hop(const uint32_t* lw, const uint16_t* rsd) {

@@ -56,43 +56,26 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
             while ((r = wk.hop(d.data(), lwh.data(), rsd.data())) == LZC_GO) {}
             if (r == LZC_FOUND) d3 = wk.acc;
         }
-        const uint32_t lev = d3 ? lzc_lcp(d.data(), (uint32_t)p, (uint32_t)p - d3, cap) : 0u;
-        if (lev == 15) R.len[p] = 15;
-        lw[0][p] = lzc_word(d3, d[p + 3], lev, cap);
+        lw[0][p] = lzc_word(d3, d[p + 3], d[p + 2], cap);
     }
     int cur = 0;
-    size_t walks = 0, copies = 0;
     for (uint32_t L = 3; L < 15; L++) {
         for (size_t p = 0; p < n; p++) {
-            const uint32_t w = lw[cur][p], cap = w >> 28, lev = (w >> 24) & 0xFu;
-            if ((w & 0xFFFFu) && lev > L) {   // the link holds for the next level too
-                lw[cur ^ 1][p] = lzc_word(w & 0xFFFFu, d[p + L + 1], lev, cap);
-                copies++;
-                continue;
-            }
+            const uint32_t w = lw[cur][p];
             LzcLevelWalk wk;
-            uint32_t nd = 0, nlev = 0;
-            if (wk.start((uint32_t)p, w, L, d[p + L - 1])) {
-                walks++;
-                if (lev != L) { printf("lev %u at level %u (p=%zu)\n", lev, L, p); exit(3); }
+            uint32_t nd = 0;
+            if (wk.start((uint32_t)p, w, L)) {
                 int r;
                 while ((r = wk.hop(lw[cur].data(), rsd.data())) == LZC_GO) {}
-                if (r == LZC_FOUND) {
-                    nd = wk.acc;
-                    nlev = lzc_lcp(d.data(), (uint32_t)p, (uint32_t)p - nd, cap);
-                    if (nlev <= L) { printf("lcp %u after a match of %u (p=%zu)\n", nlev, L + 1, p); exit(3); }
-                    if (nlev == 15) R.len[p] = 15;
-                } else { R.len[p] = (uint8_t)L; R.off[p] = wk.last; }
+                if (r == LZC_FOUND) nd = wk.acc;
+                else { R.len[p] = (uint8_t)L; R.off[p] = wk.last; }
             }
-            lw[cur ^ 1][p] = lzc_word(nd, d[p + L + 1], nlev, cap);
+            lw[cur ^ 1][p] = lzc_word(nd, d[p + L + 1], d[p + L], (w >> 24) & 0xFu);
         }
         cur ^= 1;
     }
-    if (getenv("LZC_STATS")) printf("  level visits: %zu walks, %zu copies, n=%zu\n", walks, copies, n);
-    for (size_t p = 0; p < n; p++) {
-        if (((lw[cur][p] & 0xFFFFu) != 0) != (R.len[p] == 15)) { printf("level-15 link and bestlen disagree at %zu\n", p); exit(3); }
-        if (R.len[p] == 15) R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p);
-    }
+    for (size_t p = 0; p < n; p++)
+        if (lw[cur][p] & 0xFFFFu) { R.len[p] = 15; R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p); }
     return R;
 }
 
