@@ -387,3 +387,22 @@ def test_agmvcli_on_dropin_decode_script(golden):
             px = np.frombuffer(d[54:], dtype=np.uint8).reshape(g["h"], g["w"], 3).astype(np.uint32)
             frame = px[..., 2] << 16 | px[..., 1] << 8 | px[..., 0]
             assert sha256(frame.astype(np.uint32).tobytes()) == g["decoded_frame_sha256"][k]
+
+
+@pytest.mark.gpu
+def test_encode_agmv_dropin_on_the_reference_foxlogo_bmps(golden):
+    """examples/simple_video/simple_video.c, served by the drop-in: CreateAGMV + AGMV_EncodeAGMV on a directory of the
+    reference's own 24-bit BMP files (the first 20 frames of examples/simple_video/foxlogo, tests/golden/foxlogo/)."""
+    g = golden["fixtures"]["foxlogo_I_LOW"]
+    lib = _dropin()
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as td:
+        os.symlink(os.path.join(GOLDEN_DIR, g["dir"]), os.path.join(td, "fx"))   # the reference formats paths into char[60]
+        os.chdir(td)
+        try:
+            h = lib.CreateAGMV(g["create_n"], g["w"], g["h"], g["fps"])
+            lib.AGMV_EncodeAGMV(h, b"o.agmv", b"fx", g["base"].encode(), 1, 1, g["n"], g["w"], g["h"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+            data = open("o.agmv", "rb").read()
+        finally:
+            os.chdir(cwd)
+    assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()

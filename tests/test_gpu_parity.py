@@ -658,3 +658,80 @@ def test_lzss_run_table_option_is_exact():
         c.close()
     finally:
         del os.environ["AGMVB_LZ_RUNS"]
+
+
+# ---- the bench's own configuration, pinned (BASELINE config 3 / 4 profile: OPT_III, HIGH quality, LZSS) ----------------
+def test_1080p_high_quality_prefix_against_oracle(ctx):
+    """What bench.py times is OPT_III / HIGH at 1080p: 19-bit histogram bins, the (2,2,3) palette pick box, far more distinct
+    colours through the quantiser's miss path. 32 source frames (24 encoded: I and P frames, every schedule slot), GPU stream
+    byte-identical to the restated reference encoder, GPU decode equal to the restated reference decoder."""
+    frames = synth_frames(1920, 1080, 32, seed=1234)
+    data, n_enc = ctx.encode_sequence(frames, 31, 24, OPT["III"], QUALITY["HIGH"], LZSS)
+    assert n_enc == 21
+    ref = oracle_encode(frames, 31, 24, OPT["III"], QUALITY["HIGH"], LZSS)
+    assert data.tobytes() == ref
+    dec = ctx.decode_all(ref)
+    rc, odec = oracle_decode(ref)
+    assert rc == 0 and np.array_equal(dec, odec)
+
+
+def test_4k_high_quality_prefix_against_oracle(ctx):
+    """BASELINE config 4's frame size with the bench profile (3840x2160, OPT_III / HIGH): 8 source frames."""
+    frames = synth_frames(3840, 2160, 8, seed=1234)
+    data, n_enc = ctx.encode_sequence(frames, 7, 24, OPT["III"], QUALITY["HIGH"], LZSS)
+    assert n_enc == 3
+    ref = oracle_encode(frames, 7, 24, OPT["III"], QUALITY["HIGH"], LZSS)
+    assert data.tobytes() == ref
+    dec = ctx.decode_all(ref)
+    rc, odec = oracle_decode(ref)
+    assert rc == 0 and np.array_equal(dec, odec)
+
+
+# ---- the reference's own content (tests/golden/make_fixture_golden.py) ----------------------------------------------------
+@pytest.mark.parametrize("name", ["agmv_splash.agmv", "FOXLOGO.agmv"])
+def test_shipped_streams_decode_like_the_reference(ctx, golden, name):
+    """The .agmv files the reference ships (root agmv_splash.agmv, examples/simple_decoding/FOXLOGO.agmv; encoder build
+    unknown, both carry a 16-bit audio track): every frame and the whole track equal the unmodified reference's decode."""
+    g = golden["fixtures"][name]
+    data = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
+    assert sha256(data) == g["input_sha256"]
+    sid, w, h, n = ctx.dec_open(data)
+    assert [n, h, w] == g["decoded_shape"]
+    frames = ctx.dec_frames(sid, n, w, h)
+    pcm = ctx.dec_audio(sid)
+    ctx.dec_close(sid)
+    assert [sha256(f.tobytes()) for f in frames] == g["decoded_frame_sha256"]
+    assert sha256(frames.tobytes()) == g["decoded_sha256"]
+    assert pcm.dtype == (np.uint16 if g["audio"]["bits"] == 16 else np.uint8) and pcm.size == g["audio"]["samples"]
+    assert sha256(pcm.tobytes()) == g["audio"]["sha256"]
+
+
+def test_shipped_stream_with_damaged_header_is_rejected(ctx, golden):
+    """agmv_spash.agmv has bits_per_sample = 36904: AGMV_DecodeHeader returns INVALID_HEADER_FORMATTING_ERR (src/agmv_decode.c:110-113)."""
+    g = golden["fixtures"]["agmv_spash.agmv"]
+    data = open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
+    assert sha256(data) == g["input_sha256"] and g["rc"] == 1
+    import libagmv_b200
+    with pytest.raises(libagmv_b200.AgmvError) as e:
+        ctx.dec_open(data)
+    assert e.value.code == 1
+
+
+def test_foxlogo_bmp_files_encode_like_the_reference(ctx, golden):
+    """Real input: the first 20 BMP files of examples/simple_video/foxlogo (24-bit, 320x240), encoded as
+    examples/simple_video/simple_video.c does (OPT_I, LOW, LZSS). GPU stream == the unmodified reference's file."""
+    from agmv_testlib import oracle
+    g = golden["fixtures"]["foxlogo_I_LOW"]
+    lib = oracle()
+    lib.orc_read_bmp24.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.c_size_t]
+    frames = np.zeros((g["n"], g["h"], g["w"]), dtype=np.uint32)
+    for k in range(g["n"]):
+        w, h = C.c_int(), C.c_int()
+        rc = lib.orc_read_bmp24(os.path.join(GOLDEN_DIR, g["dir"], f"{g['base']}{k + 1}.bmp").encode(), C.byref(w), C.byref(h),
+                                frames[k].ctypes.data_as(C.POINTER(C.c_uint32)), frames[k].size)
+        assert rc == 0 and (w.value, h.value) == (g["w"], g["h"])
+    data, n_enc = ctx.encode_sequence(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+    assert (len(data), sha256(data.tobytes())) == (g["size"], g["sha256"])
+    assert data.tobytes() == open(os.path.join(GOLDEN_DIR, g["file"]), "rb").read()
+    dec = ctx.decode_all(data.tobytes())
+    assert [sha256(f.tobytes()) for f in dec] == g["decoded_frame_sha256"]
