@@ -436,7 +436,7 @@ def run_b200(args):
     usize_total, csize_total = float(us.sum()), float(cs.sum())
     n_interp = int((sb >= 0).sum())
     stats = {"P": P, "n_src": n_local, "n_enc": n_enc, "n_interp": n_interp, "usize": usize_total, "csize": csize_total,
-             "lz_levels": 15, "lz_groups": max(1, prof.get("lz_init", (1, 0))[0] // max(1, args.steps))}
+             "lz_levels": 12, "lz_groups": max(1, prof.get("lz_link", (1, 0))[0] // max(1, args.steps))}
     # dominant kernel class by device time inside the timed region
     roof = None
     if prof:
@@ -501,10 +501,9 @@ ALG_BYTES = {
     "quantize": lambda s: 4.0 * s["P"] * (s["n_enc"] + s["n_interp"]) + 2.0 * s["P"] * s["n_enc"],
     "classify": lambda s: 2.0 * s["P"] * s["n_enc"] * 1.75 + s["n_enc"] * s["P"] / 16,
     "emit": lambda s: 2.0 * s["P"] * s["n_enc"] + s["usize"],
-    "rx_scatter": lambda s: s["usize"] * s["lz_levels"],
-    "lz_group": lambda s: s["usize"] * s["lz_levels"] * 3 + s["usize"],
-    "lz_small": lambda s: s["usize"],
-    "lz_tiny": lambda s: s["usize"],
+    "lz_link": lambda s: s["usize"],
+    "lz_link3": lambda s: s["usize"],
+    "lz_level": lambda s: s["usize"] * 12,
     "lz_pack": lambda s: s["usize"] + s["csize"],
     "lz77": lambda s: s["usize"] + s["csize"],
     "expand": lambda s: s["csize"] + s["usize"],
@@ -512,10 +511,11 @@ ALG_BYTES = {
     "reconstruct": lambda s: s["usize"] + 4.0 * s["P"] * s["n_enc"],
 }
 ALG_RULE = {
-    "rx_scatter": "K4 reads usize and writes csize once; each of the 15 refinement scatters is charged one pass over the bitstream (usize bytes) per launch",
-    "lz_group": "per launch (reduce / partials / apply, 15 levels): one pass over the bitstream bytes (usize / launch on average)",
-    "lz_small": "K4 levels 4..15 of the small groups, in shared memory: charged one pass over the bitstream (usize bytes) per launch; "
-                "it reads 16 B per position (position + group words, each window twice), gathers 12 key bytes and writes one 4-byte match record",
+    "lz_level": "K4 reads usize and writes csize once for the whole stage; each of its 12 chain-level passes has to see every bitstream byte "
+                "once, so a level launch is charged one pass over the bitstream (usize bytes); it actually streams 9 B per position "
+                "(4-byte link word in and out, one key byte) and gathers 4 B per chain hop",
+    "lz_link": "K4 hash links: one pass over the bitstream (usize bytes) per launch",
+    "lz_link3": "K4 level-3 links: one pass over the bitstream (usize bytes) per launch",
     "expand": "D2: csize in + usize out",
     "lz77": "K4 (LZ77 flavour): usize in + csize out",
     "reconstruct": "D3: usize in + 4*W*H out per frame",
@@ -533,33 +533,75 @@ except Exception:
 # --------------------------------------------------------------------------------------
 # CPU legs: the reference's own implementation on the host cores
 # --------------------------------------------------------------------------------------
-def cpu_clip_roundtrip(n_src, procs, use_ref):
-    """Each of `procs` processes encodes its own n_src-frame 1080p clip (OPT_III/HIGH/LZSS) and decodes it.
-    Returns (seconds wall, frames total)."""
-    from agmv_testlib import REF_DIR  # noqa: F401
+def cpu_clips(n_src, procs, use_ref, quality="HIGH", size=(1920, 1080)):
+    """Each of `procs` processes encodes its own n_src-frame clip (OPT_III / `quality` / LZSS) and decodes it without export.
+    The workers time the encode and the decode themselves (tests/cpu_worker.py); the processes run side by side, so the
+    aggregate rate is frames / the slowest worker's time. Returns a dict, or None if a worker failed."""
     worker = os.path.join(ROOT, "tests", "cpu_worker.py")
     t0 = time.perf_counter()
-    ps = [subprocess.Popen([sys.executable, worker, str(n_src), str(1000 + k), "ref" if use_ref else "port"],
+    ps = [subprocess.Popen([sys.executable, worker, str(n_src), str(1000 + k), "ref" if use_ref else "port", str(size[0]), str(size[1]), quality],
                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for k in range(procs)]
     outs = [p.communicate()[0] for p in ps]
-    dt = time.perf_counter() - t0
-    ok = all(p.returncode == 0 for p in ps)
-    return dt, n_src * procs, ok, outs
+    wall = time.perf_counter() - t0
+    if not all(p.returncode == 0 for p in ps):
+        return None
+    rows = []
+    for o in outs:
+        t = o.split()
+        rows.append({t[i]: float(t[i + 1]) for i in range(0, len(t) - 1, 2)})
+    enc = max(r["encode_s"] for r in rows)
+    dec = max(r["decode_s"] for r in rows)
+    both = max(r["encode_s"] + r["decode_s"] for r in rows)
+    n_enc = sum(r["frames"] for r in rows)
+    return {"procs": procs, "source_frames": n_src * procs, "encoded_frames": int(n_enc), "encode_s": enc, "decode_s": dec, "roundtrip_s": both,
+            "palette_s": max(r["palette_s"] for r in rows), "wall_s": wall,
+            "roundtrip_source_fps": n_src * procs / max(both, 1e-6), "encode_source_fps": n_src * procs / max(enc, 1e-6), "decode_fps": n_enc / max(dec, 1e-6)}
 
 
-def cpu_baseline(args, bounded_seconds=25):
+def reference_unmodified(procs):
+    """The UNMODIFIED reference (oracle/_ref, gcc -O2 from /root/reference) on a prefix it can finish: 8 source frames of the
+    config-3 profile at LOW quality (HIGH needs ~357 s of AGMV_BubbleSort before the first frame), one
+    process on one core and `procs` processes side by side; the sort's fixed cost is measured on a 64x64 clip, where nothing
+    else takes time. Decode = the per-frame public API without BMP export."""
+    from agmv_testlib import have_ref
+    if not have_ref():
+        return {"unavailable": "oracle/_ref not built (needs the reference sources at build time)"}
+    out = {"clip": "8 source frames 1920x1080, AGMV_OPT_III, AGMV_LOW_QUALITY, LZSS (3 encoded frames)"}
+    fixed = cpu_clips(8, 1, True, "LOW", (64, 64))
+    one = cpu_clips(8, 1, True, "LOW")
+    if fixed:
+        out["fixed_palette_s_low_quality"] = fixed["encode_s"]
+    if one:
+        out["one_core"] = {k: one[k] for k in ("encode_s", "decode_s", "roundtrip_source_fps", "encode_source_fps", "decode_fps", "encoded_frames")}
+        if fixed:
+            out["one_core"]["encode_s_per_encoded_frame_after_fixed"] = (one["encode_s"] - fixed["encode_s"]) / max(1, one["encoded_frames"])
+    if procs > 1:
+        many = cpu_clips(8, procs, True, "LOW")
+        if many:
+            out["all_cores"] = {k: many[k] for k in ("procs", "encode_s", "decode_s", "roundtrip_source_fps", "encode_source_fps", "decode_fps")}
+    return out
+
+
+def cpu_baseline(args, bounded_seconds=25, with_reference=True):
     if _ALL_CPUS:
         os.sched_setaffinity(0, _ALL_CPUS)   # the CPU legs use every host core, not just the ones next to GPU 0
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_src = 8
-    dt, frames, ok, outs = cpu_clip_roundtrip(n_src, procs, use_ref=False)
-    return {"value": frames / dt if ok else None, "unit": UNIT, "cores": procs, "kind": "port",
-            "per_core": (frames / dt / procs) if ok else None,
-            "sample": f"{procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), oracle port encode + decode, "
-                      f"{dt:.1f} s wall",
+    r = cpu_clips(n_src, procs, use_ref=False)
+    one = cpu_clips(n_src, 1, use_ref=False)
+    line = {"value": r["roundtrip_source_fps"] if r else None, "unit": UNIT, "cores": procs, "kind": "port",
+            "per_core": (r["roundtrip_source_fps"] / procs) if r else None,
+            "encode_source_fps": r["encode_source_fps"] if r else None, "decode_fps": r["decode_fps"] if r else None,
+            "palette_s": r["palette_s"] if r else None,
+            "one_core": {k: one[k] for k in ("roundtrip_source_fps", "encode_source_fps", "decode_fps", "encode_s", "decode_s", "palette_s")} if one else None,
+            "sample": f"{procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), oracle port encode + no-export decode, "
+                      f"timed inside the workers (slowest worker: {r['roundtrip_s']:.1f} s)" if r else "worker failed",
             "note": "oracle/agmv_oracle.c (qsort instead of the reference's O(n^2) bubble sort, memoised quantiser): faster than the "
-                    "unmodified reference, so this flatters the CPU"}
+                    "unmodified reference, so this flatters the CPU; the unmodified reference is timed beside it on a LOW-quality prefix"}
+    if with_reference:
+        line["reference_unmodified"] = reference_unmodified(procs)
+    return line
 
 
 def run_reference(args):
@@ -569,20 +611,23 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, args.cpu_procs or cores))
     n_src = 8
-    vals, dts = [], []
+    vals, dts, last = [], [], None
     for _ in range(args.warmup + args.steps):
-        dt, frames, ok, _ = cpu_clip_roundtrip(n_src, procs, use_ref=False)
-        vals.append(frames / dt)
-        dts.append(dt)
+        r = cpu_clips(n_src, procs, use_ref=False)
+        vals.append(r["roundtrip_source_fps"])
+        dts.append(r["roundtrip_s"])
+        last = r
     vals, dts = vals[args.warmup:], dts[args.warmup:]
     v = float(np.mean(vals))
-    sample = (f"each step: {procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), encode + decode with the "
-              f"oracle port of the reference algorithm")
+    sample = (f"each step: {procs} processes x one {n_src}-source-frame 1080p clip (OPT_III, HIGH, LZSS), encode + no-export decode with the "
+              f"oracle port of the reference algorithm, timed inside the workers")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": float(np.mean(dts)) * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic",
             "config": {"workload": "BASELINE config 3 profile (1920x1080, AGMV_OPT_III, AGMV_HIGH_QUALITY, LZSS), bounded sample"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
+                             "encode_source_fps": last["encode_source_fps"], "decode_fps": last["decode_fps"], "palette_s": last["palette_s"],
+                             "reference_unmodified": reference_unmodified(procs)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 

@@ -158,9 +158,7 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
         ctx->own_stream = true;
     }
     ctx->lc.st = ctx->st;
-    if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess ||
-        cudaFuncSetAttribute(lz_scatter_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SCATTER_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(lz_small_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(pal_pick_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536) != cudaSuccess) {
         delete ctx;
         return ERR_CUDA;
     }
@@ -431,8 +429,6 @@ extern "C" int agmvb_enc_get_iframe_entries(agmvb_ctx* ctx, uint16_t* entries) {
 static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
     LzWork& w = ctx->lz;
     const uint32_t cap_before = w.cap_n;
-    static const bool legacy = getenv("AGMVB_LZ_LEGACY") && atoi(getenv("AGMVB_LZ_LEGACY")) != 0;
-    w.legacy = legacy;
     if (n + 64 > w.cap_n || !w.bestlen) {
         uint32_t cap = std::max<uint32_t>(n + n / 4 + 4096, 1u << 20);
         int k = 0;
@@ -442,44 +438,20 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
             k++;
             return OK;
         };
+        // occurrence-chain match finder (lzchain.cuh): 19 B per position
         TRY(grab(cap, (void**)&w.bestlen));
         TRY(grab((size_t)cap * 4, (void**)&w.match_rec));
         TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
-        if (!legacy) {
-            // occurrence-chain match finder (lzchain.cuh): 19 B per position
-            TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
-            TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
-            TRY(grab((size_t)cap * 2, (void**)&w.rsd));
-            TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
-            int sms = 148;
-            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-            int per3 = 5, perl = 6;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k, LZC_THREADS, 0);
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k, LZC_THREADS, 0);
-            w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
-            w.level_blocks = (uint32_t)(sms * std::max(1, perl));
-        } else {
-            for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.A[l]));
-            for (int l = 0; l <= LZ_LEVELS; l++) TRY(grab((size_t)cap * 4, (void**)&w.GS[l]));
-            TRY(grab((size_t)cap * 4, (void**)&w.gs_tmp));
-            TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[0]));
-            TRY(grab((size_t)cap * 4, (void**)&w.gs_carry[1]));
-            TRY(grab((size_t)(LZ_LEVELS + 1) * 257 * 4, (void**)&w.bstart));
-            TRY(grab(256 * 4, (void**)&w.bytehist));
-            {
-                const size_t ct = cdiv(cap, LZ_TILE) + 1;
-                TRY(grab((ct * 257 + 4) * 4, (void**)&w.chain_mem));
-            }
-            w.fused = getenv("AGMVB_LZ_FUSED") ? atoi(getenv("AGMVB_LZ_FUSED")) != 0 : false;
-            TRY(grab((size_t)cap * 4, (void**)&w.dig4[0]));
-            TRY(grab((size_t)cap * 4, (void**)&w.dig4[1]));
-            uint32_t nt = cdiv(cap, RX_TILE);
-            TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[0]));
-            TRY(grab((size_t)256 * nt * 4, (void**)&w.tile_hist[1]));
-            TRY(grab(((size_t)cdiv((size_t)256 * nt, SCAN_TILE) + 2 * (size_t)cdiv(cap, SCAN_TILE) + 16) * 4, (void**)&w.scan_ws));
-            w.runs = getenv("AGMVB_LZ_RUNS") ? atoi(getenv("AGMVB_LZ_RUNS")) != 0 : false;
-            if (w.runs) TRY(grab((size_t)cap * 4, (void**)&w.run_ws));
-        }
+        TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
+        TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
+        TRY(grab((size_t)cap * 2, (void**)&w.rsd));
+        TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
+        int sms = 148, per3 = 5, perl = 6;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k, LZC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k, LZC_THREADS, 0);
+        w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
+        w.level_blocks = (uint32_t)(sms * std::max(1, perl));
         w.cap_n = cap;
     }
     size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 16;
@@ -538,14 +510,12 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     }
     CK(cudaMemcpyAsync(ctx->lz.segs, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->lz.seg_len, slen.data(), F * 4, cudaMemcpyHostToDevice, ctx->st));
-    std::vector<LzcItem> items;
-    if (!ctx->lz.legacy) {   // (frame, range) work items of the serial hash-link kernel
-        lzc_build_items(h_fs, F, items);
-        TRY(ensure(ctx, ctx->lzbuf[60], (items.size() + 1) * sizeof(LzcItem)));
-        ctx->lz.items = ctx->lzbuf[60].as<LzcItem>();
-        ctx->lz.n_items = (uint32_t)items.size();
-        if (!items.empty()) CK(cudaMemcpyAsync(ctx->lz.items, items.data(), items.size() * sizeof(LzcItem), cudaMemcpyHostToDevice, ctx->st));
-    }
+    std::vector<LzcItem> items;   // (frame, range) work items of the serial hash-link kernel
+    lzc_build_items(h_fs, F, items);
+    TRY(ensure(ctx, ctx->lzbuf[60], (items.size() + 1) * sizeof(LzcItem)));
+    ctx->lz.items = ctx->lzbuf[60].as<LzcItem>();
+    ctx->lz.n_items = (uint32_t)items.size();
+    if (!items.empty()) CK(cudaMemcpyAsync(ctx->lz.items, items.data(), items.size() * sizeof(LzcItem), cudaMemcpyHostToDevice, ctx->st));
     lzss_encode_batch(ctx->lz, d_bs, ctx->fs.as<uint32_t>(), F, n, ntile, max_usize, first_fc, ctx->image.as<uint8_t>() + ctx->image_bytes, ctx->lc);
     CK(cudaStreamSynchronize(ctx->st));  // segs / slen are stack vectors
     TRY(check_launch(ctx, "lzss"));
@@ -594,8 +564,7 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
         ctx->image = nb;
     }
     CK(cudaMemsetAsync(ctx->l77_out.p, 0, ((size_t)n + F + 16) * 4, ctx->st));
-    static const bool window_scan = getenv("AGMVB_LZ77_SCAN") && atoi(getenv("AGMVB_LZ77_SCAN")) != 0;
-    if (window_scan || n == 0) {
+    if (n == 0) {   // nothing but empty frames: no candidate lists to build, the plain per-frame kernel writes the empty payloads
         KL(ctx->lc, KC_LZ77, (lz77_encode_k<<<F, L77_THREADS, 0, ctx->st>>>(d_bs, d_fs, d_stale, ctx->l77_persist.as<uint8_t>(), d_wbase,
                                                                           ctx->l77_out.as<uint32_t>(), d_bits)));
     } else {
@@ -648,8 +617,7 @@ static int lz77_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs,
     return OK;
 }
 
-static const uint32_t LZ_GROUP_TARGET_LEGACY = 64u << 20;  // positions per LZSS batch (149 B of workspace each: ~10 GB)
-static const uint32_t LZ_GROUP_TARGET = 1000u << 20;       // chain path: 19 B of workspace per position (<= 19 GB)
+static const uint32_t LZ_GROUP_TARGET = 1000u << 20;       // positions per LZSS batch: 19 B of workspace each (<= 19 GB)
 
 // classify + assemble n frames whose entries are on the device; runs LZSS group by group
 static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_t F, uint32_t first_fc) {
@@ -680,8 +648,7 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
     for (uint32_t g0 = 0; g0 < F;) {
         uint32_t g1 = g0 + 1;
         // LZ77 keeps 4 B of workspace per position and wants every frame of the batch in flight at once (one CTA per frame)
-        static const bool lz_legacy = getenv("AGMVB_LZ_LEGACY") && atoi(getenv("AGMVB_LZ_LEGACY")) != 0;
-        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : (lz_legacy ? LZ_GROUP_TARGET_LEGACY : LZ_GROUP_TARGET);
+        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : LZ_GROUP_TARGET;
         while (g1 < F && fs[g1 + 1] - fs[g0] <= target) g1++;
         rebased.resize(g1 - g0 + 1);
         for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
@@ -1382,12 +1349,7 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         OrbitTables tb;
         tb.exit_tab = ctx->d_oexit.as<uint8_t>(); tb.w_tab = ctx->d_ow.as<uint16_t>(); tb.entry_tab = ctx->d_oentry.as<uint8_t>();
         tb.cumbase = ctx->d_ocum.as<uint32_t>(); tb.final_pos = ctx->d_ofinal.as<uint32_t>(); tb.final_cum = tb.final_pos + F;
-        static const int expand_pc = getenv("AGMVB_EXPAND_PC") ? atoi(getenv("AGMVB_EXPAND_PC")) : 0;   // 1: SC fences on both sides, 2: none on the copier, 3: none on the copier + release-only fence on the parser (not yet measured)
-        if (expand_pc)  // two warps per frame: parser + copier (decode.cuh)
-            KL(ctx->lc, KC_EXPAND, (expand_pc_k<<<F, 64, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_consumed.as<uint32_t>(),
-                                                                     expand_pc == 1 ? 1 : (expand_pc == 3 ? 2 : 0))));
-        else
-            KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
+        KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
                                                                                             ctx->d_consumed.as<uint32_t>())));
         KL(ctx->lc, KC_STALE, (stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>())));
         {

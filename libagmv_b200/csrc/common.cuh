@@ -63,12 +63,13 @@ inline int cdiv(size_t a, size_t b) { return (int)((a + b - 1) / b); }
 // on the launching stream so per-kernel-class device time can be read back live.
 enum KClass {
     KC_HIST = 0, KC_PALETTE, KC_QUANT, KC_CLASSIFY, KC_BLOCKSCAN, KC_EMIT, KC_LZ_INIT, KC_RX_HIST, KC_RX_SCAN, KC_RX_SCATTER,
-    KC_LZ_GROUP, KC_LZ_PARSE, KC_LZ_PACK, KC_LZ_CHUNK, KC_EXPAND, KC_STALE, KC_INDEX, KC_RECON, KC_CHECKSUM, KC_MISC, KC_LZ77, KC_LZ_SMALL, KC_LZ_TINY, KC_AUDIO, KC_LZ_LINK, KC_LZ_LEVEL, KC_LZ_LINK3, KC_COUNT
+    KC_LZ_LINK, KC_LZ_LINK3, KC_LZ_LEVEL, KC_LZ_PARSE, KC_LZ_PACK, KC_LZ_CHUNK, KC_EXPAND, KC_STALE, KC_INDEX, KC_RECON, KC_CHECKSUM, KC_MISC,
+    KC_LZ77, KC_AUDIO, KC_COUNT
 };
 inline const char* kclass_name(int c) {
     static const char* n[] = {"hist", "palette", "quantize", "classify", "block_scan", "emit", "lz_init", "rx_hist", "rx_scan",
-                              "rx_scatter", "lz_group", "lz_parse", "lz_pack", "lz_chunk", "expand", "stale", "index", "reconstruct",
-                              "checksum", "misc", "lz77", "lz_small", "lz_tiny", "audio", "lz_link", "lz_level", "lz_link3"};
+                              "rx_scatter", "lz_link", "lz_link3", "lz_level", "lz_parse", "lz_pack", "lz_chunk", "expand", "stale", "index",
+                              "reconstruct", "checksum", "misc", "lz77", "audio"};
     return c >= 0 && c < KC_COUNT ? n[c] : "?";
 }
 struct LaunchCtx {

@@ -224,192 +224,6 @@ __global__ void __launch_bounds__(EX_WARPS * 32) expand_mrr_k(const DecFrame* __
     }
 }
 
-// ---- D2, two warps per frame ---------------------------------------------------
-// The same walk split by role (ncu, profiles/r01_expand_ncu.txt: one warp per frame issues an instruction every ~5 cycles and
-// the kernel lasts as long as one frame's serial chain). Warp 0 PARSES: stages the payload, finds the token starts, decodes and
-// settles the tokens of a chunk (offsets, lengths, distances - none of which depends on the expanded bytes) and hands the chunk
-// over through a two-slot ring in shared memory. Warp 1 COPIES: literals and matches of the chunk, in rounds as before. The
-// parser runs ahead by up to two chunks, so the copier's L2 round trips overlap the parser's dependent chain.
-// Hand-over: named barriers (ids 1-2 "slot full", 3-4 "slot free", 64 threads each: one side arrives, the other waits).
-__device__ __forceinline__ void pc_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-__device__ __forceinline__ void pc_bar_arrive(int id) { asm volatile("bar.arrive %0, 64;" ::"r"(id) : "memory"); }
-
-__global__ void __launch_bounds__(64) expand_pc_k(const DecFrame* __restrict__ fr, uint32_t F, uint8_t* __restrict__ ebuf,
-                                                  uint32_t* __restrict__ bpos_out, uint32_t* __restrict__ consumed_out, int copier_fence) {
-    __shared__ uint32_t win[EX_WIN + 3];
-    __shared__ uint32_t tk_o[32];
-    __shared__ __align__(16) uint8_t stp[EX_WIN * 32];
-    __shared__ uint32_t ch_o[2][32], ch_d[2][32], ch_m[2][32];   // per token: output offset, distance, flags | length | literal
-    __shared__ uint32_t ch_last[2];
-    const int role = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t f = blockIdx.x;
-    if (f >= F) return;
-    const DecFrame d = fr[f];
-    uint8_t* e = ebuf + d.ebuf_off;
-    const uint8_t* __restrict__ file = d.file;
-    if (d.lz77) { if (role == 0) expand_lz77_warp(d, e, file, f, lane, bpos_out, consumed_out); return; }
-    if (role == 1) {
-        // ---- copier ----
-        uint32_t slot = 0;
-        while (true) {
-            pc_bar_sync(1 + slot);
-            const uint32_t o = ch_o[slot][lane], dd = ch_d[slot][lane], m = ch_m[slot][lane];
-            const uint32_t last = ch_last[slot];
-            // The slot must have been read before the parser may refill it. A fence guarantees that but also waits for the
-            // previous chunk's global stores; without it (copier_fence == 0, experimental) the order rests on the warp issuing
-            // its shared-memory loads before the barrier arrive, and the values being consumed by the vote below.
-            if (copier_fence & 1) __threadfence_block();
-            else if (__any_sync(0xffffffffu, (o ^ dd ^ m ^ last) == 0x9E3779B9u && last > 1u)) return;   // never true: last is 0 or 1
-            __syncwarp();
-            pc_bar_arrive(3 + slot);
-            const bool active = m & 1u, lit = m & 2u;
-            const uint32_t l = (m >> 2) & 63u, w = (m >> 8) << 1;   // w >> 1 = the literal byte, as in the one-warp kernel
-            // ---- resolve the copies of this chunk ----
-            bool done = !active || l == 0;
-            if (active && lit) { e[o] = (uint8_t)(w >> 1); done = true; }
-            __syncwarp();
-            while (true) {
-                unsigned m = __ballot_sync(0xffffffffu, !done);
-                if (!m) break;
-                const uint32_t hwm = __shfl_sync(0xffffffffu, o, __ffs(m) - 1);
-                const bool can = !done && (o - dd + (l < dd ? l : dd) <= hwm);
-                if (can) {
-                    const uint8_t* src = e + o - dd;
-                    if (dd >= l) {
-                        uint8_t v[15];
-#pragma unroll
-                        for (int k = 0; k < 15; k++) if ((uint32_t)k < l) v[k] = src[k];
-#pragma unroll
-                        for (int k = 0; k < 15; k++) if ((uint32_t)k < l) e[o + k] = v[k];
-                    } else {
-                        for (uint32_t k = 0; k < l; k++) e[o + k] = src[k];  // overlapping copy: byte order matters
-                    }
-                    done = true;
-                }
-                __syncwarp();
-            }
-            __syncwarp();
-            if (last) break;
-            slot ^= 1u;
-        }
-        return;
-    }
-    // ---- parser ----
-    uint32_t slot = 0, filled = 0;
-    const uint64_t nbits = (uint64_t)d.csize * 8;
-    uint64_t bitp = 0;       // bits consumed so far (== the reference's `bits`), warp-uniform
-    uint32_t bpos = 0;       // warp-uniform
-    bool more = nbits > 0 && d.usize > 0;
-    while (more) {
-        // ---- stage the next EX_WIN payload words (plus slack for a token that straddles the end) ----
-        const uint64_t win_word0 = bitp >> 5;
-        for (int k = lane; k < EX_WIN + 3; k += 32) {
-            uint64_t b = d.data_off + (win_word0 + k) * 4;
-            uint32_t w = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) w |= (b + j < d.file_len ? (uint32_t)file[b + j] : 0u) << (8 * j);  // fread past EOF leaves 0
-            win[k] = w;
-        }
-        __syncwarp();
-        // Token length for a token starting at every bit of the window (flag bit 1: literal, 9 bits; 0: match, 21 bits), so that
-        // the serial walk below is one shared-memory byte load and one add per token. Four bits -> one 32-bit store; lanes write
-        // consecutive words.
-        for (int it = 0; it < EX_WIN / 4; it++) {
-            const int k = it * 4 + (lane >> 3), q = lane & 7;
-            const uint32_t nib = (win[k] >> (4 * q)) & 15u;
-            reinterpret_cast<uint32_t*>(stp)[k * 8 + q] = 0x15151515u - 12u * ((nib & 1u) | (nib & 2u) << 7 | (nib & 4u) << 14 | (nib & 8u) << 21);
-        }
-        __syncwarp();
-        const uint64_t wbit0 = win_word0 << 5;
-        const uint32_t limit = (uint32_t)((nbits - wbit0) < (uint64_t)(EX_WIN * 32) ? (nbits - wbit0) : (uint64_t)(EX_WIN * 32));  // tokens must start below it
-        bool window_left = true;
-        while (more && window_left) {
-            // ---- lane 0: the serial part, reduced to finding where the next <= 32 tokens start (9 or 21 bits each) ----
-            uint32_t ntok = 0;
-            const uint32_t rel0 = (uint32_t)(bitp - wbit0);
-            if (lane == 0) {
-                uint32_t rel = rel0;
-                const uint8_t* st = stp;
-                while (ntok < 32 && rel < limit) {
-                    tk_o[ntok++] = rel;
-                    rel += st[rel];
-                }
-            }
-            ntok = __shfl_sync(0xffffffffu, ntok, 0);
-            __syncwarp();
-            if (ntok == 0) { window_left = false; break; }  // next token starts beyond the staged window (or at nbits)
-            // ---- all lanes: decode one token each ----
-            const bool have = (uint32_t)lane < ntok;
-            const uint32_t rel = have ? tk_o[lane] : 0u;
-            const uint32_t w = __funnelshift_r(win[rel >> 5], win[(rel >> 5) + 1], rel & 31);
-            const bool lit = have && (w & 1u);
-            const uint32_t off_raw = (w >> 1) & 0xFFFFu, len_raw = (w >> 17) & 15u;
-            uint32_t dd = off_raw;
-            uint32_t l = !have ? 0u : (lit ? 1u : len_raw);
-            const uint32_t tbits = lit ? 9u : 21u;
-            // Output offsets = exclusive prefix of the copy lengths. The reference copies byte i of a match iff
-            // (pos - offset + i) < bpos in UNSIGNED arithmetic (src/agmv_decode.c:192-196), so with o = bpos at the token:
-            //   1 <= offset <= o          all `len` bytes from o - offset (overlap allowed);
-            //   o < offset < o + len      the first (offset - o) indices wrap and are skipped, the rest copy from index 0
-            //                             on: len - (offset - o) bytes, i.e. a match of distance o (nothing if o == 0);
-            //   otherwise                 nothing.
-            // Only damaged streams leave the first case. Lengths are settled front to back: everything before the first
-            // lane whose length changes is final.
-            uint32_t o;
-            while (true) {
-                uint32_t inc = l;
-#pragma unroll
-                for (int k = 1; k < 32; k <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, inc, k); if (lane >= k) inc += y; }
-                o = bpos + inc - l;
-                uint32_t l2 = l, d2 = dd;
-                if (have && !lit) {
-                    if (off_raw >= 1 && off_raw <= o) { l2 = len_raw; d2 = off_raw; }
-                    else if (off_raw > o && off_raw < o + len_raw && o > 0) { l2 = len_raw - (off_raw - o); d2 = o; }
-                    else { l2 = 0; d2 = off_raw; }
-                }
-                const unsigned bm = __ballot_sync(0xffffffffu, l2 != l || (l2 > 0 && d2 != dd));
-                if (!bm) break;
-                if (lane == __ffs(bm) - 1) { l = l2; dd = d2; }
-            }
-            // the reference stops before a token when bpos has reached usize
-            const unsigned stop = __ballot_sync(0xffffffffu, have && o >= d.usize);
-            const uint32_t nuse = stop ? (uint32_t)(__ffs(stop) - 1) : ntok;
-            const bool active = (uint32_t)lane < nuse;
-            // new warp-uniform state, taken from the last token actually used
-            const uint32_t lastl = nuse - 1;  // nuse >= 1: the first token of a chunk always has o == bpos < usize
-            bitp = wbit0 + __shfl_sync(0xffffffffu, rel + tbits, lastl);
-            bpos = __shfl_sync(0xffffffffu, o + l, lastl);
-            more = bitp < nbits && bpos < d.usize;
-            if ((uint32_t)(bitp - wbit0) >= limit && more) window_left = false;
-            // ---- hand the chunk to the copier ----
-            if (filled >= 2) pc_bar_sync(3 + slot);
-            ch_o[slot][lane] = o;
-            ch_d[slot][lane] = dd;
-            ch_m[slot][lane] = (active ? 1u : 0u) | (lit ? 2u : 0u) | l << 2 | ((w >> 1) & 255u) << 8;
-            if (lane == 0) ch_last[slot] = more ? 0u : 1u;
-            // publish the slot: __threadfence_block() is a MEMBAR.SC.CTA in SASS (sequentially consistent, every chunk);
-            // copier_fence & 2 selects the lighter release-only fence (experimental, not yet measured)
-            if (copier_fence & 2) asm volatile("fence.acq_rel.cta;" ::: "memory");
-            else __threadfence_block();
-            __syncwarp();
-            pc_bar_arrive(1 + slot);
-            slot ^= 1u;
-            filled++;
-        }
-    }
-    if (filled == 0) {   // empty payload: the copier still waits for a (last, empty) chunk
-        ch_o[0][lane] = 0; ch_d[0][lane] = 0; ch_m[0][lane] = 0;
-        if (lane == 0) ch_last[0] = 1u;
-        __threadfence_block();
-        __syncwarp();
-        pc_bar_arrive(1);
-    }
-    if (lane == 0) {
-        bpos_out[f] = bpos;
-        consumed_out[f] = (uint32_t)((bitp + 7) >> 3);
-    }
-}
-
 // ---- stale bytes -----------------------------------------------------------
 // stale[f*4+d] = content of the persistent bitstream buffer at index bpos_f + d
 // when frame f is walked: written by the latest earlier frame j of the same

@@ -634,32 +634,6 @@ def test_small_and_odd_frame_sizes_against_oracle(ctx):
             assert rc == 0 and np.array_equal(ctx.decode_all(want), exp), (w, h, opt, q)
 
 
-def test_lzss_run_table_option_is_exact():
-    """AGMVB_LZ_RUNS=1: the large three-equal-byte groups are resolved from run tables instead of the global levels
-    (tools/run_path_prototype.py). Off by default; it must give the same bytes."""
-    import libagmv_b200
-    rng = np.random.default_rng(31)
-    bufs = _lz_structured_buffers()
-    for nruns, lo, hi in ((3000, 3, 60), (400, 100, 900), (20000, 3, 20)):
-        parts = []
-        for k in range(nruns):
-            parts += [np.full(rng.integers(lo, hi), 0x5E, np.uint8), rng.integers(64, 70, rng.integers(1, 4), dtype=np.uint8)]
-        bufs.append(np.concatenate(parts))
-    want = [oracle_lzss(b) for b in bufs]
-    os.environ["AGMVB_LZ_RUNS"] = "1"
-    try:
-        c = libagmv_b200.Context(0)
-        got = c.test_lzss(bufs)
-        for k, (g, w) in enumerate(zip(got, want)):
-            assert (g[0], g[2]) == (w[0], w[2]) and g[1] == w[1], f"frame {k} of the batch"
-        frames = synth_frames(1920, 1080, 8, seed=1234)
-        data, _ = c.encode_sequence(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZSS)
-        assert data.tobytes() == oracle_encode(frames, 7, 24, OPT["III"], QUALITY["LOW"], LZSS)
-        c.close()
-    finally:
-        del os.environ["AGMVB_LZ_RUNS"]
-
-
 # ---- the bench's own configuration, pinned (BASELINE config 3 / 4 profile: OPT_III, HIGH quality, LZSS) ----------------
 def test_1080p_high_quality_prefix_against_oracle(ctx):
     """What bench.py times is OPT_III / HIGH at 1080p: 19-bit histogram bins, the (2,2,3) palette pick box, far more distinct
