@@ -105,6 +105,17 @@ int agmvb_enc_image_ptr(agmvb_ctx* ctx, uint8_t** dev_image, uint64_t* bytes);
 int agmvb_encode_sequence(agmvb_ctx* ctx, const uint32_t* frames, int on_device, uint32_t n_src, uint32_t w, uint32_t h,
                           uint32_t create_n, uint32_t fps, int opt, int quality, int compression,
                           uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+/* agmvb_encode_sequence over several GPUs of this process: ctxs[k] = one context per device (agmvb_create with
+ * that device); frames in HOST memory. Every GPU histograms its share of the source frames, the bins are summed over peer
+ * copies (the palette is global: src/agmv_encode.c:2371-2568), every GPU encodes a GOP-aligned range of the PDIFS schedule
+ * (:2727-2770) and copies its chunks to their final place in `out`. The bytes are those of the single-GPU call.
+ * AGMVB_LZSS only (the LZ77 coder carries state from frame to frame, :218-224). */
+int agmvb_encode_sequence_multi(agmvb_ctx* const* ctxs, int n_ctx, const uint32_t* frames, uint32_t n_src, uint32_t w, uint32_t h,
+                                uint32_t create_n, uint32_t fps, int opt, int quality, int compression,
+                                uint8_t* out, uint64_t cap, uint64_t* out_len, uint32_t* n_encoded);
+/* Range of encoded frames [first, first + count) that shard `shard` of `n_shards` takes: borders are multiples of 12 encoded
+ * frames for the LIGHT profiles (4 PDIFS groups = 3 GOPs = 16 source frames), of 4 for the HEAVY ones. */
+int agmvb_shard_range(uint32_t n_enc, int light, int n_shards, int shard, uint32_t* first, uint32_t* count);
 /* The reference's other two sequence encoders, same conventions as agmvb_encode_sequence:
  * AGMV_EncodeVideo (src/agmv_encode.c:719-2268): a pair of frames is merged only if the fraction of grey-equal pixels
  * (AGMV_CompareFrameSimilarity, src/agmv_utils.c:920-947) reaches the profile's leniency; no audio chunks;

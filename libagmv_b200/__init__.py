@@ -47,6 +47,9 @@ SYMBOLS = {
     "agmvb_enc_header": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, _u8p, C.c_uint64, _u64p]),
     "agmvb_encode_sequence": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                         C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "agmvb_encode_sequence_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                              C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_uint64, _u64p, _u32p]),
+    "agmvb_shard_range": (C.c_int, [C.c_uint32, C.c_int, C.c_int, C.c_int, _u32p, _u32p]),
     "agmvb_encode_video": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p, C.c_uint64, _u64p, _u32p]),
     "agmvb_encode_full": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
@@ -162,6 +165,17 @@ class Context:
         ln, ne = C.c_uint64(), C.c_uint32()
         self._ck(self.lib.agmvb_encode_sequence(self.h, C.c_void_p(src), on_dev, n, w, h, create_n, fps, opt, quality,
                                                 compression, C.c_void_p(out.ctypes.data), out.size, C.byref(ln), C.byref(ne)))
+        return out[:ln.value], ne.value
+
+    def encode_sequence_multi(self, others, frames, create_n, fps, opt, quality, compression=LZSS):
+        """agmvb_encode_sequence_multi: this context plus `others` (one Context per further GPU), host frames (n,h,w) uint32."""
+        frames = np.ascontiguousarray(frames, dtype=np.uint32)
+        n, h, w = frames.shape
+        out = np.empty(4096 + n * (w * h * 3 + 64), dtype=np.uint8)
+        ctxs = (C.c_void_p * (1 + len(others)))(self.h, *[o.h for o in others])
+        ln, ne = C.c_uint64(), C.c_uint32()
+        self._ck(self.lib.agmvb_encode_sequence_multi(ctxs, len(ctxs), C.c_void_p(frames.ctypes.data), n, w, h, create_n, fps, opt, quality,
+                                                      compression, C.c_void_p(out.ctypes.data), out.size, C.byref(ln), C.byref(ne)))
         return out[:ln.value], ne.value
 
     def encode_mode(self, mode, frames, create_n, fps, opt, quality, compression=LZSS):

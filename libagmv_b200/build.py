@@ -24,7 +24,7 @@ def build(force=False, verbose=False):
     cu = [os.path.join(CSRC, "api.cu")]
     deps = cu + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "agmv_b200.h")]
     if force or _newer(lib, deps):
-        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", lib] + cu + ["-lcudart"]
+        cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-shared", "-o", lib] + cu + ["-lcudart", "-lpthread"]
         subprocess.run(cmd, check=True)
     dropin_src = os.path.join(CSRC, "agmv_dropin.c")
     if os.path.exists(dropin_src):

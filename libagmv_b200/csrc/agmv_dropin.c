@@ -30,6 +30,30 @@ static char g_err[600] = "";
 const char* AGMV_B200_LastError(void) { return g_err; }
 void AGMV_B200_SetDevice(int device) { g_device = device; }
 
+/* AGMV_B200_DEVICES=0,1,2,3: one context per listed GPU for sequence encodes (first use); returns how many there are */
+static agmvb_ctx* g_multi[16];
+static int g_n_multi = -1;
+static int multi_devices(void) {
+    if (g_n_multi >= 0) return g_n_multi;
+    g_n_multi = 0;
+    const char* e = getenv("AGMV_B200_DEVICES");
+    if (!e || !*e) return 0;
+    while (*e && g_n_multi < 16) {
+        char* end = NULL;
+        long d = strtol(e, &end, 10);
+        if (end == e) break;
+        if (agmvb_create(&g_multi[g_n_multi], (int)d, NULL) != 0) {
+            fprintf(stderr, "libagmv_dropin: AGMV_B200_DEVICES: no context on GPU %ld, using one GPU\n", d);
+            for (int k = 0; k < g_n_multi; k++) agmvb_destroy(g_multi[k]);
+            g_n_multi = 0;
+            return 0;
+        }
+        g_n_multi++;
+        e = *end == ',' ? end + 1 : end;
+    }
+    return g_n_multi;
+}
+
 static agmvb_ctx* ctx_get(void) {
     if (!g_ctx) {
         int rc = agmvb_create(&g_ctx, g_device, NULL);
@@ -289,6 +313,8 @@ void AGMV_EncodeAudioChunk(FILE* file, AGMV* agmv) {
     agmv->audio_track->start_point += size;
 }
 
+static void export_gba_header(const char* filename);
+
 /* src/agmv_encode.c:2270-3657, BMP input */
 void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const char* basename, u8 img_type, u32 start_frame,
                      u32 end_frame, u32 width, u32 height, u32 frames_per_second, AGMV_OPT opt, AGMV_QUALITY quality,
@@ -324,6 +350,38 @@ void AGMV_EncodeAGMV(AGMV* agmv, const char* filename, const char* dir, const ch
     const u32 n_src = end_frame - start_frame + 1;
     const int cur_dir = dir[0] == 'c' && dir[1] == 'u' && dir[2] == 'r'; /* :2373 */
     char path[512];
+    /* AGMV_B200_DEVICES=0,1,..: the sequence is sharded by frame range over those GPUs (agmvb_encode_sequence_multi). The
+     * frames are held in host memory for that (both passes read them); sequences with an audio track or the LZ77 coder take the
+     * single-GPU path below. The file is byte-identical either way. */
+    if (multi_devices() > 1 && compression == AGMV_LZSS_COMPRESSION && agmv->header.audio_size == 0 && n_src >= 4) {
+        uint32_t* all = (uint32_t*)malloc((size_t)n_src * SP * 4);
+        size_t cap = 4096 + (size_t)n_src * (SP * 3 + 64);
+        uint8_t* outb = (uint8_t*)malloc(cap);
+        int rcm = (all && outb) ? 0 : AGMVB_ERR_MEMORY;
+        for (u32 k = 0; k < n_src && !rcm; k++) {
+            if (cur_dir) snprintf(path, sizeof path, "%s%lu.bmp", basename, start_frame + k);
+            else snprintf(path, sizeof path, "%s/%s%lu.bmp", dir, basename, start_frame + k);
+            if (load_bmp(path, width, height, all + (size_t)k * SP)) rcm = AGMVB_ERR_FILE;
+        }
+        uint64_t len = 0;
+        uint32_t ne = 0;
+        if (!rcm) rcm = agmvb_encode_sequence_multi(g_multi, g_n_multi, all, (uint32_t)n_src, (uint32_t)width, (uint32_t)height,
+                                                   (uint32_t)agmv->header.num_of_frames, (uint32_t)agmv->header.frames_per_second, (int)opt,
+                                                   (int)quality, (int)compression, outb, cap, &len, &ne);
+        if (!rcm) {
+            FILE* mf = fopen(filename, "wb");
+            if (mf) { fwrite(outb, 1, (size_t)len, mf); fclose(mf); }
+            else fprintf(stderr, "libagmv_dropin: cannot create %s\n", filename);
+        } else {
+            snprintf(g_err, sizeof g_err, "AGMV_EncodeAGMV (multi-GPU): error %d: %s", rcm, agmvb_last_error(g_multi[0]));
+            fprintf(stderr, "libagmv_dropin: %s\n", g_err);
+        }
+        free(all); free(outb);
+        g_enc.valid = 0;
+        DestroyAGMV(agmv);
+        if (!rcm && (opt == AGMV_OPT_GBA_I || opt == AGMV_OPT_GBA_II || opt == AGMV_OPT_GBA_III)) export_gba_header(filename);
+        return;
+    }
     int rc = agmvb_enc_begin(c, (uint32_t)width, (uint32_t)height, (int)opt, (int)quality, (int)compression);
     if (!rc) rc = agmvb_enc_set_audio_stub(c, 1); /* AGMV_EncodeAudioChunk after every frame: 'AGAC' 0 when there is no audio */
     if (!rc) rc = track_to_gpu(c, agmv);          /* AGMV_CompressAudio (:2667) */

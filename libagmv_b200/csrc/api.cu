@@ -8,6 +8,9 @@
 
 #include <algorithm>
 #include <vector>
+#include <thread>
+#include <mutex>
+#include <condition_variable>
 
 #include "audio.cuh"
 #include "common.cuh"
@@ -1040,6 +1043,153 @@ extern "C" int agmvb_encode_full(agmvb_ctx* ctx, const uint32_t* frames, int on_
                                  uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
                                  uint64_t* out_len, uint32_t* n_encoded) {
     return encode_sequence_impl(ctx, SEQ_FULL, frames, on_device, n_src, w, h, create_n, fps, opt, quality, compression, out, cap, out_len, n_encoded);
+}
+
+// ===========================================================================
+// one sequence over several GPUs of this process
+// ===========================================================================
+// AGMV_EncodeAGMV shards by frame range once the palette is known (P-frames only refer to the I-frame of their own group
+// of four encoded frames): every GPU histograms its share of the SOURCE frames, the bins are summed (the palette is a
+// function of every frame, src/agmv_encode.c:2371-2568), every GPU builds the identical palette and encodes a range of the
+// schedule whose borders are whole PDIFS groups and whole GOPs (12 encoded frames for the LIGHT profiles, 4 for HEAVY), and
+// the chunk images are copied straight to their final offsets of the caller's buffer. One host thread per GPU; the only
+// exchanges are the bins (peer copies over NVLink, summed on the first device) and the image sizes (host).
+__global__ void hist_sum_k(unsigned long long* __restrict__ acc, const unsigned long long* __restrict__ part, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += part[i];
+}
+
+namespace {
+struct HostBarrier {   // reusable barrier for the per-GPU host threads
+    std::mutex m;
+    std::condition_variable cv;
+    int n, waiting = 0, phase = 0;
+    explicit HostBarrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        const int ph = phase;
+        if (++waiting == n) { waiting = 0; phase++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return phase != ph; });
+    }
+};
+}  // namespace
+
+// the AGMV_EncodeAGMV schedule (src/agmv_encode.c:2727-2770, exit rule :3610-3612) for source frames 1..n_src
+static void agmv_schedule(bool light, uint32_t n_src, std::vector<int32_t>& sa, std::vector<int32_t>& sb) {
+    sa.clear(); sb.clear();
+    for (uint32_t i = 1; i <= n_src;) {
+        if (light) {
+            sa.push_back(i - 1); sb.push_back(-1);
+            sa.push_back(i); sb.push_back(i + 1);
+            sa.push_back(i + 2); sb.push_back(-1);
+            i += 4;
+        } else {
+            sa.push_back(i - 1); sb.push_back(i);
+            i += 2;
+        }
+        if (i + 4 >= n_src) break;
+    }
+}
+
+extern "C" int agmvb_shard_range(uint32_t n_enc, int light, int n_shards, int shard, uint32_t* first, uint32_t* count) {
+    if (n_shards <= 0 || shard < 0 || shard >= n_shards || !first || !count) return ERR_ARG;
+    const uint32_t group = light ? 12u : 4u;   // whole PDIFS groups and whole GOPs
+    const uint32_t units = (n_enc + group - 1) / group, per = (units + n_shards - 1) / n_shards;
+    const uint32_t a = std::min<uint64_t>((uint64_t)shard * per * group, n_enc), b = std::min<uint64_t>((uint64_t)(shard + 1) * per * group, n_enc);
+    *first = a;
+    *count = b - a;
+    return OK;
+}
+
+extern "C" int agmvb_encode_sequence_multi(agmvb_ctx* const* ctxs, int n_ctx, const uint32_t* frames, uint32_t n_src, uint32_t w, uint32_t h,
+                                           uint32_t create_n, uint32_t fps, int opt, int quality, int compression, uint8_t* out, uint64_t cap,
+                                           uint64_t* out_len, uint32_t* n_encoded) {
+    if (!ctxs || n_ctx < 1 || !frames || !out || n_src < 2) return ERR_ARG;
+    for (int k = 0; k < n_ctx; k++) if (!ctxs[k]) return ERR_ARG;
+    agmvb_ctx* ctx = ctxs[0];   // error text of argument checks
+    if (compression != COMP_LZSS) FAIL(ERR_UNSUPPORTED, "LZ77 carries its bitstream buffer from frame to frame: not sharded");
+    if (n_ctx == 1) return agmvb_encode_sequence(ctx, frames, 0, n_src, w, h, create_n, fps, opt, quality, compression, out, cap, out_len, n_encoded);
+    const bool light = opt_is_light(opt);
+    std::vector<int32_t> sa, sb;
+    if (light ? n_src < 4 : n_src < 2) FAIL(ERR_ARG, "sequence too short");
+    agmv_schedule(light, n_src, sa, sb);
+    const uint32_t n_enc = (uint32_t)sa.size();
+    std::vector<int> rc(n_ctx, OK);
+    std::vector<uint64_t> img(n_ctx, 0);
+    uint64_t hdr_len = 0;
+    HostBarrier bar(n_ctx);
+    const uint64_t fpx = (uint64_t)w * h;
+    auto fail_all = [&](int k, int code) { rc[k] = code; };
+    auto any_failed = [&]() { for (int c : rc) if (c != OK) return true; return false; };
+    auto worker = [&](int k) {
+        agmvb_ctx* c = ctxs[k];
+        int r = agmvb_enc_begin(c, w, h, opt, quality, compression);
+        if (!r) r = agmvb_enc_set_audio_stub(c, 1);
+        // pass 1: this GPU's share of the source frames
+        const uint64_t f0 = (uint64_t)n_src * k / n_ctx, f1 = (uint64_t)n_src * (k + 1) / n_ctx;
+        if (!r && f1 > f0) r = agmvb_enc_histogram(c, frames + f0 * fpx, f1 - f0, 0);
+        if (!r && cudaStreamSynchronize(c->st) != cudaSuccess) r = ERR_CUDA;
+        if (r) fail_all(k, r);
+        bar.wait();
+        if (k == 0 && !any_failed()) {   // sum on the first device, hand the total back to everybody
+            agmvb_ctx* c0 = ctxs[0];
+            const uint32_t bins = c0->mc + 1;
+            unsigned long long* tmp = c0->d_keys[0];   // free until the palette sort
+            cudaError_t e = cudaSetDevice(c0->device);
+            for (int j = 1; j < n_ctx; j++) {   // direct NVLink path where the topology has one (else the copies are staged by the driver)
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, c0->device, ctxs[j]->device) == cudaSuccess && can)
+                    if (cudaDeviceEnablePeerAccess(ctxs[j]->device, 0) != cudaSuccess) (void)cudaGetLastError();   // already enabled
+            }
+            for (int j = 1; j < n_ctx && e == cudaSuccess; j++) {
+                e = cudaMemcpyPeerAsync(tmp, c0->device, ctxs[j]->d_hist, ctxs[j]->device, (size_t)bins * 8, c0->st);
+                if (e == cudaSuccess) hist_sum_k<<<cdiv(bins, 256), 256, 0, c0->st>>>(c0->d_hist, tmp, bins);
+            }
+            for (int j = 1; j < n_ctx && e == cudaSuccess; j++)
+                e = cudaMemcpyPeerAsync(ctxs[j]->d_hist, ctxs[j]->device, c0->d_hist, c0->device, (size_t)bins * 8, c0->st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c0->st);
+            if (e != cudaSuccess) { snprintf(c0->err, sizeof c0->err, "histogram exchange: %s", cudaGetErrorString(e)); fail_all(0, ERR_CUDA); }
+        }
+        bar.wait();
+        r = any_failed() ? ERR_CUDA : OK;
+        if (!r) r = agmvb_enc_build_palette(c);   // identical on every GPU
+        uint32_t e0 = 0, cnt = 0;
+        agmvb_shard_range(n_enc, light, n_ctx, k, &e0, &cnt);
+        if (!r && k == 0) r = agmvb_enc_header(c, create_n, fps, out, cap, &hdr_len);
+        if (!r && cnt) r = agmvb_enc_frames(c, frames, n_src, 0, sa.data() + e0, sb.data() + e0, cnt, e0, &img[k]);
+        if (r) fail_all(k, r);
+        bar.wait();
+        if (any_failed()) return;
+        uint64_t off = hdr_len, total = hdr_len;
+        for (int j = 0; j < n_ctx; j++) { if (j < k) off += img[j]; total += img[j]; }
+        if (total > cap) { if (k == 0) snprintf(c->err, sizeof c->err, "output buffer too small: need %llu", (unsigned long long)total); fail_all(k, ERR_ARG); return; }
+        if (cnt) r = agmvb_enc_fetch(c, out + off, img[k], nullptr, nullptr);   // straight to its place in the file
+        if (r) fail_all(k, r);
+    };
+    std::vector<std::thread> th;
+    for (int k = 1; k < n_ctx; k++) th.emplace_back(worker, k);
+    worker(0);
+    for (auto& t : th) t.join();
+    for (int k = 0; k < n_ctx; k++)
+        if (rc[k] != OK) {
+            if (k != 0) snprintf(ctx->err, sizeof ctx->err, "GPU %d: %.400s", ctxs[k]->device, ctxs[k]->err);
+            return rc[k];
+        }
+    uint64_t total = hdr_len;
+    for (int k = 0; k < n_ctx; k++) total += img[k];
+    // back-patch (:3615-3620)
+    uint32_t adjusted = n_src - 1;
+    switch (opt) {
+        case OPT_I: case OPT_ANIM: case OPT_GBA_I: case OPT_GBA_II: adjusted /= 2; break;
+        case OPT_GBA_III: adjusted = (uint32_t)(adjusted * 0.75f); break;
+        default: adjusted = (uint32_t)(adjusted * 0.75); break;
+    }
+    put32(out + 4, n_enc);
+    const float rate = (float)adjusted / (create_n + 1);
+    put32(out + 18, (uint32_t)round(fps * rate));
+    if (out_len) *out_len = total;
+    if (n_encoded) *n_encoded = n_enc;
+    return OK;
 }
 
 // ===========================================================================
