@@ -651,7 +651,8 @@ static int assemble_and_compress(agmvb_ctx* ctx, const EntPair* h_pairs, uint32_
     for (uint32_t g0 = 0; g0 < F;) {
         uint32_t g1 = g0 + 1;
         // LZ77 keeps 4 B of workspace per position and wants every frame of the batch in flight at once (one CTA per frame)
-        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : LZ_GROUP_TARGET;
+        static const uint32_t lz_target_env = getenv("AGMVB_LZ_TARGET") ? (uint32_t)std::max(1, atoi(getenv("AGMVB_LZ_TARGET"))) << 20 : 0u;
+        const uint32_t target = ctx->compression == COMP_LZ77 ? (1u << 30) : (lz_target_env ? lz_target_env : LZ_GROUP_TARGET);
         while (g1 < F && fs[g1 + 1] - fs[g0] <= target) g1++;
         rebased.resize(g1 - g0 + 1);
         for (uint32_t k = 0; k <= g1 - g0; k++) rebased[k] = fs[g0 + k] - fs[g0];
@@ -717,9 +718,15 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
         TRY(ensure(ctx, ctx->srcpairs, F * sizeof(SrcPair)));
         TRY(ensure(ctx, ctx->entries, (size_t)F * P * 2));
         CK(cudaMemcpyAsync(ctx->srcpairs.p, sp.data(), F * sizeof(SrcPair), cudaMemcpyHostToDevice, ctx->st));
-        dim3 qgrid(cdiv(P / 4, 256), F);
-        KL(ctx->lc, KC_QUANT, (quantize_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), ctx->d_map, (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
-                                               ctx->entries.as<uint16_t>())));
+        if (ctx->d_map) {   // GBA / NDS: gather through the rescale table
+            dim3 qgrid(cdiv(P / 4, 256), F);
+            KL(ctx->lc, KC_QUANT, (quantize_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), ctx->d_map, (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256,
+                                                                          ctx->d_lut, ctx->entries.as<uint16_t>())));
+        } else {
+            dim3 qgrid(cdiv(P / 8, 256), F);
+            KL(ctx->lc, KC_QUANT, (quantize8_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
+                                                                           ctx->entries.as<uint16_t>())));
+        }
         TRY(check_launch(ctx, "quantize"));
         int last_i = -1;
         for (uint32_t k = 0; k < F; k++) {

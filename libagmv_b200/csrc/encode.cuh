@@ -22,28 +22,45 @@ __device__ __forceinline__ void hist_add(unsigned long long* hist, uint32_t q, b
     if (valid && (peers & lanemask_lt()) == 0) atomicAdd(&hist[q], (unsigned long long)__popc(peers));
 }
 
-// Four pixels per thread. When every lane of the warp holds four equal quantised colours (flat content, the
-// common case in cartoon / UI video) one MATCH round with weight 4 replaces four.
+// Four pixels per thread (one 16-byte load), so a warp sees 128 consecutive pixels. Equal quantised colours are merged by
+// RUNS of consecutive pixels rather than by MATCH rounds (profiles/r01: four MATCH per thread bound the kernel at 21 % of
+// HBM): a pixel whose bin differs from its predecessor's heads a run, the four head bitmaps (one ballot per pixel slot)
+// give every head its run length with a few bit operations, and the head issues ONE atomic for the whole run. Flat
+// content costs an atomic per run of up to 128 pixels, a gradient one per two or three pixels; equal colours that are not
+// adjacent simply take separate atomics. (A pixel in bin max_clr is dropped, as above; it still ends a run.)
 __global__ void __launch_bounds__(256) hist_vec4_k(const uint4* __restrict__ px4, uint64_t ngroups, int quality, uint32_t mc,
                                                    unsigned long long* __restrict__ hist) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint32_t lane = lane_id();
     for (uint64_t base = (uint64_t)blockIdx.x * blockDim.x; base < ngroups; base += stride) {
-        uint64_t g = base + threadIdx.x;
-        bool valid = g < ngroups;
-        uint4 v = valid ? __ldg(px4 + g) : make_uint4(0, 0, 0, 0);
-        const uint32_t q0 = quantize_color(v.x, quality), q1 = quantize_color(v.y, quality);
-        const uint32_t q2 = quantize_color(v.z, quality), q3 = quantize_color(v.w, quality);
-        const bool flat = !valid || (q0 == q1 && q1 == q2 && q2 == q3);
-        if (__all_sync(0xffffffffu, flat)) {
-            const bool ok = valid && q0 < mc;
-            const uint32_t key = ok ? q0 : 0x80000000u + lane_id();
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            if (ok && (peers & lanemask_lt()) == 0) atomicAdd(&hist[q0], 4ull * __popc(peers));
-        } else {
-            hist_add(hist, q0, valid && q0 < mc);
-            hist_add(hist, q1, valid && q1 < mc);
-            hist_add(hist, q2, valid && q2 < mc);
-            hist_add(hist, q3, valid && q3 < mc);
+        const uint64_t g = base + threadIdx.x;
+        const bool valid = g < ngroups;
+        const uint4 v = valid ? __ldg(px4 + g) : make_uint4(0, 0, 0, 0);
+        uint32_t q[4];
+        q[0] = valid ? quantize_color(v.x, quality) : 0xFFFFFFFFu;
+        q[1] = valid ? quantize_color(v.y, quality) : 0xFFFFFFFFu;
+        q[2] = valid ? quantize_color(v.z, quality) : 0xFFFFFFFFu;
+        q[3] = valid ? quantize_color(v.w, quality) : 0xFFFFFFFFu;
+        const uint32_t left = __shfl_up_sync(0xffffffffu, q[3], 1);
+        const bool h0 = lane == 0 || q[0] != left, h1 = q[1] != q[0], h2 = q[2] != q[1], h3 = q[3] != q[2];
+        unsigned hb[4];
+        hb[0] = __ballot_sync(0xffffffffu, h0);
+        hb[1] = __ballot_sync(0xffffffffu, h1);
+        hb[2] = __ballot_sync(0xffffffffu, h2);
+        hb[3] = __ballot_sync(0xffffffffu, h3);
+        const bool hd[4] = {h0, h1, h2, h3};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!hd[k] || q[k] >= mc) continue;   // not a head, or the dropped bin / padding
+            // next head after pixel position 4 * lane + k: slots k+1..3 of this lane onwards, slots 0..k of the next lane onwards
+            uint32_t next = 128u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t from = j > k ? lane : lane + 1u;
+                const unsigned m = from < 32u ? hb[j] >> from : 0u;
+                if (m) next = min(next, 4u * (from + (uint32_t)__ffs(m) - 1u) + (uint32_t)j);
+            }
+            atomicAdd(&hist[q[k]], (unsigned long long)(next - (4u * lane + (uint32_t)k)));
         }
     }
 }
@@ -209,6 +226,48 @@ __device__ __forceinline__ uint32_t lut_entry(uint32_t c, bool valid, uint16_t* 
         m = __ballot_sync(0xffffffffu, miss);
     }
     return e;
+}
+
+// grid (cdiv(P/8, 256), n_enc), unscaled profiles: eight pixels per thread. The interpolation of a byte is
+// c1 + ((c2 - c1) >> 1) = floor((c1 + c2) / 2), one halving add on the packed word; the eight table look-ups are issued
+// together and a single vote decides whether anybody missed (rare once the table is warm) - only then does the warp
+// enter the cooperative evaluation. P is a multiple of 16 (width and height are multiples of 4).
+__global__ void __launch_bounds__(256) quantize8_k(const SrcPair* __restrict__ src, uint32_t P, const uint32_t* __restrict__ pal, int npal,
+                                                   uint16_t* __restrict__ lut, uint16_t* __restrict__ entries) {
+    __shared__ uint32_t spal[512];
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = k < npal ? pal[k] : 0u;
+    __syncthreads();
+    const uint32_t f = blockIdx.y;
+    const SrcPair sp = src[f];
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 pixels
+    const bool valid = g * 8 < P;
+    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (valid) {
+        const uint4* pa = reinterpret_cast<const uint4*>(sp.a) + 2 * (size_t)g;
+        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
+        c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w;
+        if (sp.b) {
+            const uint4* pb = reinterpret_cast<const uint4*>(sp.b) + 2 * (size_t)g;
+            const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1);
+            c[0] = __vhaddu4(c[0], b0.x); c[1] = __vhaddu4(c[1], b0.y); c[2] = __vhaddu4(c[2], b0.z); c[3] = __vhaddu4(c[3], b0.w);
+            c[4] = __vhaddu4(c[4], b1.x); c[5] = __vhaddu4(c[5], b1.y); c[6] = __vhaddu4(c[6], b1.z); c[7] = __vhaddu4(c[7], b1.w);
+        }
+    }
+    uint32_t e[8];
+    bool miss = false;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        c[k] &= 0xFFFFFFu;
+        e[k] = valid ? lut[c[k]] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) miss |= e[k] == LUT_EMPTY;
+    if (__any_sync(0xffffffffu, miss)) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) e[k] = lut_entry(c[k], valid, lut, spal, npal);
+    }
+    if (valid)
+        reinterpret_cast<uint4*>(entries + (size_t)f * P)[g] = make_uint4(e[0] | e[1] << 16, e[2] | e[3] << 16, e[4] | e[5] << 16, e[6] | e[7] << 16);
 }
 
 // grid (cdiv(P/4, 256), n_enc). map (nullable): coded pixel -> source pixel (nearest-neighbour downscale, E13)

@@ -6,13 +6,18 @@
 // (step = record length). Which positions get visited is inherently serial,
 // but a tile of T positions can only be entered at one of its first S
 // offsets, so:
-//   1. orbit_spec_k  walks every tile speculatively from each of the S entry
-//                    offsets (one lane each) and records where the walk leaves
-//                    the tile and the weight it accumulated;
+//   1. orbit_spec_k  finds, for each of the S entry offsets of a tile, where a
+//                    walk from there leaves the tile and the weight it gathers.
+//                    One lane owns one tile and sweeps it BACKWARDS once: the
+//                    answer for position p is the answer for p + step(p) (or p's
+//                    own, if that already lies past the tile), kept in a ring of
+//                    the last few positions - one step per position instead of
+//                    one walk per entry offset;
 //   2. orbit_chain_k chains the tiles of each segment (a few hundred table
 //                    look-ups, one warp per segment, tables staged in smem);
-//   3. orbit_mark_k  re-walks each tile from its true entry and hands every
-//                    visited position and its running weight to a visitor.
+//   3. orbit_mark_k  re-walks each tile from its true entry (again a lane per
+//                    tile) and hands every visited position and its running
+//                    weight to a visitor.
 // Segments are independent walks (one per frame). `code[p]` is one byte per
 // position; Dec::step / Dec::weight decode it.
 #pragma once
@@ -47,12 +52,33 @@ __device__ __forceinline__ uint32_t orbit_seg_of(const OrbitSeg* __restrict__ se
     return lo;
 }
 
+// byte `i` of a stream read through aligned 32-bit words (w = the word that holds it, reloaded when i crosses into another word)
+struct OrbitBytes {
+    const uint32_t* words;   // aligned base
+    uint32_t shift0;         // byte offset of stream position 0 inside words[0]
+    uint32_t w, widx;
+    __device__ __forceinline__ void init(const uint8_t* base) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(base);
+        words = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+        shift0 = (uint32_t)(a & 3u);
+        widx = 0xFFFFFFFFu;
+        w = 0;
+    }
+    __device__ __forceinline__ uint32_t at(uint32_t i) {
+        const uint32_t b = i + shift0;
+        if ((b >> 2) != widx) { widx = b >> 2; w = __ldg(words + widx); }
+        return (w >> ((b & 3u) * 8u)) & 0xFFu;
+    }
+};
+
+constexpr int ORB_LANES = 128;   // tiles per block (one lane each)
+
 template <int S, class Dec>
-__global__ void __launch_bounds__(256) orbit_spec_k(const uint8_t* __restrict__ code, const OrbitSeg* __restrict__ segs, uint32_t nseg,
-                                                    const uint32_t* __restrict__ seg_len, uint32_t ntile, OrbitTables tb) {
-    __shared__ __align__(16) uint8_t s[8][ORB_TILE];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t tile = blockIdx.x * 8 + warp;
+__global__ void __launch_bounds__(ORB_LANES) orbit_spec_k(const uint8_t* __restrict__ code, const OrbitSeg* __restrict__ segs, uint32_t nseg,
+                                                          const uint32_t* __restrict__ seg_len, uint32_t ntile, OrbitTables tb) {
+    constexpr int RING = S <= 15 ? 16 : 64;              // >= S + 1 and a power of two
+    __shared__ uint32_t ring[RING][ORB_LANES];           // [p & (RING - 1)][lane]: exit << 24 | weight of a walk that starts at p
+    const uint32_t tile = blockIdx.x * ORB_LANES + threadIdx.x;
     if (tile >= ntile) return;
     const uint32_t sg = orbit_seg_of(segs, nseg, tile);
     const OrbitSeg seg = segs[sg];
@@ -60,18 +86,21 @@ __global__ void __launch_bounds__(256) orbit_spec_k(const uint8_t* __restrict__ 
     const uint32_t t0 = (tile - seg.tile_base) * ORB_TILE;
     if (t0 >= len) return;  // tile beyond the actual segment length: never reached by the chain
     const uint32_t end = min(t0 + ORB_TILE, len);
-    const uint8_t* c = code + seg.off;
-    for (uint32_t k = lane; k < ORB_TILE; k += 32) s[warp][k] = (t0 + k < end) ? c[t0 + k] : 0;
-    __syncwarp();
-    for (int e = lane; e < S; e += 32) {
-        uint32_t i = t0 + e, w = 0;
-        while (i < end) {
-            uint32_t cc = s[warp][i - t0];
-            w += Dec::weight(cc);
-            i += Dec::step(cc);
-        }
-        tb.exit_tab[(size_t)tile * ORB_SP + e] = (uint8_t)(i - end);
-        tb.w_tab[(size_t)tile * ORB_SP + e] = (uint16_t)w;
+    OrbitBytes c;
+    c.init(code + seg.off);
+    for (uint32_t i = end; i-- > t0;) {
+        const uint32_t cc = c.at(i);
+        const uint32_t nxt = i + Dec::step(cc);
+        uint32_t v = nxt >= end ? (nxt - end) << 24 : ring[nxt & (RING - 1)][threadIdx.x];
+        v += Dec::weight(cc);
+        ring[i & (RING - 1)][threadIdx.x] = v;
+    }
+    for (int e = 0; e < S; e++) {
+        const uint32_t i = t0 + e;
+        // an entry offset at or past the end of a short last tile leaves it at once
+        const uint32_t v = i < end ? ring[i & (RING - 1)][threadIdx.x] : (i - end) << 24;
+        tb.exit_tab[(size_t)tile * ORB_SP + e] = (uint8_t)(v >> 24);
+        tb.w_tab[(size_t)tile * ORB_SP + e] = (uint16_t)(v & 0xFFFFu);
     }
 }
 
@@ -114,11 +143,9 @@ __global__ void __launch_bounds__(128) orbit_chain_k(const OrbitSeg* __restrict_
 
 // Visitor: void operator()(uint32_t seg, uint32_t pos_in_seg, uint32_t cum_before, uint32_t code)
 template <int S, class Dec, class Visit>
-__global__ void __launch_bounds__(256) orbit_mark_k(const uint8_t* __restrict__ code, const OrbitSeg* __restrict__ segs, uint32_t nseg,
-                                                    const uint32_t* __restrict__ seg_len, uint32_t ntile, OrbitTables tb, Visit visit) {
-    __shared__ __align__(16) uint8_t s[8][ORB_TILE];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t tile = blockIdx.x * 8 + warp;
+__global__ void __launch_bounds__(ORB_LANES) orbit_mark_k(const uint8_t* __restrict__ code, const OrbitSeg* __restrict__ segs, uint32_t nseg,
+                                                          const uint32_t* __restrict__ seg_len, uint32_t ntile, OrbitTables tb, Visit visit) {
+    const uint32_t tile = blockIdx.x * ORB_LANES + threadIdx.x;
     if (tile >= ntile) return;
     const uint32_t sg = orbit_seg_of(segs, nseg, tile);
     const OrbitSeg seg = segs[sg];
@@ -126,17 +153,14 @@ __global__ void __launch_bounds__(256) orbit_mark_k(const uint8_t* __restrict__ 
     const uint32_t t0 = (tile - seg.tile_base) * ORB_TILE;
     if (t0 >= len) return;
     const uint32_t end = min(t0 + ORB_TILE, len);
-    const uint8_t* c = code + seg.off;
-    for (uint32_t k = lane; k < ORB_TILE; k += 32) s[warp][k] = (t0 + k < end) ? c[t0 + k] : 0;
-    __syncwarp();
-    if (lane == 0) {
-        uint32_t i = t0 + tb.entry_tab[tile], cum = tb.cumbase[tile];
-        while (i < end) {
-            uint32_t cc = s[warp][i - t0];
-            visit(sg, i, cum, cc);
-            cum += Dec::weight(cc);
-            i += Dec::step(cc);
-        }
+    OrbitBytes c;
+    c.init(code + seg.off);
+    uint32_t i = t0 + tb.entry_tab[tile], cum = tb.cumbase[tile];
+    while (i < end) {
+        const uint32_t cc = c.at(i);
+        visit(sg, i, cum, cc);
+        cum += Dec::weight(cc);
+        i += Dec::step(cc);
     }
 }
 
@@ -148,9 +172,9 @@ inline void orbit_run(const uint8_t* code, const OrbitSeg* d_segs, uint32_t nseg
                       Visit visit, LaunchCtx& lc, int cls) {
     static_assert(S <= ORB_SP, "too many entry offsets");
     if (nseg == 0) return;
-    if (ntile) KL(lc, cls, (orbit_spec_k<S, Dec><<<cdiv(ntile, 8), 256, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb)));
+    if (ntile) KL(lc, cls, (orbit_spec_k<S, Dec><<<cdiv(ntile, ORB_LANES), ORB_LANES, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb)));
     KL(lc, cls, (orbit_chain_k<S><<<cdiv(nseg, 4), 128, 0, lc.st>>>(d_segs, nseg, d_seg_len, tb)));
-    if (ntile) KL(lc, cls, (orbit_mark_k<S, Dec, Visit><<<cdiv(ntile, 8), 256, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb, visit)));
+    if (ntile) KL(lc, cls, (orbit_mark_k<S, Dec, Visit><<<cdiv(ntile, ORB_LANES), ORB_LANES, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb, visit)));
 }
 
 }  // namespace agmvb
