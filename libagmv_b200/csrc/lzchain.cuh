@@ -40,56 +40,88 @@ inline void lzc_build_items(const uint32_t* h_fs, uint32_t F, std::vector<LzcIte
     }
 }
 
-// The bytes of 16 steps (512 positions + 3) are staged in shared memory with coalesced word loads issued one block ahead,
-// so the serial loop never waits for global memory: a step is stage read -> hash -> table read -> match -> table write.
+// The bytes of 16 steps (512 positions + 3) are staged in shared memory by the TMA engine: one elected lane issues a 1-D
+// bulk copy (cp.async.bulk, completion counted in bytes on an mbarrier) for the NEXT block while the warp works through the
+// current one, so the serial loop never waits for global memory and spends no instructions on the staging itself: a step is
+// stage read -> hash -> table read -> match -> table write.
 constexpr int LZC_STAGE_STEPS = 16;
-constexpr int LZC_STAGE_WORDS = 32 * 5;   // 640 bytes >= 32 * 16 + 3 + 3 bytes of misalignment
+constexpr uint32_t LZC_STAGE_BYTES = 32 * LZC_STAGE_STEPS + 32;   // 512 positions + 3 bytes, + up to 15 bytes of misalignment, in 16-byte units
+
+__device__ __forceinline__ uint32_t lzc_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lzc_mbar_init(uint64_t* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(lzc_smem(bar)));
+}
+__device__ __forceinline__ void lzc_bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {   // src, dst, bytes: multiples of 16
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lzc_smem(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(lzc_smem(dst)), "l"(src), "r"(bytes),
+                 "r"(lzc_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void lzc_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LZC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LZC_DONE_%=;\n"
+        "bra LZC_WAIT_%=;\n"
+        "LZC_DONE_%=:\n"
+        "}\n" ::"r"(lzc_smem(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs,
                                                      const LzcItem* __restrict__ items, uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd) {
     extern __shared__ uint32_t lzc_tab[];
-    __shared__ uint32_t stage[2][LZC_STAGE_WORDS + 1];
+    __shared__ __align__(16) uint8_t stage[2][LZC_STAGE_BYTES];
+    __shared__ __align__(8) uint64_t bar[2];
     const LzcItem it = items[blockIdx.x];
     const uint32_t base = fs[it.frame], len = fs[it.frame + 1] - base;
     const uint32_t lane = threadIdx.x;
     for (uint32_t k = lane; k < (1u << LZC_HB); k += 32) lzc_tab[k] = 0;
+    if (lane == 0) {
+        lzc_mbar_init(&bar[0]);
+        lzc_mbar_init(&bar[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     uint32_t i0 = it.start > LZC_PREROLL ? it.start - LZC_PREROLL : 0u;
     uint32_t run_start = i0;
-    // readable words of the batch buffer: [word_lo, word_hi] (bs has 16 bytes of padding after its n bytes)
-    const uintptr_t word_lo = reinterpret_cast<uintptr_t>(bs) & ~(uintptr_t)3;
-    const uintptr_t word_hi = (reinterpret_cast<uintptr_t>(bs) + n + 12u) & ~(uintptr_t)3;
-    // block of 16 steps starting at position j0: words from the aligned address at or below byte j0 - 1
-    uint32_t regs[5];
+    // readable 16-byte units of the batch buffer: [lo16, hi16) (bs has at least 64 bytes of padding after its n bytes)
+    const uintptr_t lo16 = reinterpret_cast<uintptr_t>(bs) & ~(uintptr_t)15;
+    const uintptr_t hi16 = (reinterpret_cast<uintptr_t>(bs) + n + 48u) & ~(uintptr_t)15;
+    // block of 16 steps starting at position j0: from the 16-byte unit that holds byte j0 - 1 (the byte before its first position)
     auto block_addr = [&](uint32_t j0) {
-        const uintptr_t want = reinterpret_cast<uintptr_t>(bs) + base + j0 - 1u;   // byte before the block's first position
-        const uintptr_t a = want & ~(uintptr_t)3;
-        return a < word_lo ? word_lo : a;
+        const uintptr_t a = (reinterpret_cast<uintptr_t>(bs) + base + j0 - 1u) & ~(uintptr_t)15;
+        return a < lo16 ? lo16 : a;
     };
-    auto fetch = [&](uint32_t j0) {
+    auto issue = [&](uint32_t j0, int b) {   // one lane
         const uintptr_t a = block_addr(j0);
-#pragma unroll
-        for (int k = 0; k < 5; k++) {
-            uintptr_t x = a + 4u * (uint32_t)(k * 32 + lane);
-            if (x > word_hi) x = word_hi;
-            regs[k] = *reinterpret_cast<const uint32_t*>(x);
-        }
+        const uint32_t bytes = (uint32_t)min((uintptr_t)LZC_STAGE_BYTES, hi16 - a);
+        lzc_bulk_load(stage[b], reinterpret_cast<const void*>(a), bytes, &bar[b]);
     };
-    fetch(i0);
+    if (lane == 0) issue(i0, 0);
+    uint32_t phase = 0;   // bit b: parity the next wait on bar[b] looks for
     int buf = 0;
     for (uint32_t j0 = i0; j0 < it.end; j0 += 32 * LZC_STAGE_STEPS, buf ^= 1) {
-#pragma unroll
-        for (int k = 0; k < 5; k++) stage[buf][k * 32 + lane] = regs[k];
-        if (lane == 0) stage[buf][LZC_STAGE_WORDS] = 0;
-        __syncwarp();
-        if (j0 + 32 * LZC_STAGE_STEPS < it.end) fetch(j0 + 32 * LZC_STAGE_STEPS);
-        // byte offset of position j0 - 1 inside the staged words (-1 only for the very first byte of the buffer)
+        // the other buffer was last read one block ago (every lane is past it: the loop below ends in __syncwarp); order those
+        // generic-proxy reads before the async-proxy write, then start the next block's copy
+        if (lane == 0 && j0 + 32 * LZC_STAGE_STEPS < it.end) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(j0 + 32 * LZC_STAGE_STEPS, buf ^ 1);
+        }
+        lzc_mbar_wait(&bar[buf], (phase >> buf) & 1u);
+        phase ^= 1u << buf;
+        const uint32_t* const sw = reinterpret_cast<const uint32_t*>(stage[buf]);
+        // byte offset of position j0 - 1 inside the staged block (-1 only for the very first byte of the buffer)
         const int off0 = (int)(reinterpret_cast<uintptr_t>(bs) + base + j0 - 1u - block_addr(j0));
         const uint32_t jend = min(j0 + 32 * LZC_STAGE_STEPS, it.end);
         for (uint32_t s0 = j0; s0 < jend; s0 += 32) {
             const uint32_t i = s0 + lane;
             const int o = off0 + (int)(i - j0);
             // bytes i-1 .. i+2 (o == -1: the buffer's very first position, which has no byte before it)
-            const uint32_t w = o < 0 ? stage[buf][0] << 8 : __funnelshift_r(stage[buf][o >> 2], stage[buf][(o >> 2) + 1], (o & 3) * 8);
+            const uint32_t w = o < 0 ? sw[0] << 8 : __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8);
             const bool valid = i + 3u <= len && i < it.end;
             const uint32_t h = lzc_hash(w >> 8, LZC_HB);
             const uint32_t old = valid ? lzc_tab[h] : 0u;
