@@ -443,7 +443,6 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         };
         // occurrence-chain match finder (lzchain.cuh): 19 B per position
         TRY(grab(cap, (void**)&w.bestlen));
-        TRY(grab((size_t)cap * 4, (void**)&w.match_rec));
         TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
         TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
         TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
@@ -451,8 +450,8 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
         int sms = 148, per3 = 5, perl = 6;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k, LZC_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k, LZC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k<16>, LZC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k<16>, LZC_THREADS, 0);
         w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
         w.level_blocks = (uint32_t)(sms * std::max(1, perl));
         w.cap_n = cap;
@@ -514,7 +513,9 @@ static int lz_group(agmvb_ctx* ctx, const uint8_t* d_bs, const uint32_t* h_fs, u
     CK(cudaMemcpyAsync(ctx->lz.segs, segs.data(), F * sizeof(OrbitSeg), cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemcpyAsync(ctx->lz.seg_len, slen.data(), F * 4, cudaMemcpyHostToDevice, ctx->st));
     std::vector<LzcItem> items;   // (frame, range) work items of the serial hash-link kernel
-    lzc_build_items(h_fs, F, items);
+    static const int hb_env = getenv("AGMVB_LZ_HB") ? std::min(13, std::max(8, atoi(getenv("AGMVB_LZ_HB")))) : 0;
+    if (hb_env) ctx->lz.hash_bits = hb_env;
+    lzc_build_items(h_fs, F, items, ctx->lz.hash_bits);
     TRY(ensure(ctx, ctx->lzbuf[60], (items.size() + 1) * sizeof(LzcItem)));
     ctx->lz.items = ctx->lzbuf[60].as<LzcItem>();
     ctx->lz.n_items = (uint32_t)items.size();

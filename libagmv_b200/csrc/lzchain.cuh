@@ -29,10 +29,11 @@ constexpr int LZC_THREADS = 256;
 struct LzcItem { uint32_t frame, start, end; };            // positions [start, end) of the frame (frame-relative; start a multiple of 32)
 
 // ranges of about n / (2 x resident warps) positions, never shorter than the pre-roll (which would then dominate)
-inline void lzc_build_items(const uint32_t* h_fs, uint32_t F, std::vector<LzcItem>& items) {
+inline void lzc_build_items(const uint32_t* h_fs, uint32_t F, std::vector<LzcItem>& items, int hash_bits = LZC_HB) {
     items.clear();
     const uint64_t n = h_fs[F];
-    uint64_t range = (n / 1776u + 31u) & ~(uint64_t)31u;   // two waves of 6 one-warp blocks per SM
+    const uint64_t resident = 148ull * std::min<uint64_t>(32, (227u << 10) / (((size_t)4 << hash_bits) + 2200));   // one-warp blocks the GPU holds
+    uint64_t range = (n / (2 * resident) + 31u) & ~(uint64_t)31u;   // two waves
     if (range < LZC_PREROLL) range = LZC_PREROLL;
     for (uint32_t f = 0; f < F; f++) {
         const uint32_t len = h_fs[f + 1] - h_fs[f];
@@ -72,14 +73,14 @@ __device__ __forceinline__ void lzc_mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__ bs, uint32_t n, const uint32_t* __restrict__ fs,
-                                                     const LzcItem* __restrict__ items, uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd) {
+                                                     const LzcItem* __restrict__ items, uint32_t* __restrict__ lwh, uint16_t* __restrict__ rsd, int hb) {
     extern __shared__ uint32_t lzc_tab[];
     __shared__ __align__(16) uint8_t stage[2][LZC_STAGE_BYTES];
     __shared__ __align__(8) uint64_t bar[2];
     const LzcItem it = items[blockIdx.x];
     const uint32_t base = fs[it.frame], len = fs[it.frame + 1] - base;
     const uint32_t lane = threadIdx.x;
-    for (uint32_t k = lane; k < (1u << LZC_HB); k += 32) lzc_tab[k] = 0;
+    for (uint32_t k = lane; k < (1u << hb); k += 32) lzc_tab[k] = 0;
     if (lane == 0) {
         lzc_mbar_init(&bar[0]);
         lzc_mbar_init(&bar[1]);
@@ -123,7 +124,7 @@ __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__
             // bytes i-1 .. i+2 (o == -1: the buffer's very first position, which has no byte before it)
             const uint32_t w = o < 0 ? sw[0] << 8 : __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8);
             const bool valid = i + 3u <= len && i < it.end;
-            const uint32_t h = lzc_hash(w >> 8, LZC_HB);
+            const uint32_t h = lzc_hash(w >> 8, hb);
             const uint32_t old = valid ? lzc_tab[h] : 0u;
             const unsigned peers = __match_any_sync(0xffffffffu, valid ? h : (0x80000000u | lane));
             const unsigned lower = peers & lanemask_lt();
@@ -177,7 +178,7 @@ constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
 
 // Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
 //     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
-template <class Op>
+template <int ROUNDS, class Op>
 __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
     const uint32_t lane = lane_id();
     uint32_t qn = 0, qi = 0;
@@ -193,7 +194,7 @@ __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restri
             uint32_t ch = 0;
             if (lane == 0) ch = atomicAdd(counter, 1u);
             ch = __shfl_sync(0xffffffffu, ch, 0);
-            const uint64_t cb = (uint64_t)ch * LZC_WCHUNK;
+            const uint64_t cb = (uint64_t)ch * (32 * ROUNDS);
             if (cb >= n) more = false;
             else qn += op.sweep((uint32_t)cb, q + qn);
             __syncwarp();
@@ -213,9 +214,10 @@ __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restri
     }
 }
 
+template <int ROUNDS>
 struct LzcLink3Op {
     const uint8_t* __restrict__ bs; const uint32_t* __restrict__ fs; uint32_t F, n;
-    const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3; uint8_t* __restrict__ bestlen;
+    const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3;
     LzcLink3Walk wlk;
     uint32_t b23c;   // byte 2 | byte 3 << 8 | cap << 16 of the position being walked
     uint32_t f_cur = 0, f_prev = 0;   // frames of the first position of the last two chunks swept: the queue only holds positions of those two
@@ -224,8 +226,7 @@ struct LzcLink3Op {
         return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
     }
     __device__ __forceinline__ void put(uint32_t p, uint32_t nd, uint32_t b2, uint32_t b3, uint32_t cap) const {
-        lw3[p] = lzc_word(nd, b3, b2, cap);
-        if (!nd) bestlen[p] = 0;
+        lw3[p] = nd ? lzc_word(nd, b3, b2, cap) : lzc_dead(0u, 0u, b3);
     }
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
@@ -235,7 +236,7 @@ struct LzcLink3Op {
         f_prev = min(f_cur, f0);   // (chunks are handed out in increasing order, but not necessarily to the same warp)
         f_cur = f0;
         uint32_t qn = 0;
-        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+        for (int r0 = 0; r0 < ROUNDS; r0 += LZC_MLP) {
             uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
@@ -281,17 +282,16 @@ struct LzcLink3Op {
     }
 };
 
+template <int ROUNDS>
 struct LzcLevelOp {
     const uint8_t* __restrict__ bs; uint32_t n, L;
     const uint32_t* __restrict__ lw; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw_next;
-    uint32_t* __restrict__ match_rec; uint8_t* __restrict__ bestlen;
     LzcLevelWalk wlk;
     uint32_t nbc;   // byte L+1 | cap << 8 of the position being walked
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
-        const bool top = L + 1u == (uint32_t)LZ_MAXLEN;
         uint32_t qn = 0;
-        for (int r0 = 0; r0 < LZC_ROUNDS; r0 += LZC_MLP) {
+        for (int r0 = 0; r0 < ROUNDS; r0 += LZC_MLP) {
             uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
@@ -301,25 +301,19 @@ struct LzcLevelOp {
             }
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
-                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = lzc_link(w[j]);
                 wk[j] = 0;
                 if (dist) wk[j] = lw[p - dist];
             }
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
-                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = w[j] & 0xFFFFu;
+                const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = lzc_link(w[j]);
                 const uint32_t c = (w[j] >> 16) & 0xFFu, cap = (w[j] >> 24) & 0xFu;
                 bool pend = false;
                 if (p < n) {
-                    uint32_t nd = 0;
-                    if (dist) {
-                        if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) nd = dist;
-                        else pend = true;
-                    }
-                    if (!pend) {
-                        lw_next[p] = lzc_word(nd, nb[j], c, cap);
-                        if (nd && top) bestlen[p] = (uint8_t)LZ_MAXLEN;
-                    }
+                    if (!dist) lw_next[p] = lzc_carry(w[j], nb[j]);   // final already: the result travels on
+                    else if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) lw_next[p] = lzc_word(dist, nb[j], c, cap);
+                    else pend = true;
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, pend);
                 if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
@@ -336,27 +330,26 @@ struct LzcLevelOp {
     __device__ __forceinline__ bool step() {
         const int r = wlk.hop(lw, rsd);
         if (r == LZC_GO) return false;
-        lw_next[wlk.p] = lzc_word(r == LZC_FOUND ? wlk.acc : 0u, nbc & 0xFFu, wlk.c, nbc >> 8);
-        if (r == LZC_END) { match_rec[wlk.p] = L << 28 | LZC_RESOLVED | wlk.last; bestlen[wlk.p] = (uint8_t)L; }
-        else if (L + 1u == (uint32_t)LZ_MAXLEN) bestlen[wlk.p] = (uint8_t)LZ_MAXLEN;
+        lw_next[wlk.p] = r == LZC_FOUND ? lzc_word(wlk.acc, nbc & 0xFFu, wlk.c, nbc >> 8) : lzc_dead(L, wlk.last, nbc & 0xFFu);
         return true;
     }
 };
 
+template <int ROUNDS>
 __global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
                                                            const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
-                                                           uint32_t* __restrict__ lw3, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
-    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
-    LzcLink3Op op{bs, fs, F, n, lwh, rsd, lw3, bestlen};
-    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
+                                                           uint32_t* __restrict__ lw3, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][32 * ROUNDS + 32];
+    LzcLink3Op<ROUNDS> op{bs, fs, F, n, lwh, rsd, lw3};
+    lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5]);
 }
 
+template <int ROUNDS>
 __global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
-                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next,
-                                                           uint32_t* __restrict__ match_rec, uint8_t* __restrict__ bestlen, uint32_t* __restrict__ counter) {
-    __shared__ uint32_t q[LZC_WARPS][LZC_QCAP];
-    LzcLevelOp op{bs, n, L, lw, rsd, lw_next, match_rec, bestlen};
-    lzc_drive(op, n, counter, q[threadIdx.x >> 5]);
+                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next, uint32_t* __restrict__ counter) {
+    __shared__ uint32_t q[LZC_WARPS][32 * ROUNDS + 32];
+    LzcLevelOp<ROUNDS> op{bs, n, L, lw, rsd, lw_next};
+    lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5]);
 }
 
 __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ wbase) {
@@ -372,8 +365,7 @@ __device__ __forceinline__ void lzc_emit(uint32_t* __restrict__ out_words, uint3
     atomicOr(&out_words[w], v << sh);
     if (sh + nb > 32) atomicOr(&out_words[w + 1], v >> (32 - sh));
 }
-__global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint8_t* __restrict__ bestlen,
-                                                          const uint32_t* __restrict__ match_rec, const uint32_t* __restrict__ bitcum,
+__global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint32_t* __restrict__ bitcum,
                                                           const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
                                                           const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
     __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
@@ -390,9 +382,9 @@ __global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restr
         if (i < end) {
             const uint32_t rel = bitcum[i];
             if (rel != EMPTY32) {
-                const uint32_t l = bestlen[i];
-                if (l == (uint32_t)LZ_MAXLEN) pend = true;
-                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((match_rec[i] & 0xFFFFu) << 1) | (l << 17), 21);
+                const uint32_t w = lw15[i], l = (w >> 24) & 0xFu;
+                if (!(w & LZC_DEAD)) pend = true;   // still linked at level 15: a 15-byte match
+                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((w & 0xFFFFu) << 1) | (l << 17), 21);
                 else lzc_emit(out_words, wb, rel, 1u | ((uint32_t)bs[i] << 1), 9);
             }
         }
@@ -421,6 +413,15 @@ __global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restr
             busy = false;
         }
     }
+}
+
+// the parse's input: one byte per position, the final match length (level-15 words: dead -> its length, live -> 15)
+__global__ void __launch_bounds__(256) lzc_bestlen_k(const uint32_t* __restrict__ lw15, uint32_t n, uint8_t* __restrict__ bestlen) {
+    const uint32_t i = (blockIdx.x * 256u + threadIdx.x) * 4u;   // lw15 and bestlen are 16-byte aligned
+    if (i >= n) return;
+    const uint4 w = *reinterpret_cast<const uint4*>(lw15 + i);   // (the arrays are padded past n)
+    auto len = [](uint32_t x) { return (x & LZC_DEAD) ? (x >> 24) & 0xFu : (uint32_t)LZ_MAXLEN; };
+    *reinterpret_cast<uint32_t*>(bestlen + i) = len(w.x) | len(w.y) << 8 | len(w.z) << 16 | len(w.w) << 24;
 }
 
 }  // namespace agmvb

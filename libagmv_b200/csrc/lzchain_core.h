@@ -42,16 +42,25 @@
 namespace agmvb {
 
 constexpr uint32_t LZC_WINDOW = 65535u;     // src/agmv_encode.c:102
-constexpr uint32_t LZC_RESOLVED = 1u << 27; // match_rec: length << 28 | LZC_RESOLVED | offset
+constexpr uint32_t LZC_DEAD = 1u << 29;     // link word of a position whose match is final (see below)
 
 // Link words: low 16 bits = dist, then key bits.
 //   hash level (lzc_hashlink_k): dist to the previous position with the same 3-gram hash | byte0 << 16 | byte1 << 24
-//   level L >= 3:  dist_L | byte[p+L] << 16 | cap << 24 | (byte[p+L] != byte[p+L-1]) << 28,
+//   level L >= 3, position still growing ("live", dist_L != 0):
+//                  dist_L | byte[p+L] << 16 | cap << 24 | (byte[p+L] != byte[p+L-1]) << 28,
 //                  cap = min(15, bytes left in the frame from p on): the reference caps a match there (src/agmv_encode.c:121-123)
+//   level L >= 3, position whose match is final ("dead", dist_L == 0): the word carries the RESULT, so that no level writes
+//                  anything but its own dense output array:
+//                  offset | byte[p+L] << 16 | length << 24 | LZC_DEAD   (length 0: no match, a literal)
+//                  A dead word is copied from level to level (only its byte field changes); walkers that land on it read its
+//                  byte like any other element's and its link as 0.
 LZC_HD uint32_t lzc_hash(uint32_t gram24, int bits) { return (gram24 * 2654435761u) >> (32 - bits); }
 LZC_HD uint32_t lzc_word(uint32_t dist, uint32_t byte_l, uint32_t byte_before, uint32_t cap) {
     return dist | byte_l << 16 | cap << 24 | (byte_l != byte_before ? 1u << 28 : 0u);
 }
+LZC_HD uint32_t lzc_dead(uint32_t len, uint32_t off, uint32_t byte_l) { return off | byte_l << 16 | len << 24 | LZC_DEAD; }
+LZC_HD uint32_t lzc_link(uint32_t w) { return (w & LZC_DEAD) ? 0u : (w & 0xFFFFu); }   // dist_L of a level word
+LZC_HD uint32_t lzc_carry(uint32_t w, uint32_t byte_l) { return (w & 0xFF00FFFFu) | byte_l << 16; }   // a dead word at the next level
 
 enum { LZC_GO = 0, LZC_FOUND = 1, LZC_END = 2 };
 
@@ -90,7 +99,7 @@ struct LzcLevelWalk {
     uint32_t p, acc, last, dist, c;
     bool ext, neq;
     LZC_HDM bool start(uint32_t p_, uint32_t w, uint32_t L) {
-        p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; c = (w >> 16) & 0xFFu;
+        p = p_; acc = 0; last = 0; dist = lzc_link(w); c = (w >> 16) & 0xFFu;
         ext = L + 1u <= ((w >> 24) & 0xFu);
         neq = (w >> 28) & 1u;
         return dist != 0u;
@@ -101,7 +110,7 @@ struct LzcLevelWalk {
         const uint32_t wk = lw[p - acc];
         if (ext && ((wk >> 16) & 0xFFu) == c) return LZC_FOUND;
         last = acc;
-        dist = wk & 0xFFFFu;
+        dist = lzc_link(wk);
         if (dist == 1u && (!ext || neq)) {
             // the element stands inside a run of one byte b (its L-gram, hence p's, is all b, and neq says p's byte L is
             // not b): everything back to the run start is on the chain and carries byte L == b
@@ -109,7 +118,7 @@ struct LzcLevelWalk {
             if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }   // the window ends inside the run: p - 65535 is on the chain
             acc += r;
             last = acc;
-            dist = lw[p - acc] & 0xFFFFu;
+            dist = lzc_link(lw[p - acc]);
         }
         return dist ? LZC_GO : LZC_END;
     }
@@ -119,18 +128,18 @@ struct LzcLevelWalk {
 // window (the end of the level-15 chain). Usage: start(); while (hop(...) == LZC_GO);
 struct LzcEndWalk {
     uint32_t p, acc, last, dist;
-    LZC_HDM bool start(uint32_t p_, uint32_t w) { p = p_; acc = 0; last = 0; dist = w & 0xFFFFu; return dist != 0u; }
+    LZC_HDM bool start(uint32_t p_, uint32_t w) { p = p_; acc = 0; last = 0; dist = lzc_link(w); return dist != 0u; }
     LZC_HDM int hop(const uint32_t* lw15, const uint16_t* rsd) {
         acc += dist;
         if (acc > LZC_WINDOW) return LZC_END;
         last = acc;
-        dist = lw15[p - acc] & 0xFFFFu;
+        dist = lzc_link(lw15[p - acc]);
         if (dist == 1u) {   // inside a run: every position back to its start carries the same 15 bytes
             const uint32_t r = rsd[p - acc];
             if (acc + r > LZC_WINDOW) { last = LZC_WINDOW; return LZC_END; }
             acc += r;
             last = acc;
-            dist = lw15[p - acc] & 0xFFFFu;
+            dist = lzc_link(lw15[p - acc]);
         }
         return dist ? LZC_GO : LZC_END;
     }

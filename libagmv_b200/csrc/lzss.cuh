@@ -33,9 +33,9 @@ struct LzWork {
     uint16_t* rsd = nullptr;             // distance of every position to the start of its byte run
     LzcItem* items = nullptr;            // (frame, range) work items of lzc_hashlink_k
     uint32_t n_items = 0;
+    int hash_bits = LZC_HB;              // size of lzc_hashlink_k's table
     uint32_t* counters = nullptr;        // chunk counters of the persistent kernels (one per launch of a batch)
     uint32_t link3_blocks = 148 * 5, level_blocks = 148 * 6;   // resident blocks of the persistent walking kernels
-    uint32_t* match_rec = nullptr;       // per position with a match shorter than 15: length << 28 | LZC_RESOLVED | offset
     uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
@@ -141,21 +141,29 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
         // persistent walking kernels: enough warps to fill the GPU, chunks handed out through one counter per launch
         const uint32_t nb3 = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.link3_blocks), nb = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.level_blocks);
+        static const int rounds = getenv("AGMVB_LZ_ROUNDS") ? atoi(getenv("AGMVB_LZ_ROUNDS")) : 16;
         cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
-        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, LZC_TAB_BYTES, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd)));
-        KL(lc, KC_LZ_LINK3, (lzc_link3_k<<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.bestlen, wk.counters)));
+        KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, (size_t)4 << wk.hash_bits, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd, wk.hash_bits)));
+        if (rounds == 4) KL(lc, KC_LZ_LINK3, (lzc_link3_k<4><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
+        else if (rounds == 8) KL(lc, KC_LZ_LINK3, (lzc_link3_k<8><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
+        else KL(lc, KC_LZ_LINK3, (lzc_link3_k<16><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
-            KL(lc, KC_LZ_LEVEL, (lzc_level_k<<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], wk.match_rec, wk.bestlen,
-                                                                         wk.counters + (L - LZ_MINLEN + 1))));
+        {
+            uint32_t* const cnt = wk.counters + (L - LZ_MINLEN + 1);
+            if (rounds == 4) KL(lc, KC_LZ_LEVEL, (lzc_level_k<4><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
+            else if (rounds == 8) KL(lc, KC_LZ_LEVEL, (lzc_level_k<8><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
+            else KL(lc, KC_LZ_LEVEL, (lzc_level_k<16><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
+        }
         lw15 = wk.lw[cur];
+        KL(lc, KC_LZ_LEVEL, (lzc_bestlen_k<<<cdiv(cdiv(n, 4u), 256u), 256, 0, st>>>(lw15, n, wk.bestlen)));
     }
     orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
     if (n > 0) {
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
         dim3 pgrid(cdiv(max_usize, (uint32_t)LZC_BCHUNK), F);
-        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bestlen, wk.match_rec, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
+        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);

@@ -56,26 +56,26 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
             while ((r = wk.hop(d.data(), lwh.data(), rsd.data())) == LZC_GO) {}
             if (r == LZC_FOUND) d3 = wk.acc;
         }
-        lw[0][p] = lzc_word(d3, d[p + 3], d[p + 2], cap);
+        lw[0][p] = d3 ? lzc_word(d3, d[p + 3], d[p + 2], cap) : lzc_dead(0u, 0u, d[p + 3]);
     }
     int cur = 0;
     for (uint32_t L = 3; L < 15; L++) {
         for (size_t p = 0; p < n; p++) {
             const uint32_t w = lw[cur][p];
             LzcLevelWalk wk;
-            uint32_t nd = 0;
             if (wk.start((uint32_t)p, w, L)) {
                 int r;
                 while ((r = wk.hop(lw[cur].data(), rsd.data())) == LZC_GO) {}
-                if (r == LZC_FOUND) nd = wk.acc;
-                else { R.len[p] = (uint8_t)L; R.off[p] = wk.last; }
-            }
-            lw[cur ^ 1][p] = lzc_word(nd, d[p + L + 1], d[p + L], (w >> 24) & 0xFu);
+                lw[cur ^ 1][p] = r == LZC_FOUND ? lzc_word(wk.acc, d[p + L + 1], d[p + L], (w >> 24) & 0xFu) : lzc_dead(L, wk.last, d[p + L + 1]);
+            } else lw[cur ^ 1][p] = lzc_carry(w, d[p + L + 1]);
         }
         cur ^= 1;
     }
-    for (size_t p = 0; p < n; p++)
-        if (lw[cur][p] & 0xFFFFu) { R.len[p] = 15; R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p); }
+    for (size_t p = 0; p < n; p++) {   // level-15 words: dead = (length, offset), live = a 15-byte match whose earliest start ends its chain
+        const uint32_t w = lw[cur][p];
+        if (w & LZC_DEAD) { R.len[p] = (uint8_t)((w >> 24) & 0xFu); R.off[p] = R.len[p] ? (w & 0xFFFFu) : 0u; }
+        else { R.len[p] = 15; R.off[p] = lzc_chain_end(lw[cur].data(), rsd.data(), (uint32_t)p); }
+    }
     return R;
 }
 
