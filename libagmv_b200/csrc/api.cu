@@ -448,10 +448,11 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
         TRY(grab((size_t)cap * 2, (void**)&w.rsd));
         TRY(grab(64 * sizeof(uint32_t), (void**)&w.counters));
+        TRY(grab(((size_t)cap / LZC_WCHUNK + 2) * 4, (void**)&w.cframe));
         int sms = 148, per3 = 5, perl = 6;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k<16>, LZC_THREADS, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k<16>, LZC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per3, lzc_link3_k<LZC_ROUNDS>, LZC_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perl, lzc_level_k<LZC_ROUNDS>, LZC_THREADS, 0);
         w.link3_blocks = (uint32_t)(sms * std::max(1, per3));
         w.level_blocks = (uint32_t)(sms * std::max(1, perl));
         w.cap_n = cap;

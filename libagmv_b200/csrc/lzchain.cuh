@@ -286,17 +286,99 @@ template <int ROUNDS>
 struct LzcLevelOp {
     const uint8_t* __restrict__ bs; uint32_t n, L;
     const uint32_t* __restrict__ lw; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw_next;
+    const uint32_t* __restrict__ fs; const uint32_t* __restrict__ cframe;
     LzcLevelWalk wlk;
     uint32_t nbc;   // byte L+1 | cap << 8 of the position being walked
+    // The sweep settles a position without a walk in two cases:
+    //   * first hop: the most recent occurrence of its L-gram also carries its byte L (the link stays);
+    //   * right neighbour (lzchain_core.h, "neighbour rule"): the level-L word of p+1 names the only candidate - its link if it
+    //     is live (p's new link), its offset if it died at L-1 (then p dies at L with that offset) - and one byte compare
+    //     (the byte before the candidate against byte p) confirms it.
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
+        return cbase + LZC_WCHUNK + 16u <= n ? sweep_full(cbase, q) : sweep_tail(cbase, q);
+    }
+    // four bytes starting at byte address a (any alignment), through two aligned words
+    static __device__ __forceinline__ uint32_t bytes4(const uint8_t* a) {
+        const uintptr_t u = reinterpret_cast<uintptr_t>(a);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
+        return __funnelshift_r(wp[0], wp[1], (uint32_t)(u & 3u) * 8u);
+    }
+    // a whole chunk well inside the buffer: every lane owns four consecutive positions of each 128-position group, so the
+    // level words move as 16-byte loads / stores and three of the four right neighbours are the lane's own registers
+    __device__ __forceinline__ uint32_t sweep_full(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
+        const uint32_t f0 = cframe[cbase / LZC_WCHUNK];   // frame of the chunk's first position
+        uint32_t qn = 0;
+#pragma unroll 1
+        for (uint32_t g0 = 0; g0 < (uint32_t)LZC_WCHUNK; g0 += 128) {
+            const uint32_t p0 = cbase + g0 + lane * 4u;
+            const uint4 wv = *reinterpret_cast<const uint4*>(lw + p0);
+            const uint32_t wnext = lw[cbase + g0 + 128u];
+            const uint32_t nb4 = bytes4(bs + p0 + L + 1u), bq4 = bytes4(bs + p0);
+            uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w}, wk[4], x[4], bk[4], out[4];
+            uint32_t wn = __shfl_down_sync(0xffffffffu, w[0], 1);
+            if (lane == 31) wn = wnext;
+            const uint32_t wr[4] = {w[1], w[2], w[3], wn};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t p = p0 + i, dist = lzc_link(w[i]);
+                wk[i] = 0; x[i] = 0; bk[i] = 0x100u;
+                if (dist) {
+                    wk[i] = lw[p - dist];
+                    const uint32_t xr = wr[i] & 0xFFFFu;
+                    const bool cand = (wr[i] & LZC_DEAD) ? (L >= 4u && ((wr[i] >> 24) & 0xFu) == L - 1u) : (L + 1u <= ((w[i] >> 24) & 0xFu));
+                    if (cand && xr && xr <= p) { x[i] = xr | (wr[i] & LZC_DEAD); bk[i] = bs[p - xr]; }
+                }
+            }
+            unsigned pendm = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint32_t p = p0 + i, dist = lzc_link(w[i]);
+                const uint32_t c = (w[i] >> 16) & 0xFFu, cap = (w[i] >> 24) & 0xFu, nb = (nb4 >> (8 * i)) & 0xFFu;
+                out[i] = lzc_carry(w[i], nb);   // final already: the result travels on
+                if (dist) {
+                    if (L + 1u <= cap && ((wk[i] >> 16) & 0xFFu) == c) out[i] = lzc_word(dist, nb, c, cap);
+                    else {
+                        bool pend = true;
+                        if (bk[i] == ((bq4 >> (8 * i)) & 0xFFu)) {
+                            uint32_t f = f0;
+                            while (fs[f + 1] <= p) f++;
+                            const uint32_t xr = x[i] & 0xFFFFu;
+                            if (p - xr >= fs[f]) {   // the candidate lies inside p's frame
+                                out[i] = (x[i] & LZC_DEAD) ? lzc_dead(L, xr, nb) : lzc_word(xr, nb, c, cap);
+                                pend = false;
+                            }
+                        }
+                        if (pend) pendm |= 1u << i;
+                    }
+                }
+            }
+            *reinterpret_cast<uint4*>(lw_next + p0) = make_uint4(out[0], out[1], out[2], out[3]);   // (a pending position's word is rewritten by its walk)
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool pend = (pendm >> i) & 1u;
+                const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                if (pend) q[qn + __popc(bal & lanemask_lt())] = p0 + i;
+                qn += __popc(bal);
+            }
+        }
+        return qn;
+    }
+    __device__ __forceinline__ uint32_t sweep_tail(uint32_t cbase, uint32_t* q) {
+        const uint32_t lane = lane_id();
+        const uint32_t f0 = cframe[cbase / LZC_WCHUNK];   // frame of the chunk's first position
         uint32_t qn = 0;
         for (int r0 = 0; r0 < ROUNDS; r0 += LZC_MLP) {
-            uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP];
+            uint32_t w[LZC_MLP], nb[LZC_MLP], wk[LZC_MLP], x[LZC_MLP], bkq[LZC_MLP];
+            uint32_t wnext = LZC_DEAD;   // word of the position after this group of rounds
+            {
+                const uint32_t pn = cbase + (r0 + LZC_MLP) * 32;
+                if (pn < n) wnext = lw[pn];
+            }
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
                 const uint32_t p = cbase + (r0 + j) * 32 + lane;
-                w[j] = 0; nb[j] = 0;
+                w[j] = LZC_DEAD; nb[j] = 0;
                 if (p < n) { w[j] = lw[p]; nb[j] = bs[p + L + 1]; }
             }
 #pragma unroll
@@ -304,6 +386,19 @@ struct LzcLevelOp {
                 const uint32_t p = cbase + (r0 + j) * 32 + lane, dist = lzc_link(w[j]);
                 wk[j] = 0;
                 if (dist) wk[j] = lw[p - dist];
+                // candidate from the right neighbour's word
+                uint32_t wr = __shfl_down_sync(0xffffffffu, w[j], 1);
+                const uint32_t w0 = j + 1 < LZC_MLP ? __shfl_sync(0xffffffffu, w[j + 1 < LZC_MLP ? j + 1 : j], 0) : wnext;
+                if (lane == 31) wr = w0;
+                x[j] = 0; bkq[j] = 1;
+                if (dist) {
+                    const uint32_t xr = wr & 0xFFFFu;
+                    const bool cand = (wr & LZC_DEAD) ? (L >= 4u && ((wr >> 24) & 0xFu) == L - 1u) : (L + 1u <= ((w[j] >> 24) & 0xFu));
+                    if (cand && xr && xr <= p) {
+                        x[j] = xr | (wr & LZC_DEAD);
+                        bkq[j] = (uint32_t)bs[p - xr] ^ (uint32_t)bs[p];   // 0: the byte before the candidate is p's byte
+                    }
+                }
             }
 #pragma unroll
             for (int j = 0; j < LZC_MLP; j++) {
@@ -313,7 +408,18 @@ struct LzcLevelOp {
                 if (p < n) {
                     if (!dist) lw_next[p] = lzc_carry(w[j], nb[j]);   // final already: the result travels on
                     else if (L + 1u <= cap && ((wk[j] >> 16) & 0xFFu) == c) lw_next[p] = lzc_word(dist, nb[j], c, cap);
-                    else pend = true;
+                    else {
+                        pend = true;
+                        if (x[j] && !bkq[j]) {
+                            uint32_t f = f0;
+                            while (fs[f + 1] <= p) f++;
+                            const uint32_t xr = x[j] & 0xFFFFu;
+                            if (p - xr >= fs[f]) {   // the candidate lies inside p's frame
+                                lw_next[p] = (x[j] & LZC_DEAD) ? lzc_dead(L, xr, nb[j]) : lzc_word(xr, nb[j], c, cap);
+                                pend = false;
+                            }
+                        }
+                    }
                 }
                 const unsigned bal = __ballot_sync(0xffffffffu, pend);
                 if (pend) q[qn + __popc(bal & lanemask_lt())] = p;
@@ -346,10 +452,18 @@ __global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __rest
 
 template <int ROUNDS>
 __global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
-                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next, uint32_t* __restrict__ counter) {
+                                                           const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next, const uint32_t* __restrict__ fs,
+                                                           const uint32_t* __restrict__ cframe, uint32_t* __restrict__ counter) {
+    static_assert(32 * ROUNDS == LZC_WCHUNK, "cframe is indexed by LZC_WCHUNK-position chunks");
     __shared__ uint32_t q[LZC_WARPS][32 * ROUNDS + 32];
-    LzcLevelOp<ROUNDS> op{bs, n, L, lw, rsd, lw_next};
+    LzcLevelOp<ROUNDS> op{bs, n, L, lw, rsd, lw_next, fs, cframe};
     lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5]);
+}
+
+// frame of the first position of every LZC_WCHUNK-position chunk
+__global__ void lzc_cframe_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t n, uint32_t* __restrict__ cframe) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((uint64_t)c * LZC_WCHUNK < n) cframe[c] = lzc_frame_of(fs, F, c * LZC_WCHUNK);
 }
 
 __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_t* __restrict__ wbase) {

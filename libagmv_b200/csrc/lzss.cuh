@@ -34,6 +34,7 @@ struct LzWork {
     LzcItem* items = nullptr;            // (frame, range) work items of lzc_hashlink_k
     uint32_t n_items = 0;
     int hash_bits = LZC_HB;              // size of lzc_hashlink_k's table
+    uint32_t* cframe = nullptr;          // frame of the first position of every LZC_WCHUNK-position chunk
     uint32_t* counters = nullptr;        // chunk counters of the persistent kernels (one per launch of a batch)
     uint32_t link3_blocks = 148 * 5, level_blocks = 148 * 6;   // resident blocks of the persistent walking kernels
     uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
@@ -141,20 +142,14 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
         // persistent walking kernels: enough warps to fill the GPU, chunks handed out through one counter per launch
         const uint32_t nb3 = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.link3_blocks), nb = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.level_blocks);
-        static const int rounds = getenv("AGMVB_LZ_ROUNDS") ? atoi(getenv("AGMVB_LZ_ROUNDS")) : 16;
         cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
+        KL(lc, KC_LZ_LINK, (lzc_cframe_k<<<cdiv(cdiv(n, LZC_WCHUNK), 256), 256, 0, st>>>(fs, F, n, wk.cframe)));
         KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, (size_t)4 << wk.hash_bits, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd, wk.hash_bits)));
-        if (rounds == 4) KL(lc, KC_LZ_LINK3, (lzc_link3_k<4><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
-        else if (rounds == 8) KL(lc, KC_LZ_LINK3, (lzc_link3_k<8><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
-        else KL(lc, KC_LZ_LINK3, (lzc_link3_k<16><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
+        KL(lc, KC_LZ_LINK3, (lzc_link3_k<LZC_ROUNDS><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
-        {
-            uint32_t* const cnt = wk.counters + (L - LZ_MINLEN + 1);
-            if (rounds == 4) KL(lc, KC_LZ_LEVEL, (lzc_level_k<4><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
-            else if (rounds == 8) KL(lc, KC_LZ_LEVEL, (lzc_level_k<8><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
-            else KL(lc, KC_LZ_LEVEL, (lzc_level_k<16><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], cnt)));
-        }
+            KL(lc, KC_LZ_LEVEL, (lzc_level_k<LZC_ROUNDS><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], fs, wk.cframe,
+                                                                                     wk.counters + (L - LZ_MINLEN + 1))));
         lw15 = wk.lw[cur];
         KL(lc, KC_LZ_LEVEL, (lzc_bestlen_k<<<cdiv(cdiv(n, 4u), 256u), 256, 0, st>>>(lw15, n, wk.bestlen)));
     }

@@ -27,9 +27,10 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
     lw[0].resize(n); lw[1].resize(n);
     std::vector<uint16_t> rsd(n);
     Result R; R.len.assign(n, 0); R.off.assign(n, 0);
-    std::vector<uint32_t> rem(n);
+    std::vector<uint32_t> rem(n), fstart(n);
     for (size_t f = 0; f + 1 < fs.size(); f++) {
         const size_t base = fs[f], len = fs[f + 1] - fs[f];
+        for (size_t i = 0; i < len; i++) fstart[base + i] = (uint32_t)base;
         std::vector<uint32_t> tab((size_t)1 << HB, 0);
         size_t runstart = 0;
         for (size_t i = 0; i < len; i++) {
@@ -63,6 +64,20 @@ static Result chain_pipeline(const std::vector<uint8_t>& data, const std::vector
         for (size_t p = 0; p < n; p++) {
             const uint32_t w = lw[cur][p];
             LzcLevelWalk wk;
+            // the sweep's two shortcuts (lzchain.cuh, LzcLevelOp::sweep): first hop, then the right neighbour's candidate
+            const uint32_t dist = lzc_link(w), cap = (w >> 24) & 0xFu;
+            if (dist && L + 1u <= cap && ((lw[cur][p - dist] >> 16) & 0xFFu) == ((w >> 16) & 0xFFu)) {
+                lw[cur ^ 1][p] = lzc_word(dist, d[p + L + 1], d[p + L], cap);
+                continue;
+            }
+            if (dist && p + 1 < n) {
+                const uint32_t wr = lw[cur][p + 1], xr = wr & 0xFFFFu;
+                const bool cand = (wr & LZC_DEAD) ? (L >= 4u && ((wr >> 24) & 0xFu) == L - 1u) : (L + 1u <= cap);
+                if (cand && xr && xr <= p && d[p - xr] == d[p] && p - xr >= fstart[p]) {
+                    lw[cur ^ 1][p] = (wr & LZC_DEAD) ? lzc_dead(L, xr, d[p + L + 1]) : lzc_word(xr, d[p + L + 1], d[p + L], cap);
+                    continue;
+                }
+            }
             if (wk.start((uint32_t)p, w, L)) {
                 int r;
                 while ((r = wk.hop(lw[cur].data(), rsd.data())) == LZC_GO) {}
