@@ -125,6 +125,15 @@ __global__ void __launch_bounds__(32) lzc_hashlink_k(const uint8_t* __restrict__
             const uint32_t w = o < 0 ? sw[0] << 8 : __funnelshift_r(sw[o >> 2], sw[(o >> 2) + 1], (o & 3) * 8);
             const bool valid = i + 3u <= len && i < it.end;
             const uint32_t h = lzc_hash(w >> 8, hb);
+            if (s0 + 32u <= it.start) {
+                // pre-roll (it.start is a multiple of 32): only the table and the run start matter, and "most recent position
+                // of this hash" is a maximum - one shared-memory atomic per lane, no vote, nothing for the next step to wait for
+                if (valid) atomicMax(&lzc_tab[h], i + 1u);
+                const unsigned balp = __ballot_sync(0xffffffffu, i < len && (i == 0 || ((w >> 8) & 0xFFu) != (w & 0xFFu)));
+                if (balp) run_start = s0 + (31u - (uint32_t)__clz(balp));
+                __syncwarp();
+                continue;
+            }
             const uint32_t old = valid ? lzc_tab[h] : 0u;
             const unsigned peers = __match_any_sync(0xffffffffu, valid ? h : (0x80000000u | lane));
             const unsigned lower = peers & lanemask_lt();
@@ -179,7 +188,7 @@ constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
 // Op: uint32_t sweep(cbase, q) appends the chunk's unfinished positions to q and returns their number;
 //     begin(p) loads a queued position's walk; step() takes one hop and returns true (after writing the result) when done.
 template <int ROUNDS, class Op>
-__device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q) {
+__device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restrict__ counter, uint32_t* q, int refill_min = 1) {
     const uint32_t lane = lane_id();
     uint32_t qn = 0, qi = 0;
     bool more = true, busy = false;
@@ -201,7 +210,8 @@ __device__ __forceinline__ void lzc_drive(Op& op, uint32_t n, uint32_t* __restri
             continue;
         }
         const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (qi < qn && idle) {
+        // refill in batches: a begin() costs the whole warp its instructions whether one lane or thirty-two take a position
+        if (qi < qn && (__popc(idle) >= refill_min || idle == 0xffffffffu)) {
             const uint32_t my = qi + __popc(idle & lanemask_lt());
             if (!busy && my < qn) { op.begin(q[my]); busy = true; }
             qi = min(qn, qi + (uint32_t)__popc(idle));
@@ -453,11 +463,11 @@ __global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __rest
 template <int ROUNDS>
 __global__ void __launch_bounds__(LZC_THREADS) lzc_level_k(const uint8_t* __restrict__ bs, uint32_t n, uint32_t L, const uint32_t* __restrict__ lw,
                                                            const uint16_t* __restrict__ rsd, uint32_t* __restrict__ lw_next, const uint32_t* __restrict__ fs,
-                                                           const uint32_t* __restrict__ cframe, uint32_t* __restrict__ counter) {
+                                                           const uint32_t* __restrict__ cframe, uint32_t* __restrict__ counter, int refill_min) {
     static_assert(32 * ROUNDS == LZC_WCHUNK, "cframe is indexed by LZC_WCHUNK-position chunks");
     __shared__ uint32_t q[LZC_WARPS][32 * ROUNDS + 32];
     LzcLevelOp<ROUNDS> op{bs, n, L, lw, rsd, lw_next, fs, cframe};
-    lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5]);
+    lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5], refill_min);
 }
 
 // frame of the first position of every LZC_WCHUNK-position chunk

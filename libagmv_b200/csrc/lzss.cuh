@@ -146,10 +146,11 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         KL(lc, KC_LZ_LINK, (lzc_cframe_k<<<cdiv(cdiv(n, LZC_WCHUNK), 256), 256, 0, st>>>(fs, F, n, wk.cframe)));
         KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, (size_t)4 << wk.hash_bits, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd, wk.hash_bits)));
         KL(lc, KC_LZ_LINK3, (lzc_link3_k<LZC_ROUNDS><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
+        static const int refill_min = getenv("AGMVB_LZ_REFILL") ? atoi(getenv("AGMVB_LZ_REFILL")) : 8;
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
             KL(lc, KC_LZ_LEVEL, (lzc_level_k<LZC_ROUNDS><<<nb, LZC_THREADS, 0, st>>>(bs, n, L, wk.lw[cur], wk.rsd, wk.lw[cur ^ 1], fs, wk.cframe,
-                                                                                     wk.counters + (L - LZ_MINLEN + 1))));
+                                                                                     wk.counters + (L - LZ_MINLEN + 1), refill_min)));
         lw15 = wk.lw[cur];
         KL(lc, KC_LZ_LEVEL, (lzc_bestlen_k<<<cdiv(cdiv(n, 4u), 256u), 256, 0, st>>>(lw15, n, wk.bestlen)));
     }
