@@ -193,6 +193,18 @@ int agmvb_dec_seek(agmvb_ctx* ctx, int stream, uint32_t frame_index);
 int agmvb_dec_open_raw(agmvb_ctx* ctx, uint32_t w, uint32_t h, int version, const uint32_t pal0[256], const uint32_t pal1[256], int* stream);
 int agmvb_dec_chunk(agmvb_ctx* ctx, int stream, const uint8_t* payload, uint64_t payload_len, uint32_t usize, uint32_t csize,
                     uint32_t frame_count, uint32_t* out_px, uint32_t* bpos, uint32_t* consumed);
+/* The frame-ahead queue behind AGMV_PlayAGMV's loop (src/agmv_playback.c:102-115): n consecutive frame
+ * chunks in one call. slab = a piece of the file that holds all n chunks; payload_off[k] = slab offset of the first byte
+ * after chunk k's 16-byte 'AGFC' header; frames are decoded with frame_count = first_frame_count + k. Outputs per frame:
+ * pixels (host, n*w*h), bitstream->pos and payload bytes consumed (bpos / consumed: n entries each, nullable). */
+int agmvb_dec_chunks(agmvb_ctx* ctx, int stream, const uint8_t* slab, uint64_t slab_len, uint32_t n, const uint64_t* payload_off,
+                     const uint32_t* usize, const uint32_t* csize, uint32_t first_frame_count, uint32_t* out_px, uint32_t* bpos,
+                     uint32_t* consumed);
+/* Put the decoder state of a stream aside / bring it back (pixels, I-frame snapshot, carried bitstream buffer - what the
+ * reference keeps in the AGMV handle, include/agmv_defines.h:131-162), so that frames decoded ahead of the caller can be
+ * withdrawn when the caller seeks (AGMV_SkipTo, src/agmv_playback.c:94-100) instead of taking them. */
+int agmvb_dec_snapshot(agmvb_ctx* ctx, int stream);
+int agmvb_dec_restore(agmvb_ctx* ctx, int stream);
 
 /* ---- measurement utilities ------------------------------------------------------ */
 /* Fill dev_out with n synthetic w x h frames t = first_t .. first_t+n-1 (the deterministic integer generator

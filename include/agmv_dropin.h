@@ -133,6 +133,10 @@ void to_80bitfloat(u32 num, u8 bytes[10]);
 
 /* not part of the reference: last error text of the GPU layer, and the device to use (default 0) */
 const char* AGMV_B200_LastError(void);
+/* Frame-ahead queue behind AGMV_DecodeFrameChunk (what AGMV_PlayAGMV's loop, src/agmv_playback.c:102-115, calls per frame):
+ * frames answered from the queue, batches decoded ahead, batches withdrawn because the caller went elsewhere.
+ * Depth: environment AGMV_B200_AHEAD (default 8, 1 = off). */
+void AGMV_B200_PlayQueueStats(unsigned long* hits, unsigned long* batches, unsigned long* rollbacks);
 void AGMV_B200_SetDevice(int device);
 
 #ifdef __cplusplus

@@ -69,6 +69,9 @@ SYMBOLS = {
     "agmvb_dec_seek": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32]),
     "agmvb_dec_open_raw": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, _u32p, _u32p, C.POINTER(C.c_int)]),
     "agmvb_dec_chunk": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, _u32p, _u32p, _u32p]),
+    "agmvb_dec_chunks": (C.c_int, [C.c_void_p, C.c_int, _u8p, C.c_uint64, C.c_uint32, C.POINTER(C.c_uint64), _u32p, _u32p, C.c_uint32, _u32p, _u32p, _u32p]),
+    "agmvb_dec_snapshot": (C.c_int, [C.c_void_p, C.c_int]),
+    "agmvb_dec_restore": (C.c_int, [C.c_void_p, C.c_int]),
     "agmvb_synth_frames": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "agmvb_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "agmvb_profile_classes": (C.c_int, []),

@@ -594,14 +594,52 @@ static uint32_t pal_sum(const AGMV* a) {
     return s;
 }
 
-static int bound_stream(agmvb_ctx* c, AGMV* agmv, int* stream) {
+/* ---- frame-ahead queue (the loop it serves: AGMV_PlayAGMV, src/agmv_playback.c:102-115) ----
+ * A caller that takes frame chunks one after the other (every player does) gets the next AGMV_B200_AHEAD chunks decoded in one
+ * batch behind its back; the following calls are answered from host memory as long as they arrive where a sequential
+ * caller arrives (same FILE*, the predicted 'AGFC' offset, frame_count one higher). Anything else - a seek, a changed
+ * frame_count, another file - withdraws the frames not taken yet: the decoder state is put back to what it was before the
+ * batch and the frames the caller did take are decoded again, so the handle is in exactly the state the reference's would be. */
+#define PLAY_AHEAD_MAX 32
+typedef struct { long pos; u32 frame_count, frame_num, usize, csize; uint32_t bpos, consumed; } PlayEnt;
+typedef struct {
+    FILE* file;
+    int n, head;                 /* frames decoded in the current batch / already handed out */
+    PlayEnt ent[PLAY_AHEAD_MAX];
+    uint64_t poff[PLAY_AHEAD_MAX];
+    uint32_t us[PLAY_AHEAD_MAX], cs[PLAY_AHEAD_MAX], bp[PLAY_AHEAD_MAX], co[PLAY_AHEAD_MAX];
+    uint32_t* px; size_t px_cap;  /* n * P pixels */
+    uint8_t* slab; size_t slab_len, slab_cap; long slab_pos;
+    int streak;                  /* sequential calls in a row */
+    long last_end; u32 last_fc;  /* cursor and frame_count the previous call left behind */
+} PlayQ;
+static PlayQ g_play[MAX_BOUND];
+static unsigned long g_play_hits, g_play_batches, g_play_rollbacks;
+/* test / tuning hook: frames answered from the queue, batches decoded ahead, batches withdrawn */
+void AGMV_B200_PlayQueueStats(unsigned long* hits, unsigned long* batches, unsigned long* rollbacks) {
+    if (hits) *hits = g_play_hits;
+    if (batches) *batches = g_play_batches;
+    if (rollbacks) *rollbacks = g_play_rollbacks;
+}
+static int play_ahead(void) {   /* read per call: a player may change its mind (and so do the tests) */
+    const char* e = getenv("AGMV_B200_AHEAD");
+    int v = e ? atoi(e) : 8;
+    if (v < 1) v = 1;
+    if (v > PLAY_AHEAD_MAX) v = PLAY_AHEAD_MAX;
+    return v;
+}
+static void play_reset(PlayQ* q) { q->n = q->head = 0; q->streak = 0; q->file = NULL; }
+
+static int bound_stream_slot(agmvb_ctx* c, AGMV* agmv, int* stream, int* slot_out, int* fresh) {
     int slot = -1;
+    *fresh = 0;
     uint32_t ps = pal_sum(agmv);
     for (int k = 0; k < MAX_BOUND; k++) if (g_bound[k].key == agmv) slot = k;
     if (slot >= 0) {
         if (g_bound[slot].w == agmv->header.width && g_bound[slot].h == agmv->header.height &&
             g_bound[slot].version == agmv->header.version && g_bound[slot].palsum == ps && agmv->frame_count != 0) {
             *stream = g_bound[slot].stream;
+            *slot_out = slot;
             return 0;
         }
         agmvb_dec_close(c, g_bound[slot].stream); /* new stream on an old handle (or a rewind to frame 0) */
@@ -609,6 +647,9 @@ static int bound_stream(agmvb_ctx* c, AGMV* agmv, int* stream) {
     }
     for (int k = 0; k < MAX_BOUND && slot < 0; k++) if (!g_bound[k].key) slot = k;
     if (slot < 0) { agmvb_dec_close(c, g_bound[0].stream); slot = 0; }
+    play_reset(&g_play[slot]);
+    *fresh = 1;
+    *slot_out = slot;
     uint32_t p0[256], p1[256];
     for (int i = 0; i < 256; i++) { p0[i] = (uint32_t)agmv->header.palette0[i]; p1[i] = (uint32_t)agmv->header.palette1[i]; }
     int rc = agmvb_dec_open_raw(c, (uint32_t)agmv->header.width, (uint32_t)agmv->header.height, agmv->header.version, p0, p1, stream);
@@ -618,31 +659,150 @@ static int bound_stream(agmvb_ctx* c, AGMV* agmv, int* stream) {
     return 0;
 }
 
+/* hand frame `e` of the queue to the caller: everything AGMV_DecodeFrameChunk leaves in the handle and the FILE */
+static void play_serve(PlayQ* q, int k, FILE* file, AGMV* agmv) {
+    const PlayEnt* e = &q->ent[k];
+    const size_t P = (size_t)agmv->header.width * agmv->header.height;
+    const uint32_t* px = q->px + (size_t)k * P;
+    memcpy(agmv->frame_chunk->fourcc, "AGFC", 4);
+    agmv->frame_chunk->frame_num = e->frame_num;
+    agmv->frame_chunk->uncompressed_size = e->usize;
+    agmv->frame_chunk->compressed_size = e->csize;
+    for (size_t i = 0; i < P; i++) agmv->frame->img_data[i] = px[i];
+    if (agmv->frame_count % 4 == 0) for (size_t i = 0; i < P; i++) agmv->iframe->img_data[i] = px[i];
+    agmv->bitstream->pos = e->bpos;
+    agmv->frame_count++;
+    fseek(file, e->pos + 16 + (long)e->consumed, SEEK_SET); /* where the reference's bit reader leaves the cursor */
+    q->last_end = e->pos + 16 + (long)e->consumed;
+    q->last_fc = (u32)agmv->frame_count;
+}
+
+/* the caller left the predicted path with frames of the batch not taken: decoder state back to before the batch, then the
+ * frames that were taken once more */
+static int play_withdraw(agmvb_ctx* c, PlayQ* q, int stream) {
+    int rc = 0;
+    if (q->head < q->n) {
+        g_play_rollbacks++;
+        rc = agmvb_dec_restore(c, stream);
+        if (!rc && q->head > 0)
+            rc = agmvb_dec_chunks(c, stream, q->slab, q->slab_len, (uint32_t)q->head, q->poff, q->us, q->cs, q->ent[0].frame_count, q->px, NULL, NULL);
+    }
+    q->n = q->head = 0;
+    q->streak = 0;
+    return rc;
+}
+
+/* make q->slab hold the file from q->slab_pos up to (at least) relative offset `upto`; returns bytes available */
+static size_t slab_fill(PlayQ* q, FILE* file, size_t upto) {
+    if (upto <= q->slab_len) return q->slab_len;
+    size_t want = upto + (256u << 10);
+    if (want > q->slab_cap) {
+        uint8_t* nb = (uint8_t*)realloc(q->slab, want * 2);
+        if (!nb) return q->slab_len;
+        q->slab = nb; q->slab_cap = want * 2;
+    }
+    if (fseek(file, q->slab_pos + (long)q->slab_len, SEEK_SET) != 0) return q->slab_len;
+    q->slab_len += fread(q->slab + q->slab_len, 1, want - q->slab_len, file);
+    return q->slab_len;
+}
+
 /* src/agmv_decode.c:145-410 */
 int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
+    agmvb_ctx* c = ctx_get();
+    const long pos0 = ftell(file);
+    const size_t P = (size_t)agmv->header.width * agmv->header.height;
+    int stream = -1, slot = 0, fresh = 0;
+    int rcb = c ? bound_stream_slot(c, agmv, &stream, &slot, &fresh) : 0;
+    PlayQ* q = &g_play[slot];
+    if (c && !rcb && q->head < q->n) {
+        const PlayEnt* e = &q->ent[q->head];
+        if (q->file == file && e->pos == pos0 && e->frame_count == (u32)agmv->frame_count) { /* the sequential caller */
+            agmv->bitstream->pos = 0;
+            play_serve(q, q->head++, file, agmv);
+            g_play_hits++;
+            return NO_ERR;
+        }
+        rcb = play_withdraw(c, q, stream);
+        fseek(file, pos0, SEEK_SET);
+    }
     agmv->bitstream->pos = 0;
     read_fourcc(file, agmv->frame_chunk->fourcc);
     agmv->frame_chunk->frame_num = r32(file);
     agmv->frame_chunk->uncompressed_size = r32(file);
     agmv->frame_chunk->compressed_size = r32(file);
     if (memcmp(agmv->frame_chunk->fourcc, "AGFC", 4)) return INVALID_HEADER_FORMATTING_ERR;
-    agmvb_ctx* c = ctx_get();
     if (!c) return MEMORY_CORRUPTION_ERR;
     const u32 usize = agmv->frame_chunk->uncompressed_size, csize = agmv->frame_chunk->compressed_size;
-    const size_t P = (size_t)agmv->header.width * agmv->header.height;
     const long data_start = ftell(file);
     /* csize comes from the file: never allocate past what the file still holds */
     long here = data_start, end_pos = data_start;
     if (fseek(file, 0, SEEK_END) == 0) { end_pos = ftell(file); fseek(file, here, SEEK_SET); }
     size_t left = end_pos > here ? (size_t)(end_pos - here) : 0;
+    /* a caller that keeps taking the next chunk gets the following ones decoded with this one */
+    const int sequential = !fresh && q->streak >= 0 && (u32)agmv->frame_count == q->last_fc && pos0 >= q->last_end && q->last_fc != 0;
+    q->streak = sequential ? q->streak + 1 : 0;
+    const int ahead = play_ahead();
+    if (!rcb && ahead > 1 && q->streak >= 2 && (size_t)csize <= left && (uint64_t)usize <= 2 * (uint64_t)P + 64) {
+        /* collect up to `ahead` chunks: the next one is looked for where AGMV_FindNextFrameChunk (src/agmv_utils.c:140-166)
+         * would find it for a caller whose cursor stands after this payload */
+        q->slab_pos = pos0; q->slab_len = 0; q->file = file;
+        int n = 0;
+        size_t at = 0; /* slab offset of chunk n's 'AGFC' */
+        while (n < ahead) {
+            if (slab_fill(q, file, at + 16) < at + 16) break;
+            const uint8_t* h = q->slab + at;
+            if (memcmp(h, "AGFC", 4)) break;
+            uint32_t fn, us, cs;
+            memcpy(&fn, h + 4, 4); memcpy(&us, h + 8, 4); memcpy(&cs, h + 12, 4);
+            if ((uint64_t)us > 2 * (uint64_t)P + 64) break;
+            const size_t pay_end = at + 16 + (size_t)cs;
+            const size_t have = slab_fill(q, file, pay_end + 64);
+            if (have < pay_end && n > 0) break; /* a payload that runs past the end of the file is left to the single path */
+            q->ent[n].pos = pos0 + (long)at; q->ent[n].frame_count = (u32)agmv->frame_count + (u32)n;
+            q->ent[n].frame_num = fn; q->ent[n].usize = us; q->ent[n].csize = cs;
+            q->poff[n] = at + 16; q->us[n] = us; q->cs[n] = cs;
+            n++;
+            /* next 'AGFC' at or after the end of this payload (look at most 1 MB further) */
+            size_t scan = pay_end, found = (size_t)-1;
+            while (found == (size_t)-1 && scan < pay_end + (1u << 20)) {
+                const size_t got = slab_fill(q, file, scan + 4096);
+                if (got < scan + 4) break;
+                const size_t lim = got - 3 < scan + 4096 ? got - 3 : scan + 4096;
+                for (size_t i = scan; i < lim; i++) if (q->slab[i] == 'A' && !memcmp(q->slab + i, "AGFC", 4)) { found = i; break; }
+                scan = lim;
+            }
+            if (found == (size_t)-1) break;
+            at = found;
+        }
+        if (n > 1) {
+            if (q->px_cap < (size_t)n * P) {
+                free(q->px);
+                q->px = (uint32_t*)malloc((size_t)ahead * P * 4);
+                q->px_cap = q->px ? (size_t)ahead * P : 0;
+            }
+            int rc = q->px ? agmvb_dec_snapshot(c, stream) : 1;
+            if (!rc) {
+                rc = agmvb_dec_chunks(c, stream, q->slab, q->slab_len, (uint32_t)n, q->poff, q->us, q->cs, (uint32_t)agmv->frame_count, q->px, q->bp, q->co);
+                if (rc) agmvb_dec_restore(c, stream); /* a damaged chunk further on: this frame alone, below */
+            }
+            if (!rc) {
+                for (int k = 0; k < n; k++) { q->ent[k].bpos = q->bp[k]; q->ent[k].consumed = q->co[k]; }
+                q->n = n; q->head = 1;
+                g_play_batches++;
+                play_serve(q, 0, file, agmv);
+                return NO_ERR;
+            }
+        }
+        q->n = q->head = 0;
+        fseek(file, data_start, SEEK_SET);
+    }
     size_t want = (size_t)csize + 64;
     if (want > left + 64) want = left + 64;
     uint8_t* pay = (uint8_t*)malloc(want);
     uint32_t* px = (uint32_t*)malloc(P * 4);
     if (!pay || !px) { free(pay); free(px); return MEMORY_CORRUPTION_ERR; }
     size_t got = fread(pay, 1, want, file);
-    int stream = -1;
-    int rc = bound_stream(c, agmv, &stream);
+    int rc = rcb;
     uint32_t bpos = 0, consumed = 0;
     if (!rc) rc = agmvb_dec_chunk(c, stream, pay, got, (uint32_t)usize, (uint32_t)csize, (uint32_t)agmv->frame_count, px, &bpos, &consumed);
     if (!rc) {
@@ -651,6 +811,8 @@ int AGMV_DecodeFrameChunk(FILE* file, AGMV* agmv) {
         agmv->bitstream->pos = bpos;
         agmv->frame_count++;
         fseek(file, data_start + (long)consumed, SEEK_SET); /* where the reference's bit reader leaves the cursor */
+        q->last_end = data_start + (long)consumed;
+        q->last_fc = (u32)agmv->frame_count;
     }
     free(pay); free(px);
     if (rc) {

@@ -49,9 +49,12 @@ struct DecStream {
     uint32_t persist_len = 0;
     uint32_t* d_ring = nullptr;     // optional ring of frames for agmvb_dec_batch without outputs
     uint32_t last_bpos = 0, last_consumed = 0;
-    bool raw = false;               // fed chunk by chunk (agmvb_dec_chunk): the vectors hold one entry
+    bool raw = false;               // fed chunk by chunk (agmvb_dec_chunk / agmvb_dec_chunks): the vectors hold the chunks of one call
+    uint32_t raw_base = 0;          // frame_count of the first chunk of that call
     uint64_t file_cap = 0;
-    size_t at(uint32_t g) const { return raw ? 0 : g; }
+    uint8_t* d_snap = nullptr;      // agmvb_dec_snapshot: pixels, I-frame snapshot, carried bitstream buffer
+    bool snap_valid = false;
+    size_t at(uint32_t g) const { return raw ? g - raw_base : g; }
 };
 
 }  // namespace
@@ -95,6 +98,8 @@ struct agmvb_ctx {
     std::vector<DecStream> streams;
     std::vector<DecStream> parked;   // buffers of closed streams, reused by later opens
     DBuf d_frames, d_ebuf, d_bpos, d_consumed, d_stale, d_recs, d_steps, d_out, d_cksum, d_count;
+    uint32_t* info_bpos = nullptr;      // host arrays a single-stream call wants filled per frame (agmvb_dec_chunks)
+    uint32_t* info_consumed = nullptr;
     DBuf d_code, d_segs, d_seglen, d_oexit, d_ow, d_oentry, d_ocum, d_ofinal;
 };
 
@@ -170,7 +175,7 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
 }
 
 static void free_stream(DecStream& s) {
-    cudaFree(s.d_file); cudaFree(s.d_pal); cudaFree(s.d_img); cudaFree(s.d_ifr); cudaFree(s.d_persist); cudaFree(s.d_ring);
+    cudaFree(s.d_file); cudaFree(s.d_pal); cudaFree(s.d_img); cudaFree(s.d_ifr); cudaFree(s.d_persist); cudaFree(s.d_ring); cudaFree(s.d_snap);
     s = DecStream();
 }
 
@@ -1251,6 +1256,7 @@ static void park_stream(agmvb_ctx* ctx, DecStream& s) {
     DecStream k;
     k.d_file = s.d_file; k.file_cap = s.file_cap; k.d_pal = s.d_pal; k.d_img = s.d_img; k.d_ifr = s.d_ifr; k.d_persist = s.d_persist;
     k.persist_len = s.persist_len; k.d_ring = s.d_ring; k.w = s.w; k.h = s.h;
+    cudaFree(s.d_snap);
     if (ctx->parked.size() < 1024) ctx->parked.push_back(k); else free_stream(k);
     s = DecStream();
 }
@@ -1570,6 +1576,8 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
                 CK(cudaMemcpyAsync(&d.last_consumed, ctx->d_consumed.as<uint32_t>() + (s * cn + cn - 1), 4, cudaMemcpyDeviceToHost, ctx->st));
             }
         }
+        if (S == 1 && ctx->info_bpos) CK(cudaMemcpyAsync(ctx->info_bpos + c0, ctx->d_bpos.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, ctx->st));
+        if (S == 1 && ctx->info_consumed) CK(cudaMemcpyAsync(ctx->info_consumed + c0, ctx->d_consumed.p, (size_t)cn * 4, cudaMemcpyDeviceToHost, ctx->st));
         CK(cudaStreamSynchronize(ctx->st));  // host vectors are rebuilt for the next chunk
         for (uint32_t s = 0; s < S; s++) ctx->streams[ids[s]].next += cn;
     }
@@ -1670,8 +1678,8 @@ extern "C" int agmvb_dec_chunk(agmvb_ctx* ctx, int stream, const uint8_t* payloa
     }
     CK(cudaMemcpyAsync(d.d_file, payload, payload_len, cudaMemcpyHostToDevice, ctx->st));
     d.file_len = payload_len;
-    d.data_off[0] = 0; d.usize[0] = usize; d.csize[0] = csize;
-    d.next = frame_count;
+    d.data_off.assign(1, 0); d.usize.assign(1, usize); d.csize.assign(1, csize);
+    d.next = d.raw_base = frame_count;
     TRY(ensure(ctx, ctx->d_out, P * 4));
     uint32_t* o = ctx->d_out.as<uint32_t>();
     TRY(dec_batch_impl(ctx, &stream, 1, 1, &o, nullptr));
@@ -1679,6 +1687,72 @@ extern "C" int agmvb_dec_chunk(agmvb_ctx* ctx, int stream, const uint8_t* payloa
     CK(cudaStreamSynchronize(ctx->st));
     if (bpos) *bpos = d.last_bpos;
     if (consumed) *consumed = d.last_consumed;
+    return OK;
+}
+
+// n consecutive frame chunks of one stream in one call - the frame-ahead queue behind AGMV_PlayAGMV's loop
+// (src/agmv_playback.c:102-115). slab: a piece of the file that holds all n chunks, payload_off[k] = offset in
+// the slab of the first byte after chunk k's 16-byte header (so the bit reader sees the real bytes after a payload, as
+// fread does). Outputs per frame: pixels (host, n*w*h), bitstream->pos, payload bytes consumed.
+extern "C" int agmvb_dec_chunks(agmvb_ctx* ctx, int stream, const uint8_t* slab, uint64_t slab_len, uint32_t n, const uint64_t* payload_off,
+                                const uint32_t* usize, const uint32_t* csize, uint32_t first_frame_count, uint32_t* out_px, uint32_t* bpos,
+                                uint32_t* consumed) {
+    if (!ctx || !slab || !payload_off || !usize || !csize || !out_px || n == 0) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open || !ctx->streams[stream].raw)
+        FAIL(ERR_ARG, "bad raw stream handle");
+    DecStream& d = ctx->streams[stream];
+    const size_t P = (size_t)d.w * d.h;
+    for (uint32_t k = 0; k < n; k++) {
+        if (usize[k] > 2 * P + 64) FAIL(ERR_MEMORY, "uncompressed size %u exceeds the reference's bitstream buffer", usize[k]);
+        if (payload_off[k] > slab_len) FAIL(ERR_ARG, "chunk %u lies outside the slab", k);
+    }
+    if (slab_len + 64 > d.file_cap) {
+        CK(cudaStreamSynchronize(ctx->st));
+        if (d.d_file) CK(cudaFree(d.d_file));
+        d.file_cap = slab_len * 2 + 4096;
+        CK(cudaMalloc(&d.d_file, d.file_cap));
+    }
+    CK(cudaMemcpyAsync(d.d_file, slab, slab_len, cudaMemcpyHostToDevice, ctx->st));
+    d.file_len = slab_len;
+    d.data_off.assign(payload_off, payload_off + n); d.usize.assign(usize, usize + n); d.csize.assign(csize, csize + n);
+    d.next = d.raw_base = first_frame_count;
+    TRY(ensure(ctx, ctx->d_out, (size_t)n * P * 4));
+    uint32_t* o = ctx->d_out.as<uint32_t>();
+    ctx->info_bpos = bpos; ctx->info_consumed = consumed;
+    const int rc = dec_batch_impl(ctx, &stream, 1, n, &o, nullptr);
+    ctx->info_bpos = ctx->info_consumed = nullptr;
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out_px, o, (size_t)n * P * 4, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return OK;
+}
+
+// Decoder state of a stream (what the reference keeps in the AGMV handle: frame pixels, I-frame copy, bitstream buffer) put
+// aside / brought back, so that frames decoded ahead of the caller can be withdrawn when the caller seeks instead.
+extern "C" int agmvb_dec_snapshot(agmvb_ctx* ctx, int stream) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open) FAIL(ERR_ARG, "bad stream handle");
+    DecStream& d = ctx->streams[stream];
+    const size_t P = (size_t)d.w * d.h;
+    if (!d.d_snap) CK(cudaMalloc(&d.d_snap, P * 8 + d.persist_len));
+    CK(cudaMemcpyAsync(d.d_snap, d.d_img, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d.d_snap + P * 4, d.d_ifr, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d.d_snap + P * 8, d.d_persist, d.persist_len, cudaMemcpyDeviceToDevice, ctx->st));
+    d.snap_valid = true;
+    return OK;
+}
+extern "C" int agmvb_dec_restore(agmvb_ctx* ctx, int stream) {
+    if (!ctx) return ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    if (stream < 0 || (size_t)stream >= ctx->streams.size() || !ctx->streams[stream].open || !ctx->streams[stream].snap_valid)
+        FAIL(ERR_ARG, "no snapshot to restore");
+    DecStream& d = ctx->streams[stream];
+    const size_t P = (size_t)d.w * d.h;
+    CK(cudaMemcpyAsync(d.d_img, d.d_snap, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d.d_ifr, d.d_snap + P * 4, P * 4, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d.d_persist, d.d_snap + P * 8, d.persist_len, cudaMemcpyDeviceToDevice, ctx->st));
     return OK;
 }
 

@@ -406,3 +406,79 @@ def test_encode_agmv_dropin_on_the_reference_foxlogo_bmps(golden):
         finally:
             os.chdir(cwd)
     assert (len(data), sha256(data)) == (g["size"], g["sha256"]), lib.AGMV_B200_LastError()
+
+
+class FrameChunk(C.Structure):
+    _fields_ = [("fourcc", C.c_char * 4), ("frame_num", UL), ("uncompressed_size", UL), ("compressed_size", UL)]
+
+
+def _play_visit(lib, libc, path, raw, offs, plan, ahead):
+    """Visit the frames of a stream in `plan` order the way a player does (AGMV_SkipTo for a jump, AGMV_FindNextFrameChunk for the
+    next frame, then AGMV_DecodeFrameChunk); returns per visit (frame sha256, bitstream->pos, file cursor) and the queue's counters."""
+    os.environ["AGMV_B200_AHEAD"] = str(ahead)
+    st0 = [C.c_ulong(), C.c_ulong(), C.c_ulong()]
+    lib.AGMV_B200_PlayQueueStats(*[C.byref(x) for x in st0])
+    f = libc.fopen(path.encode(), b"rb")
+    h = lib.CreateAGMV(0, int.from_bytes(raw[8:12], "little"), int.from_bytes(raw[12:16], "little"), 16)
+    assert lib.AGMV_DecodeHeader(f, h) == 0
+    a = h.contents
+    a.frame.contents.width = a.iframe.contents.width = a.header.width
+    a.frame.contents.height = a.iframe.contents.height = a.header.height
+    a.frame_count = 0
+    P = int(a.header.width * a.header.height)
+    out, prev = [], -2
+    for k in plan:
+        if k != prev + 1:
+            libc.fseek(f, offs[k], 0)
+            a.frame_count = k
+        else:
+            libc.fseek(f, raw.find(b"AGFC", libc.ftell(f)), 0)
+        assert lib.AGMV_DecodeFrameChunk(f, h) == 0, lib.AGMV_B200_LastError()
+        px = np.ctypeslib.as_array(a.frame.contents.img_data, shape=(P,)).astype(np.uint32)
+        ipx = np.ctypeslib.as_array(a.iframe.contents.img_data, shape=(P,)).astype(np.uint32)
+        fc = C.cast(a.frame_chunk, C.POINTER(FrameChunk)).contents   # include/agmv_defines.h: AGMV_FRAME_CHUNK
+        out.append((sha256(px.tobytes()), sha256(ipx.tobytes()), int(a.bitstream.contents.pos), libc.ftell(f), int(a.frame_count),
+                    bytes(fc.fourcc), int(fc.frame_num), int(fc.uncompressed_size), int(fc.compressed_size)))
+        prev = k
+    libc.fclose(f)
+    lib.DestroyAGMV(h)
+    st1 = [C.c_ulong(), C.c_ulong(), C.c_ulong()]
+    lib.AGMV_B200_PlayQueueStats(*[C.byref(x) for x in st1])
+    os.environ.pop("AGMV_B200_AHEAD", None)
+    return out, [b.value - a_.value for a_, b in zip(st0, st1)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("comp", [LZSS, 2])
+def test_play_queue_is_invisible(tmp_path, comp):
+    """the frame-ahead queue behind AGMV_DecodeFrameChunk (AGMV_PlayAGMV's loop, src/agmv_playback.c:102-115).
+    A 60-frame stream is played straight through and then with jumps in the middle of batches (AGMV_SkipTo,
+    src/agmv_playback.c:94-100); with the queue on (depth 8 and 5) every visit must leave exactly what the one-frame-per-call
+    path leaves in the handle and the FILE - pixels, I-frame copy, bitstream->pos, cursor, frame_count, chunk fields - and
+    the queue must actually have served frames and withdrawn batches."""
+    lib, libc = _dropin(), _libc()
+    lib.AGMV_B200_PlayQueueStats.argtypes = [C.POINTER(C.c_ulong)] * 3
+    frames = synth_frames(96, 80, 80, seed=77)
+    ctx = libagmv_b200.Context(0)
+    data, n_enc = ctx.encode_sequence(frames, 79, 24, OPT["III"], QUALITY["LOW"], comp)
+    ctx.close()
+    raw = data.tobytes()
+    path = str(tmp_path / "play.agmv")
+    open(path, "wb").write(raw)
+    offs, p = [], raw.find(b"AGFC")
+    while p >= 0:
+        offs.append(p)
+        cs = int.from_bytes(raw[p + 12:p + 16], "little")
+        p = raw.find(b"AGFC", p + 16 + cs)
+    assert len(offs) == n_enc >= 56
+    straight = list(range(n_enc))
+    jumps = list(range(0, 11)) + [4, 5, 6, 7, 8, 9] + [40, 41, 42] + [12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23] + [3] + list(range(44, n_enc)) + [0, 1, 2, 3]
+    for plan in (straight, jumps):
+        base, st = _play_visit(lib, libc, path, raw, offs, plan, 1)
+        assert st == [0, 0, 0]
+        for depth in (8, 5):
+            got, st = _play_visit(lib, libc, path, raw, offs, plan, depth)
+            assert got == base, (comp, depth, [i for i, (x, y) in enumerate(zip(got, base)) if x != y][:5])
+            assert st[0] > len(plan) // 3 and st[1] >= 2, st
+            if plan is jumps:
+                assert st[2] >= 3, st
