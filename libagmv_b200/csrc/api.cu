@@ -1559,8 +1559,17 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         // carry the state over: expanded-bitstream leftovers, last pixels, last I-frame snapshot
         for (uint32_t s = 0; s < S; s++) {
             DecStream& d = ctx->streams[ids[s]];
-            KL(ctx->lc, KC_STALE, (persist_update_k<<<cdiv(d.persist_len, 256), 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), s * cn, cn, ctx->d_ebuf.as<uint8_t>(),
-                                                                             d.d_persist, d.persist_len)));
+            // no frame of the chunk wrote at or beyond its expansion bound: only indices below the largest one can change
+            uint64_t reach = 0;
+            for (uint32_t k = 0; k < cn; k++) {
+                const uint32_t g = d.next + k;
+                const uint64_t e = d.lz77 ? std::min<uint64_t>((uint64_t)(d.csize[d.at(g)] / 4 + 1) * 256, d.persist_len) : d.usize[d.at(g)];
+                reach = std::max<uint64_t>(reach, e + DEC_SLACK);
+            }
+            const uint32_t plen = (uint32_t)std::min<uint64_t>(d.persist_len, reach);
+            if (plen)
+                KL(ctx->lc, KC_STALE, (persist_update_k<<<cdiv(plen, 256), 256, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), s * cn, cn, ctx->d_ebuf.as<uint8_t>(),
+                                                                                 d.d_persist, plen)));
         }
         if (c0 + cn == count) {
             for (uint32_t s = 0; s < S; s++) {

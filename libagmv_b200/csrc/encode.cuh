@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(256) quantize8_k(const SrcPair* __restrict__ s
     uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (valid) {
         const uint4* pa = reinterpret_cast<const uint4*>(sp.a) + 2 * (size_t)g;
-        const uint4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
+        const uint4 a0 = __ldcs(pa), a1 = __ldcs(pa + 1);   // streamed once: evict-first, the colour table keeps the L2
         c[0] = a0.x; c[1] = a0.y; c[2] = a0.z; c[3] = a0.w; c[4] = a1.x; c[5] = a1.y; c[6] = a1.z; c[7] = a1.w;
         if (sp.b) {
             const uint4* pb = reinterpret_cast<const uint4*>(sp.b) + 2 * (size_t)g;
-            const uint4 b0 = __ldg(pb), b1 = __ldg(pb + 1);
+            const uint4 b0 = __ldcs(pb), b1 = __ldcs(pb + 1);
             c[0] = __vhaddu4(c[0], b0.x); c[1] = __vhaddu4(c[1], b0.y); c[2] = __vhaddu4(c[2], b0.z); c[3] = __vhaddu4(c[3], b0.w);
             c[4] = __vhaddu4(c[4], b1.x); c[5] = __vhaddu4(c[5], b1.y); c[6] = __vhaddu4(c[6], b1.z); c[7] = __vhaddu4(c[7], b1.w);
         }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) quantize8_k(const SrcPair* __restrict__ s
         for (int k = 0; k < 8; k++) e[k] = lut_entry(c[k], valid, lut, spal, npal);
     }
     if (valid)
-        reinterpret_cast<uint4*>(entries + (size_t)f * P)[g] = make_uint4(e[0] | e[1] << 16, e[2] | e[3] << 16, e[4] | e[5] << 16, e[6] | e[7] << 16);
+        __stcs(reinterpret_cast<uint4*>(entries + (size_t)f * P) + g, make_uint4(e[0] | e[1] << 16, e[2] | e[3] << 16, e[4] | e[5] << 16, e[6] | e[7] << 16));
 }
 
 // grid (cdiv(P/4, 256), n_enc). map (nullable): coded pixel -> source pixel (nearest-neighbour downscale, E13)
