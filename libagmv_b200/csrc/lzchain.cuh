@@ -313,66 +313,78 @@ struct LzcLevelOp {
         const uint32_t* wp = reinterpret_cast<const uint32_t*>(u & ~(uintptr_t)3);
         return __funnelshift_r(wp[0], wp[1], (uint32_t)(u & 3u) * 8u);
     }
-    // a whole chunk well inside the buffer: every lane owns four consecutive positions of each 128-position group, so the
-    // level words move as 16-byte loads / stores and three of the four right neighbours are the lane's own registers
+    // a whole chunk well inside the buffer, in two steps. (1) Dense: every lane owns four consecutive positions of each
+    // 128-position group, so the level words move as 16-byte loads / stores; a live position takes its first hop and, if that
+    // does not settle it, is queued. (2) Compact: the queued positions, one per lane, try the right-neighbour rule (two more
+    // words from L1, two byte gathers); what is left stays queued for the walks. The rule costs nothing for the majority
+    // whose first hop succeeds.
     __device__ __forceinline__ uint32_t sweep_full(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
-        const uint32_t f0 = cframe[cbase / LZC_WCHUNK];   // frame of the chunk's first position
         uint32_t qn = 0;
 #pragma unroll 1
         for (uint32_t g0 = 0; g0 < (uint32_t)LZC_WCHUNK; g0 += 128) {
             const uint32_t p0 = cbase + g0 + lane * 4u;
             const uint4 wv = *reinterpret_cast<const uint4*>(lw + p0);
-            const uint32_t wnext = lw[cbase + g0 + 128u];
-            const uint32_t nb4 = bytes4(bs + p0 + L + 1u), bq4 = bytes4(bs + p0);
-            uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w}, wk[4], x[4], bk[4], out[4];
-            uint32_t wn = __shfl_down_sync(0xffffffffu, w[0], 1);
-            if (lane == 31) wn = wnext;
-            const uint32_t wr[4] = {w[1], w[2], w[3], wn};
+            const uint32_t nb4 = bytes4(bs + p0 + L + 1u);
+            uint32_t w[4] = {wv.x, wv.y, wv.z, wv.w}, wk[4], out[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint32_t p = p0 + i, dist = lzc_link(w[i]);
-                wk[i] = 0; x[i] = 0; bk[i] = 0x100u;
-                if (dist) {
-                    wk[i] = lw[p - dist];
-                    const uint32_t xr = wr[i] & 0xFFFFu;
-                    const bool cand = (wr[i] & LZC_DEAD) ? (L >= 4u && ((wr[i] >> 24) & 0xFu) == L - 1u) : (L + 1u <= ((w[i] >> 24) & 0xFu));
-                    if (cand && xr && xr <= p) { x[i] = xr | (wr[i] & LZC_DEAD); bk[i] = bs[p - xr]; }
-                }
+                const uint32_t dist = lzc_link(w[i]);
+                wk[i] = 0;
+                if (dist) wk[i] = lw[p0 + i - dist];
             }
             unsigned pendm = 0;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint32_t p = p0 + i, dist = lzc_link(w[i]);
+                const uint32_t dist = lzc_link(w[i]);
                 const uint32_t c = (w[i] >> 16) & 0xFFu, cap = (w[i] >> 24) & 0xFu, nb = (nb4 >> (8 * i)) & 0xFFu;
-                out[i] = lzc_carry(w[i], nb);   // final already: the result travels on
+                out[i] = lzc_carry(w[i], nb);   // final already: the result travels on (a queued position's word is rewritten later)
                 if (dist) {
                     if (L + 1u <= cap && ((wk[i] >> 16) & 0xFFu) == c) out[i] = lzc_word(dist, nb, c, cap);
-                    else {
-                        bool pend = true;
-                        if (bk[i] == ((bq4 >> (8 * i)) & 0xFFu)) {
-                            uint32_t f = f0;
-                            while (fs[f + 1] <= p) f++;
-                            const uint32_t xr = x[i] & 0xFFFFu;
-                            if (p - xr >= fs[f]) {   // the candidate lies inside p's frame
-                                out[i] = (x[i] & LZC_DEAD) ? lzc_dead(L, xr, nb) : lzc_word(xr, nb, c, cap);
-                                pend = false;
-                            }
-                        }
-                        if (pend) pendm |= 1u << i;
+                    else pendm |= 1u << i;
+                }
+            }
+            *reinterpret_cast<uint4*>(lw_next + p0) = make_uint4(out[0], out[1], out[2], out[3]);
+            if (__any_sync(0xffffffffu, pendm != 0u)) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const bool pend = (pendm >> i) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, pend);
+                    if (pend) q[qn + __popc(bal & lanemask_lt())] = p0 + i;
+                    qn += __popc(bal);
+                }
+            }
+        }
+        __syncwarp();
+        // (2) right-neighbour rule over the queue, compacting it in place (the write index never passes the read index)
+        const uint32_t f0 = cframe[cbase / LZC_WCHUNK];   // frame of the chunk's first position
+        uint32_t keep = 0;
+        for (uint32_t b0 = 0; b0 < qn; b0 += 32) {
+            const bool have = b0 + lane < qn;
+            const uint32_t p = have ? q[b0 + lane] : 0u;
+            bool pend = have;
+            if (have) {
+                const uint32_t w = lw[p], wr = lw[p + 1], xr = wr & 0xFFFFu;
+                const uint32_t cap = (w >> 24) & 0xFu;
+                const bool dead_r = wr & LZC_DEAD;
+                const bool cand = dead_r ? (L >= 4u && ((wr >> 24) & 0xFu) == L - 1u) : (L + 1u <= cap);
+                if (cand && xr && xr <= p && bs[p - xr] == bs[p]) {
+                    uint32_t f = f0;
+                    while (fs[f + 1] <= p) f++;
+                    if (p - xr >= fs[f]) {   // the candidate lies inside p's frame
+                        const uint32_t nb = bs[p + L + 1], c = (w >> 16) & 0xFFu;
+                        lw_next[p] = dead_r ? lzc_dead(L, xr, nb) : lzc_word(xr, nb, c, cap);
+                        pend = false;
                     }
                 }
             }
-            *reinterpret_cast<uint4*>(lw_next + p0) = make_uint4(out[0], out[1], out[2], out[3]);   // (a pending position's word is rewritten by its walk)
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const bool pend = (pendm >> i) & 1u;
-                const unsigned bal = __ballot_sync(0xffffffffu, pend);
-                if (pend) q[qn + __popc(bal & lanemask_lt())] = p0 + i;
-                qn += __popc(bal);
-            }
+            const unsigned bal = __ballot_sync(0xffffffffu, pend);
+            __syncwarp();
+            if (pend) q[keep + __popc(bal & lanemask_lt())] = p;
+            keep += __popc(bal);
+            __syncwarp();
         }
-        return qn;
+        return keep;
     }
     __device__ __forceinline__ uint32_t sweep_tail(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
