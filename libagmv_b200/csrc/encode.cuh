@@ -337,12 +337,9 @@ __global__ void __launch_bounds__(256) similarity_k(const SrcPair* __restrict__ 
 // and AGMV_Assemble{I,P}FrameBitstream (:354-527). Record byte: type << 6 | len.
 // ---------------------------------------------------------------------------
 
-__device__ __forceinline__ bool within2(uint32_t a, uint32_t b) {
-    int dr = (int)((a >> 16) & 255) - (int)((b >> 16) & 255);
-    int dg = (int)((a >> 8) & 255) - (int)((b >> 8) & 255);
-    int db = (int)(a & 255) - (int)(b & 255);
-    return abs(dr) <= 2 && abs(dg) <= 2 && abs(db) <= 2;
-}
+// |a - b| <= 2 on each of the three colour bytes (top byte 0 on both sides): per-byte absolute difference and compare on the
+// packed word (classify_k was issue-bound at 73 % with the scalar form, profiles/r02_ncu_summary.txt)
+__device__ __forceinline__ bool within2(uint32_t a, uint32_t b) { return __vcmpgtu4(__vabsdiffu4(a, b), 0x02020202u) == 0u; }
 __device__ __forceinline__ uint32_t code_len(uint32_t e, int dual) { return (dual && (e & 255u) >= 127u) ? 2u : 1u; }
 
 struct EntPair { const uint16_t* ent; const uint16_t* ient; };  // ient == nullptr: I-frame
