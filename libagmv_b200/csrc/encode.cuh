@@ -27,7 +27,9 @@ __device__ __forceinline__ void hist_add(unsigned long long* hist, uint32_t q, b
 // HBM): a pixel whose bin differs from its predecessor's heads a run, the four head bitmaps (one ballot per pixel slot)
 // give every head its run length with a few bit operations, and the head issues ONE atomic for the whole run. Flat
 // content costs an atomic per run of up to 128 pixels, a gradient one per two or three pixels; equal colours that are not
-// adjacent simply take separate atomics. (A pixel in bin max_clr is dropped, as above; it still ends a run.)
+// adjacent simply take separate atomics. (A pixel in bin max_clr is dropped, as above; it still ends a run.) The first
+// version took four ballots and a 4 x 4 search per head: issue-bound at 76 % with 44 instructions per pixel
+// (profiles/r02_ncu_summary.txt).
 __global__ void __launch_bounds__(256) hist_vec4_k(const uint4* __restrict__ px4, uint64_t ngroups, int quality, uint32_t mc,
                                                    unsigned long long* __restrict__ hist) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -42,25 +44,22 @@ __global__ void __launch_bounds__(256) hist_vec4_k(const uint4* __restrict__ px4
         q[2] = valid ? quantize_color(v.z, quality) : 0xFFFFFFFFu;
         q[3] = valid ? quantize_color(v.w, quality) : 0xFFFFFFFFu;
         const uint32_t left = __shfl_up_sync(0xffffffffu, q[3], 1);
-        const bool h0 = lane == 0 || q[0] != left, h1 = q[1] != q[0], h2 = q[2] != q[1], h3 = q[3] != q[2];
-        unsigned hb[4];
-        hb[0] = __ballot_sync(0xffffffffu, h0);
-        hb[1] = __ballot_sync(0xffffffffu, h1);
-        hb[2] = __ballot_sync(0xffffffffu, h2);
-        hb[3] = __ballot_sync(0xffffffffu, h3);
-        const bool hd[4] = {h0, h1, h2, h3};
+        const bool hd[4] = {lane == 0 || q[0] != left, q[1] != q[0], q[2] != q[1], q[3] != q[2]};
+        // where the run of this lane's LAST head ends: at the first head of the next lane that has one (one ballot, one
+        // shuffle); every earlier head of the lane ends at the next head of the same lane (registers only)
+        const unsigned anyb = __ballot_sync(0xffffffffu, hd[0] | hd[1] | hd[2] | hd[3]);
+        const uint32_t first = hd[0] ? 0u : (hd[1] ? 1u : (hd[2] ? 2u : (hd[3] ? 3u : 4u)));
+        const unsigned above = lane < 31u ? anyb >> (lane + 1u) : 0u;
+        const uint32_t nl = above ? lane + (uint32_t)__ffs(above) : 32u;
+        const uint32_t nfirst = __shfl_sync(0xffffffffu, first, (int)(nl & 31u));
+        uint32_t nx = nl < 32u ? 4u * nl + nfirst : 128u;   // pixel position (0..128) of the next head after this lane
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (!hd[k] || q[k] >= mc) continue;   // not a head, or the dropped bin / padding
-            // next head after pixel position 4 * lane + k: slots k+1..3 of this lane onwards, slots 0..k of the next lane onwards
-            uint32_t next = 128u;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t from = j > k ? lane : lane + 1u;
-                const unsigned m = from < 32u ? hb[j] >> from : 0u;
-                if (m) next = min(next, 4u * (from + (uint32_t)__ffs(m) - 1u) + (uint32_t)j);
+        for (int k = 3; k >= 0; k--) {
+            const uint32_t at = 4u * lane + (uint32_t)k;
+            if (hd[k]) {
+                if (q[k] < mc) atomicAdd(&hist[q[k]], (unsigned long long)(nx - at));   // (the dropped bin / padding still ends a run)
+                nx = at;
             }
-            atomicAdd(&hist[q[k]], (unsigned long long)(next - (4u * lane + (uint32_t)k)));
         }
     }
 }
