@@ -448,7 +448,6 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         };
         // occurrence-chain match finder (lzchain.cuh): 19 B per position
         TRY(grab(cap, (void**)&w.bestlen));
-        TRY(grab((size_t)cap * 4 + 16, (void**)&w.bitcum));
         TRY(grab((size_t)cap * 4, (void**)&w.lw[0]));
         TRY(grab((size_t)cap * 4, (void**)&w.lw[1]));
         TRY(grab((size_t)cap * 2, (void**)&w.rsd));
@@ -482,6 +481,8 @@ static int ensure_lz(agmvb_ctx* ctx, uint32_t n, uint32_t F) {
         TRY(ensure(ctx, ctx->lzbuf[50], ptile * ORB_SP * 2)); w.orb.w_tab = ctx->lzbuf[50].as<uint16_t>();
         TRY(ensure(ctx, ctx->lzbuf[51], ptile)); w.orb.entry_tab = ctx->lzbuf[51].as<uint8_t>();
         TRY(ensure(ctx, ctx->lzbuf[47], ptile * 4)); w.orb.cumbase = ctx->lzbuf[47].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[46], ptile * LZ15_SLOTS * 4)); w.list15 = ctx->lzbuf[46].as<uint32_t>();
+        TRY(ensure(ctx, ctx->lzbuf[45], ptile)); w.cnt15 = ctx->lzbuf[45].as<uint8_t>();
         w.cap_frames = capF;
     }
     return OK;

@@ -9,9 +9,8 @@
 //   lzc_link3_k     thread per position: hash chain -> level-3 link (most recent earlier occurrence of the 3 bytes).
 //   lzc_level_k     x12, thread per position: level L -> L+1 (lzc_level). A position whose match stops growing writes its
 //                   final (length, offset) on the spot.
-//   (orbit.cuh)     greedy parse over bestlen[].
-//   lzc_pack_k      token emission; 15-byte matches find their earliest start here (lzc_chain_end), parse-visited
-//                   positions only.
+//   (orbit.cuh, lzss.cuh)  greedy parse over bestlen[]; its last pass emits the tokens (lz_emit_mark_k) except the 15-byte
+//                   matches, which find their earliest start by a chain walk (lz_pack15_k), parse-visited positions only.
 // Workspace: 19 bytes per bitstream byte.
 #pragma once
 #include "common.cuh"
@@ -181,7 +180,7 @@ __device__ __forceinline__ uint32_t lzc_frame_of(const uint32_t* __restrict__ fs
 constexpr int LZC_ROUNDS = 16;
 constexpr int LZC_WCHUNK = 32 * LZC_ROUNDS;           // positions per chunk
 constexpr int LZC_WARPS = LZC_THREADS / 32;
-constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (lzc_pack_k)
+constexpr int LZC_BCHUNK = LZC_WCHUNK * LZC_WARPS;    // positions per block (grid sizing of the persistent kernels)
 constexpr int LZC_MLP = 4;                            // rounds of a sweep in flight together
 constexpr int LZC_QCAP = LZC_WCHUNK + 32;             // queue words per warp
 
@@ -493,64 +492,13 @@ __global__ void lzc_wbase_k(const uint32_t* __restrict__ fs, uint32_t F, uint32_
     if (i <= F) wbase[i] = (uint32_t)(((uint64_t)fs[i] * 9u) >> 5) + 3u * i;
 }
 
-// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165). Same two phases as the
-// walking kernels: literals and matches shorter than 15 bytes are emitted in the sweep, the 15-byte matches of the parse
-// (the only positions whose earliest start is still unknown) walk their level-15 chain to its end with lane refill.
+// token emission (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165): lzss.cuh emits from the
+// parse's last pass (lz_emit_mark_k) and walks the 15-byte matches' chains in lz_pack15_k
 __device__ __forceinline__ void lzc_emit(uint32_t* __restrict__ out_words, uint32_t wb, uint32_t rel, uint32_t v, uint32_t nb) {
     const uint32_t w = wb + (rel >> 5), sh = rel & 31;
     atomicOr(&out_words[w], v << sh);
     if (sh + nb > 32) atomicOr(&out_words[w + 1], v >> (32 - sh));
 }
-__global__ void __launch_bounds__(LZC_THREADS) lzc_pack_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, const uint32_t* __restrict__ bitcum,
-                                                          const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
-                                                          const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words) {
-    __shared__ uint16_t q[LZC_WARPS][LZC_WCHUNK];
-    const uint32_t f = blockIdx.y;  // one grid row per frame: no search for the frame of a position
-    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
-    const uint32_t cbase = fs[f] + blockIdx.x * LZC_BCHUNK + warp * LZC_WCHUNK, end = fs[f + 1];
-    if (cbase >= end) return;
-    const uint32_t wb = wbase[f];
-    uint32_t qn = 0;
-#pragma unroll 4
-    for (int r = 0; r < LZC_ROUNDS; r++) {
-        const uint32_t i = cbase + r * 32 + lane;
-        bool pend = false;
-        if (i < end) {
-            const uint32_t rel = bitcum[i];
-            if (rel != EMPTY32) {
-                const uint32_t w = lw15[i], l = (w >> 24) & 0xFu;
-                if (!(w & LZC_DEAD)) pend = true;   // still linked at level 15: a 15-byte match
-                else if (l >= (uint32_t)LZ_MINLEN) lzc_emit(out_words, wb, rel, ((w & 0xFFFFu) << 1) | (l << 17), 21);
-                else lzc_emit(out_words, wb, rel, 1u | ((uint32_t)bs[i] << 1), 9);
-            }
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pend);
-        if (pend) q[warp][qn + __popc(bal & lanemask_lt())] = (uint16_t)(r * 32 + lane);
-        qn += __popc(bal);
-    }
-    __syncwarp();
-    uint32_t qi = 0;
-    bool busy = false;
-    LzcEndWalk wlk;
-    for (;;) {
-        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
-        if (qi < qn && idle) {
-            const uint32_t my = qi + __popc(idle & lanemask_lt());
-            if (!busy && my < qn) {
-                const uint32_t p = cbase + q[warp][my];
-                wlk.start(p, lw15[p]);   // a 15-byte match: the link is never 0
-                busy = true;
-            }
-            qi += __popc(idle);
-        }
-        if (!__any_sync(0xffffffffu, busy)) break;
-        if (busy && wlk.hop(lw15, rsd) != LZC_GO) {
-            lzc_emit(out_words, wb, bitcum[wlk.p], (wlk.last << 1) | ((uint32_t)LZ_MAXLEN << 17), 21);
-            busy = false;
-        }
-    }
-}
-
 // the parse's input: one byte per position, the final match length (level-15 words: dead -> its length, live -> 15)
 __global__ void __launch_bounds__(256) lzc_bestlen_k(const uint32_t* __restrict__ lw15, uint32_t n, uint8_t* __restrict__ bestlen) {
     const uint32_t i = (blockIdx.x * 256u + threadIdx.x) * 4u;   // lw15 and bestlen are 16-byte aligned

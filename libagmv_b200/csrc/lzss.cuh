@@ -37,7 +37,8 @@ struct LzWork {
     uint32_t* cframe = nullptr;          // frame of the first position of every LZC_WCHUNK-position chunk
     uint32_t* counters = nullptr;        // chunk counters of the persistent kernels (one per launch of a batch)
     uint32_t link3_blocks = 148 * 5, level_blocks = 148 * 6;   // resident blocks of the persistent walking kernels
-    uint32_t* bitcum = nullptr;          // per position: bit offset inside the frame's output if the parse visits it
+    uint32_t* list15 = nullptr;          // per parse tile: its 15-byte matches (position in tile | bit cursor in tile << 10)
+    uint8_t* cnt15 = nullptr;            // per parse tile: how many
     OrbitTables orb;                     // greedy-parse tables (cap_n / ORB_TILE + cap_frames tiles)
     OrbitSeg* segs = nullptr;            // cap_frames
     uint32_t* seg_len = nullptr;         // cap_frames
@@ -58,11 +59,98 @@ struct LzStep {
     __device__ static uint32_t step(uint32_t c) { return c >= (uint32_t)LZ_MINLEN ? c : 1u; }
     __device__ static uint32_t weight(uint32_t c) { return c >= (uint32_t)LZ_MINLEN ? 21u : 9u; }  // bits per token
 };
-struct LzVisit {
-    const OrbitSeg* segs;
-    uint32_t* bitcum;
-    __device__ void operator()(uint32_t sg, uint32_t pos, uint32_t cum, uint32_t) const { bitcum[segs[sg].off + pos] = cum; }
-};
+// ---- token emission from the parse itself (bit writer: src/agmv_utils.c:86-112; token layout src/agmv_encode.c:146-165) ----
+// The last step of the orbit re-walks every tile from its true entry with the running bit cursor in a register: the lane
+// that walks a tile emits its literals and its matches shorter than 15 bytes on the spot (the level-15 word of a finished
+// position holds its offset) and notes the tile's 15-byte matches - whose earliest start is the end of a chain walk - in a
+// small per-tile list for lz_pack15_k. (Round 2 first wrote a bit cursor per visited position for a separate pack kernel:
+// 141 M scattered 4-byte stores per step, an ECC sector fill each, then a dense read of that array.)
+constexpr int LZ15_SLOTS = 72;   // >= ceil(1024 / 15) matches of 15 bytes start in a tile
+__global__ void __launch_bounds__(ORB_LANES) lz_emit_mark_k(const uint8_t* __restrict__ code, const OrbitSeg* __restrict__ segs, uint32_t nseg,
+                                                            const uint32_t* __restrict__ seg_len, uint32_t ntile, OrbitTables tb,
+                                                            const uint8_t* __restrict__ bs, const uint32_t* __restrict__ lw15,
+                                                            const uint32_t* __restrict__ wbase, uint32_t* __restrict__ out_words,
+                                                            uint32_t* __restrict__ list15, uint8_t* __restrict__ cnt15) {
+    const uint32_t tile = blockIdx.x * ORB_LANES + threadIdx.x;
+    if (tile >= ntile) return;
+    const uint32_t sg = orbit_seg_of(segs, nseg, tile);
+    const OrbitSeg seg = segs[sg];
+    const uint32_t len = seg_len[sg];
+    const uint32_t t0 = (tile - seg.tile_base) * ORB_TILE;
+    uint32_t n15 = 0;
+    if (t0 < len) {
+        const uint32_t end = min(t0 + ORB_TILE, len);
+        const uint32_t wb = wbase[sg];
+        const uint8_t* const d = bs + seg.off;
+        const uint32_t* const lw = lw15 + seg.off;
+        OrbitBytes c;
+        c.init(code + seg.off);
+        const uint32_t cum0 = tb.cumbase[tile];
+        uint32_t i = t0 + tb.entry_tab[tile], cum = cum0;
+        while (i < end) {
+            const uint32_t l = c.at(i);
+            if (l < (uint32_t)LZ_MINLEN) {
+                lzc_emit(out_words, wb, cum, 1u | ((uint32_t)d[i] << 1), 9);
+                cum += 9; i += 1;
+            } else {
+                if (l < (uint32_t)LZ_MAXLEN) lzc_emit(out_words, wb, cum, ((lw[i] & 0xFFFFu) << 1) | (l << 17), 21);
+                else list15[(size_t)tile * LZ15_SLOTS + n15++] = (i - t0) | (cum - cum0) << 10;
+                cum += 21; i += l;
+            }
+        }
+    }
+    cnt15[tile] = (uint8_t)n15;
+}
+
+// the 15-byte matches of the parse: each walks its level-15 chain to the end (lane refill as in the level kernels); a warp
+// takes LZ15_GROUP consecutive tiles
+constexpr int LZ15_GROUP = 8;
+__global__ void __launch_bounds__(LZC_THREADS) lz_pack15_k(const OrbitSeg* __restrict__ segs, uint32_t nseg, uint32_t ntile, OrbitTables tb,
+                                                           const uint32_t* __restrict__ lw15, const uint16_t* __restrict__ rsd,
+                                                           const uint32_t* __restrict__ wbase, const uint32_t* __restrict__ list15,
+                                                           const uint8_t* __restrict__ cnt15, uint32_t* __restrict__ out_words) {
+    __shared__ uint32_t q[LZC_WARPS][LZ15_GROUP * LZ15_SLOTS];   // tile in group << 28 | list entry
+    __shared__ uint32_t tpos[LZC_WARPS][LZ15_GROUP], tcum[LZC_WARPS][LZ15_GROUP], twb[LZC_WARPS][LZ15_GROUP];
+    const uint32_t warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t tile0 = (blockIdx.x * LZC_WARPS + warp) * LZ15_GROUP;
+    if (tile0 >= ntile) return;
+    uint32_t qn = 0;
+    for (uint32_t g = 0; g < (uint32_t)LZ15_GROUP && tile0 + g < ntile; g++) {
+        const uint32_t tile = tile0 + g, cnt = cnt15[tile];
+        if (lane == 0) {
+            const uint32_t sg = orbit_seg_of(segs, nseg, tile);
+            tpos[warp][g] = (uint32_t)segs[sg].off + (tile - segs[sg].tile_base) * ORB_TILE;
+            tcum[warp][g] = tb.cumbase[tile];
+            twb[warp][g] = wbase[sg];
+        }
+        for (uint32_t k = lane; k < cnt; k += 32) q[warp][qn + k] = g << 28 | list15[(size_t)tile * LZ15_SLOTS + k];
+        qn += cnt;
+    }
+    __syncwarp();
+    uint32_t qi = 0, rel = 0, wb = 0;
+    bool busy = false;
+    LzcEndWalk wlk;
+    for (;;) {
+        const unsigned idle = __ballot_sync(0xffffffffu, !busy);
+        if (qi < qn && idle) {
+            const uint32_t my = qi + __popc(idle & lanemask_lt());
+            if (!busy && my < qn) {
+                const uint32_t e = q[warp][my], g = e >> 28;
+                const uint32_t p = tpos[warp][g] + (e & 1023u);
+                rel = tcum[warp][g] + ((e >> 10) & 0x3FFFFu);
+                wb = twb[warp][g];
+                wlk.start(p, lw15[p]);   // a 15-byte match: the link is never 0
+                busy = true;
+            }
+            qi += __popc(idle);
+        }
+        if (!__any_sync(0xffffffffu, busy)) break;
+        if (busy && wlk.hop(lw15, rsd) != LZC_GO) {
+            lzc_emit(out_words, wb, rel, (wlk.last << 1) | ((uint32_t)LZ_MAXLEN << 17), 21);
+            busy = false;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(1024) lz_finalize_k(uint32_t F, uint32_t stub, const uint32_t* __restrict__ total_bits,
                                                       uint32_t* __restrict__ outbits, uint32_t* __restrict__ csize,
@@ -139,7 +227,6 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
     KL(lc, KC_LZ_INIT, (lzc_wbase_k<<<cdiv(F + 1, 256), 256, 0, st>>>(fs, F, wk.wbase)));
     const uint32_t* lw15 = wk.lw[0];
     if (n > 0) {
-        cudaMemsetAsync(wk.bitcum, 0xFF, (size_t)n * 4, st);
         // persistent walking kernels: enough warps to fill the GPU, chunks handed out through one counter per launch
         const uint32_t nb3 = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.link3_blocks), nb = std::min<uint32_t>(cdiv(n, LZC_BCHUNK), wk.level_blocks);
         cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
@@ -154,12 +241,14 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         lw15 = wk.lw[cur];
         KL(lc, KC_LZ_LEVEL, (lzc_bestlen_k<<<cdiv(cdiv(n, 4u), 256u), 256, 0, st>>>(lw15, n, wk.bestlen)));
     }
-    orbit_run<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, LzVisit{wk.segs, wk.bitcum}, lc, KC_LZ_PARSE);
-    if (n > 0) {
+    orbit_prepare<LZ_MAXLEN, LzStep>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, lc, KC_LZ_PARSE);
+    if (n > 0 && ntile) {
         size_t words = (((size_t)n * 9) >> 5) + 3 * (size_t)F + 4;
         cudaMemsetAsync(wk.out_words, 0, words * 4, st);
-        dim3 pgrid(cdiv(max_usize, (uint32_t)LZC_BCHUNK), F);
-        KL(lc, KC_LZ_PACK, (lzc_pack_k<<<pgrid, LZC_THREADS, 0, st>>>(bs, fs, wk.bitcum, lw15, wk.rsd, wk.wbase, wk.out_words)));
+        KL(lc, KC_LZ_PARSE, (lz_emit_mark_k<<<cdiv(ntile, ORB_LANES), ORB_LANES, 0, st>>>(wk.bestlen, wk.segs, F, wk.seg_len, ntile, wk.orb, bs, lw15, wk.wbase,
+                                                                                          wk.out_words, wk.list15, wk.cnt15)));
+        KL(lc, KC_LZ_PACK, (lz_pack15_k<<<cdiv(ntile, LZC_WARPS * LZ15_GROUP), LZC_THREADS, 0, st>>>(wk.segs, F, ntile, wk.orb, lw15, wk.rsd, wk.wbase, wk.list15,
+                                                                                                     wk.cnt15, wk.out_words)));
     }
     KL(lc, KC_LZ_CHUNK, (lz_finalize_k<<<1, 1024, 0, st>>>(F, wk.stub_bytes, wk.orb.final_cum, wk.outbits, wk.csize, wk.chunk_off)));
     dim3 grid(32, F);

@@ -167,13 +167,21 @@ __global__ void __launch_bounds__(ORB_LANES) orbit_mark_k(const uint8_t* __restr
 // host-side: number of tiles of a segment of (at most) `cap_len` positions
 inline uint32_t orbit_tiles(uint32_t cap_len) { return (cap_len + ORB_TILE - 1) / ORB_TILE; }
 
-template <int S, class Dec, class Visit>
-inline void orbit_run(const uint8_t* code, const OrbitSeg* d_segs, uint32_t nseg, const uint32_t* d_seg_len, uint32_t ntile, OrbitTables tb,
-                      Visit visit, LaunchCtx& lc, int cls) {
+// steps 1 and 2 only: entry offset and running weight of every tile (tb.entry_tab / tb.cumbase), end of every segment
+template <int S, class Dec>
+inline void orbit_prepare(const uint8_t* code, const OrbitSeg* d_segs, uint32_t nseg, const uint32_t* d_seg_len, uint32_t ntile, OrbitTables tb,
+                          LaunchCtx& lc, int cls) {
     static_assert(S <= ORB_SP, "too many entry offsets");
     if (nseg == 0) return;
     if (ntile) KL(lc, cls, (orbit_spec_k<S, Dec><<<cdiv(ntile, ORB_LANES), ORB_LANES, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb)));
     KL(lc, cls, (orbit_chain_k<S><<<cdiv(nseg, 4), 128, 0, lc.st>>>(d_segs, nseg, d_seg_len, tb)));
+}
+
+template <int S, class Dec, class Visit>
+inline void orbit_run(const uint8_t* code, const OrbitSeg* d_segs, uint32_t nseg, const uint32_t* d_seg_len, uint32_t ntile, OrbitTables tb,
+                      Visit visit, LaunchCtx& lc, int cls) {
+    if (nseg == 0) return;
+    orbit_prepare<S, Dec>(code, d_segs, nseg, d_seg_len, ntile, tb, lc, cls);
     if (ntile) KL(lc, cls, (orbit_mark_k<S, Dec, Visit><<<cdiv(ntile, ORB_LANES), ORB_LANES, 0, lc.st>>>(code, d_segs, nseg, d_seg_len, ntile, tb, visit)));
 }
 
