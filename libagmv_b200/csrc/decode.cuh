@@ -291,18 +291,29 @@ __global__ void __launch_bounds__(256) index_steps_k(const DecFrame* __restrict_
     const int dual = fr[f].dual;
     const uint8_t* e = ebuf + fr[f].ebuf_off;
     uint8_t* c = code + fr[f].ebuf_off;
-    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < limit; p += gridDim.x * blockDim.x) {
-        const uint32_t b = e[p];
+    const uint32_t lane = lane_id();
+    for (uint32_t p0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); p0 < limit; p0 += gridDim.x * blockDim.x) {   // warp-uniform trip count
+        const uint32_t p = p0 + lane;
+        const uint32_t b = e[p];   // (the expansion is readable 72 bytes past `limit`)
+        // A NORMAL record holds sixteen codes of one or two bytes (index 127 escapes to a second byte): its length is a walk
+        // over "is an escape code" bits of the 32 bytes behind the flag. Nearly every warp meets a byte 0x2F, so a per-lane
+        // loop over e[] ran in every warp with one or two lanes active (82 % issue utilisation,
+        // profiles/r02_ncu_summary.txt). Two votes give the bits of this warp's 64 bytes; every lane walks its own window of
+        // them in registers, unconditionally.
+        uint32_t q = 16;
+        if (dual) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, (b & 0x7fu) == 127u);
+            const unsigned m1 = __ballot_sync(0xffffffffu, (e[p + 32u] & 0x7fu) == 127u);
+            const unsigned m = lane == 31u ? m1 : __funnelshift_r(m0, m1, lane + 1u);   // bit i: byte p + 1 + i is an escape code
+            q = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) q += 1u + ((m >> q) & 1u);
+        }
         uint32_t st = 1, w = 0;
         if (b == COPY_FLAG) w = 1;
         else if (b == FILL_FLAG) { w = 1; st = 2 + ((dual && (e[p + 1] & 0x7fu) == 127u) ? 1u : 0u); }
-        else if (b == NORMAL_FLAG) {
-            w = 1;
-            uint32_t q = p + 1;
-            for (int k = 0; k < 16; k++) q += (dual && (e[q] & 0x7fu) == 127u) ? 2u : 1u;
-            st = q - p;
-        }
-        c[p] = (uint8_t)(st | w << 7);
+        else if (b == NORMAL_FLAG) { w = 1; st = 1u + q; }
+        if (p < limit) c[p] = (uint8_t)(st | w << 7);
     }
 }
 
