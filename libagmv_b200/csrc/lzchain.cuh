@@ -229,7 +229,7 @@ struct LzcLink3Op {
     const uint32_t* __restrict__ lwh; const uint16_t* __restrict__ rsd; uint32_t* __restrict__ lw3;
     LzcLink3Walk wlk;
     uint32_t b23c;   // byte 2 | byte 3 << 8 | cap << 16 of the position being walked
-    uint32_t f_cur = 0, f_prev = 0;   // frames of the first position of the last two chunks swept: the queue only holds positions of those two
+    const uint32_t* __restrict__ cframe;   // frame of the first position of every LZC_WCHUNK-position chunk (lzc_cframe_k)
     __device__ __forceinline__ uint32_t cap_of(uint32_t f, uint32_t p) const {   // min(15, bytes left in p's frame); f = a frame at or before p's
         while (fs[f + 1] <= p) f++;
         return min(fs[f + 1] - p, (uint32_t)LZ_MAXLEN);
@@ -239,11 +239,7 @@ struct LzcLink3Op {
     }
     __device__ __forceinline__ uint32_t sweep(uint32_t cbase, uint32_t* q) {
         const uint32_t lane = lane_id();
-        uint32_t f0 = 0;
-        if (lane == 0) f0 = lzc_frame_of(fs, F, cbase);
-        f0 = __shfl_sync(0xffffffffu, f0, 0);
-        f_prev = min(f_cur, f0);   // (chunks are handed out in increasing order, but not necessarily to the same warp)
-        f_cur = f0;
+        const uint32_t f0 = cframe[cbase / LZC_WCHUNK];
         uint32_t qn = 0;
         for (int r0 = 0; r0 < ROUNDS; r0 += LZC_MLP) {
             uint32_t w[LZC_MLP], b23[LZC_MLP], cap[LZC_MLP], wk[LZC_MLP], k2[LZC_MLP];
@@ -279,7 +275,7 @@ struct LzcLink3Op {
         return qn;
     }
     __device__ __forceinline__ void begin(uint32_t p) {
-        const uint32_t cp = cap_of(f_prev, p);
+        const uint32_t cp = cap_of(cframe[p / LZC_WCHUNK], p);
         b23c = (uint32_t)bs[p + 2] | (uint32_t)bs[p + 3] << 8 | cp << 16;
         wlk.start(p, lwh[p], b23c & 0xFFu, cp);
     }
@@ -465,9 +461,11 @@ struct LzcLevelOp {
 template <int ROUNDS>
 __global__ void __launch_bounds__(LZC_THREADS) lzc_link3_k(const uint8_t* __restrict__ bs, const uint32_t* __restrict__ fs, uint32_t F, uint32_t n,
                                                            const uint32_t* __restrict__ lwh, const uint16_t* __restrict__ rsd,
-                                                           uint32_t* __restrict__ lw3, uint32_t* __restrict__ counter) {
+                                                           uint32_t* __restrict__ lw3, const uint32_t* __restrict__ cframe, uint32_t* __restrict__ counter) {
+    static_assert(32 * ROUNDS == LZC_WCHUNK, "cframe is indexed by LZC_WCHUNK-position chunks");
     __shared__ uint32_t q[LZC_WARPS][32 * ROUNDS + 32];
     LzcLink3Op<ROUNDS> op{bs, fs, F, n, lwh, rsd, lw3};
+    op.cframe = cframe;
     lzc_drive<ROUNDS>(op, n, counter, q[threadIdx.x >> 5]);
 }
 

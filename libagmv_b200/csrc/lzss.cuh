@@ -232,7 +232,7 @@ inline void lzss_encode_batch(LzWork& wk, const uint8_t* bs, const uint32_t* fs,
         cudaMemsetAsync(wk.counters, 0, 16 * sizeof(uint32_t), st);
         KL(lc, KC_LZ_LINK, (lzc_cframe_k<<<cdiv(cdiv(n, LZC_WCHUNK), 256), 256, 0, st>>>(fs, F, n, wk.cframe)));
         KL(lc, KC_LZ_LINK, (lzc_hashlink_k<<<wk.n_items, 32, (size_t)4 << wk.hash_bits, st>>>(bs, n, fs, wk.items, wk.lw[1], wk.rsd, wk.hash_bits)));
-        KL(lc, KC_LZ_LINK3, (lzc_link3_k<LZC_ROUNDS><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.counters)));
+        KL(lc, KC_LZ_LINK3, (lzc_link3_k<LZC_ROUNDS><<<nb3, LZC_THREADS, 0, st>>>(bs, fs, F, n, wk.lw[1], wk.rsd, wk.lw[0], wk.cframe, wk.counters)));
         static const int refill_min = getenv("AGMVB_LZ_REFILL") ? atoi(getenv("AGMVB_LZ_REFILL")) : 8;
         int cur = 0;
         for (uint32_t L = LZ_MINLEN; L < (uint32_t)LZ_MAXLEN; L++, cur ^= 1)
