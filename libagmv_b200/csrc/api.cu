@@ -98,6 +98,7 @@ struct agmvb_ctx {
     std::vector<DecStream> streams;
     std::vector<DecStream> parked;   // buffers of closed streams, reused by later opens
     DBuf d_frames, d_ebuf, d_bpos, d_consumed, d_stale, d_recs, d_steps, d_out, d_cksum, d_count;
+    DBuf d_keeps;   // per (stream, block) of a chunk: some frame's block keeps pixels of the frame before it (index_walk)
     uint32_t* info_bpos = nullptr;      // host arrays a single-stream call wants filled per frame (agmvb_dec_chunks)
     uint32_t* info_consumed = nullptr;
     DBuf d_code, d_segs, d_seglen, d_oexit, d_ow, d_oentry, d_ocum, d_ofinal;
@@ -125,6 +126,40 @@ static cudaError_t copy_pieces(void* dst, const void* src, size_t bytes, cudaMem
     }
     return cudaSuccess;
 }
+
+// Transfer gate: the bulk host<->device transfers of the contexts that share a device (a whole sequence up, its decoded frames
+// down) go through the link one at a time per direction, first come first served. Several sequences in flight otherwise copy
+// at the same time, each at a fraction of the link rate, finish together, then compute together, then download together - they
+// stay in step, and link, SMs and the other direction take turns idling (tools/pcie_probe.py: 55.6 GB/s up, 57.3 down, 95-99
+// both at once on this pool; four ungated sequences moved 51 GB/s in total). Gated, a sequence uploads at the full rate while
+// the others compute and download, and the upload direction - the larger one - stays busy. AGMVB_XFER_GATE=0 disables it.
+struct XferGate {
+    std::mutex m[2];   // 0: host -> device, 1: device -> host
+};
+static XferGate& xfer_gate(int device) {
+    static XferGate gates[64];
+    return gates[device & 63];
+}
+static bool xfer_gate_on() {
+    static const bool on = !(getenv("AGMVB_XFER_GATE") && atoi(getenv("AGMVB_XFER_GATE")) == 0);
+    return on;
+}
+// everything queued on the context's stream so far completes first (so the gate is held for the copy alone), then the copy
+// runs to completion inside the gate
+struct GatedXfer {
+    std::unique_lock<std::mutex> lk;
+    GatedXfer(agmvb_ctx* ctx, int dir, cudaStream_t st) {
+        if (!xfer_gate_on()) return;
+        cudaStreamSynchronize(st);
+        lk = std::unique_lock<std::mutex>(xfer_gate(ctx->device).m[dir]);
+    }
+    cudaError_t finish(cudaStream_t st) {   // call after queueing the copy
+        if (!lk.owns_lock()) return cudaSuccess;
+        cudaError_t e = cudaStreamSynchronize(st);
+        lk.unlock();
+        return e;
+    }
+};
 
 static int ensure(agmvb_ctx* ctx, DBuf& b, size_t bytes) {
     if (b.cap >= bytes && b.p) return OK;
@@ -962,7 +997,11 @@ static int encode_sequence_impl(agmvb_ctx* ctx, int mode, const uint32_t* frames
         CK(cudaMemGetInfo(&free_b, &total_b));
         if (bytes + (8ull << 30) < free_b + ctx->seqbuf.cap) {
             TRY(ensure(ctx, ctx->seqbuf, bytes));
-            TRY(upload_frames(ctx, frames, 0, n_src, (uint64_t)w * h, ctx->seqbuf.as<uint32_t>()));
+            {
+                GatedXfer gate(ctx, 0, ctx->st);
+                TRY(upload_frames(ctx, frames, 0, n_src, (uint64_t)w * h, ctx->seqbuf.as<uint32_t>()));
+                CK(gate.finish(ctx->st));
+            }
             frames = ctx->seqbuf.as<uint32_t>();
             on_device = 1;
         }
@@ -1466,6 +1505,10 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
 
     std::vector<DecFrame> fr;
     std::vector<DecStep> steps;
+    std::vector<RecMeta> rmeta;
+    std::vector<uint32_t*> rdst;
+    std::vector<RecStream> rstreams;
+    std::vector<uint8_t> stepbuf;
     for (uint32_t c0 = 0; c0 < count; c0 += C) {
         const uint32_t cn = std::min(C, count - c0);
         const uint32_t F = S * cn;
@@ -1489,7 +1532,6 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         TRY(ensure(ctx, ctx->d_consumed, (size_t)F * 4));
         TRY(ensure(ctx, ctx->d_stale, (size_t)F * 4));
         TRY(ensure(ctx, ctx->d_recs, (size_t)F * B * 4));
-        TRY(ensure(ctx, ctx->d_steps, F * sizeof(DecStep)));
         CK(cudaMemcpyAsync(ctx->d_frames.p, fr.data(), F * sizeof(DecFrame), cudaMemcpyHostToDevice, ctx->st));
         const DecFrame* dfr = ctx->d_frames.as<DecFrame>();
         // block-index segments: one per frame over the safe prefix of its expansion
@@ -1515,6 +1557,15 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         OrbitTables tb;
         tb.exit_tab = ctx->d_oexit.as<uint8_t>(); tb.w_tab = ctx->d_ow.as<uint16_t>(); tb.entry_tab = ctx->d_oentry.as<uint8_t>();
         tb.cumbase = ctx->d_ocum.as<uint32_t>(); tb.final_pos = ctx->d_ofinal.as<uint32_t>(); tb.final_cum = tb.final_pos + F;
+        // Frame-parallel reconstruction of the frames between snapshots (see below) when every frame goes to its own buffer, the
+        // picture is more than one block wide and no checksums are wanted; AGMVB_RECON_SERIAL=1 keeps everything in order.
+        static const bool serial_only = getenv("AGMVB_RECON_SERIAL") && atoi(getenv("AGMVB_RECON_SERIAL")) != 0;
+        bool par = !serial_only && (W >> 2) > 1 && cn > 1 && !cks;
+        for (uint32_t s = 0; s < S; s++) par = par && outs[s] != nullptr;
+        if (par) {
+            TRY(ensure(ctx, ctx->d_keeps, (size_t)S * B));
+            CK(cudaMemsetAsync(ctx->d_keeps.p, 0, (size_t)S * B, ctx->st));
+        }
         KL(ctx->lc, KC_EXPAND, (expand_mrr_k<<<cdiv(F, EX_WARPS), EX_WARPS * 32, 0, ctx->st>>>(dfr, F, ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(),
                                                                                             ctx->d_consumed.as<uint32_t>())));
         KL(ctx->lc, KC_STALE, (stale_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>())));
@@ -1526,13 +1577,28 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
         orbit_run<33, IndexStep>(ctx->d_code.as<uint8_t>(), ctx->d_segs.as<OrbitSeg>(), F, ctx->d_seglen.as<uint32_t>(), ntile, tb,
                                  IndexVisit{ctx->d_recs.as<uint32_t>(), B}, ctx->lc, KC_INDEX);
         KL(ctx->lc, KC_INDEX, (index_tail_k<<<cdiv(F, 64), 64, 0, ctx->st>>>(dfr, ctx->d_bpos.as<uint32_t>(), F, ctx->d_ebuf.as<uint8_t>(), ctx->d_stale.as<uint8_t>(), B,
-                                                                            tb.final_pos, tb.final_cum, ctx->d_recs.as<uint32_t>())));
+                                                                            tb.final_pos, tb.final_cum, ctx->d_recs.as<uint32_t>(), par ? ctx->d_keeps.as<uint8_t>() : nullptr, cn)));
         TRY(check_launch(ctx, "expand/index"));
         // reconstruction, frame by frame; step layout [k][s]
+        // Reconstruction. Layout of the per-frame arrays: [k][s]. A block whose pixels can depend on the previous frame (it keeps
+        // them in some frame of the chunk: d_keeps; or it is the last block) is walked through every frame in order; every other
+        // block only through the snapshot frames (frame_count % 4 == 0), and the runs of frames between those are painted in
+        // one parallel launch afterwards (recon_p_k). Ring output (a later snapshot frame would overwrite one still needed),
+        // one-block-wide pictures (the last-block FILL reads the block's own previous pixels) and checksum calls walk
+        // every block through every frame.
         steps.resize(F);
-        for (uint32_t k = 0; k < cn; k++)
-            for (uint32_t s = 0; s < S; s++) {
-                DecStream& d = ctx->streams[ids[s]];
+        rmeta.resize(F);
+        rdst.resize(F);
+        rstreams.resize(S);
+        const uint32_t KA = cn / 4 + 2;                     // snapshot frames a stream can have in the chunk
+        std::vector<RecMeta> ameta(par ? (size_t)KA * S : 0);
+        std::vector<uint32_t*> adst(par ? (size_t)KA * S : 0, nullptr);
+        std::vector<RecStream> astreams(par ? S : 0);
+        std::vector<RecRun> runs;
+        for (uint32_t s = 0; s < S; s++) {
+            DecStream& d = ctx->streams[ids[s]];
+            uint32_t na = 0;
+            for (uint32_t k = 0; k < cn; k++) {
                 const uint32_t g = d.next + k;       // global frame index == frame_count before this frame
                 const uint32_t gi = g % 4 == 0 ? (g >= 4 ? g - 4 : EMPTY32) : g - g % 4;  // frame holding the I snapshot
                 const uint32_t call_first = d.next - c0;  // first frame of this API call
@@ -1542,19 +1608,59 @@ static int dec_batch_impl(agmvb_ctx* ctx, const int* ids, uint32_t S, uint32_t c
                 else x.prev = outs[s] ? outs[s] + (size_t)(c0 + k - 1) * P : d.d_ring + (size_t)((g - 1) % DEC_RING) * P;
                 if (gi == EMPTY32 || gi < call_first) x.ifr = d.d_ifr;
                 else x.ifr = outs[s] ? outs[s] + (size_t)(gi - call_first) * P : d.d_ring + (size_t)(gi % DEC_RING) * P;
-                x.recs = ctx->d_recs.as<uint32_t>() + (size_t)(s * cn + k) * B;
-                x.ebuf = ctx->d_ebuf.as<uint8_t>() + fr[s * cn + k].ebuf_off;
-                x.bpos = ctx->d_bpos.as<uint32_t>() + (s * cn + k);
-                x.stale = ctx->d_stale.as<uint8_t>() + (size_t)(s * cn + k) * 4;
-                x.pal = d.d_pal;
-                x.dual = d.dual;
+                x.fidx = s * cn + k;
+                x.ebuf_off = fr[s * cn + k].ebuf_off;
                 x.is_snap = g % 4 == 0;
-                x.cksum = cks ? ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 + k : nullptr;
+                rmeta[k * S + s] = RecMeta{x.ebuf_off, x.fidx, k | (x.is_snap ? 0x80000000u : 0u)};
+                rdst[k * S + s] = x.dst;
+                if (!astreams.empty() && par) {
+                    if (x.is_snap) {
+                        if (na == 0) astreams[s] = RecStream{x.prev, x.ifr, d.d_pal, nullptr, d.dual, 0};
+                        ameta[(size_t)na * S + s] = rmeta[k * S + s];
+                        adst[(size_t)na * S + s] = x.dst;
+                        na++;
+                    } else if (!runs.empty() && runs.back().sidx == s && runs.back().first + runs.back().n == k && k > 0 && !steps[(k - 1) * S + s].is_snap) {
+                        runs.back().n++;
+                    } else {
+                        runs.push_back(RecRun{x.ifr, x.prev, k, 1, s, 0});   // behind a snapshot frame of the chunk x.ifr is that frame's buffer
+                    }
+                }
             }
-        CK(cudaMemcpyAsync(ctx->d_steps.p, steps.data(), F * sizeof(DecStep), cudaMemcpyHostToDevice, ctx->st));
+            if (runs.size() > 65535) par = false;   // (grid.y of recon_p_k) everything in order then: keeps is not passed on
+            unsigned long long* ck = cks ? ctx->d_cksum.as<unsigned long long>() + (size_t)s * count + c0 : nullptr;
+            rstreams[s] = RecStream{steps[s].prev, steps[s].ifr, d.d_pal, ck, d.dual, cn};
+            if (!astreams.empty()) { astreams[s].cksum = ck; astreams[s].count = na; astreams[s].pal = d.d_pal; astreams[s].dual = d.dual; }
+        }
         {
+            // one upload: [all frames: position data, destinations, stream descriptors][snapshot frames: the same][runs]
+            auto put = [&](const void* src, size_t bytes) {
+                const size_t at = (stepbuf.size() + 15) & ~(size_t)15;
+                stepbuf.resize(at + bytes);
+                if (bytes) memcpy(stepbuf.data() + at, src, bytes);
+                return at;
+            };
+            stepbuf.clear();
+            const size_t o_meta = put(rmeta.data(), F * sizeof(RecMeta)), o_dst = put(rdst.data(), F * sizeof(uint32_t*)),
+                         o_str = put(rstreams.data(), S * sizeof(RecStream));
+            const size_t o_ameta = put(ameta.data(), ameta.size() * sizeof(RecMeta)), o_adst = put(adst.data(), adst.size() * sizeof(uint32_t*)),
+                         o_astr = put(astreams.data(), astreams.size() * sizeof(RecStream)), o_runs = put(runs.data(), runs.size() * sizeof(RecRun));
+            TRY(ensure(ctx, ctx->d_steps, stepbuf.size()));
+            CK(cudaMemcpyAsync(ctx->d_steps.p, stepbuf.data(), stepbuf.size(), cudaMemcpyHostToDevice, ctx->st));
+            const uint8_t* ds = ctx->d_steps.as<uint8_t>();
+            const RecBase rb{ctx->d_recs.as<uint32_t>(), ctx->d_ebuf.as<uint8_t>(), ctx->d_bpos.as<uint32_t>(), ctx->d_stale.as<uint8_t>()};
+            const uint8_t* keeps = par ? ctx->d_keeps.as<uint8_t>() : nullptr;
+            const RecList all{reinterpret_cast<const RecMeta*>(ds + o_meta), reinterpret_cast<uint32_t* const*>(ds + o_dst), reinterpret_cast<const RecStream*>(ds + o_str)};
+            const RecList snaps{reinterpret_cast<const RecMeta*>(ds + o_ameta), reinterpret_cast<uint32_t* const*>(ds + o_adst),
+                                reinterpret_cast<const RecStream*>(ds + o_astr)};
             dim3 grid(cdiv(B, 128), S);
-            KL(ctx->lc, KC_RECON, (reconstruct_k<<<grid, 128, 0, ctx->st>>>(ctx->d_steps.as<DecStep>(), cn, S, W, H)));
+            static const int minb = getenv("AGMVB_RECON_MINB") ? atoi(getenv("AGMVB_RECON_MINB")) : 5;   // resident blocks per SM the kernel is compiled for
+            if (minb >= 7) KL(ctx->lc, KC_RECON, (reconstruct_k<7><<<grid, 128, 0, ctx->st>>>(par ? snaps : all, all, rb, S, W, H, keeps)));
+            else if (minb == 6) KL(ctx->lc, KC_RECON, (reconstruct_k<6><<<grid, 128, 0, ctx->st>>>(par ? snaps : all, all, rb, S, W, H, keeps)));
+            else KL(ctx->lc, KC_RECON, (reconstruct_k<5><<<grid, 128, 0, ctx->st>>>(par ? snaps : all, all, rb, S, W, H, keeps)));
+            if (par && !runs.empty()) {
+                dim3 pgrid(cdiv(B, 128), (unsigned)runs.size());
+                KL(ctx->lc, KC_RECON, (recon_p_k<<<pgrid, 128, 0, ctx->st>>>(reinterpret_cast<const RecRun*>(ds + o_runs), all.meta, all.dsts, all.streams, rb, S, W, H, keeps)));
+            }
         }
         TRY(check_launch(ctx, "reconstruct"));
         // carry the state over: expanded-bitstream leftovers, last pixels, last I-frame snapshot
@@ -1619,12 +1725,17 @@ extern "C" int agmvb_dec_frames(agmvb_ctx* ctx, int stream, uint32_t count, uint
         TRY(ensure(ctx, ctx->d_out, (size_t)cn * P * 4));
         uint32_t* o = ctx->d_out.as<uint32_t>();
         TRY(dec_batch_impl(ctx, &stream, 1, cn, &o, nullptr));
-        if (ctx->host_fmt == 0) CK(copy_pieces(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
-        else {
+        if (ctx->host_fmt == 0) {
+            GatedXfer gate(ctx, 1, ctx->st);
+            CK(copy_pieces(out + (size_t)c0 * P, o, (size_t)cn * P * 4, cudaMemcpyDeviceToHost, ctx->st));
+            CK(gate.finish(ctx->st));
+        } else {
             const uint64_t npx = (uint64_t)cn * P;
             TRY(ensure(ctx, ctx->raw24, npx * 3 + 16));
             KL(ctx->lc, KC_MISC, (pack_bgr24_k<<<(unsigned)cdiv(cdiv(npx, 4), 256), 256, 0, ctx->st>>>(o, npx, ctx->raw24.as<uint8_t>())));
+            GatedXfer gate(ctx, 1, ctx->st);
             CK(copy_pieces(reinterpret_cast<uint8_t*>(out) + (size_t)c0 * P * 3, ctx->raw24.p, npx * 3, cudaMemcpyDeviceToHost, ctx->st));
+            CK(gate.finish(ctx->st));
         }
         CK(cudaStreamSynchronize(ctx->st));
     }

@@ -329,7 +329,11 @@ struct IndexVisit {
 };
 
 // The reference's walk from byte offset bp / block b to the end of the frame (src/agmv_decode.c:224-399).
-__device__ inline void index_walk(const VBuf& v, uint32_t bpos, int dual, uint32_t B, uint32_t bp, uint32_t b, uint32_t* __restrict__ rec) {
+// keeps[b] (nullable) is set for every block that keeps pixels of the frame before this one: a record the walk never reached or
+// left half-way. The reference's csize drops the last partial byte of a frame's payload (src/agmv_encode.c:176), so the last
+// block or two of nearly every frame are such blocks.
+__device__ inline void index_walk(const VBuf& v, uint32_t bpos, int dual, uint32_t B, uint32_t bp, uint32_t b, uint32_t* __restrict__ rec,
+                                  uint8_t* __restrict__ keeps) {
     bool invalid = false;
     for (; b < B; b++) {
         if (bp > bpos) break;
@@ -344,7 +348,7 @@ __device__ inline void index_walk(const VBuf& v, uint32_t bpos, int dual, uint32
             uint32_t at = bp;
             uint32_t c = v[bp++];
             if (dual && (c & 0x7fu) == 127u) bp++;
-            if (bp > bpos) { rec[b] = EMPTY32; b++; break; }
+            if (bp > bpos) { rec[b] = EMPTY32; if (keeps) keeps[b] = 1; b++; break; }
             rec[b] = at << 2 | BT_FILL;
         } else if (fl == COPY_FLAG) {
             rec[b] = bp << 2 | BT_COPY;
@@ -359,36 +363,55 @@ __device__ inline void index_walk(const VBuf& v, uint32_t bpos, int dual, uint32
             }
             rec[b] = wrote_any ? (at << 2 | BT_NORMAL) : EMPTY32;
         }
+        if ((esc || invalid) && keeps) keeps[b] = 1;
         if (esc) { b++; break; }
     }
-    for (; b < B; b++) rec[b] = EMPTY32;
+    for (; b < B; b++) { rec[b] = EMPTY32; if (keeps) keeps[b] = 1; }
 }
 
 __global__ void __launch_bounds__(64) index_tail_k(const DecFrame* __restrict__ fr, const uint32_t* __restrict__ bpos_arr, uint32_t F,
                                                    const uint8_t* __restrict__ ebuf, const uint8_t* __restrict__ stale, uint32_t B,
                                                    const uint32_t* __restrict__ final_pos, const uint32_t* __restrict__ final_cum,
-                                                   uint32_t* __restrict__ recs) {
+                                                   uint32_t* __restrict__ recs, uint8_t* __restrict__ keeps, uint32_t frames_per_stream) {
     uint32_t f = blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= F) return;
     const uint32_t bpos = bpos_arr[f];
     const VBuf v{ebuf + fr[f].ebuf_off, bpos, stale + f * 4};
     uint32_t b0 = final_cum[f];
-    index_walk(v, bpos, fr[f].dual, B, final_pos[f], b0 < B ? b0 : B, recs + (size_t)f * B);
+    // keeps: one byte per (stream, block), set by any frame of the stream (all writers store the same value)
+    index_walk(v, bpos, fr[f].dual, B, final_pos[f], b0 < B ? b0 : B, recs + (size_t)f * B, keeps ? keeps + (size_t)(f / frames_per_stream) * B : nullptr);
 }
 
 // ---- D3b ----------------------------------------------------------------------
-struct DecStep {              // one frame to reconstruct (host-built)
+struct DecStep {              // one frame to reconstruct (host side: where its pieces live)
     uint32_t* dst;
-    const uint32_t* prev;     // pixels before this frame (read for the FIRST step of a launch only)
-    const uint32_t* ifr;      // I-frame snapshot before this frame (read for the first step only)
-    const uint32_t* recs;
-    const uint8_t* ebuf;
-    const uint32_t* bpos;
-    const uint8_t* stale;
-    const uint32_t* pal;      // pal0[256] then pal1[256]
-    int dual;
+    const uint32_t* prev;     // pixels before this frame
+    const uint32_t* ifr;      // I-frame snapshot before this frame
+    uint32_t fidx;            // the frame's number in the chunk's per-frame arrays (records, bpos, stale bytes)
+    uint64_t ebuf_off;        // its expansion inside the chunk's expansion buffer
     int is_snap;              // frame_count % 4 == 0: the frame becomes the I-frame snapshot after it is written
-    unsigned long long* cksum; // nullable: receives sum over pixels of value * (2654435761 + 2 * pixel index)
+};
+// what the kernels read per frame: 16 bytes of position data and the destination, as two arrays [frame of the launch][stream]
+struct RecMeta {
+    uint64_t ebuf_off;
+    uint32_t fidx;
+    uint32_t kf;              // bit 31: the frame becomes the snapshot; bits 0-30: the frame's checksum slot
+};
+struct RecStream {            // per stream of a launch
+    const uint32_t* prev;     // pixels before the first frame of the launch
+    const uint32_t* ifr;      // I-frame snapshot before the first frame
+    const uint32_t* pal;      // pal0[256] then pal1[256]
+    unsigned long long* cksum; // nullable: slot k receives the sum over the frame's pixels of value * (2654435761 + 2 * pixel index)
+    int dual;
+    uint32_t count;           // frames of this stream in the launch
+};
+struct RecBase { const uint32_t* recs; const uint8_t* ebuf; const uint32_t* bpos; const uint8_t* stale; };
+// frames that are not snapshots come in runs of at most three behind their snapshot frame (recon_p_k)
+struct RecRun {
+    const uint32_t* snap;     // the snapshot the run's COPY blocks show
+    const uint32_t* prev;     // pixels before the run's first frame
+    uint32_t first, n;        // frames first .. first + n - 1 of the launch's [frame][stream] arrays
+    uint32_t sidx, pad;
 };
 
 __device__ __forceinline__ uint32_t read_color(const VBuf& v, uint32_t& bp, const uint32_t* spal, int dual) {
@@ -411,88 +434,203 @@ __device__ __forceinline__ uint32_t record_pixel(uint32_t r, const VBuf& v, cons
     return bp <= v.bpos ? col : prev;
 }
 
-// grid (cdiv(B,128), n_streams): one thread per 4x4 block position walks the `count` frames of its stream in
-// order, keeping the block's previous pixels and its I-frame snapshot in registers. A frame therefore costs one
-// read of its records and codes and one 16-byte-per-row write of its pixels: COPY blocks and blocks a short frame
-// never reaches (they keep the previous frame) read nothing from HBM. The thread of the last block
-// also tracks pixel (3,1) of the block to its left for the reference's last-block FILL quirk (src/agmv_decode.c:264-266).
-__global__ void __launch_bounds__(128) reconstruct_k(const DecStep* __restrict__ steps, uint32_t count, uint32_t S, uint32_t W, uint32_t H) {
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// One block of one frame (src/agmv_decode.c:224-399 for a single block). `ifr`: the snapshot's pixels of the block; `pdst`:
+// the previous frame, read back only by a block the frame's walk never reached or left half-way (it keeps those pixels,
+// damaged or truncated frames); `fill_last`: the colour a FILL record of the LAST block takes instead of its own
+// (img[(x-1)+(y+1)*W] as the frame has left it so far, src/agmv_decode.c:264-266).
+__device__ __forceinline__ void paint_block(uint32_t r, const VBuf& v, const uint32_t* spal, int dual, const uint32_t (&ifr)[16], const uint32_t* pdst,
+                                            size_t pix0, uint32_t W, bool last, uint32_t fill_last, uint32_t (&cur)[16]) {
+    if (r == EMPTY32) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint4 p = *reinterpret_cast<const uint4*>(pdst + pix0 + (size_t)j * W);
+            cur[j * 4] = p.x; cur[j * 4 + 1] = p.y; cur[j * 4 + 2] = p.z; cur[j * 4 + 3] = p.w;
+        }
+    } else if ((r & 3u) == BT_COPY) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) cur[i] = ifr[i];
+    } else if ((r & 3u) == BT_FILL) {
+        uint32_t bp = r >> 2;
+        uint32_t col = read_color(v, bp, spal, dual);
+        if (last) col = fill_last;
+#pragma unroll
+        for (int i = 0; i < 16; i++) cur[i] = col;
+    } else {
+        uint32_t bp = r >> 2;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const uint32_t col = read_color(v, bp, spal, dual);
+            cur[i] = bp <= v.bpos ? col : pdst[pix0 + (size_t)(i >> 2) * W + (i & 3)];   // codes past the data: the pixel stays
+        }
+    }
+}
+__device__ __forceinline__ void store_block(uint32_t* dst, size_t pix0, uint32_t W, const uint32_t (&cur)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(dst + pix0 + (size_t)j * W) = make_uint4(cur[j * 4], cur[j * 4 + 1], cur[j * 4 + 2], cur[j * 4 + 3]);
+}
+__device__ __forceinline__ void checksum_block(unsigned long long* slot, bool valid, size_t pix0, uint32_t W, const uint32_t (&cur)[16]) {
+    unsigned long long acc = 0;
+    if (valid) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const unsigned long long idx = (unsigned long long)pix0 + (unsigned long long)(i >> 2) * W + (i & 3);
+            acc += (unsigned long long)cur[i] * (2654435761ull + 2ull * idx);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (lane_id() == 0) atomicAdd(slot, acc);
+}
+
+// The in-order kernel. grid (cdiv(B, 128), n_streams): one thread per 4x4 block position walks frames of its stream in order
+// with the block's I-frame snapshot in registers; a frame costs one read of its record and codes and four 16-byte row writes,
+// COPY blocks read nothing. A frame is a chain of dependent loads (position data -> record -> codes -> store) and the chain,
+// not the bandwidth, sets the pace: 4.7 us per frame and 23 % of DRAM peak whether a thread owns a block or a block row,
+// whether the loads of later frames are issued ahead or not (profiles/r02_ncu_summary.txt; a kernel that only writes the
+// same pattern runs at 5.9 TB/s, tools/probes/write_pattern.cu). So a thread walks only the frames its block needs in order:
+//   * a block that keeps pixels of the previous frame in some frame of the chunk (`keeps`, index_walk), and the last block
+//     (its FILL colour follows the neighbour's pixel frame by frame): every frame - list 1;
+//   * any other block: the snapshot frames only (frame_count % 4 == 0: a COPY shows the previous snapshot) - list 0; the frames
+//     between them are painted by recon_p_k afterwards, all at once.
+// keeps == nullptr: every block walks list 1 (ring output, one-block-wide pictures, checksums).
+// The position data of frame k+3, the record and bpos of frame k+2 and an L2 prefetch of the codes of frame k+1 are issued
+// before frame k is painted.
+struct RecList { const RecMeta* meta; uint32_t* const* dsts; const RecStream* streams; };
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) reconstruct_k(const RecList snaps, const RecList all, const RecBase base, uint32_t S, uint32_t W, uint32_t H,
+                                                           const uint8_t* __restrict__ keeps) {
     __shared__ uint32_t spal[512];
     const uint32_t sidx = blockIdx.y;
-    const DecStep s0 = steps[sidx];
-    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = s0.pal[k];
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = all.streams[sidx].pal[k];
     __syncthreads();
     const uint32_t bw = W >> 2, B = bw * (H >> 2);
     const uint32_t bb = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = bb < B;
     const uint32_t b = valid ? bb : B - 1;  // surplus threads shadow the last block and write nothing
+    const bool last = b == B - 1;
+    const bool full = !keeps || last || keeps[(size_t)sidx * B + b] != 0;
+    const RecList L = full ? all : snaps;
+    const RecStream st = L.streams[sidx];
+    const uint32_t count = st.count;
+    if (count == 0) return;
+    const RecMeta* __restrict__ meta = L.meta;
+    uint32_t* const* __restrict__ dsts = L.dsts;
     const uint32_t x = (b % bw) * 4, y = (b / bw) * 4;
-    uint32_t prev[16], ifr[16];
+    const size_t pix0 = (size_t)y * W + x;
+    const int dual = st.dual;
+    uint32_t ifr[16];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        uint4 p = *reinterpret_cast<const uint4*>(s0.prev + (size_t)(y + j) * W + x);
-        uint4 q = *reinterpret_cast<const uint4*>(s0.ifr + (size_t)(y + j) * W + x);
-        prev[j * 4] = p.x; prev[j * 4 + 1] = p.y; prev[j * 4 + 2] = p.z; prev[j * 4 + 3] = p.w;
+        const uint4 q = *reinterpret_cast<const uint4*>(st.ifr + pix0 + (size_t)j * W);
         ifr[j * 4] = q.x; ifr[j * 4 + 1] = q.y; ifr[j * 4 + 2] = q.z; ifr[j * 4 + 3] = q.w;
     }
-    const bool last = b == B - 1;
-    uint32_t nb_prev = 0, nb_ifr = 0;  // pixel (x-1, y+1): pixel (3,1) of the left neighbour (or, one block wide, the previous row's end)
-    if (last) {
-        nb_prev = s0.prev[(size_t)(y + 1) * W + x - 1];
-        nb_ifr = s0.ifr[(size_t)(y + 1) * W + x - 1];
-    }
+    const size_t nb_pix = pix0 + W - 1;   // pixel (x-1, y+1): pixel (3,1) of the left neighbour (one block wide: pixel (3,0) of this block)
+    uint32_t nb_ifr = last ? st.ifr[nb_pix] : 0u, nb_prev = last ? st.prev[nb_pix] : 0u;   // (the left neighbour's pixel is another thread's: followed in registers)
+    const uint32_t* pdst = st.prev;        // the previous frame's pixels
+    auto meta_at = [&](uint32_t k) { return meta[(size_t)(k < count ? k : count - 1) * S + sidx]; };
+    RecMeta m0 = meta_at(0), m1 = meta_at(1), m2 = meta_at(2);
+    uint32_t r0 = base.recs[(size_t)m0.fidx * B + b], q0 = base.bpos[m0.fidx], n0 = last && bw > 1 ? base.recs[(size_t)m0.fidx * B + b - 1] : 0u;
+    uint32_t r1 = base.recs[(size_t)m1.fidx * B + b], q1 = base.bpos[m1.fidx], n1 = last && bw > 1 ? base.recs[(size_t)m1.fidx * B + b - 1] : 0u;
+    uint32_t* d0 = dsts[sidx];
     for (uint32_t k = 0; k < count; k++) {
-        const DecStep s = steps[(size_t)k * S + sidx];
-        const uint32_t r = s.recs[b];
-        const VBuf v{s.ebuf, *s.bpos, s.stale};
+        const RecMeta m3 = meta_at(k + 3);
+        const uint32_t r2 = base.recs[(size_t)m2.fidx * B + b], q2 = base.bpos[m2.fidx];
+        const uint32_t n2 = last && bw > 1 ? base.recs[(size_t)m2.fidx * B + b - 1] : 0u;
+        uint32_t* const d1 = dsts[(size_t)(k + 1 < count ? k + 1 : k) * S + sidx];
+        if (r1 != EMPTY32 && (r1 & 3u) != BT_COPY) {
+            const uint8_t* c1 = base.ebuf + m1.ebuf_off + (r1 >> 2);
+            prefetch_l2(c1);
+            if ((r1 & 3u) == BT_NORMAL) prefetch_l2(c1 + 32);
+        }
+        // ---- frame k ----
+        const VBuf v{base.ebuf + m0.ebuf_off, q0, base.stale + (size_t)m0.fidx * 4};
         uint32_t cur[16];
         uint32_t nb_cur = 0;
-        if (last) nb_cur = bw > 1 ? record_pixel(s.recs[b - 1], v, spal, s.dual, 7, nb_prev, nb_ifr) : prev[3];
-        if (r == EMPTY32) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) cur[i] = prev[i];
-        } else if ((r & 3u) == BT_COPY) {
-#pragma unroll
-            for (int i = 0; i < 16; i++) cur[i] = ifr[i];
-        } else if ((r & 3u) == BT_FILL) {
-            uint32_t bp = r >> 2;
-            uint32_t col = read_color(v, bp, spal, s.dual);
-            if (last) col = nb_cur;  // the last block takes img[(x-1)+(y+1)*W] as this frame has left it so far
-#pragma unroll
-            for (int i = 0; i < 16; i++) cur[i] = col;
-        } else {
-            uint32_t bp = r >> 2;
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                uint32_t col = read_color(v, bp, spal, s.dual);
-                cur[i] = bp <= v.bpos ? col : prev[i];
-            }
+        if (last) {
+            // pixel (x-1, y+1) as this frame has left it when the last block is painted
+            if (bw > 1) nb_cur = record_pixel(n0, v, spal, dual, 7, nb_prev, nb_ifr);
+            else nb_cur = pdst[nb_pix];   // this block's own pixel (3,0) before the frame
         }
-        if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                *reinterpret_cast<uint4*>(s.dst + (size_t)(y + j) * W + x) = make_uint4(cur[j * 4], cur[j * 4 + 1], cur[j * 4 + 2], cur[j * 4 + 3]);
-        }
-        if (s.cksum) {  // uniform per launch
-            unsigned long long acc = 0;
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const unsigned long long idx = (unsigned long long)(y + (i >> 2)) * W + x + (i & 3);
-                    acc += (unsigned long long)cur[i] * (2654435761ull + 2ull * idx);
-                }
-            }
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-            if (lane_id() == 0) atomicAdd(s.cksum, acc);
-        }
-#pragma unroll
-        for (int i = 0; i < 16; i++) prev[i] = cur[i];
-        if (s.is_snap) {
+        paint_block(r0, v, spal, dual, ifr, pdst, pix0, W, last, nb_cur, cur);
+        if (valid) store_block(d0, pix0, W, cur);
+        if (st.cksum) checksum_block(st.cksum + (m0.kf & 0x7fffffffu), valid, pix0, W, cur);   // (only with keeps == nullptr: all lanes walk the same list)
+        if (m0.kf >> 31) {
 #pragma unroll
             for (int i = 0; i < 16; i++) ifr[i] = cur[i];
+            if (last) nb_ifr = nb_cur;
         }
-        if (last) { nb_prev = nb_cur; if (s.is_snap) nb_ifr = nb_cur; }
+        nb_prev = nb_cur;
+        pdst = d0; d0 = d1;
+        m0 = m1; m1 = m2; m2 = m3;
+        r0 = r1; r1 = r2; q0 = q1; q1 = q2; n0 = n1; n1 = n2;
+    }
+}
+
+// The frames between snapshots. A frame that is not a snapshot depends on its snapshot frame (COPY blocks) and - damaged or
+// truncated frames only - on the frame before it; once the snapshot frames are written (reconstruct_k over those alone), all
+// runs of up to three such frames are independent of each other: grid (cdiv(B, 128), runs), a thread paints its block in the
+// run's frames, the snapshot's pixels of the block read once if some record of the run is COPY. 1122 of config 3's 1497
+// frames become one bandwidth-bound launch instead of 1122 steps of the chain. Blocks on reconstruct_k's list 1 are skipped.
+__global__ void __launch_bounds__(128) recon_p_k(const RecRun* __restrict__ runs, const RecMeta* __restrict__ meta, uint32_t* const* __restrict__ dsts,
+                                                 const RecStream* __restrict__ streams, const RecBase base, uint32_t S, uint32_t W, uint32_t H,
+                                                 const uint8_t* __restrict__ keeps) {
+    __shared__ uint32_t spal[512];
+    const RecRun run = runs[blockIdx.y];
+    const uint32_t sidx = run.sidx;
+    const RecStream st = streams[sidx];
+    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = st.pal[k];
+    __syncthreads();
+    const uint32_t bw = W >> 2, B = bw * (H >> 2);
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B - 1 || keeps[(size_t)sidx * B + b]) return;   // the last block and the blocks that keep previous pixels: reconstruct_k
+    const bool valid = true, last = false;
+    const uint32_t x = (b % bw) * 4, y = (b / bw) * 4;
+    const size_t pix0 = (size_t)y * W + x;
+    const int dual = st.dual;
+    const size_t nb_pix = pix0 + W - 1;
+    RecMeta m[3];
+    uint32_t r[3], q[3], nr[3];
+    bool any_copy = false;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const uint32_t k = run.first + min((uint32_t)i, run.n - 1);
+        m[i] = meta[(size_t)k * S + sidx];
+        r[i] = base.recs[(size_t)m[i].fidx * B + b];
+        q[i] = base.bpos[m[i].fidx];
+        nr[i] = last && bw > 1 ? base.recs[(size_t)m[i].fidx * B + b - 1] : 0u;
+        any_copy = any_copy || (r[i] != EMPTY32 && (r[i] & 3u) == BT_COPY);
+    }
+    uint32_t ifr[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) ifr[i] = 0;
+    if (any_copy) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint4 s4 = *reinterpret_cast<const uint4*>(run.snap + pix0 + (size_t)j * W);
+            ifr[j * 4] = s4.x; ifr[j * 4 + 1] = s4.y; ifr[j * 4 + 2] = s4.z; ifr[j * 4 + 3] = s4.w;
+        }
+    }
+    const uint32_t nb_ifr = last ? run.snap[nb_pix] : 0u;
+    uint32_t nb_prev = last ? run.prev[nb_pix] : 0u;
+    const uint32_t* pdst = run.prev;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        if ((uint32_t)i < run.n) {
+            const VBuf v{base.ebuf + m[i].ebuf_off, q[i], base.stale + (size_t)m[i].fidx * 4};
+            uint32_t cur[16];
+            uint32_t nb_cur = 0;
+            if (last) {
+                if (bw > 1) nb_cur = record_pixel(nr[i], v, spal, dual, 7, nb_prev, nb_ifr);
+                else nb_cur = pdst[nb_pix];
+            }
+            paint_block(r[i], v, spal, dual, ifr, pdst, pix0, W, last, nb_cur, cur);
+            uint32_t* const d = dsts[(size_t)(run.first + i) * S + sidx];
+            if (valid) store_block(d, pix0, W, cur);
+            nb_prev = nb_cur;
+            pdst = d;
+        }
     }
 }
 

@@ -24,6 +24,20 @@ KEYS = [("gpu__time_duration.sum", "time"), ("dram__bytes_read.sum", "dram read"
         ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle"),
         ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_throttle"),
         ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch"),
+        ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction"),
+        ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "stall imc_miss"),
+        ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch"),
+        ("smsp__average_warps_issue_stalled_drain_per_issue_active.ratio", "stall drain"),
+        ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "stall tex_throttle"),
+        ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
+        ("smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "stall sleeping"),
+        ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar"),
+        ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1TEX % of peak"),
+        ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 % of peak"),
+        ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "global load sectors"),
+        ("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "global load requests"),
+        ("l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "global store sectors"),
+        ("smsp__inst_executed_op_local_ld.sum", "local loads"), ("smsp__inst_executed_op_local_st.sum", "local stores"),
         ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem bank conflicts"), ("lts__t_sectors_data_ecc.sum", "L2 ECC fill sectors")]
 
 
