@@ -328,7 +328,9 @@ def run_b200(args):
         bpp = 3 if args.e2e_pixels == "bgr24" else 4
 
         class Worker:
-            def __init__(self, k):
+            def __init__(self, k, e2e_frames=e2e_frames):
+                self.nf = e2e_frames
+                n_dec = len(pdifs_schedule(e2e_frames, light)[0])
                 self.ctx = ctx if k == 0 else libagmv_b200.Context(local)
                 # host pixels in the reference's own frame format: the packed B,G,R rows of 24-bit BMP files (AGMVB_PIX_BGR24)
                 self.ctx.set_host_format(1 if bpp == 3 else 0)
@@ -340,13 +342,14 @@ def run_b200(args):
                 else:
                     self.host_frames.copy_(frames[:e2e_frames])
                 self.out_host = torch.empty(4096 + e2e_frames * (P // 2), dtype=torch.uint8, pin_memory=True)
-                self.dec_host = torch.empty((len(sa_e), H, W, bpp) if bpp == 3 else (len(sa_e), H, W),
+                self.dec_host = torch.empty((n_dec, H, W, bpp) if bpp == 3 else (n_dec, H, W),
                                             dtype=torch.uint8 if bpp == 3 else torch.int32, pin_memory=True)
                 self.h2d = self.d2h = 0
                 self.err = None
 
             def step(self):
                 c = self.ctx
+                e2e_frames = self.nf
                 hf = self.host_frames.numpy()
                 data, ne = c.encode_sequence(hf if bpp == 3 else hf.view(np.uint32), e2e_frames - 1, 24, OPT_III, HIGH, COMP,
                                              out=self.out_host.numpy())
@@ -416,6 +419,32 @@ def run_b200(args):
                    "note": f"{n_streams} independent {e2e_frames}-frame sequences at a time per GPU (one host thread + context each): "
                            "agmvb_encode_sequence + agmvb_dec_open/agmvb_dec_frames on pinned host buffers "
                            + ("(packed 24-bit BMP pixel rows in and out, AGMVB_PIX_BGR24)" if bpp == 3 else "(u32 pixels)") + ", host wall clock"}
+        # second figure: ONE sequence of the whole configuration (all of this GPU's source frames) host to host, nothing else in
+        # flight - upload, encode, fetch, open, decode and download follow each other, as a single AGMV_EncodeAGMV +
+        # AGMV_DecodeAGMV caller sees them
+        if e2e is not None and not args.no_e2e_single:
+            workers = None
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            try:
+                wk = Worker(0, n_local)
+                wk.step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    wk.step()
+                barrier()
+                dt1 = (time.perf_counter() - t0) / 2
+                if world > 1:
+                    t = torch.tensor([dt1], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    dt1 = float(t.item())
+                e2e["single_sequence"] = {"value": n_local * world / dt1, "unit": UNIT, "frames": n_local,
+                                          "note": "one sequence per GPU, nothing overlapped: upload + encode + fetch + open + decode + download in turn"}
+                del wk
+            except Exception as e:
+                log(f"single-sequence e2e leg failed on rank {rank}: {e}")
         ctx.set_host_format(0)
         workers = None
 
@@ -886,10 +915,11 @@ def main():
     ap.add_argument("--frames", type=int, default=2000, help="source frames per GPU (BASELINE config 3: 2000)")
     ap.add_argument("--compression", default="lzss", choices=["lzss", "lz77"], help="entropy coder (BASELINE config 3: lzss; lz77 = SURVEY 8f N2)")
     ap.add_argument("--e2e-frames", type=int, default=512)
-    ap.add_argument("--e2e-streams", type=int, default=4, help="independent sequences in flight per GPU in the e2e leg")
+    ap.add_argument("--e2e-streams", type=int, default=6, help="independent sequences in flight per GPU in the e2e leg")
     ap.add_argument("--e2e-pixels", default="bgr24", choices=["bgr24", "u32"], help="host pixel format of the e2e leg")
     ap.add_argument("--e2e-iters", type=int, default=0, help="sequences per worker in the e2e leg (default max(8, steps))")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-single", action="store_true", help="skip the one-sequence-of-the-whole-configuration figure of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-procs", type=int, default=0)
     args = ap.parse_args()

@@ -230,7 +230,8 @@ int agmvb_test_lzss(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_s
  * one handle do; every byte of that buffer starts as persist_fill (the reference: 0). out + out_off[f]: frame f's tokens. */
 int agmvb_test_lz77(agmvb_ctx* ctx, const uint8_t* data, const uint32_t* frame_start, uint32_t F, int persist_fill,
                     uint8_t* out, uint64_t out_cap, uint64_t* out_off, uint32_t* csize);
-/* AGMV_FindNearestEntry / AGMV_FindNearestColor over n colours (src/agmv_utils.c:785-895) */
+/* AGMV_FindNearestEntry / AGMV_FindNearestColor over n colours (src/agmv_utils.c:785-895). dual: bit 0 = two palettes;
+ * bit 1 = compute the entries of all 2^24 colours first, as calls that encode long sequences do, and read the answers there */
 int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint64_t n, const uint32_t pal0[256],
                         const uint32_t pal1[256], int dual, uint16_t* entries);
 /* AGMV_Assemble{I,P}FrameBitstream on ready-made entries (src/agmv_encode.c:354-527) */

@@ -383,12 +383,12 @@ class Context:
                                           _p(cs, _u32p)))
         return [(int(cs[k]), out[int(off[k]):int(off[k + 1])].tobytes()) for k in range(len(arrs))]
 
-    def test_quantize(self, colors, pal0, pal1, dual):
+    def test_quantize(self, colors, pal0, pal1, dual, full_table=False):
         colors = np.ascontiguousarray(colors, np.uint32)
         pal0 = np.ascontiguousarray(pal0, np.uint32)
         pal1 = np.ascontiguousarray(pal1, np.uint32)
         ent = np.zeros(colors.size, np.uint16)
-        self._ck(self.lib.agmvb_test_quantize(self.h, _p(colors, _u32p), colors.size, _p(pal0, _u32p), _p(pal1, _u32p), 1 if dual else 0,
+        self._ck(self.lib.agmvb_test_quantize(self.h, _p(colors, _u32p), colors.size, _p(pal0, _u32p), _p(pal1, _u32p), (1 if dual else 0) | (2 if full_table else 0),
                                               _p(ent, _u16p)))
         return ent
 

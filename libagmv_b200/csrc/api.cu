@@ -76,6 +76,7 @@ struct agmvb_ctx {
     uint32_t h_pal[512];
     bool pal_valid = false;
     uint16_t* d_lut = nullptr;  // 2^24
+    bool lut_full = false;      // every colour's entry is in the table (lut_fill_k)
     uint32_t* d_map = nullptr;  // coded pixel -> source pixel (GBA / NDS profiles)
     uint16_t* d_ient = nullptr; // persistent I-frame entries
     size_t ient_px = 0;
@@ -209,6 +210,8 @@ extern "C" int agmvb_create(agmvb_ctx** out, int device, void* cuda_stream) {
     return OK;
 }
 
+constexpr uint32_t DEC_RING = 8;   // frames of a stream's output ring (agmvb_dec_batch without output buffers)
+
 static void free_stream(DecStream& s) {
     cudaFree(s.d_file); cudaFree(s.d_pal); cudaFree(s.d_img); cudaFree(s.d_ifr); cudaFree(s.d_persist); cudaFree(s.d_ring); cudaFree(s.d_snap);
     s = DecStream();
@@ -228,7 +231,7 @@ extern "C" void agmvb_destroy(agmvb_ctx* ctx) {
     DBuf* bufs[] = {&ctx->stage, &ctx->entries, &ctx->rec, &ctx->boff, &ctx->bs, &ctx->fs, &ctx->image, &ctx->srcpairs, &ctx->entpairs,
                     &ctx->scanws, &ctx->small, &ctx->seqbuf, &ctx->d_frames, &ctx->d_ebuf, &ctx->d_bpos, &ctx->d_consumed, &ctx->d_stale, &ctx->d_recs,
                     &ctx->d_steps, &ctx->d_out, &ctx->d_cksum, &ctx->d_count, &ctx->d_code, &ctx->d_segs, &ctx->d_seglen, &ctx->d_oexit, &ctx->d_ow,
-                    &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal};
+                    &ctx->d_oentry, &ctx->d_ocum, &ctx->d_ofinal, &ctx->d_keeps};
     for (DBuf* b : bufs) cudaFree(b->p);
     for (DBuf& b : ctx->lzbuf) cudaFree(b.p);
     cudaFree(ctx->at_pcm.p); cudaFree(ctx->at_sample.p); cudaFree(ctx->at_idx.p); cudaFree(ctx->at_lut.p);
@@ -332,6 +335,7 @@ extern "C" int agmvb_enc_begin(agmvb_ctx* ctx, uint32_t src_w, uint32_t src_h, i
     if (!ctx->d_lut) CK(cudaMalloc(&ctx->d_lut, sizeof(uint16_t) << 24));
     CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(unsigned long long) * (524287 + 1), ctx->st));
     CK(cudaMemsetAsync(ctx->d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));
+    ctx->lut_full = false;
     if (ctx->d_ient && ctx->ient_px != P) { CK(cudaStreamSynchronize(ctx->st)); CK(cudaFree(ctx->d_ient)); ctx->d_ient = nullptr; }
     if (!ctx->d_ient) { CK(cudaMalloc(&ctx->d_ient, P * 2)); ctx->ient_px = P; }
     CK(cudaMemsetAsync(ctx->d_ient, 0, P * 2, ctx->st));
@@ -450,6 +454,7 @@ extern "C" int agmvb_enc_set_palette(agmvb_ctx* ctx, const uint32_t pal0[256], c
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaMemcpyAsync(ctx->d_pal, ctx->h_pal, 512 * 4, cudaMemcpyHostToDevice, ctx->st));
     CK(cudaMemsetAsync(ctx->d_lut, 0xFF, sizeof(uint16_t) << 24, ctx->st));  // the memo table belongs to a palette
+    ctx->lut_full = false;
     CK(cudaStreamSynchronize(ctx->st));
     ctx->pal_valid = true;
     return OK;
@@ -732,6 +737,14 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
                                               : std::max<size_t>(4, std::min<size_t>(1024, (4096ull << 20) / (P * 2)));
     if (qb_env) qb = qb_env;
     const uint32_t QB = (uint32_t)std::min(qb, qb_off);
+    // enough pixels ahead to pay for the whole colour table at once (about 1 ms, encode.cuh lut_fill_k): no quantiser launch of
+    // this palette meets an empty entry afterwards. AGMVB_LUT_FILL_PX overrides the threshold (pixels of the call; 0 = always).
+    static const uint64_t fill_from = getenv("AGMVB_LUT_FILL_PX") ? strtoull(getenv("AGMVB_LUT_FILL_PX"), nullptr, 10) : (1ull << 27);
+    if (!ctx->lut_full && (uint64_t)n_enc * P >= fill_from) {
+        KL(ctx->lc, KC_QUANT, (lut_fill_k<<<(1u << 24) / 1024u, 256, 0, ctx->st>>>(ctx->d_pal, ctx->dual ? 512 : 256, reinterpret_cast<uint2*>(ctx->d_lut))));
+        TRY(check_launch(ctx, "lut_fill"));
+        ctx->lut_full = true;
+    }
     std::vector<SrcPair> sp;
     std::vector<EntPair> ep;
     for (uint32_t q0 = 0; q0 < n_enc; q0 += QB) {
@@ -767,8 +780,12 @@ extern "C" int agmvb_enc_frames(agmvb_ctx* ctx, const uint32_t* frames, uint64_t
                                                                           ctx->d_lut, ctx->entries.as<uint16_t>())));
         } else {
             dim3 qgrid(cdiv(P / 8, 256), F);
-            KL(ctx->lc, KC_QUANT, (quantize8_k<<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256, ctx->d_lut,
-                                                                           ctx->entries.as<uint16_t>())));
+            if (ctx->lut_full)
+                KL(ctx->lc, KC_QUANT, (quantize8_k<true><<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256,
+                                                                                     ctx->d_lut, ctx->entries.as<uint16_t>())));
+            else
+                KL(ctx->lc, KC_QUANT, (quantize8_k<false><<<qgrid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), (uint32_t)P, ctx->d_pal, ctx->dual ? 512 : 256,
+                                                                                      ctx->d_lut, ctx->entries.as<uint16_t>())));
         }
         TRY(check_launch(ctx, "quantize"));
         int last_i = -1;
@@ -1297,7 +1314,21 @@ static void park_stream(agmvb_ctx* ctx, DecStream& s) {
     k.d_file = s.d_file; k.file_cap = s.file_cap; k.d_pal = s.d_pal; k.d_img = s.d_img; k.d_ifr = s.d_ifr; k.d_persist = s.d_persist;
     k.persist_len = s.persist_len; k.d_ring = s.d_ring; k.w = s.w; k.h = s.h;
     cudaFree(s.d_snap);
-    if (ctx->parked.size() < 1024) ctx->parked.push_back(k); else free_stream(k);
+    // bounded: the oldest parked buffers go first (AGMVB_PARK_MB per context, default a third of the device's memory; 0 = park nothing)
+    static const uint64_t park_cap = [] {
+        if (getenv("AGMVB_PARK_MB")) return strtoull(getenv("AGMVB_PARK_MB"), nullptr, 10) << 20;
+        size_t free_b = 0, total_b = 0;
+        return cudaMemGetInfo(&free_b, &total_b) == cudaSuccess ? (unsigned long long)(total_b / 3) : (8192ull << 20);
+    }();
+    auto bytes_of = [](const DecStream& c) { return c.file_cap + (uint64_t)c.w * c.h * 8 + c.persist_len + (c.d_ring ? (uint64_t)DEC_RING * c.w * c.h * 4 : 0) + 2048; };
+    ctx->parked.push_back(k);
+    uint64_t total = 0;
+    for (const DecStream& c : ctx->parked) total += bytes_of(c);
+    while (!ctx->parked.empty() && (total > park_cap || ctx->parked.size() > 1024)) {
+        total -= bytes_of(ctx->parked.front());
+        free_stream(ctx->parked.front());
+        ctx->parked.erase(ctx->parked.begin());
+    }
     s = DecStream();
 }
 static bool unpark_stream(agmvb_ctx* ctx, DecStream& s, uint64_t file_bytes, size_t P) {
@@ -1333,7 +1364,14 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
         const uint8_t* p = file + 38 + 3 * i;
         pal[i] = (uint32_t)p[0] << 16 | (uint32_t)p[1] << 8 | p[2];  // AGIDL_RGB(r,g,b,RGB_888)
     }
+    // W and H come from the file: bound what a damaged header can make this call allocate (AGMVB_MAX_PIXELS, default 2^28)
+    static const uint64_t max_px = getenv("AGMVB_MAX_PIXELS") ? strtoull(getenv("AGMVB_MAX_PIXELS"), nullptr, 10) : (1ull << 28);
+    if ((uint64_t)W * H > max_px) FAIL(ERR_UNSUPPORTED, "%u x %u pixels exceed AGMVB_MAX_PIXELS", W, H);
     DecStream s;
+    struct Guard {   // every error return below releases what the stream holds on the device
+        DecStream* s;
+        ~Guard() { if (s) free_stream(*s); }
+    } guard{&s};
     s.w = W; s.h = H; s.n_frames = nfr; s.version = (uint32_t)version; s.dual = dual; s.lz77 = version >= 3; s.file_len = len;
     const uint32_t audio_duration = get32(file + 22);
     const size_t P = (size_t)W * H;
@@ -1387,9 +1425,9 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
         cursor = 38 + pal_bytes;
         for (uint32_t i = 0; i < nfr; i++) {
             int64_t at = find_next_agfc(file, len, cursor);
-            if (at < 0 || (uint64_t)at + 16 > len) { free_stream(s); FAIL(ERR_HEADER, "frame chunk %u not found", i); }
+            if (at < 0 || (uint64_t)at + 16 > len) FAIL(ERR_HEADER, "frame chunk %u not found", i);
             uint32_t us = get32(file + at + 8), cs = get32(file + at + 12);
-            if (us > 2 * P + 64) { free_stream(s); FAIL(ERR_MEMORY, "frame %u too large", i); }
+            if (us > 2 * P + 64) FAIL(ERR_MEMORY, "frame %u too large", i);
             s.data_off.push_back((uint64_t)at + 16); s.usize.push_back(us); s.csize.push_back(cs);
             cursor = (uint64_t)at + 16 + lzss_consumed_host(file, len, (uint64_t)at + 16, us, cs);
             if (audio_duration != 0) {
@@ -1405,6 +1443,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     for (size_t k = 0; k < ctx->streams.size(); k++) if (!ctx->streams[k].open) { id = (int)k; break; }
     if (id < 0) { ctx->streams.push_back(DecStream()); id = (int)ctx->streams.size() - 1; }
     ctx->streams[id] = s;
+    guard.s = nullptr;
     *stream = id;
     if (w) *w = W;
     if (h) *h = H;
@@ -1468,7 +1507,6 @@ extern "C" int agmvb_dec_seek(agmvb_ctx* ctx, int stream, uint32_t frame_index) 
     return OK;
 }
 
-constexpr uint32_t DEC_RING = 8;
 
 // Decode the next `count` frames of each listed stream (all of one size).
 // outs[s]: device destination (count*P pixels) or nullptr for the per-stream ring.
@@ -2035,10 +2073,13 @@ extern "C" int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint6
                                    int dual, uint16_t* entries) {
     if (!ctx || !colors || !pal0 || !entries || (n & 3) || n > 0xFFFFFFFCull) return ERR_ARG;
     CK(cudaSetDevice(ctx->device));
+    const bool fill = dual & 2;   // bit 1: compute the whole table first (lut_fill_k), as long sequences do
+    dual &= 1;
     uint32_t pal[512];
     memset(pal, 0, sizeof pal);
     memcpy(pal, pal0, 1024);
     if (dual && pal1) memcpy(pal + 256, pal1, 1024);
+    for (int i = 0; i < 512; i++) pal[i] &= 0xFFFFFFu;
     uint32_t* d_pal; uint16_t* d_lut;
     CK(cudaMalloc(&d_pal, 2048));
     CK(cudaMalloc(&d_lut, sizeof(uint16_t) << 24));
@@ -2051,6 +2092,7 @@ extern "C" int agmvb_test_quantize(agmvb_ctx* ctx, const uint32_t* colors, uint6
     SrcPair sp{ctx->stage.as<uint32_t>(), nullptr};
     CK(cudaMemcpyAsync(ctx->srcpairs.p, &sp, sizeof sp, cudaMemcpyHostToDevice, ctx->st));
     dim3 grid(cdiv(n / 4, 256), 1);
+    if (fill) KL(ctx->lc, KC_QUANT, (lut_fill_k<<<(1u << 24) / 1024u, 256, 0, ctx->st>>>(d_pal, dual ? 512 : 256, reinterpret_cast<uint2*>(d_lut))));
     KL(ctx->lc, KC_QUANT, (quantize_k<<<grid, 256, 0, ctx->st>>>(ctx->srcpairs.as<SrcPair>(), nullptr, (uint32_t)n, d_pal, dual ? 512 : 256, d_lut, ctx->entries.as<uint16_t>())));
     TRY(check_launch(ctx, "quantize"));
     CK(cudaMemcpyAsync(entries, ctx->entries.p, n * 2, cudaMemcpyDeviceToHost, ctx->st));

@@ -227,15 +227,47 @@ __device__ __forceinline__ uint32_t lut_entry(uint32_t c, bool valid, uint16_t* 
     return e;
 }
 
+// The whole table at once: 2^24 colours x 512 entries is 8.6 G distances - about a millisecond of dp4a on this GPU, less
+// than what the cooperative miss path costs while a long sequence warms the table up (the first 1070-frame batch of the
+// bench configuration quantised at 7.6 us per frame cold against 4.8 us warm, profiles/r02_ncu_summary.txt). Used when a
+// call encodes enough pixels to pay for it (api.cu); the quantisers then never meet an empty entry.
+// Ordering: key = d * 512 + j with d = c.c + p.p - 2 c.p; c.c is the same for every j, so the minimum of
+// (p.p * 512 + j) - 1024 c.p (signed) picks the same entry, and j = key & 511.
+// grid 2^24 / 1024 blocks of 256 threads, four consecutive colours per thread.
+__global__ void __launch_bounds__(256) lut_fill_k(const uint32_t* __restrict__ pal, int npal, uint2* __restrict__ lut4) {
+    __shared__ uint2 sp[512];
+    for (int k = threadIdx.x; k < npal; k += blockDim.x) {
+        const uint32_t p = pal[k];
+        sp[k] = make_uint2(p, __dp4a(p, p, 0u) * 512u + (uint32_t)k);
+    }
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t c0 = t * 4u;
+    int b0 = 0x7fffffff, b1 = 0x7fffffff, b2 = 0x7fffffff, b3 = 0x7fffffff;
+#pragma unroll 8
+    for (int j = 0; j < npal; j++) {
+        const uint2 e = sp[j];
+        b0 = min(b0, (int)e.y - 1024 * (int)__dp4a(c0, e.x, 0u));
+        b1 = min(b1, (int)e.y - 1024 * (int)__dp4a(c0 + 1u, e.x, 0u));
+        b2 = min(b2, (int)e.y - 1024 * (int)__dp4a(c0 + 2u, e.x, 0u));
+        b3 = min(b3, (int)e.y - 1024 * (int)__dp4a(c0 + 3u, e.x, 0u));
+    }
+    lut4[t] = make_uint2(((uint32_t)b0 & 511u) | ((uint32_t)b1 & 511u) << 16, ((uint32_t)b2 & 511u) | ((uint32_t)b3 & 511u) << 16);
+}
+
 // grid (cdiv(P/8, 256), n_enc), unscaled profiles: eight pixels per thread. The interpolation of a byte is
 // c1 + ((c2 - c1) >> 1) = floor((c1 + c2) / 2), one halving add on the packed word; the eight table look-ups are issued
 // together and a single vote decides whether anybody missed (rare once the table is warm) - only then does the warp
 // enter the cooperative evaluation. P is a multiple of 16 (width and height are multiples of 4).
+// FULL: the table holds every colour (lut_fill_k): no miss check.
+template <bool FULL>
 __global__ void __launch_bounds__(256) quantize8_k(const SrcPair* __restrict__ src, uint32_t P, const uint32_t* __restrict__ pal, int npal,
                                                    uint16_t* __restrict__ lut, uint16_t* __restrict__ entries) {
-    __shared__ uint32_t spal[512];
-    for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = k < npal ? pal[k] : 0u;
-    __syncthreads();
+    __shared__ uint32_t spal[FULL ? 1 : 512];
+    if (!FULL) {
+        for (int k = threadIdx.x; k < 512; k += blockDim.x) spal[k] = k < npal ? pal[k] : 0u;
+        __syncthreads();
+    }
     const uint32_t f = blockIdx.y;
     const SrcPair sp = src[f];
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;  // group of 8 pixels
@@ -259,11 +291,13 @@ __global__ void __launch_bounds__(256) quantize8_k(const SrcPair* __restrict__ s
         c[k] &= 0xFFFFFFu;
         e[k] = valid ? lut[c[k]] : 0u;
     }
+    if (!FULL) {
 #pragma unroll
-    for (int k = 0; k < 8; k++) miss |= e[k] == LUT_EMPTY;
-    if (__any_sync(0xffffffffu, miss)) {
+        for (int k = 0; k < 8; k++) miss |= e[k] == LUT_EMPTY;
+        if (__any_sync(0xffffffffu, miss)) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) e[k] = lut_entry(c[k], valid, lut, spal, npal);
+            for (int k = 0; k < 8; k++) e[k] = lut_entry(c[k], valid, lut, spal, npal);
+        }
     }
     if (valid)
         __stcs(reinterpret_cast<uint4*>(entries + (size_t)f * P) + g, make_uint4(e[0] | e[1] << 16, e[2] | e[3] << 16, e[4] | e[5] << 16, e[6] | e[7] << 16));

@@ -70,8 +70,9 @@ def test_lzss_window_boundary_large(ctx):
 
 
 # ---- K2: quantise ---------------------------------------------------------------
+@pytest.mark.parametrize("full_table", [False, True])   # memoised on demand / all 2^24 entries computed first (lut_fill_k)
 @pytest.mark.parametrize("dual", [1, 0])
-def test_quantize_against_oracle(ctx, dual):
+def test_quantize_against_oracle(ctx, dual, full_table):
     frames = synth_frames(96, 80, 6, seed=3)
     p0, p1 = _palettes(frames, QUALITY["LOW"], OPT["III"] if dual else OPT["II"])
     rng = np.random.default_rng(2)
@@ -79,7 +80,7 @@ def test_quantize_against_oracle(ctx, dual):
     cols = np.concatenate([p0, p1, (p0 + 0x010101) & 0xFFFFFF, rng.integers(0, 1 << 24, 200000, dtype=np.uint32),
                            np.arange(256, dtype=np.uint32) * 0x010101]).astype(np.uint32)
     cols = np.concatenate([cols, np.zeros((-len(cols)) % 4, np.uint32)])
-    ent = ctx.test_quantize(cols, p0, p1, dual)
+    ent = ctx.test_quantize(cols, p0, p1, dual, full_table)
     lib = oracle()
     exp = np.zeros(cols.size, np.uint16)
     lib.orc_quantize_frame(ptr(cols, C.POINTER(C.c_uint32)), cols.size, ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)),
@@ -95,6 +96,7 @@ def test_quantize_degenerate_palette_ties(ctx):
     p1 = p0.copy()
     cols = np.array([0, 0x808080, 0x7f7f7f, 0xFFFFFF, 0x404040, 0xC0C0C0, 0x123456, 0xFEFEFE], np.uint32)
     ent = ctx.test_quantize(cols, p0, p1, 1)
+    assert np.array_equal(ent, ctx.test_quantize(cols, p0, p1, 1, full_table=True))
     lib = oracle()
     exp = np.array([lib.orc_nearest_entry(ptr(p0, C.POINTER(C.c_uint32)), ptr(p1, C.POINTER(C.c_uint32)), 1, int(c)) for c in cols], np.uint16)
     assert np.array_equal(ent, exp)
