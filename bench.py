@@ -422,7 +422,15 @@ def run_b200(args):
         # second figure: ONE sequence of the whole configuration (all of this GPU's source frames) host to host, nothing else in
         # flight - upload, encode, fetch, open, decode and download follow each other, as a single AGMV_EncodeAGMV +
         # AGMV_DecodeAGMV caller sees them
-        if e2e is not None and not args.no_e2e_single:
+        single_need = n_local * P * bpp * 1.75 + n_local * (P // 2) + 4096      # pinned bytes: frames in, decoded frames out, stream
+        try:
+            import psutil
+            single_ok = single_need < psutil.virtual_memory().total / max(1, world) / 2.5
+        except Exception:
+            single_ok = world == 1
+        if e2e is not None and not args.no_e2e_single and not single_ok:
+            e2e["single_sequence"] = {"skipped": f"{single_need / 1e9:.1f} GB of pinned host memory per rank for one {n_local}-frame sequence does not fit {world} ranks on this host"}
+        if e2e is not None and not args.no_e2e_single and single_ok:
             workers = None
             import gc
             gc.collect()

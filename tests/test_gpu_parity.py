@@ -436,6 +436,39 @@ def test_lz77_720p_against_oracle(ctx):
     assert np.array_equal(ctx.decode_all(want), ref_frames)
 
 
+def test_concurrent_sequences_through_the_transfer_gate(golden):
+    """Four contexts on one device, one host thread each, host buffers in and out (bench.py's e2e leg): the bulk transfers
+    queue up at the per-direction gate of csrc/api.cu; every thread must get the bytes and pixels a lone context gets."""
+    import threading
+    import libagmv_b200
+    g = golden["encode"]["syn96x80_III_LOW"]
+    frames = np.ascontiguousarray(synth_frames(g["w"], g["h"], g["n"], seed=g["seed"]))
+    res, errs = {}, []
+
+    def work(k):
+        try:
+            c = libagmv_b200.Context(0)
+            for it in range(3):
+                data, _ = c.encode_sequence(frames, g["create_n"], g["fps"], OPT[g["opt"]], QUALITY[g["quality"]], LZSS)
+                sid, w, h, n = c.dec_open(data.tobytes())
+                out = c.dec_frames(sid, n, w, h)
+                c.dec_close(sid)
+                res[(k, it)] = (sha256(data.tobytes()), [sha256(out[j].tobytes()) for j in range(n)])
+            c.close()
+        except Exception as e:  # surfaced below
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(k,)) for k in range(4)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    assert len(res) == 12
+    for v in res.values():
+        assert v == (g["sha256"], g["decoded_frame_sha256"])
+
+
 def test_bgr24_host_frames_equal_u32_path(ctx, golden):
     """AGMVB_PIX_BGR24: packed BMP pixel rows in, packed rows out - same stream bytes and same pixels as the u32 path."""
     g = golden["encode"]["syn96x80_III_LOW"]
