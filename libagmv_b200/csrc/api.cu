@@ -1266,12 +1266,21 @@ extern "C" int agmvb_encode_sequence_multi(agmvb_ctx* const* ctxs, int n_ctx, co
 // ===========================================================================
 // decoder
 // ===========================================================================
-__global__ void count_fourcc_k(const uint8_t* __restrict__ d, uint64_t len, uint32_t fourcc, unsigned long long* __restrict__ count) {
-    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool hit = false;
-    if (i + 4 <= len) hit = (d[i] | d[i + 1] << 8 | d[i + 2] << 16 | (uint32_t)d[i + 3] << 24) == fourcc;
-    unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (m && lane_id() == 0) atomicAdd(count, (unsigned long long)__popc(m));
+// occurrences of a four-byte tag at any byte offset; sixteen offsets per thread from five aligned words (the file image is
+// 16-byte aligned and followed by at least 64 readable zero bytes)
+__global__ void __launch_bounds__(256) count_fourcc_k(const uint8_t* __restrict__ d, uint64_t len, uint32_t fourcc, unsigned long long* __restrict__ count) {
+    const uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16u;
+    uint32_t hits = 0;
+    if (i0 < len) {
+        const uint4 a = *reinterpret_cast<const uint4*>(d + i0);
+        const uint32_t w[5] = {a.x, a.y, a.z, a.w, *reinterpret_cast<const uint32_t*>(d + i0 + 16)};
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            hits += __funnelshift_r(w[k >> 2], w[(k >> 2) + 1], (k & 3) * 8) == fourcc && i0 + k + 4 <= len;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
+    if (hits && lane_id() == 0) atomicAdd(count, (unsigned long long)hits);
 }
 
 // Walk the file the way AGMV_DecodeAGMV does: AGMV_FindNextFrameChunk (src/agmv_utils.c:140-166) checks the
@@ -1415,7 +1424,7 @@ extern "C" int agmvb_dec_open(agmvb_ctx* ctx, const uint8_t* file, uint64_t len,
     // stray 'AGFC' inside a payload would make the chunk walk depend on where the bit reader stopped
     TRY(ensure(ctx, ctx->d_count, 8));
     CK(cudaMemsetAsync(ctx->d_count.p, 0, 8, ctx->st));
-    KL(ctx->lc, KC_MISC, (count_fourcc_k<<<cdiv(len, 256), 256, 0, ctx->st>>>(s.d_file, len, 0x43464741u, ctx->d_count.as<unsigned long long>())));
+    KL(ctx->lc, KC_MISC, (count_fourcc_k<<<cdiv(cdiv(len, 16), 256), 256, 0, ctx->st>>>(s.d_file, len, 0x43464741u, ctx->d_count.as<unsigned long long>())));
     unsigned long long hits = 0;
     CK(cudaMemcpyAsync(&hits, ctx->d_count.p, 8, cudaMemcpyDeviceToHost, ctx->st));
     CK(cudaStreamSynchronize(ctx->st));

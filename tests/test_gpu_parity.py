@@ -283,6 +283,32 @@ def test_decode_damaged_payloads_like_the_reference(ctx, golden, name):
         assert np.array_equal(got, exp), f"trial {trial}"
 
 
+def test_stray_chunk_tag_inside_a_payload(ctx, golden):
+    """'AGFC' inside a payload: AGMV_FindNextFrameChunk (src/agmv_utils.c:140-166) may stop there, depending on where the bit
+    reader left the cursor. The decoder counts the tag's occurrences on the device (sixteen byte offsets per thread) and
+    replays the cursor walk when the count is off; the pictures must be the restated reference's. Offsets chosen to land
+    on every alignment of the tag within a 16-byte unit, word boundaries included."""
+    g = golden["encode"]["syn96x80_III_LOW"]
+    with open(os.path.join(GOLDEN_DIR, g["file"]), "rb") as f:
+        clean = f.read()
+    ranges = [r for r in _chunk_ranges(clean) if r[1] >= 64]
+    checked = 0
+    for k in range(16):
+        data = bytearray(clean)
+        start, cs = ranges[k % len(ranges)]
+        at = (start + cs // 2) // 16 * 16 + k          # tag at byte k of a 16-byte unit
+        if at + 4 > start + cs:
+            continue
+        data[at:at + 4] = b"AGFC"
+        data = bytes(data)
+        rc, exp = oracle_decode(data)
+        if rc != 0:
+            continue
+        assert np.array_equal(ctx.decode_all(data), exp), f"tag at unit offset {k}"
+        checked += 1
+    assert checked >= 8
+
+
 def test_4k_prefix_against_oracle(ctx):
     """BASELINE config 4's frame size (3840x2160, OPT_III): 8 source frames, GPU bytes and frames == oracle."""
     frames = synth_frames(3840, 2160, 8, seed=1234)
