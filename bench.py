@@ -324,7 +324,7 @@ def run_b200(args):
             else:
                 e2e_frames //= 2
         sa_e, sb_e = pdifs_schedule(e2e_frames, light)
-        iters = args.e2e_iters if args.e2e_iters > 0 else max(8, args.steps)   # the pipeline of sequences needs a few rounds to fill and drain
+        iters = args.e2e_iters if args.e2e_iters > 0 else max(16, args.steps)   # the pipeline of sequences needs a few rounds to fill and drain; run to run the leg varies by ~5 %
         bpp = 3 if args.e2e_pixels == "bgr24" else 4
 
         class Worker:
@@ -925,7 +925,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=512)
     ap.add_argument("--e2e-streams", type=int, default=6, help="independent sequences in flight per GPU in the e2e leg")
     ap.add_argument("--e2e-pixels", default="bgr24", choices=["bgr24", "u32"], help="host pixel format of the e2e leg")
-    ap.add_argument("--e2e-iters", type=int, default=0, help="sequences per worker in the e2e leg (default max(8, steps))")
+    ap.add_argument("--e2e-iters", type=int, default=0, help="sequences per worker in the e2e leg (default max(16, steps))")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-single", action="store_true", help="skip the one-sequence-of-the-whole-configuration figure of the e2e leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
