@@ -196,6 +196,10 @@ def run_b200(args):
 
     n_local = args.frames                      # source frames per GPU
     COMP = 2 if args.compression == "lz77" else LZSS_C
+    if COMP == 2 and world > 1:
+        # AGMV_LZ77 carries its bitstream buffer from frame to frame (src/agmv_encode.c:218-224): frame-range shards of one
+        # sequence would each start from an empty buffer and the assembled file would not be the single-process stream
+        raise SystemExit("--compression lz77 is not sharded across GPUs (DESIGN.md section 8, N2): run it with --gpus 1")
     n_total = n_local * world
     P = W * H
     # inputs resident in HBM before the timed region
